@@ -1,0 +1,125 @@
+/*
+ * lumen_b200.h -- C ABI of the B200-native Path integrator (liblumen_b200.so, CUDA sm_100a).
+ *
+ * This is the drop-in boundary for Lumen's `Path` integrator. Reference interface being replaced:
+ *   class Integrator { init(); render(); update(); destroy(); create_accel(); output_tex; frame_num; }
+ *       src/RayTracer/Integrator.h:14-33, src/RayTracer/Path.h:4-23, src/RayTracer/Path.cpp:4-70
+ *   scene upload                     src/RayTracer/LumenScene.cpp:134-216
+ *   acceleration-structure build     src/RayTracer/Integrator.cpp:137-160, src/Framework/AccelerationStructure.cpp:171-315
+ *   per-frame dispatch               src/RayTracer/Path.cpp:27-59 -> vkCmdTraceRaysKHR(W, H, 1)
+ * Mapping (see INTEGRATION.md for the C++ shim `class PathB200 final : public Integrator`):
+ *   RayTracer::init                  -> lmb_create, lmb_upload_scene
+ *   Integrator::create_accel         -> lmb_build_accel
+ *   Path::init / Integrator::init    -> lmb_init(width, height)
+ *   Path::render (one frame)         -> lmb_render(pc, ubo, frame_num, 1)   (batched: n_frames > 1)
+ *   output_tex readback (F10 -> EXR) -> lmb_download
+ *   Path::destroy / cleanup          -> lmb_destroy
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary. Every call returns 0 on success or a
+ * negative lmb_status; nothing throws. Calls on one context must be serialised by the caller; one context drives one
+ * GPU (one process per GPU; see DESIGN.md "Multi-GPU").
+ */
+#ifndef LUMEN_B200_H
+#define LUMEN_B200_H
+
+#include <stdint.h>
+#include "lmb_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lmb_ctx lmb_ctx;
+
+enum lmb_status {
+	LMB_OK = 0,
+	LMB_ERR_INVALID = -1,   /* bad argument or call order */
+	LMB_ERR_CUDA = -2,      /* CUDA runtime error, see lmb_last_error */
+	LMB_ERR_NO_DEVICE = -3, /* no usable CUDA device: there is no CPU fallback */
+	LMB_ERR_OOM = -4
+};
+
+/* Film update rule for lmb_render. */
+enum lmb_film_mode {
+	/* path.rgen:102-112: running mean in frame order, NaN samples skipped, alpha = 1. Requires frame_stride == 1. */
+	LMB_FILM_RUNNING_MEAN = 0,
+	/* Sharded rendering: rgb += sample, alpha += 1 per non-NaN sample. After the cross-GPU sum, lmb_resolve divides.  */
+	LMB_FILM_SUM = 1
+};
+
+typedef struct lmb_stats {
+	uint64_t rays_closest; /* continuation rays (path.rgen:48) */
+	uint64_t rays_shadow;  /* any-hit rays (pt_commons.glsl:21) */
+	uint64_t rays_probe;   /* MIS BSDF-probe rays (pt_commons.glsl:32) */
+	uint64_t nodes_visited;
+	uint64_t tris_tested;
+	uint64_t nan_samples;  /* samples dropped by the NaN guard */
+	uint64_t frames;       /* frames rendered since lmb_init / lmb_reset_stats */
+	uint64_t kernel_launches; /* CUDA kernels launched by lmb_render since lmb_init / lmb_reset_stats */
+	float ms_render;       /* device time of all lmb_render calls (CUDA events on the context's stream) */
+	float ms_extend;       /* closest-hit traversal kernels */
+	float ms_shade;        /* shade + NEE generation kernels */
+	float ms_connect;      /* shadow / MIS-probe traversal + connect kernels */
+	float ms_film;         /* ray generation + film kernels */
+	float ms_build_accel;  /* last lmb_build_accel: total */
+	float ms_build_morton; /* flatten + bounds + Morton codes */
+	float ms_build_sort;   /* radix sort */
+	float ms_build_tree;   /* Karras hierarchy */
+	float ms_build_refit;  /* bottom-up AABB refit + node packing */
+} lmb_stats;
+
+typedef struct lmb_hit {
+	float t, b1, b2;
+	uint32_t prim; /* global triangle id (prim meshes concatenated in order); 0xFFFFFFFF = miss */
+} lmb_hit;
+
+/* Creates a context on CUDA device `device_id`. Fails with LMB_ERR_NO_DEVICE when there is none. */
+int lmb_create(lmb_ctx** out, int device_id);
+void lmb_destroy(lmb_ctx* ctx);
+const char* lmb_last_error(const lmb_ctx* ctx); /* ctx may be NULL: error of the last failed lmb_create */
+
+/* Copies the scene arrays to the device (LumenScene.cpp:134-216). Invalidates any previous accel. */
+int lmb_upload_scene(lmb_ctx* ctx, const lmb_scene_desc* scene);
+/* Builds the world-space LBVH on the GPU: Morton codes -> radix sort -> Karras hierarchy -> bottom-up refit. */
+int lmb_build_accel(lmb_ctx* ctx);
+/* Allocates the RGBA32F film ("output_tex", Integrator.cpp:33-40) and the wavefront state for width x height.
+ * `frames_in_flight` = how many frames (samples per pixel) one wavefront batch carries; 0 picks a default. */
+int lmb_init(lmb_ctx* ctx, uint32_t width, uint32_t height, uint32_t frames_in_flight);
+
+/* Renders frames first_frame, first_frame + frame_stride, ... (n_frames of them) and updates the film.
+ * pc->frame_num is ignored; RNG seed of a sample is (x, y, frame, 0) exactly as path.rgen:23. Synchronous. */
+int lmb_render(lmb_ctx* ctx, const lmb_pc_path* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames,
+			   uint32_t frame_stride, int film_mode);
+/* Zeroes the film (Path::update resets frame_num to 0 on camera change; sum mode needs an explicit clear). */
+int lmb_clear_film(lmb_ctx* ctx);
+/* LMB_FILM_SUM epilogue: rgb /= alpha (pixels with alpha 0 stay 0), alpha = 1. */
+int lmb_resolve(lmb_ctx* ctx);
+/* Copies the film to host memory: width*height*4 floats, row-major, pixel (x, y) at 4*(y*width + x). */
+int lmb_download(lmb_ctx* ctx, float* rgba);
+/* Copies a host image into the film (resume an accumulation; also used by tests). */
+int lmb_upload_film(lmb_ctx* ctx, const float* rgba);
+/* Device pointer of the film and the CUDA stream (cudaStream_t) the context works on, for zero-copy consumers
+ * (e.g. an NCCL all-reduce issued by the caller). */
+int lmb_film_device_ptr(lmb_ctx* ctx, void** dptr, uint64_t* n_floats);
+int lmb_stream(lmb_ctx* ctx, void** cuda_stream);
+
+/* on != 0: time extend / shade / connect / film separately (adds a host sync per bounce; off by default). */
+int lmb_set_profile_stages(lmb_ctx* ctx, int on);
+int lmb_get_stats(lmb_ctx* ctx, lmb_stats* out);
+int lmb_reset_stats(lmb_ctx* ctx);
+
+/* Raw ray queries against the built accel; rays = n x 8 floats (ox, oy, oz, tmin, dx, dy, dz, tmax), HOST pointers. */
+int lmb_trace_closest(lmb_ctx* ctx, const float* rays, uint32_t n, lmb_hit* hits);
+int lmb_trace_any(lmb_ctx* ctx, const float* rays, uint32_t n, uint8_t* occluded);
+/* Same on DEVICE pointers, timed with CUDA events (ms_out may be NULL); `repeat` launches back to back. */
+int lmb_trace_closest_device(lmb_ctx* ctx, const void* d_rays, uint32_t n, void* d_hits, uint32_t repeat, float* ms_out);
+
+/* LBVH read-back for the bit-exact topology check. n = triangle count.
+ * left/right: n-1, parent: 2n-1, leaf_prim / morton: n, keys: n (uint64), aabb: 6*(2n-1). NULL pointers are skipped. */
+int lmb_accel_num_tris(lmb_ctx* ctx, uint32_t* n);
+int lmb_accel_download(lmb_ctx* ctx, uint32_t* left, uint32_t* right, uint32_t* parent, uint32_t* leaf_prim, uint32_t* morton,
+					   uint64_t* keys, float* aabb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUMEN_B200_H */

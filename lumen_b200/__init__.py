@@ -6,3 +6,4 @@ Layout (only what the hot path needs):
   host.py, integrator.py   ctypes mirrors used by tests/ and bench.py
 """
 from . import host  # noqa: F401
+from . import integrator  # noqa: F401

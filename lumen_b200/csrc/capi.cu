@@ -1,0 +1,345 @@
+// capi.cu -- implementation of the C ABI declared in include/lumen_b200.h (context lifetime, scene upload, film I/O,
+// ray-query entry points). No CPU fallback: every entry point needs a CUDA device and says so when there is none.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "context.h"
+
+static thread_local std::string g_create_error;
+
+namespace lmb {
+
+int set_error(lmb_ctx* ctx, int code, const std::string& msg) {
+	if (ctx)
+		ctx->err = msg;
+	else
+		g_create_error = msg;
+	return code;
+}
+
+int check_cuda(lmb_ctx* ctx, cudaError_t e, const char* what) {
+	if (e == cudaSuccess) return 0;
+	const int code = (e == cudaErrorMemoryAllocation) ? LMB_ERR_OOM : LMB_ERR_CUDA;
+	return set_error(ctx, code, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+namespace {
+template <typename T>
+int upload(lmb_ctx* ctx, const T* host, size_t count, const T** dev_out) {
+	void* d = nullptr;
+	LMB_CUDA(ctx, cudaMalloc(&d, std::max<size_t>(count, 1) * sizeof(T)));
+	ctx->scene_allocs.push_back(d);
+	if (count) LMB_CUDA(ctx, cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+	*dev_out = (const T*)d;
+	return 0;
+}
+
+void free_scene(lmb_ctx* ctx) {
+	for (void* p : ctx->scene_allocs) cudaFree(p);
+	ctx->scene_allocs.clear();
+	ctx->scene = DeviceScene{};
+	ctx->scene_loaded = false;
+	free_bvh(ctx);
+}
+}  // namespace
+}  // namespace lmb
+
+using namespace lmb;
+
+extern "C" {
+
+const char* lmb_last_error(const lmb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int lmb_create(lmb_ctx** out, int device_id) {
+	if (!out) return set_error(nullptr, LMB_ERR_INVALID, "lmb_create: out is NULL");
+	int n = 0;
+	const cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0)
+		return set_error(nullptr, LMB_ERR_NO_DEVICE,
+						 std::string("lmb_create: no CUDA device (") + cudaGetErrorString(e) + "); lumen_b200 has no CPU fallback");
+	if (device_id < 0 || device_id >= n) return set_error(nullptr, LMB_ERR_INVALID, "lmb_create: device_id out of range");
+	lmb_ctx* ctx = new lmb_ctx();
+	ctx->device = device_id;
+	if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+		const std::string msg = std::string("lmb_create: ") + cudaGetErrorString(cudaGetLastError());
+		delete ctx;
+		return set_error(nullptr, LMB_ERR_CUDA, msg);
+	}
+	cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_id);
+	for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+	*out = ctx;
+	return LMB_OK;
+}
+
+void lmb_destroy(lmb_ctx* ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	wavefront_free(ctx);
+	cudaFree(ctx->film);
+	free_scene(ctx);
+	for (auto& ev : ctx->ev) cudaEventDestroy(ev);
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+int lmb_upload_scene(lmb_ctx* ctx, const lmb_scene_desc* sd) {
+	if (!ctx || !sd) return LMB_ERR_INVALID;
+	cudaSetDevice(ctx->device);
+	free_scene(ctx);
+	DeviceScene& sc = ctx->scene;
+	int rc;
+	if ((rc = upload(ctx, sd->vertices, sd->n_vertices, &sc.vertices))) return rc;
+	if ((rc = upload(ctx, sd->indices, sd->n_indices, &sc.indices))) return rc;
+	if ((rc = upload(ctx, sd->materials, sd->n_materials, &sc.materials))) return rc;
+	if ((rc = upload(ctx, sd->prim_infos, sd->n_prim_meshes, &sc.prim_infos))) return rc;
+	if ((rc = upload(ctx, sd->world_matrices, 16 * (size_t)sd->n_prim_meshes, &sc.world_matrices))) return rc;
+	if ((rc = upload(ctx, sd->inv_world_matrices, 16 * (size_t)sd->n_prim_meshes, &sc.inv_world_matrices))) return rc;
+	if ((rc = upload(ctx, sd->lights, sd->n_lights, &sc.lights))) return rc;
+	// global triangle numbering: prim meshes concatenated in order (one TLAS instance per mesh, Integrator.cpp:148-158)
+	std::vector<uint32_t> tri_mesh, tri_local;
+	for (uint32_t m = 0; m < sd->n_prim_meshes; m++) {
+		const uint32_t nt = sd->prim_idx_counts[m] / 3;
+		for (uint32_t t = 0; t < nt; t++) tri_mesh.push_back(m), tri_local.push_back(t);
+	}
+	if ((rc = upload(ctx, tri_mesh.data(), tri_mesh.size(), &sc.tri_mesh))) return rc;
+	if ((rc = upload(ctx, tri_local.data(), tri_local.size(), &sc.tri_local))) return rc;
+	// textures: RGBA8 texels + sRGB decode table (VK_FORMAT_R8G8B8A8_SRGB, LumenScene.cpp:204-213)
+	std::vector<const uint8_t*> tex_ptrs;
+	std::vector<uint2> tex_dims;
+	for (uint32_t i = 0; i < sd->n_textures; i++) {
+		const uint8_t* d = nullptr;
+		if ((rc = upload(ctx, sd->textures[i].rgba8, 4 * (size_t)sd->textures[i].width * sd->textures[i].height, &d))) return rc;
+		tex_ptrs.push_back(d);
+		tex_dims.push_back(make_uint2(sd->textures[i].width, sd->textures[i].height));
+	}
+	const uint8_t* const* d_ptrs = nullptr;
+	if ((rc = upload(ctx, tex_ptrs.data(), tex_ptrs.size(), (const uint8_t* const**)&d_ptrs))) return rc;
+	sc.tex_data = d_ptrs;
+	if ((rc = upload(ctx, tex_dims.data(), tex_dims.size(), &sc.tex_dims))) return rc;
+	float lut[256];
+	for (int i = 0; i < 256; i++) {
+		const double c = i / 255.0;
+		lut[i] = (float)(c <= 0.04045 ? c / 12.92 : pow((c + 0.055) / 1.055, 2.4));
+	}
+	if ((rc = upload(ctx, lut, 256, &sc.srgb_lut))) return rc;
+	sc.n_tris = (uint32_t)tri_mesh.size();
+	sc.n_prim_meshes = sd->n_prim_meshes;
+	sc.n_lights = sd->n_lights;
+	sc.n_textures = sd->n_textures;
+	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host staging vectors go out of scope
+	ctx->scene_loaded = true;
+	return LMB_OK;
+}
+
+int lmb_build_accel(lmb_ctx* ctx) {
+	if (!ctx) return LMB_ERR_INVALID;
+	if (!ctx->scene_loaded) return set_error(ctx, LMB_ERR_INVALID, "lmb_build_accel: no scene uploaded");
+	cudaSetDevice(ctx->device);
+	return build_lbvh(ctx);
+}
+
+int lmb_init(lmb_ctx* ctx, uint32_t width, uint32_t height, uint32_t frames_in_flight) {
+	if (!ctx || width == 0 || height == 0) return set_error(ctx, LMB_ERR_INVALID, "lmb_init: bad size");
+	cudaSetDevice(ctx->device);
+	cudaFree(ctx->film);
+	ctx->film = nullptr;
+	ctx->width = width, ctx->height = height;
+	LMB_CUDA(ctx, cudaMalloc((void**)&ctx->film, (size_t)width * height * 16));
+	LMB_CUDA(ctx, cudaMemsetAsync(ctx->film, 0, (size_t)width * height * 16, ctx->stream));
+	const int rc = wavefront_alloc(ctx, frames_in_flight);
+	if (rc) return rc;
+	return lmb_reset_stats(ctx);
+}
+
+int lmb_render(lmb_ctx* ctx, const lmb_pc_path* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames, uint32_t frame_stride,
+			   int film_mode) {
+	if (!ctx || !pc || !ubo) return LMB_ERR_INVALID;
+	if (!ctx->bvh.built) return set_error(ctx, LMB_ERR_INVALID, "lmb_render: call lmb_build_accel first");
+	if (!ctx->film) return set_error(ctx, LMB_ERR_INVALID, "lmb_render: call lmb_init first");
+	if (pc->size_x != ctx->width || pc->size_y != ctx->height) return set_error(ctx, LMB_ERR_INVALID, "lmb_render: PCPath size != lmb_init size");
+	if (frame_stride == 0) frame_stride = 1;
+	if (film_mode == LMB_FILM_RUNNING_MEAN && frame_stride != 1)
+		return set_error(ctx, LMB_ERR_INVALID, "lmb_render: running-mean film needs frame_stride 1");
+	if (film_mode != LMB_FILM_RUNNING_MEAN && film_mode != LMB_FILM_SUM) return set_error(ctx, LMB_ERR_INVALID, "lmb_render: bad film_mode");
+	if (pc->num_lights <= 0 && pc->direct_lighting)
+		; /* scenes without lights never enter NEE only if every material is specular; sample_light_Li would index lights[0] */
+	cudaSetDevice(ctx->device);
+	if (n_frames == 0) return LMB_OK;
+	return wavefront_render(ctx, *pc, *ubo, first_frame, n_frames, frame_stride, film_mode);
+}
+
+int lmb_clear_film(lmb_ctx* ctx) {
+	if (!ctx || !ctx->film) return LMB_ERR_INVALID;
+	cudaSetDevice(ctx->device);
+	LMB_CUDA(ctx, cudaMemsetAsync(ctx->film, 0, (size_t)ctx->width * ctx->height * 16, ctx->stream));
+	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LMB_OK;
+}
+
+int lmb_resolve(lmb_ctx* ctx) {
+	if (!ctx || !ctx->film) return LMB_ERR_INVALID;
+	cudaSetDevice(ctx->device);
+	const int rc = launch_resolve(ctx);
+	if (rc) return rc;
+	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LMB_OK;
+}
+
+int lmb_download(lmb_ctx* ctx, float* rgba) {
+	if (!ctx || !ctx->film || !rgba) return LMB_ERR_INVALID;
+	cudaSetDevice(ctx->device);
+	LMB_CUDA(ctx, cudaMemcpyAsync(rgba, ctx->film, (size_t)ctx->width * ctx->height * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LMB_OK;
+}
+
+int lmb_upload_film(lmb_ctx* ctx, const float* rgba) {
+	if (!ctx || !ctx->film || !rgba) return LMB_ERR_INVALID;
+	cudaSetDevice(ctx->device);
+	LMB_CUDA(ctx, cudaMemcpyAsync(ctx->film, rgba, (size_t)ctx->width * ctx->height * 16, cudaMemcpyHostToDevice, ctx->stream));
+	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LMB_OK;
+}
+
+int lmb_film_device_ptr(lmb_ctx* ctx, void** dptr, uint64_t* n_floats) {
+	if (!ctx || !ctx->film || !dptr) return LMB_ERR_INVALID;
+	*dptr = ctx->film;
+	if (n_floats) *n_floats = (uint64_t)ctx->width * ctx->height * 4;
+	return LMB_OK;
+}
+
+int lmb_stream(lmb_ctx* ctx, void** cuda_stream) {
+	if (!ctx || !cuda_stream) return LMB_ERR_INVALID;
+	*cuda_stream = (void*)ctx->stream;
+	return LMB_OK;
+}
+
+int lmb_set_profile_stages(lmb_ctx* ctx, int on) {
+	if (!ctx) return LMB_ERR_INVALID;
+	ctx->profile_stages = on != 0;
+	return LMB_OK;
+}
+
+int lmb_get_stats(lmb_ctx* ctx, lmb_stats* out) {
+	if (!ctx || !out) return LMB_ERR_INVALID;
+	cudaSetDevice(ctx->device);
+	if (ctx->wf.stats) {
+		unsigned long long h[ST_COUNT];
+		LMB_CUDA(ctx, cudaMemcpyAsync(h, ctx->wf.stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+		LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ctx->stats.rays_closest = h[ST_CLOSEST], ctx->stats.rays_shadow = h[ST_SHADOW], ctx->stats.rays_probe = h[ST_PROBE];
+		ctx->stats.nodes_visited = h[ST_NODES], ctx->stats.tris_tested = h[ST_TRIS], ctx->stats.nan_samples = h[ST_NAN];
+	}
+	*out = ctx->stats;
+	return LMB_OK;
+}
+
+int lmb_reset_stats(lmb_ctx* ctx) {
+	if (!ctx) return LMB_ERR_INVALID;
+	cudaSetDevice(ctx->device);
+	const lmb_stats keep = ctx->stats;
+	ctx->stats = lmb_stats{};
+	ctx->stats.ms_build_accel = keep.ms_build_accel, ctx->stats.ms_build_morton = keep.ms_build_morton;
+	ctx->stats.ms_build_sort = keep.ms_build_sort, ctx->stats.ms_build_tree = keep.ms_build_tree;
+	ctx->stats.ms_build_refit = keep.ms_build_refit;
+	if (ctx->wf.stats) {
+		LMB_CUDA(ctx, cudaMemsetAsync(ctx->wf.stats, 0, ST_COUNT * 8, ctx->stream));
+		LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	}
+	return LMB_OK;
+}
+
+static int ensure_stats(lmb_ctx* ctx) {
+	if (ctx->wf.stats) return 0;
+	LMB_CUDA(ctx, cudaMalloc((void**)&ctx->wf.stats, ST_COUNT * 8));
+	LMB_CUDA(ctx, cudaMemsetAsync(ctx->wf.stats, 0, ST_COUNT * 8, ctx->stream));
+	return 0;
+}
+
+int lmb_trace_closest(lmb_ctx* ctx, const float* rays, uint32_t n, lmb_hit* hits) {
+	if (!ctx || !rays || !hits) return LMB_ERR_INVALID;
+	if (!ctx->bvh.built) return set_error(ctx, LMB_ERR_INVALID, "lmb_trace_closest: call lmb_build_accel first");
+	cudaSetDevice(ctx->device);
+	if (n == 0) return LMB_OK;
+	int rc = ensure_stats(ctx);
+	if (rc) return rc;
+	float4 *d_rays = nullptr, *d_hits = nullptr;
+	LMB_CUDA(ctx, cudaMalloc((void**)&d_rays, (size_t)n * 32));
+	LMB_CUDA(ctx, cudaMalloc((void**)&d_hits, (size_t)n * 16));
+	LMB_CUDA(ctx, cudaMemcpyAsync(d_rays, rays, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream));
+	rc = launch_trace_closest(ctx, d_rays, n, d_hits);
+	if (!rc) rc = check_cuda(ctx, cudaMemcpyAsync(hits, d_hits, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream), "copy hits");
+	if (!rc) rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "lmb_trace_closest");
+	cudaFree(d_rays), cudaFree(d_hits);
+	return rc;
+}
+
+int lmb_trace_any(lmb_ctx* ctx, const float* rays, uint32_t n, uint8_t* occluded) {
+	if (!ctx || !rays || !occluded) return LMB_ERR_INVALID;
+	if (!ctx->bvh.built) return set_error(ctx, LMB_ERR_INVALID, "lmb_trace_any: call lmb_build_accel first");
+	cudaSetDevice(ctx->device);
+	if (n == 0) return LMB_OK;
+	int rc = ensure_stats(ctx);
+	if (rc) return rc;
+	float4* d_rays = nullptr;
+	uint8_t* d_occ = nullptr;
+	LMB_CUDA(ctx, cudaMalloc((void**)&d_rays, (size_t)n * 32));
+	LMB_CUDA(ctx, cudaMalloc((void**)&d_occ, n));
+	LMB_CUDA(ctx, cudaMemcpyAsync(d_rays, rays, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream));
+	rc = launch_trace_any(ctx, d_rays, n, d_occ);
+	if (!rc) rc = check_cuda(ctx, cudaMemcpyAsync(occluded, d_occ, n, cudaMemcpyDeviceToHost, ctx->stream), "copy occ");
+	if (!rc) rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "lmb_trace_any");
+	cudaFree(d_rays), cudaFree(d_occ);
+	return rc;
+}
+
+int lmb_trace_closest_device(lmb_ctx* ctx, const void* d_rays, uint32_t n, void* d_hits, uint32_t repeat, float* ms_out) {
+	if (!ctx || !d_rays || !d_hits) return LMB_ERR_INVALID;
+	if (!ctx->bvh.built) return set_error(ctx, LMB_ERR_INVALID, "lmb_trace_closest_device: call lmb_build_accel first");
+	cudaSetDevice(ctx->device);
+	int rc = ensure_stats(ctx);
+	if (rc) return rc;
+	if (repeat == 0) repeat = 1;
+	cudaEventRecord(ctx->ev[6], ctx->stream);
+	for (uint32_t r = 0; r < repeat && !rc; r++) rc = launch_trace_closest(ctx, (const float4*)d_rays, n, (float4*)d_hits);
+	cudaEventRecord(ctx->ev[7], ctx->stream);
+	if (rc) return rc;
+	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (ms_out) cudaEventElapsedTime(ms_out, ctx->ev[6], ctx->ev[7]);
+	return LMB_OK;
+}
+
+int lmb_accel_num_tris(lmb_ctx* ctx, uint32_t* n) {
+	if (!ctx || !n || !ctx->bvh.built) return LMB_ERR_INVALID;
+	*n = ctx->bvh.n;
+	return LMB_OK;
+}
+
+int lmb_accel_download(lmb_ctx* ctx, uint32_t* left, uint32_t* right, uint32_t* parent, uint32_t* leaf_prim, uint32_t* morton, uint64_t* keys,
+					   float* aabb) {
+	if (!ctx || !ctx->bvh.built) return LMB_ERR_INVALID;
+	cudaSetDevice(ctx->device);
+	const DeviceBvh& b = ctx->bvh;
+	const size_t n = b.n;
+	if (n == 0) return LMB_OK;
+	auto get = [&](void* dst, const void* src, size_t bytes) -> int {
+		if (!dst || bytes == 0) return 0;
+		return check_cuda(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream), "lmb_accel_download");
+	};
+	int rc;
+	if ((rc = get(left, b.left, (n - 1) * 4))) return rc;
+	if ((rc = get(right, b.right, (n - 1) * 4))) return rc;
+	if ((rc = get(parent, b.parent, (2 * n - 1) * 4))) return rc;
+	if ((rc = get(leaf_prim, b.leaf_prim, n * 4))) return rc;
+	if ((rc = get(morton, b.morton, n * 4))) return rc;
+	if ((rc = get(keys, b.keys, n * 8))) return rc;
+	if ((rc = get(aabb, b.aabb, 6 * (2 * n - 1) * 4))) return rc;
+	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LMB_OK;
+}
+
+}  // extern "C"

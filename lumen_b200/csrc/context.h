@@ -1,0 +1,112 @@
+// context.h -- internal state of an lmb_ctx (one GPU, one stream).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "lmb_types.h"
+#include "lumen_b200.h"
+
+namespace lmb {
+
+// Scene arrays as the kernels see them (device pointers).
+struct DeviceScene {
+	const lmb_vertex* vertices;
+	const uint32_t* indices;
+	const lmb_material* materials;
+	const lmb_prim_mesh_info* prim_infos;
+	const float* world_matrices;
+	const float* inv_world_matrices;
+	const lmb_light* lights;
+	const uint32_t* tri_mesh;   // global triangle id -> prim mesh index
+	const uint32_t* tri_local;  // global triangle id -> mesh-local triangle number
+	const uint8_t* const* tex_data;  // per texture: RGBA8 texels
+	const uint2* tex_dims;
+	const float* srgb_lut;  // 256 entries
+	uint32_t n_tris, n_prim_meshes, n_lights, n_textures;
+};
+
+struct DeviceBvh {
+	// canonical LBVH (parity surface)
+	uint32_t* morton = nullptr;    // n, by global id
+	uint64_t* keys = nullptr;      // n, sorted
+	uint64_t* keys_tmp = nullptr;  // n, radix ping-pong
+	uint32_t* leaf_prim = nullptr; // n
+	uint32_t* left = nullptr;      // n-1
+	uint32_t* right = nullptr;     // n-1
+	uint32_t* parent = nullptr;    // 2n-1
+	float* aabb = nullptr;         // 6*(2n-1)
+	uint32_t* arrive = nullptr;    // n-1 refit counters
+	uint32_t* bounds_enc = nullptr;  // 6 ordered-uint encoded scene bounds
+	float4* tri_world = nullptr;   // 3n, by global id
+	// traversal layout
+	float4* nodes = nullptr;  // 4*(n-1)
+	float4* tris = nullptr;   // 3n, leaf order
+	uint32_t* radix_hist = nullptr;
+	uint32_t n = 0;
+	bool built = false;
+};
+
+// Wavefront state, struct-of-arrays over path slots (slot = frame_in_batch * W*H + y*W + x).
+struct Wavefront {
+	uint32_t n_slots = 0;
+	float4* ray_o = nullptr;   // origin.xyz, tmin
+	float4* ray_d = nullptr;   // direction.xyz, tmax
+	float4* hit = nullptr;     // t, b1, b2, prim (bits)
+	float4* thr = nullptr;     // throughput.xyz, rng counter (bits)
+	float4* col = nullptr;     // radiance.xyz, flags (bits): bit0 last_specular
+	float4* nee = nullptr;     // 8 float4 per slot, see wavefront.cu
+	uint32_t* queue[2] = {nullptr, nullptr};
+	uint32_t* nee_queue = nullptr;
+	uint32_t* counters = nullptr;  // [0],[1]: queue sizes; [2]: nee queue size; [3..]: work-fetch cursors
+	unsigned long long* stats = nullptr;  // device counters, see StatSlot
+	uint32_t frames_in_flight = 0;
+};
+
+enum StatSlot { ST_CLOSEST = 0, ST_SHADOW, ST_PROBE, ST_NODES, ST_TRIS, ST_NAN, ST_COUNT };
+
+}  // namespace lmb
+
+struct lmb_ctx {
+	int device = 0;
+	int sm_count = 0;
+	cudaStream_t stream = nullptr;
+	std::string err;
+	// scene
+	bool scene_loaded = false;
+	lmb::DeviceScene scene{};
+	std::vector<void*> scene_allocs;
+	std::vector<lmb_prim_mesh_info> h_prim_infos;
+	std::vector<uint32_t> h_idx_counts;
+	lmb::DeviceBvh bvh;
+	// film / wavefront
+	uint32_t width = 0, height = 0;
+	float4* film = nullptr;
+	lmb::Wavefront wf;
+	// stats
+	lmb_stats stats{};
+	bool profile_stages = false;
+	cudaEvent_t ev[8]{};
+};
+
+namespace lmb {
+int set_error(lmb_ctx* ctx, int code, const std::string& msg);
+int check_cuda(lmb_ctx* ctx, cudaError_t e, const char* what);
+int build_lbvh(lmb_ctx* ctx);
+void free_bvh(lmb_ctx* ctx);
+int wavefront_alloc(lmb_ctx* ctx, uint32_t frames_in_flight);
+void wavefront_free(lmb_ctx* ctx);
+int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& ubo, uint32_t first_frame, uint32_t n_frames, uint32_t stride,
+					 int film_mode);
+int launch_trace_closest(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits);
+int launch_trace_any(lmb_ctx* ctx, const float4* d_rays, uint32_t n, uint8_t* d_occ);
+int launch_resolve(lmb_ctx* ctx);
+}  // namespace lmb
+
+#define LMB_CUDA(ctx, call)                                            \
+	do {                                                               \
+		const int _rc = lmb::check_cuda((ctx), (call), #call);         \
+		if (_rc != 0) return _rc;                                      \
+	} while (0)

@@ -1,0 +1,474 @@
+// wavefront.cu -- the path integrator as wavefront kernels (replaces the single vkCmdTraceRaysKHR(W, H, 1) dispatch of
+// src/RayTracer/Path.cpp:39-58 / path.rgen main()).
+//
+// One path slot per (pixel, frame-in-batch). Per bounce, in stream order:
+//   k_extend   closest-hit traversal of every live continuation ray          (path.rgen:48)
+//   k_shade    hit record, material, emission, NEE sample generation, BSDF   (path.rgen:49-100, pt_commons.glsl:3-20,28-30)
+//              sample, throughput, Russian roulette; writes next ray + NEE record
+//   k_connect  shadow any-hit ray + MIS probe closest-hit ray, MIS weights,   (pt_commons.glsl:21-40, path.rgen:78)
+//              radiance accumulation
+// then k_film applies the running-mean / sum film update in frame order       (path.rgen:102-112).
+// RNG state is a pure function of (x, y, frame, draw counter), so reordering paths across kernels cannot change any
+// sample; every float expression keeps the order of the GLSL (see vec.cuh).
+//
+// HBM bytes per path-bounce (algorithmic): ray 32 rd + hit 16 wr (extend); ray 32 + hit 16 + state 32 rd, state 32 +
+// ray 32 + NEE 128 wr, ~200 B scene gathers (shade); NEE 128 + col 16 rd, col 16 wr (connect). Film: 16 B per sample.
+#include <cooperative_groups.h>
+#include <stdio.h>
+
+#include "context.h"
+#include "scene_device.cuh"
+#include "trace.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace lmb {
+
+namespace {
+
+constexpr float T_MIN = 0.001f;    // path.rgen:19
+constexpr float T_MAX = 10000.0f;  // path.rgen:20
+
+struct RenderParams {
+	M4 inv_view, inv_proj;
+	V3 sky_col;
+	uint32_t width, height, n_pix;
+	uint32_t first_frame, frame_stride;  // frame of batch slot fb = first_frame + fb * frame_stride
+	uint32_t n_active;                    // live slots this batch = n_batch_frames * n_pix
+	int32_t num_lights, max_depth, light_triangle_count;
+	uint32_t dir_light_idx, direct_lighting;
+};
+
+enum Counter { CNT_Q0 = 0, CNT_Q1 = 1, CNT_NEE = 2, CNT_COUNT = 8 };
+
+// NEE record: 8 float4 planes of n_slots each
+enum NeePlane { NEE_P = 0, NEE_WI, NEE_LDIR, NEE_PROBE_WI, NEE_F2, NEE_LE, NEE_T, NEE_POS, NEE_PLANES };
+constexpr uint32_t NEE_FLAG_SHADOW_CONTRIB = 1u;  // pdf_light_w > 0
+constexpr uint32_t NEE_FLAG_PROBE = 2u;           // area light and bsdf_pdf != 0
+
+__device__ __forceinline__ float4 f4(const V3& v, float w) { return make_float4(v.x, v.y, v.z, w); }
+__device__ __forceinline__ V3 xyz(const float4& v) { return V3{v.x, v.y, v.z}; }
+
+// warp-aggregated append; callable from divergent code
+__device__ __forceinline__ uint32_t queue_push(uint32_t* counter) {
+	cg::coalesced_group g = cg::coalesced_threads();
+	uint32_t base = 0;
+	if (g.thread_rank() == 0) base = atomicAdd(counter, g.size());
+	return g.shfl(base, 0) + g.thread_rank();
+}
+
+__device__ __forceinline__ void flush_stats(unsigned long long* stats, int slot, uint32_t v) {
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+	if ((threadIdx.x & 31) == 0 && v) atomicAdd(&stats[slot], (unsigned long long)v);
+}
+
+__global__ void k_set_counters(uint32_t* counters, uint32_t q0, uint32_t q1, uint32_t nee) {
+	counters[CNT_Q0] = q0;
+	counters[CNT_Q1] = q1;
+	counters[CNT_NEE] = nee;
+}
+__global__ void k_zero_counters(uint32_t* counters, int a, int b) {
+	counters[a] = 0;
+	counters[b] = 0;
+}
+
+// path.rgen:23-45 + sample_camera (commons.glsl:30-33)
+__global__ void __launch_bounds__(256) k_raygen(RenderParams rp, float4* __restrict__ ray_o, float4* __restrict__ ray_d, float4* __restrict__ thr,
+												 float4* __restrict__ col, uint32_t* __restrict__ queue) {
+	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < rp.n_active; slot += gridDim.x * blockDim.x) {
+		const uint32_t fb = slot / rp.n_pix, pix = slot - fb * rp.n_pix;
+		const uint32_t px = pix % rp.width, py = pix / rp.width;
+		Rng seed{px, py, rp.first_frame + fb * rp.frame_stride, 0u};
+		const float j0 = rand1(seed);
+		const float j1 = rand1(seed);
+		const V2 pixel = v2((float)px, (float)py) + 0.5f;
+		const V2 rands = v2(j0, j1) - 0.5f;
+		const V2 in_uv = (pixel + rands) / v2((float)rp.width, (float)rp.height);
+		const V2 d = in_uv * 2.0f - 1.0f;
+		const V3 origin = lmb::xyz(mul(rp.inv_view, v4(0, 0, 0, 1)));
+		const V4 target = mul(rp.inv_proj, v4(d.x, d.y, 1, 1));
+		const V3 direction = lmb::xyz(mul(rp.inv_view, v4(normalize(lmb::xyz(target)), 0)));
+		ray_o[slot] = f4(origin, T_MIN);
+		ray_d[slot] = f4(direction, T_MAX);
+		thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed.w));
+		col[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+		queue[slot] = slot;
+	}
+}
+
+__global__ void __launch_bounds__(128) k_extend(BvhView bvh, const uint32_t* __restrict__ counters, int q, const uint32_t* __restrict__ queue,
+												 const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float4* __restrict__ hit,
+												 unsigned long long* stats) {
+	const uint32_t count = counters[q];
+	uint32_t nodes = 0, tris = 0, rays = 0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+		const uint32_t slot = queue[i];
+		const float4 o = ray_o[slot], d = ray_d[slot];
+		const Hit h = trace_ray<false>(bvh, xyz(o), xyz(d), o.w, d.w, nodes, tris);
+		hit[slot] = make_float4(h.t, h.b1, h.b2, __uint_as_float(h.prim));
+		rays++;
+	}
+	flush_stats(stats, ST_CLOSEST, rays);
+	flush_stats(stats, ST_NODES, nodes);
+	flush_stats(stats, ST_TRIS, tris);
+}
+
+__global__ void __launch_bounds__(128) k_shade(RenderParams rp, DeviceScene sc, int depth, uint32_t* __restrict__ counters, int q,
+												const uint32_t* __restrict__ queue, uint32_t* __restrict__ queue_next, uint32_t* __restrict__ nee_queue,
+												float4* __restrict__ ray_o, float4* __restrict__ ray_d, const float4* __restrict__ hit,
+												float4* __restrict__ thr, float4* __restrict__ colb, float4* __restrict__ nee, uint32_t n_slots) {
+	const uint32_t count = counters[q];
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+		const uint32_t slot = queue[i];
+		const float4 h4 = hit[slot];
+		const float4 t4 = thr[slot];
+		const float4 c4 = colb[slot];
+		const float4 o4 = ray_o[slot], d4 = ray_d[slot];
+		V3 throughput = xyz(t4);
+		V3 col = xyz(c4);
+		const bool last_specular_in = (__float_as_uint(c4.w) & 1u) != 0;
+		const uint32_t prim = __float_as_uint(h4.w);
+		V3 origin = xyz(o4);
+		V3 direction = xyz(d4);
+		const uint32_t fb = slot / rp.n_pix, pix = slot - fb * rp.n_pix;
+		Rng seed{pix % rp.width, pix / rp.width, rp.first_frame + fb * rp.frame_stride, __float_as_uint(t4.w)};
+
+		if (prim == 0xFFFFFFFFu) {  // path.rgen:49-55
+			if (depth > 0 || rp.direct_lighting == 1) col += throughput * shade_atmosphere(sc, rp.dir_light_idx, rp.sky_col, origin, direction, T_MAX);
+			colb[slot] = f4(col, c4.w);
+			continue;
+		}
+		const HitPayload payload = build_hit(sc, prim, h4.y, h4.z);
+		const lmb_material hit_mat = load_material(sc, payload.material_idx, payload.uv);
+		if ((depth == 0 && rp.direct_lighting == 1) || last_specular_in) col += throughput * v3(hit_mat.emissive_factor);
+		if (depth >= rp.max_depth - 1) {
+			colb[slot] = f4(col, c4.w);
+			continue;
+		}
+		const V3 wo = -direction;
+		V3 n_s = payload.n_s;
+		bool side = true;
+		V3 n_g = payload.n_g;
+		if (dot(payload.n_g, wo) < 0.0f) n_g = -n_g;
+		if (dot(n_g, payload.n_s) < 0) {
+			n_s = -n_s;
+			side = false;
+		}
+		origin = offset_ray(payload.pos, n_g);
+		const bool last_specular = (hit_mat.bsdf_props & LMB_FLAG_SPECULAR) != 0;
+		if (!last_specular && (depth > 0 || rp.direct_lighting == 1)) {
+			// uniform_sample_light up to the two traceRayEXT calls (pt_commons.glsl:3-20, 28-30)
+			const V4 r4 = rand4(seed);
+			const LightSample ls = sample_light_Li(sc, r4, payload.pos, rp.num_lights);
+			const V3 p = offset_ray2(payload.pos, n_s);
+			float bsdf_pdf;
+			const float cos_x = dot(n_s, ls.wi);
+			const V3 f = eval_bsdf(n_s, wo, hit_mat, side, ls.wi, bsdf_pdf);
+			uint32_t flags = 0;
+			V3 ldir = v3(0.0f);
+			if (ls.pdf_w > 0) {
+				flags |= NEE_FLAG_SHADOW_CONTRIB;
+				const float mis_weight = ((ls.flags >> 5) & 1u) ? 1.0f : 1.0f / (1.0f + bsdf_pdf / ls.pdf_w);
+				ldir = mis_weight * f * fabsf(cos_x) * ls.Le / ls.pdf_w;
+			}
+			const uint32_t ni = queue_push(&counters[CNT_NEE]);
+			nee_queue[ni] = slot;
+			nee[NEE_P * (size_t)n_slots + slot] = f4(p, ls.wi_len - LMB_EPS);
+			nee[NEE_LDIR * (size_t)n_slots + slot] = f4(ldir, ls.pdf_a);
+			nee[NEE_T * (size_t)n_slots + slot] = f4(throughput, __uint_as_float(ls.instance_idx));
+			if ((ls.flags & 0x7u) == LMB_LIGHT_AREA) {
+				const V3 r3 = rand3(seed);
+				const BsdfSample bs = sample_bsdf(n_s, wo, hit_mat, 1, side, r3);
+				if (bs.pdf != 0) {
+					flags |= NEE_FLAG_PROBE;
+					nee[NEE_PROBE_WI * (size_t)n_slots + slot] = f4(bs.wi, bs.pdf);
+					nee[NEE_F2 * (size_t)n_slots + slot] = f4(bs.f, fabsf(bs.cos_theta));
+					nee[NEE_LE * (size_t)n_slots + slot] = f4(ls.Le, __uint_as_float(ls.triangle_idx));
+					nee[NEE_POS * (size_t)n_slots + slot] = f4(payload.pos, 0.0f);
+				}
+			}
+			nee[NEE_WI * (size_t)n_slots + slot] = f4(ls.wi, __uint_as_float(flags));
+		}
+		// path.rgen:81-100
+		const V3 r3 = rand3(seed);
+		const BsdfSample bs = sample_bsdf(n_s, wo, hit_mat, 1, side, r3);
+		direction = bs.wi;
+		bool alive = bs.pdf != 0;
+		if (alive) {
+			throughput *= bs.f * fabsf(bs.cos_theta) / bs.pdf;
+			float rr_scale = 1.0f;
+			if (has_prop(hit_mat.bsdf_props, LMB_FLAG_TRANSMISSION)) rr_scale *= side ? 1.0f / hit_mat.ior : hit_mat.ior;
+			if (depth > 3) {
+				const float rr_prob = gmin(0.95f, luminance(throughput) * rr_scale);
+				if (rr_prob == 0 || rr_prob < rand1(seed))
+					alive = false;
+				else
+					throughput /= rr_prob;
+			}
+		}
+		colb[slot] = f4(col, __uint_as_float(last_specular ? 1u : 0u));
+		if (alive) {
+			thr[slot] = f4(throughput, __uint_as_float(seed.w));
+			ray_o[slot] = f4(origin, T_MIN);
+			ray_d[slot] = f4(direction, T_MAX);
+			queue_next[queue_push(&counters[q ^ 1])] = slot;
+		}
+	}
+}
+
+__global__ void __launch_bounds__(128) k_connect(RenderParams rp, DeviceScene sc, BvhView bvh, const uint32_t* __restrict__ counters,
+												  const uint32_t* __restrict__ nee_queue, const float4* __restrict__ nee, const float4* __restrict__ hit,
+												  float4* __restrict__ colb, uint32_t n_slots, unsigned long long* stats) {
+	const uint32_t count = counters[CNT_NEE];
+	uint32_t nodes = 0, tris = 0, n_shadow = 0, n_probe = 0;
+	const float light_pick_pdf = 1.0f / (float)rp.light_triangle_count;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+		const uint32_t slot = nee_queue[i];
+		const float4 p4 = nee[NEE_P * (size_t)n_slots + slot];
+		const float4 wi4 = nee[NEE_WI * (size_t)n_slots + slot];
+		const float4 l4 = nee[NEE_LDIR * (size_t)n_slots + slot];
+		const float4 t4 = nee[NEE_T * (size_t)n_slots + slot];
+		const uint32_t flags = __float_as_uint(wi4.w);
+		const V3 p = xyz(p4);
+		V3 res = v3(0.0f);
+		n_shadow++;
+		const Hit sh = trace_ray<true>(bvh, p, xyz(wi4), 0.0f, p4.w, nodes, tris);
+		if (sh.prim == 0xFFFFFFFFu && (flags & NEE_FLAG_SHADOW_CONTRIB)) res += xyz(l4);
+		if (flags & NEE_FLAG_PROBE) {
+			const float4 pw4 = nee[NEE_PROBE_WI * (size_t)n_slots + slot];
+			const float4 f4v = nee[NEE_F2 * (size_t)n_slots + slot];
+			const float4 le4 = nee[NEE_LE * (size_t)n_slots + slot];
+			const V3 pos = xyz(nee[NEE_POS * (size_t)n_slots + slot]);
+			const V3 wi = xyz(pw4);
+			const float bsdf_pdf = pw4.w;
+			n_probe++;
+			const Hit ph = trace_ray<false>(bvh, p, wi, T_MIN, T_MAX, nodes, tris);
+			// ray.rmiss leaves the stale payload of the surface being shaded; the reference compares its ids
+			float b1 = ph.b1, b2 = ph.b2;
+			uint32_t prim = ph.prim;
+			if (prim == 0xFFFFFFFFu) {
+				const float4 h4 = hit[slot];
+				prim = __float_as_uint(h4.w), b1 = h4.y, b2 = h4.z;
+			}
+			if (sc.tri_local[prim] == __float_as_uint(le4.w) && sc.tri_mesh[prim] == __float_as_uint(t4.w)) {
+				const HitPayload pl = build_hit(sc, prim, b1, b2);
+				const float wi_len = length(pl.pos - pos);
+				const float g = fabsf(dot(pl.n_s, -wi)) / (wi_len * wi_len);
+				const float mis_weight = 1.0f / (1 + l4.w / (g * bsdf_pdf));
+				res += xyz(f4v) * mis_weight * f4v.w * xyz(le4) / bsdf_pdf;
+			}
+		}
+		const float4 c4 = colb[slot];
+		const V3 col = xyz(c4) + xyz(t4) * res / light_pick_pdf;
+		colb[slot] = f4(col, c4.w);
+	}
+	flush_stats(stats, ST_SHADOW, n_shadow);
+	flush_stats(stats, ST_PROBE, n_probe);
+	flush_stats(stats, ST_NODES, nodes);
+	flush_stats(stats, ST_TRIS, tris);
+}
+
+// path.rgen:102-112, applied for the batch's frames in order
+__global__ void __launch_bounds__(256) k_film(RenderParams rp, uint32_t n_batch_frames, int film_mode, const float4* __restrict__ colb,
+											   float4* __restrict__ film, unsigned long long* stats) {
+	uint32_t nan_count = 0;
+	for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < rp.n_pix; pix += gridDim.x * blockDim.x) {
+		float4 acc = film[pix];
+		for (uint32_t fb = 0; fb < n_batch_frames; fb++) {
+			const V3 col = xyz(colb[(size_t)fb * rp.n_pix + pix]);
+			const float lum = luminance(col);
+			if (lum != lum) {
+				nan_count++;
+				continue;
+			}
+			if (film_mode == LMB_FILM_RUNNING_MEAN) {
+				const uint32_t frame = rp.first_frame + fb * rp.frame_stride;
+				if (frame > 0) {
+					const float w = 1.0f / float(frame + 1);
+					const V3 m = mix(xyz(acc), col, w);
+					acc = make_float4(m.x, m.y, m.z, 1.0f);
+				} else {
+					acc = make_float4(col.x, col.y, col.z, 1.0f);
+				}
+			} else {
+				acc = make_float4(acc.x + col.x, acc.y + col.y, acc.z + col.z, acc.w + 1.0f);
+			}
+		}
+		film[pix] = acc;
+	}
+	flush_stats(stats, ST_NAN, nan_count);
+}
+
+__global__ void __launch_bounds__(256) k_resolve(uint32_t n_pix, float4* film) {
+	for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n_pix; pix += gridDim.x * blockDim.x) {
+		const float4 a = film[pix];
+		film[pix] = a.w > 0.0f ? make_float4(a.x / a.w, a.y / a.w, a.z / a.w, 1.0f) : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+	}
+}
+
+__global__ void __launch_bounds__(128) k_trace_closest(BvhView bvh, const float4* __restrict__ rays, uint32_t n, float4* __restrict__ hits,
+														unsigned long long* stats) {
+	uint32_t nodes = 0, tris = 0, cnt = 0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const float4 o = rays[2 * (size_t)i], d = rays[2 * (size_t)i + 1];
+		const Hit h = trace_ray<false>(bvh, xyz(o), xyz(d), o.w, d.w, nodes, tris);
+		hits[i] = make_float4(h.t, h.b1, h.b2, __uint_as_float(h.prim));
+		cnt++;
+	}
+	if (stats) {
+		flush_stats(stats, ST_CLOSEST, cnt);
+		flush_stats(stats, ST_NODES, nodes);
+		flush_stats(stats, ST_TRIS, tris);
+	}
+}
+
+__global__ void __launch_bounds__(128) k_trace_any(BvhView bvh, const float4* __restrict__ rays, uint32_t n, uint8_t* __restrict__ occ,
+													unsigned long long* stats) {
+	uint32_t nodes = 0, tris = 0, cnt = 0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const float4 o = rays[2 * (size_t)i], d = rays[2 * (size_t)i + 1];
+		const Hit h = trace_ray<true>(bvh, xyz(o), xyz(d), o.w, d.w, nodes, tris);
+		occ[i] = h.prim != 0xFFFFFFFFu;
+		cnt++;
+	}
+	if (stats) {
+		flush_stats(stats, ST_SHADOW, cnt);
+		flush_stats(stats, ST_NODES, nodes);
+		flush_stats(stats, ST_TRIS, tris);
+	}
+}
+
+BvhView view_of(const lmb_ctx* ctx) { return BvhView{ctx->bvh.nodes, ctx->bvh.tris, ctx->bvh.n}; }
+
+}  // namespace
+
+int wavefront_alloc(lmb_ctx* ctx, uint32_t frames_in_flight) {
+	wavefront_free(ctx);
+	Wavefront& wf = ctx->wf;
+	const uint64_t n_pix = (uint64_t)ctx->width * ctx->height;
+	if (frames_in_flight == 0) {
+		// default: about 8 M path slots in flight (enough to fill 148 SMs many times over), at most 64 frames
+		frames_in_flight = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (8ull << 20) / std::max<uint64_t>(n_pix, 1)));
+	}
+	const uint64_t n_slots = n_pix * frames_in_flight;
+	if (n_slots == 0 || n_slots > 0x7FFFFFFFull) return set_error(ctx, LMB_ERR_INVALID, "width*height*frames_in_flight out of range");
+	wf.n_slots = (uint32_t)n_slots;
+	wf.frames_in_flight = frames_in_flight;
+	auto alloc = [&](void** p, size_t bytes) { return check_cuda(ctx, cudaMalloc(p, bytes), "cudaMalloc(wavefront)"); };
+	int rc;
+	if ((rc = alloc((void**)&wf.ray_o, n_slots * 16))) return rc;
+	if ((rc = alloc((void**)&wf.ray_d, n_slots * 16))) return rc;
+	if ((rc = alloc((void**)&wf.hit, n_slots * 16))) return rc;
+	if ((rc = alloc((void**)&wf.thr, n_slots * 16))) return rc;
+	if ((rc = alloc((void**)&wf.col, n_slots * 16))) return rc;
+	if ((rc = alloc((void**)&wf.nee, n_slots * 16 * NEE_PLANES))) return rc;
+	if ((rc = alloc((void**)&wf.queue[0], n_slots * 4))) return rc;
+	if ((rc = alloc((void**)&wf.queue[1], n_slots * 4))) return rc;
+	if ((rc = alloc((void**)&wf.nee_queue, n_slots * 4))) return rc;
+	if ((rc = alloc((void**)&wf.counters, CNT_COUNT * 4))) return rc;
+	if ((rc = alloc((void**)&wf.stats, ST_COUNT * 8))) return rc;
+	LMB_CUDA(ctx, cudaMemsetAsync(wf.stats, 0, ST_COUNT * 8, ctx->stream));
+	return 0;
+}
+
+void wavefront_free(lmb_ctx* ctx) {
+	Wavefront& wf = ctx->wf;
+	cudaFree(wf.ray_o), cudaFree(wf.ray_d), cudaFree(wf.hit), cudaFree(wf.thr), cudaFree(wf.col), cudaFree(wf.nee);
+	cudaFree(wf.queue[0]), cudaFree(wf.queue[1]), cudaFree(wf.nee_queue), cudaFree(wf.counters), cudaFree(wf.stats);
+	wf = Wavefront{};
+}
+
+int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& ubo, uint32_t first_frame, uint32_t n_frames, uint32_t stride,
+					 int film_mode) {
+	Wavefront& wf = ctx->wf;
+	cudaStream_t st = ctx->stream;
+	RenderParams rp;
+	auto load = [](const float* p) {
+		M4 m;
+		for (int c = 0; c < 4; c++) m.c[c] = V4{p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]};
+		return m;
+	};
+	rp.inv_view = load(ubo.inv_view);
+	rp.inv_proj = load(ubo.inv_projection);
+	rp.sky_col = V3{pc.sky_col[0], pc.sky_col[1], pc.sky_col[2]};
+	rp.width = ctx->width, rp.height = ctx->height, rp.n_pix = ctx->width * ctx->height;
+	rp.frame_stride = stride;
+	rp.num_lights = pc.num_lights, rp.max_depth = pc.max_depth, rp.light_triangle_count = pc.light_triangle_count;
+	rp.dir_light_idx = pc.dir_light_idx, rp.direct_lighting = pc.direct_lighting;
+	const BvhView bvh = view_of(ctx);
+	const int grid_wide = ctx->sm_count * 16;
+	const int grid_256 = ctx->sm_count * 8;
+	float ms;
+	const bool prof = ctx->profile_stages;  // per-stage timing serialises the bounce loop; off by default
+	cudaEventRecord(ctx->ev[0], st);
+	for (uint32_t done = 0; done < n_frames;) {
+		const uint32_t nb = std::min(wf.frames_in_flight, n_frames - done);
+		rp.first_frame = first_frame + done * stride;
+		rp.n_active = nb * rp.n_pix;
+		if (prof) cudaEventRecord(ctx->ev[1], st);
+		k_set_counters<<<1, 1, 0, st>>>(wf.counters, rp.n_active, 0, 0);
+		k_raygen<<<grid_256, 256, 0, st>>>(rp, wf.ray_o, wf.ray_d, wf.thr, wf.col, wf.queue[0]);
+		ctx->stats.kernel_launches += 2;
+		if (prof) {
+			cudaEventRecord(ctx->ev[2], st);
+			cudaEventSynchronize(ctx->ev[2]);
+			cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+			ctx->stats.ms_film += ms;
+		}
+		int q = 0;
+		for (int depth = 0; depth < std::max(pc.max_depth, 1); depth++) {
+			if (prof) cudaEventRecord(ctx->ev[1], st);
+			k_extend<<<grid_wide, 128, 0, st>>>(bvh, wf.counters, q, wf.queue[q], wf.ray_o, wf.ray_d, wf.hit, wf.stats);
+			if (prof) cudaEventRecord(ctx->ev[2], st);
+			k_zero_counters<<<1, 1, 0, st>>>(wf.counters, q ^ 1, CNT_NEE);  // next continuation queue and NEE queue start empty
+			k_shade<<<grid_wide, 128, 0, st>>>(rp, ctx->scene, depth, wf.counters, q, wf.queue[q], wf.queue[q ^ 1], wf.nee_queue, wf.ray_o, wf.ray_d,
+											   wf.hit, wf.thr, wf.col, wf.nee, wf.n_slots);
+			if (prof) cudaEventRecord(ctx->ev[3], st);
+			k_connect<<<grid_wide, 128, 0, st>>>(rp, ctx->scene, bvh, wf.counters, wf.nee_queue, wf.nee, wf.hit, wf.col, wf.n_slots, wf.stats);
+			ctx->stats.kernel_launches += 4;
+			if (prof) {
+				cudaEventRecord(ctx->ev[4], st);
+				cudaEventSynchronize(ctx->ev[4]);
+				cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+				ctx->stats.ms_extend += ms;
+				cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+				ctx->stats.ms_shade += ms;
+				cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
+				ctx->stats.ms_connect += ms;
+			}
+			q ^= 1;
+		}
+		if (prof) cudaEventRecord(ctx->ev[1], st);
+		k_film<<<grid_256, 256, 0, st>>>(rp, nb, film_mode, wf.col, ctx->film, wf.stats);
+		ctx->stats.kernel_launches += 1;
+		if (prof) {
+			cudaEventRecord(ctx->ev[2], st);
+			cudaEventSynchronize(ctx->ev[2]);
+			cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+			ctx->stats.ms_film += ms;
+		}
+		done += nb;
+	}
+	cudaEventRecord(ctx->ev[5], st);
+	LMB_CUDA(ctx, cudaStreamSynchronize(st));
+	LMB_CUDA(ctx, cudaGetLastError());
+	cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[5]);
+	ctx->stats.ms_render += ms;
+	ctx->stats.frames += n_frames;
+	return 0;
+}
+
+int launch_trace_closest(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits) {
+	k_trace_closest<<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(view_of(ctx), d_rays, n, d_hits, ctx->wf.stats);
+	return check_cuda(ctx, cudaGetLastError(), "k_trace_closest");
+}
+int launch_trace_any(lmb_ctx* ctx, const float4* d_rays, uint32_t n, uint8_t* d_occ) {
+	k_trace_any<<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(view_of(ctx), d_rays, n, d_occ, ctx->wf.stats);
+	return check_cuda(ctx, cudaGetLastError(), "k_trace_any");
+}
+int launch_resolve(lmb_ctx* ctx) {
+	k_resolve<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->width * ctx->height, ctx->film);
+	return check_cuda(ctx, cudaGetLastError(), "k_resolve");
+}
+
+}  // namespace lmb
