@@ -93,9 +93,10 @@ int lmb_render(lmb_ctx* ctx, const lmb_pc_path* pc, const lmb_scene_ubo* ubo, ui
 int lmb_clear_film(lmb_ctx* ctx);
 /* LMB_FILM_SUM epilogue: rgb /= alpha (pixels with alpha 0 stay 0), alpha = 1. */
 int lmb_resolve(lmb_ctx* ctx);
-/* Copies the film to host memory: width*height*4 floats, row-major, pixel (x, y) at 4*(y*width + x). */
+/* Copies the film to `rgba` (host or device pointer, resolved by UVA): width*height*4 floats, row-major, pixel (x, y) at
+ * 4*(y*width + x). */
 int lmb_download(lmb_ctx* ctx, float* rgba);
-/* Copies a host image into the film (resume an accumulation; also used by tests). */
+/* Copies an image (host or device pointer) into the film: resume an accumulation, or write back a reduced sum. */
 int lmb_upload_film(lmb_ctx* ctx, const float* rgba);
 /* Device pointer of the film and the CUDA stream (cudaStream_t) the context works on, for zero-copy consumers
  * (e.g. an NCCL all-reduce issued by the caller). */

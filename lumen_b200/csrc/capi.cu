@@ -32,7 +32,10 @@ int upload(lmb_ctx* ctx, const T* host, size_t count, const T** dev_out) {
 	void* d = nullptr;
 	LMB_CUDA(ctx, cudaMalloc(&d, std::max<size_t>(count, 1) * sizeof(T)));
 	ctx->scene_allocs.push_back(d);
-	if (count) LMB_CUDA(ctx, cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+	if (count)
+		LMB_CUDA(ctx, cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+	else
+		LMB_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(T), ctx->stream));  // e.g. a scene without lights reads one all-zero Light
 	*dev_out = (const T*)d;
 	return 0;
 }
@@ -165,8 +168,6 @@ int lmb_render(lmb_ctx* ctx, const lmb_pc_path* pc, const lmb_scene_ubo* ubo, ui
 	if (film_mode == LMB_FILM_RUNNING_MEAN && frame_stride != 1)
 		return set_error(ctx, LMB_ERR_INVALID, "lmb_render: running-mean film needs frame_stride 1");
 	if (film_mode != LMB_FILM_RUNNING_MEAN && film_mode != LMB_FILM_SUM) return set_error(ctx, LMB_ERR_INVALID, "lmb_render: bad film_mode");
-	if (pc->num_lights <= 0 && pc->direct_lighting)
-		; /* scenes without lights never enter NEE only if every material is specular; sample_light_Li would index lights[0] */
 	cudaSetDevice(ctx->device);
 	if (n_frames == 0) return LMB_OK;
 	return wavefront_render(ctx, *pc, *ubo, first_frame, n_frames, frame_stride, film_mode);
@@ -192,7 +193,7 @@ int lmb_resolve(lmb_ctx* ctx) {
 int lmb_download(lmb_ctx* ctx, float* rgba) {
 	if (!ctx || !ctx->film || !rgba) return LMB_ERR_INVALID;
 	cudaSetDevice(ctx->device);
-	LMB_CUDA(ctx, cudaMemcpyAsync(rgba, ctx->film, (size_t)ctx->width * ctx->height * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	LMB_CUDA(ctx, cudaMemcpyAsync(rgba, ctx->film, (size_t)ctx->width * ctx->height * 16, cudaMemcpyDefault, ctx->stream));
 	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return LMB_OK;
 }
@@ -200,7 +201,7 @@ int lmb_download(lmb_ctx* ctx, float* rgba) {
 int lmb_upload_film(lmb_ctx* ctx, const float* rgba) {
 	if (!ctx || !ctx->film || !rgba) return LMB_ERR_INVALID;
 	cudaSetDevice(ctx->device);
-	LMB_CUDA(ctx, cudaMemcpyAsync(ctx->film, rgba, (size_t)ctx->width * ctx->height * 16, cudaMemcpyHostToDevice, ctx->stream));
+	LMB_CUDA(ctx, cudaMemcpyAsync(ctx->film, rgba, (size_t)ctx->width * ctx->height * 16, cudaMemcpyDefault, ctx->stream));
 	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return LMB_OK;
 }

@@ -150,7 +150,9 @@ struct LightSample {
 inline LightSample sample_light_Li(const orc_scene& s, const vec4& rands, const vec3& p, int num_lights) {
 	LightSample o;
 	o.light_idx = (uint)(rands.x * (float)num_lights);
-	const lmb_light& light = s.sd.lights[o.light_idx];
+	// a scene without lights has no light buffer in the reference (LumenScene.cpp:134); both sides read one all-zero Light
+	static const lmb_light zero_light{};
+	const lmb_light& light = s.sd.n_lights ? s.sd.lights[o.light_idx] : zero_light;
 	const uint type = light.light_flags & 0x7u;
 	o.flags = light.light_flags;
 	switch (type) {
