@@ -16,7 +16,7 @@ resolved. Ranks take disjoint frame indices (frame = first + rank + k*N): per-GP
 `e2e`    = same metric through the public C-ABI calls with HOST buffers inside the timed region: per step the push
            constants + camera UBO are handed over from host memory (lmb_render copies them) and the resolved RGBA32F film is
            downloaded to pinned host memory (lmb_download).
-`roofline` is for the dominant kernels (BVH traversal: k_extend + k_connect), from a separately profiled pass.
+`roofline` is for the dominant kernel (k_trace, BVH traversal of all ray types), from a separately profiled pass.
 `cpu_baseline` = the CPU oracle (C++/glm restatement of the reference shaders, OpenMP) on a bounded sample.
 """
 import argparse
@@ -237,16 +237,16 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-        trav_ms = ps.ms_extend + ps.ms_connect
+        trav_ms = ps.ms_extend
         trav_bytes = ps.nodes_visited * NODE_BYTES + ps.tris_tested * TRI_BYTES + ps.rays * (RAY_BYTES + HIT_BYTES)
-        n_trav_launches = 2 * MAX_DEPTH
+        n_trav_launches = MAX_DEPTH
         achieved = trav_bytes / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else 0.0
         roofline = {
-            "bound": "hbm", "kernel": "k_extend + k_connect (BVH traversal, closest + any-hit)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "bound": "hbm", "kernel": "k_trace (persistent BVH traversal: continuation + shadow + MIS-probe rays)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
             "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": trav_bytes / n_trav_launches, "avg_launch_ms": trav_ms / n_trav_launches,
             "bytes_per_ray": trav_bytes / max(ps.rays, 1), "nodes_per_ray": ps.nodes_visited / max(ps.rays, 1), "tris_per_ray": ps.tris_tested / max(ps.rays, 1),
-            "stage_ms": {"extend": ps.ms_extend, "shade": ps.ms_shade, "connect": ps.ms_connect, "raygen_film": ps.ms_film, "total": ps.ms_render},
+            "stage_ms": {"trace": ps.ms_extend, "shade": ps.ms_shade, "connect": ps.ms_connect, "raygen_sky_film": ps.ms_film, "total": ps.ms_render},
             "note": "algorithmic bytes = nodes*64 + tris*48 + rays*48; the 15 MB BVH is L2-resident, so achieved/HBM-peak above 1 is possible and means the kernel is latency/issue bound, not DRAM bound",
         }
         cpu_baseline = None

@@ -56,10 +56,10 @@ typedef struct lmb_stats {
 	uint64_t frames;       /* frames rendered since lmb_init / lmb_reset_stats */
 	uint64_t kernel_launches; /* CUDA kernels launched by lmb_render since lmb_init / lmb_reset_stats */
 	float ms_render;       /* device time of all lmb_render calls (CUDA events on the context's stream) */
-	float ms_extend;       /* closest-hit traversal kernels */
-	float ms_shade;        /* shade + NEE generation kernels */
-	float ms_connect;      /* shadow / MIS-probe traversal + connect kernels */
-	float ms_film;         /* ray generation + film kernels */
+	float ms_extend;       /* k_trace: BVH traversal of continuation + shadow + MIS-probe rays (profile_stages only) */
+	float ms_shade;        /* k_shade: hit record, NEE generation, BSDF sampling */
+	float ms_connect;      /* k_connect: MIS weights + radiance accumulation */
+	float ms_film;         /* ray generation + sky (k_miss) + film kernels */
 	float ms_build_accel;  /* last lmb_build_accel: total */
 	float ms_build_morton; /* flatten + bounds + Morton codes */
 	float ms_build_sort;   /* radix sort */

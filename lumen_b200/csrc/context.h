@@ -60,6 +60,11 @@ struct Wavefront {
 	float4* nee = nullptr;     // 8 float4 per slot, see wavefront.cu
 	uint32_t* queue[2] = {nullptr, nullptr};
 	uint32_t* nee_queue = nullptr;
+	uint32_t* miss_queue = nullptr;  // escaped rays awaiting the sky march (k_miss)
+	uint32_t* trace_queue = nullptr; // typed ray entries for k_trace: slot | type << 30 (up to 3 per slot)
+	float4* probe_hit = nullptr;     // MIS-probe closest hit per slot
+	uint32_t* shadow_occ = nullptr;  // shadow-ray result per slot
+	uint32_t* trace_cursor = nullptr;  // work-fetch cursor of the array ray queries
 	uint32_t* counters = nullptr;  // [0],[1]: queue sizes; [2]: nee queue size; [3..]: work-fetch cursors
 	unsigned long long* stats = nullptr;  // device counters, see StatSlot
 	uint32_t frames_in_flight = 0;

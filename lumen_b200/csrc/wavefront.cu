@@ -1,13 +1,14 @@
 // wavefront.cu -- the path integrator as wavefront kernels (replaces the single vkCmdTraceRaysKHR(W, H, 1) dispatch of
 // src/RayTracer/Path.cpp:39-58 / path.rgen main()).
 //
-// One path slot per (pixel, frame-in-batch). Per bounce, in stream order:
-//   k_extend   closest-hit traversal of every live continuation ray          (path.rgen:48)
-//   k_shade    hit record, material, emission, NEE sample generation, BSDF   (path.rgen:49-100, pt_commons.glsl:3-20,28-30)
-//              sample, throughput, Russian roulette; writes next ray + NEE record
-//   k_connect  shadow any-hit ray + MIS probe closest-hit ray, MIS weights,   (pt_commons.glsl:21-40, path.rgen:78)
-//              radiance accumulation
-// then k_film applies the running-mean / sum film update in frame order       (path.rgen:102-112).
+// One path slot per (pixel, frame-in-batch). Per bounce d, in stream order:
+//   k_trace    ONE persistent traversal kernel for every ray in flight: continuation rays into bounce d (path.rgen:48),
+//              and the shadow any-hit + MIS-probe closest-hit rays bounce d-1 generated (pt_commons.glsl:21-22, 32)
+//   k_connect  MIS weights and radiance accumulation of bounce d-1's light samples (pt_commons.glsl:23-40, path.rgen:78)
+//   k_shade    hit record, material, emission, NEE sample generation, BSDF sample, throughput, Russian roulette
+//              (path.rgen:49-100, pt_commons.glsl:3-20,28-30); writes the next ray, the NEE record and its two rays
+// then k_miss evaluates the sky for escaped rays (commons.glsl:156-168) and k_film applies the running-mean / sum film
+// update in frame order (path.rgen:102-112).
 // RNG state is a pure function of (x, y, frame, draw counter), so reordering paths across kernels cannot change any
 // sample; every float expression keeps the order of the GLSL (see vec.cuh).
 //
@@ -18,7 +19,7 @@
 
 #include "context.h"
 #include "scene_device.cuh"
-#include "trace.cuh"
+#include "trace_persistent.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -39,12 +40,16 @@ struct RenderParams {
 	uint32_t dir_light_idx, direct_lighting;
 };
 
-enum Counter { CNT_Q0 = 0, CNT_Q1 = 1, CNT_NEE = 2, CNT_COUNT = 8 };
+enum Counter { CNT_Q0 = 0, CNT_Q1 = 1, CNT_NEE = 2, CNT_MISS = 3, CNT_TRACE = 4, CNT_CURSOR = 5, CNT_COUNT = 8 };
+
+// trace queue entry = slot | type << 30
+constexpr uint32_t RAY_CONTINUE = 0u, RAY_SHADOW = 1u, RAY_PROBE = 2u, SLOT_MASK = 0x3FFFFFFFu;
 
 // NEE record: 8 float4 planes of n_slots each
 enum NeePlane { NEE_P = 0, NEE_WI, NEE_LDIR, NEE_PROBE_WI, NEE_F2, NEE_LE, NEE_T, NEE_POS, NEE_PLANES };
 constexpr uint32_t NEE_FLAG_SHADOW_CONTRIB = 1u;  // pdf_light_w > 0
 constexpr uint32_t NEE_FLAG_PROBE = 2u;           // area light and bsdf_pdf != 0
+constexpr uint32_t NEE_FLAG_STALE_MATCH = 4u;     // the surface being shaded IS the sampled light triangle (see k_connect)
 
 __device__ __forceinline__ float4 f4(const V3& v, float w) { return make_float4(v.x, v.y, v.z, w); }
 __device__ __forceinline__ V3 xyz(const float4& v) { return V3{v.x, v.y, v.z}; }
@@ -62,19 +67,27 @@ __device__ __forceinline__ void flush_stats(unsigned long long* stats, int slot,
 	if ((threadIdx.x & 31) == 0 && v) atomicAdd(&stats[slot], (unsigned long long)v);
 }
 
-__global__ void k_set_counters(uint32_t* counters, uint32_t q0, uint32_t q1, uint32_t nee) {
-	counters[CNT_Q0] = q0;
-	counters[CNT_Q1] = q1;
-	counters[CNT_NEE] = nee;
+__global__ void k_begin_batch(uint32_t* counters, uint32_t n_active) {
+	counters[CNT_Q0] = n_active;
+	counters[CNT_Q1] = 0;
+	counters[CNT_NEE] = 0;
+	counters[CNT_MISS] = 0;
+	counters[CNT_TRACE] = n_active;
+	counters[CNT_CURSOR] = 0;
 }
-__global__ void k_zero_counters(uint32_t* counters, int a, int b) {
-	counters[a] = 0;
-	counters[b] = 0;
+// before k_shade(d): the next path queue, the NEE queue and the trace queue start empty
+__global__ void k_begin_shade(uint32_t* counters, int q_next) {
+	counters[q_next] = 0;
+	counters[CNT_NEE] = 0;
+	counters[CNT_TRACE] = 0;
+	counters[CNT_CURSOR] = 0;
 }
 
 // path.rgen:23-45 + sample_camera (commons.glsl:30-33)
 __global__ void __launch_bounds__(256) k_raygen(RenderParams rp, float4* __restrict__ ray_o, float4* __restrict__ ray_d, float4* __restrict__ thr,
-												 float4* __restrict__ col, uint32_t* __restrict__ queue) {
+												 float4* __restrict__ col, uint32_t* __restrict__ queue, uint32_t* __restrict__ trace_queue,
+												 unsigned long long* stats) {
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_CLOSEST], (unsigned long long)rp.n_active);
 	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < rp.n_active; slot += gridDim.x * blockDim.x) {
 		const uint32_t fb = slot / rp.n_pix, pix = slot - fb * rp.n_pix;
 		const uint32_t px = pix % rp.width, py = pix / rp.width;
@@ -93,31 +106,52 @@ __global__ void __launch_bounds__(256) k_raygen(RenderParams rp, float4* __restr
 		thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed.w));
 		col[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
 		queue[slot] = slot;
+		trace_queue[slot] = slot | (RAY_CONTINUE << 30);
 	}
 }
 
-__global__ void __launch_bounds__(128) k_extend(BvhView bvh, const uint32_t* __restrict__ counters, int q, const uint32_t* __restrict__ queue,
-												 const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float4* __restrict__ hit,
-												 unsigned long long* stats) {
-	const uint32_t count = counters[q];
-	uint32_t nodes = 0, tris = 0, rays = 0;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-		const uint32_t slot = queue[i];
-		const float4 o = ray_o[slot], d = ray_d[slot];
-		const Hit h = trace_ray<false>(bvh, xyz(o), xyz(d), o.w, d.w, nodes, tris);
-		hit[slot] = make_float4(h.t, h.b1, h.b2, __uint_as_float(h.prim));
-		rays++;
+// Ray source of the wavefront: typed queue entries over the path-state and NEE planes.
+struct WavefrontSource {
+	const uint32_t* __restrict__ queue;
+	const float4* __restrict__ ray_o;
+	const float4* __restrict__ ray_d;
+	const float4* __restrict__ nee;
+	float4* __restrict__ hit;
+	float4* __restrict__ probe_hit;
+	uint32_t* __restrict__ shadow_occ;
+	uint32_t n_slots;
+	__device__ __forceinline__ void load(uint32_t i, V3& o, V3& d, float& tmin, float& tmax, bool& any) const {
+		const uint32_t e = queue[i], type = e >> 30, slot = e & SLOT_MASK;
+		if (type == RAY_CONTINUE) {
+			const float4 o4 = ray_o[slot], d4 = ray_d[slot];
+			o = xyz(o4), d = xyz(d4), tmin = o4.w, tmax = d4.w, any = false;
+		} else if (type == RAY_SHADOW) {  // pt_commons.glsl:21-22: tmin 0, tmax = wi_len - EPS, terminate on first hit
+			const float4 p4 = nee[NEE_P * (size_t)n_slots + slot];
+			o = xyz(p4), d = xyz(nee[NEE_WI * (size_t)n_slots + slot]), tmin = 0.0f, tmax = p4.w, any = true;
+		} else {  // pt_commons.glsl:32
+			o = xyz(nee[NEE_P * (size_t)n_slots + slot]), d = xyz(nee[NEE_PROBE_WI * (size_t)n_slots + slot]), tmin = T_MIN, tmax = T_MAX, any = false;
+		}
 	}
-	flush_stats(stats, ST_CLOSEST, rays);
-	flush_stats(stats, ST_NODES, nodes);
-	flush_stats(stats, ST_TRIS, tris);
+	__device__ __forceinline__ void store(uint32_t i, const Hit& h, bool) const {
+		const uint32_t e = queue[i], type = e >> 30, slot = e & SLOT_MASK;
+		if (type == RAY_SHADOW)
+			shadow_occ[slot] = h.prim != 0xFFFFFFFFu;
+		else
+			(type == RAY_CONTINUE ? hit : probe_hit)[slot] = make_float4(h.t, h.b1, h.b2, __uint_as_float(h.prim));
+	}
+};
+
+__global__ void __launch_bounds__(LMB_TRACE_THREADS) k_trace(BvhView bvh, WavefrontSource src, uint32_t* counters, unsigned long long* stats) {
+	trace_persistent(bvh, src, counters[CNT_TRACE], &counters[CNT_CURSOR], stats, -1, -1);
 }
 
 __global__ void __launch_bounds__(128) k_shade(RenderParams rp, DeviceScene sc, int depth, uint32_t* __restrict__ counters, int q,
 												const uint32_t* __restrict__ queue, uint32_t* __restrict__ queue_next, uint32_t* __restrict__ nee_queue,
-												float4* __restrict__ ray_o, float4* __restrict__ ray_d, const float4* __restrict__ hit,
-												float4* __restrict__ thr, float4* __restrict__ colb, float4* __restrict__ nee, uint32_t n_slots) {
+												uint32_t* __restrict__ miss_queue, uint32_t* __restrict__ trace_queue, float4* __restrict__ ray_o,
+												float4* __restrict__ ray_d, const float4* __restrict__ hit, float4* __restrict__ thr, float4* __restrict__ colb,
+												float4* __restrict__ nee, uint32_t n_slots, unsigned long long* stats) {
 	const uint32_t count = counters[q];
+	uint32_t n_cont = 0, n_shadow = 0, n_probe = 0;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
 		const uint32_t slot = queue[i];
 		const float4 h4 = hit[slot];
@@ -134,8 +168,16 @@ __global__ void __launch_bounds__(128) k_shade(RenderParams rp, DeviceScene sc, 
 		Rng seed{pix % rp.width, pix / rp.width, rp.first_frame + fb * rp.frame_stride, __float_as_uint(t4.w)};
 
 		if (prim == 0xFFFFFFFFu) {  // path.rgen:49-55
-			if (depth > 0 || rp.direct_lighting == 1) col += throughput * shade_atmosphere(sc, rp.dir_light_idx, rp.sky_col, origin, direction, T_MAX);
-			colb[slot] = f4(col, c4.w);
+			if (depth > 0 || rp.direct_lighting == 1) {
+				if (rp.dir_light_idx == 0xFFFFFFFFu) {
+					col += throughput * rp.sky_col;  // shade_atmosphere's constant-sky branch (commons.glsl:157-159)
+					colb[slot] = f4(col, c4.w);
+				} else {
+					// the 64 x 8 step sky march is ~10^4 flops: deferred to k_miss so that it runs on full warps. The path is
+					// dead, so ray_o / ray_d / thr / col of this slot stay as they are until then.
+					miss_queue[queue_push(&counters[CNT_MISS])] = slot;
+				}
+			}
 			continue;
 		}
 		const HitPayload payload = build_hit(sc, prim, h4.y, h4.z);
@@ -173,6 +215,8 @@ __global__ void __launch_bounds__(128) k_shade(RenderParams rp, DeviceScene sc, 
 			}
 			const uint32_t ni = queue_push(&counters[CNT_NEE]);
 			nee_queue[ni] = slot;
+			trace_queue[queue_push(&counters[CNT_TRACE])] = slot | (RAY_SHADOW << 30);
+			n_shadow++;
 			nee[NEE_P * (size_t)n_slots + slot] = f4(p, ls.wi_len - LMB_EPS);
 			nee[NEE_LDIR * (size_t)n_slots + slot] = f4(ldir, ls.pdf_a);
 			nee[NEE_T * (size_t)n_slots + slot] = f4(throughput, __uint_as_float(ls.instance_idx));
@@ -181,10 +225,21 @@ __global__ void __launch_bounds__(128) k_shade(RenderParams rp, DeviceScene sc, 
 				const BsdfSample bs = sample_bsdf(n_s, wo, hit_mat, 1, side, r3);
 				if (bs.pdf != 0) {
 					flags |= NEE_FLAG_PROBE;
+					// ray.rmiss writes only material_idx: when the probe misses, the reference still compares the ids of the
+					// payload left by the previous trace, i.e. of the surface being shaded, and then uses its pos / n_s
+					// (wi_len = |pos - pos| = 0). That can only match when this surface is the sampled light triangle.
+					float g_stale = 0.0f;
+					if (payload.triangle_idx == ls.triangle_idx && payload.instance_idx == ls.instance_idx) {
+						flags |= NEE_FLAG_STALE_MATCH;
+						const float wi_len = length(payload.pos - payload.pos);
+						g_stale = fabsf(dot(payload.n_s, -bs.wi)) / (wi_len * wi_len);
+					}
 					nee[NEE_PROBE_WI * (size_t)n_slots + slot] = f4(bs.wi, bs.pdf);
 					nee[NEE_F2 * (size_t)n_slots + slot] = f4(bs.f, fabsf(bs.cos_theta));
 					nee[NEE_LE * (size_t)n_slots + slot] = f4(ls.Le, __uint_as_float(ls.triangle_idx));
-					nee[NEE_POS * (size_t)n_slots + slot] = f4(payload.pos, 0.0f);
+					nee[NEE_POS * (size_t)n_slots + slot] = f4(payload.pos, g_stale);
+					trace_queue[queue_push(&counters[CNT_TRACE])] = slot | (RAY_PROBE << 30);
+					n_probe++;
 				}
 			}
 			nee[NEE_WI * (size_t)n_slots + slot] = f4(ls.wi, __uint_as_float(flags));
@@ -212,48 +267,52 @@ __global__ void __launch_bounds__(128) k_shade(RenderParams rp, DeviceScene sc, 
 			ray_o[slot] = f4(origin, T_MIN);
 			ray_d[slot] = f4(direction, T_MAX);
 			queue_next[queue_push(&counters[q ^ 1])] = slot;
+			trace_queue[queue_push(&counters[CNT_TRACE])] = slot | (RAY_CONTINUE << 30);
+			n_cont++;
 		}
 	}
+	flush_stats(stats, ST_CLOSEST, n_cont);
+	flush_stats(stats, ST_SHADOW, n_shadow);
+	flush_stats(stats, ST_PROBE, n_probe);
 }
 
-__global__ void __launch_bounds__(128) k_connect(RenderParams rp, DeviceScene sc, BvhView bvh, const uint32_t* __restrict__ counters,
-												  const uint32_t* __restrict__ nee_queue, const float4* __restrict__ nee, const float4* __restrict__ hit,
-												  float4* __restrict__ colb, uint32_t n_slots, unsigned long long* stats) {
+// pt_commons.glsl:23-27, 33-39 and the accumulation of path.rgen:78, once both rays of the light sample are traced
+__global__ void __launch_bounds__(128) k_connect(RenderParams rp, DeviceScene sc, const uint32_t* __restrict__ counters,
+												  const uint32_t* __restrict__ nee_queue, const float4* __restrict__ nee, const float4* __restrict__ probe_hit,
+												  const uint32_t* __restrict__ shadow_occ, float4* __restrict__ colb, uint32_t n_slots) {
 	const uint32_t count = counters[CNT_NEE];
-	uint32_t nodes = 0, tris = 0, n_shadow = 0, n_probe = 0;
 	const float light_pick_pdf = 1.0f / (float)rp.light_triangle_count;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
 		const uint32_t slot = nee_queue[i];
-		const float4 p4 = nee[NEE_P * (size_t)n_slots + slot];
 		const float4 wi4 = nee[NEE_WI * (size_t)n_slots + slot];
 		const float4 l4 = nee[NEE_LDIR * (size_t)n_slots + slot];
 		const float4 t4 = nee[NEE_T * (size_t)n_slots + slot];
 		const uint32_t flags = __float_as_uint(wi4.w);
-		const V3 p = xyz(p4);
 		V3 res = v3(0.0f);
-		n_shadow++;
-		const Hit sh = trace_ray<true>(bvh, p, xyz(wi4), 0.0f, p4.w, nodes, tris);
-		if (sh.prim == 0xFFFFFFFFu && (flags & NEE_FLAG_SHADOW_CONTRIB)) res += xyz(l4);
+		if (shadow_occ[slot] == 0u && (flags & NEE_FLAG_SHADOW_CONTRIB)) res += xyz(l4);
 		if (flags & NEE_FLAG_PROBE) {
 			const float4 pw4 = nee[NEE_PROBE_WI * (size_t)n_slots + slot];
 			const float4 f4v = nee[NEE_F2 * (size_t)n_slots + slot];
 			const float4 le4 = nee[NEE_LE * (size_t)n_slots + slot];
-			const V3 pos = xyz(nee[NEE_POS * (size_t)n_slots + slot]);
+			const float4 pos4 = nee[NEE_POS * (size_t)n_slots + slot];
 			const V3 wi = xyz(pw4);
 			const float bsdf_pdf = pw4.w;
-			n_probe++;
-			const Hit ph = trace_ray<false>(bvh, p, wi, T_MIN, T_MAX, nodes, tris);
-			// ray.rmiss leaves the stale payload of the surface being shaded; the reference compares its ids
-			float b1 = ph.b1, b2 = ph.b2;
-			uint32_t prim = ph.prim;
-			if (prim == 0xFFFFFFFFu) {
-				const float4 h4 = hit[slot];
-				prim = __float_as_uint(h4.w), b1 = h4.y, b2 = h4.z;
+			const float4 ph = probe_hit[slot];
+			const uint32_t prim = __float_as_uint(ph.w);
+			bool match = false;
+			float g = 0.0f;
+			if (prim != 0xFFFFFFFFu) {
+				if (sc.tri_local[prim] == __float_as_uint(le4.w) && sc.tri_mesh[prim] == __float_as_uint(t4.w)) {
+					const HitPayload pl = build_hit(sc, prim, ph.y, ph.z);
+					const float wi_len = length(pl.pos - xyz(pos4));
+					g = fabsf(dot(pl.n_s, -wi)) / (wi_len * wi_len);
+					match = true;
+				}
+			} else if (flags & NEE_FLAG_STALE_MATCH) {
+				g = pos4.w;
+				match = true;
 			}
-			if (sc.tri_local[prim] == __float_as_uint(le4.w) && sc.tri_mesh[prim] == __float_as_uint(t4.w)) {
-				const HitPayload pl = build_hit(sc, prim, b1, b2);
-				const float wi_len = length(pl.pos - pos);
-				const float g = fabsf(dot(pl.n_s, -wi)) / (wi_len * wi_len);
+			if (match) {
 				const float mis_weight = 1.0f / (1 + l4.w / (g * bsdf_pdf));
 				res += xyz(f4v) * mis_weight * f4v.w * xyz(le4) / bsdf_pdf;
 			}
@@ -262,10 +321,22 @@ __global__ void __launch_bounds__(128) k_connect(RenderParams rp, DeviceScene sc
 		const V3 col = xyz(c4) + xyz(t4) * res / light_pick_pdf;
 		colb[slot] = f4(col, c4.w);
 	}
-	flush_stats(stats, ST_SHADOW, n_shadow);
-	flush_stats(stats, ST_PROBE, n_probe);
-	flush_stats(stats, ST_NODES, nodes);
-	flush_stats(stats, ST_TRIS, tris);
+}
+
+// Escaped rays with a sun + sky light: col += throughput * shade_atmosphere(...) (path.rgen:50-53, commons.glsl:156-168).
+// A path misses at most once and nothing is added to its radiance afterwards, so running this after the bounce loop keeps
+// the order of the float additions.
+__global__ void __launch_bounds__(128) k_miss(RenderParams rp, DeviceScene sc, const uint32_t* __restrict__ counters, const uint32_t* __restrict__ miss_queue,
+											   const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ thr,
+											   float4* __restrict__ colb) {
+	const uint32_t count = counters[CNT_MISS];
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+		const uint32_t slot = miss_queue[i];
+		const float4 c4 = colb[slot];
+		const V3 sky = shade_atmosphere(sc, rp.dir_light_idx, rp.sky_col, xyz(ray_o[slot]), xyz(ray_d[slot]), T_MAX);
+		const V3 col = xyz(c4) + xyz(thr[slot]) * sky;
+		colb[slot] = f4(col, c4.w);
+	}
 }
 
 // path.rgen:102-112, applied for the batch's frames in order
@@ -306,36 +377,26 @@ __global__ void __launch_bounds__(256) k_resolve(uint32_t n_pix, float4* film) {
 	}
 }
 
-__global__ void __launch_bounds__(128) k_trace_closest(BvhView bvh, const float4* __restrict__ rays, uint32_t n, float4* __restrict__ hits,
-														unsigned long long* stats) {
-	uint32_t nodes = 0, tris = 0, cnt = 0;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		const float4 o = rays[2 * (size_t)i], d = rays[2 * (size_t)i + 1];
-		const Hit h = trace_ray<false>(bvh, xyz(o), xyz(d), o.w, d.w, nodes, tris);
-		hits[i] = make_float4(h.t, h.b1, h.b2, __uint_as_float(h.prim));
-		cnt++;
+// Ray source over a plain array of (o, tmin, d, tmax) rays: lmb_trace_closest / lmb_trace_any
+struct ArraySource {
+	const float4* __restrict__ rays;
+	float4* __restrict__ hits;
+	uint8_t* __restrict__ occ;
+	bool any_hit;
+	__device__ __forceinline__ void load(uint32_t i, V3& o, V3& d, float& tmin, float& tmax, bool& any) const {
+		const float4 o4 = rays[2 * (size_t)i], d4 = rays[2 * (size_t)i + 1];
+		o = xyz(o4), d = xyz(d4), tmin = o4.w, tmax = d4.w, any = any_hit;
 	}
-	if (stats) {
-		flush_stats(stats, ST_CLOSEST, cnt);
-		flush_stats(stats, ST_NODES, nodes);
-		flush_stats(stats, ST_TRIS, tris);
+	__device__ __forceinline__ void store(uint32_t i, const Hit& h, bool) const {
+		if (any_hit)
+			occ[i] = h.prim != 0xFFFFFFFFu;
+		else
+			hits[i] = make_float4(h.t, h.b1, h.b2, __uint_as_float(h.prim));
 	}
-}
+};
 
-__global__ void __launch_bounds__(128) k_trace_any(BvhView bvh, const float4* __restrict__ rays, uint32_t n, uint8_t* __restrict__ occ,
-													unsigned long long* stats) {
-	uint32_t nodes = 0, tris = 0, cnt = 0;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		const float4 o = rays[2 * (size_t)i], d = rays[2 * (size_t)i + 1];
-		const Hit h = trace_ray<true>(bvh, xyz(o), xyz(d), o.w, d.w, nodes, tris);
-		occ[i] = h.prim != 0xFFFFFFFFu;
-		cnt++;
-	}
-	if (stats) {
-		flush_stats(stats, ST_SHADOW, cnt);
-		flush_stats(stats, ST_NODES, nodes);
-		flush_stats(stats, ST_TRIS, tris);
-	}
+__global__ void __launch_bounds__(LMB_TRACE_THREADS) k_trace_array(BvhView bvh, ArraySource src, uint32_t n, uint32_t* cursor, unsigned long long* stats) {
+	trace_persistent(bvh, src, n, cursor, stats, ST_CLOSEST, ST_SHADOW);
 }
 
 BvhView view_of(const lmb_ctx* ctx) { return BvhView{ctx->bvh.nodes, ctx->bvh.tris, ctx->bvh.n}; }
@@ -351,7 +412,7 @@ int wavefront_alloc(lmb_ctx* ctx, uint32_t frames_in_flight) {
 		frames_in_flight = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (8ull << 20) / std::max<uint64_t>(n_pix, 1)));
 	}
 	const uint64_t n_slots = n_pix * frames_in_flight;
-	if (n_slots == 0 || n_slots > 0x7FFFFFFFull) return set_error(ctx, LMB_ERR_INVALID, "width*height*frames_in_flight out of range");
+	if (n_slots == 0 || n_slots > 0x3FFFFFFFull) return set_error(ctx, LMB_ERR_INVALID, "width*height*frames_in_flight out of range");
 	wf.n_slots = (uint32_t)n_slots;
 	wf.frames_in_flight = frames_in_flight;
 	auto alloc = [&](void** p, size_t bytes) { return check_cuda(ctx, cudaMalloc(p, bytes), "cudaMalloc(wavefront)"); };
@@ -365,6 +426,10 @@ int wavefront_alloc(lmb_ctx* ctx, uint32_t frames_in_flight) {
 	if ((rc = alloc((void**)&wf.queue[0], n_slots * 4))) return rc;
 	if ((rc = alloc((void**)&wf.queue[1], n_slots * 4))) return rc;
 	if ((rc = alloc((void**)&wf.nee_queue, n_slots * 4))) return rc;
+	if ((rc = alloc((void**)&wf.miss_queue, n_slots * 4))) return rc;
+	if ((rc = alloc((void**)&wf.trace_queue, n_slots * 4 * 3))) return rc;
+	if ((rc = alloc((void**)&wf.probe_hit, n_slots * 16))) return rc;
+	if ((rc = alloc((void**)&wf.shadow_occ, n_slots * 4))) return rc;
 	if ((rc = alloc((void**)&wf.counters, CNT_COUNT * 4))) return rc;
 	if ((rc = alloc((void**)&wf.stats, ST_COUNT * 8))) return rc;
 	LMB_CUDA(ctx, cudaMemsetAsync(wf.stats, 0, ST_COUNT * 8, ctx->stream));
@@ -374,7 +439,7 @@ int wavefront_alloc(lmb_ctx* ctx, uint32_t frames_in_flight) {
 void wavefront_free(lmb_ctx* ctx) {
 	Wavefront& wf = ctx->wf;
 	cudaFree(wf.ray_o), cudaFree(wf.ray_d), cudaFree(wf.hit), cudaFree(wf.thr), cudaFree(wf.col), cudaFree(wf.nee);
-	cudaFree(wf.queue[0]), cudaFree(wf.queue[1]), cudaFree(wf.nee_queue), cudaFree(wf.counters), cudaFree(wf.stats);
+	cudaFree(wf.queue[0]), cudaFree(wf.queue[1]), cudaFree(wf.nee_queue), cudaFree(wf.miss_queue), cudaFree(wf.trace_queue), cudaFree(wf.probe_hit), cudaFree(wf.shadow_occ), cudaFree(wf.trace_cursor), cudaFree(wf.counters), cudaFree(wf.stats);
 	wf = Wavefront{};
 }
 
@@ -398,6 +463,7 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 	const BvhView bvh = view_of(ctx);
 	const int grid_wide = ctx->sm_count * 16;
 	const int grid_256 = ctx->sm_count * 8;
+	const int grid_trace = ctx->sm_count * 7;  // persistent: 7 blocks x 32 KB stack fit one SM's shared memory
 	float ms;
 	const bool prof = ctx->profile_stages;  // per-stage timing serialises the bounce loop; off by default
 	cudaEventRecord(ctx->ev[0], st);
@@ -406,8 +472,8 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 		rp.first_frame = first_frame + done * stride;
 		rp.n_active = nb * rp.n_pix;
 		if (prof) cudaEventRecord(ctx->ev[1], st);
-		k_set_counters<<<1, 1, 0, st>>>(wf.counters, rp.n_active, 0, 0);
-		k_raygen<<<grid_256, 256, 0, st>>>(rp, wf.ray_o, wf.ray_d, wf.thr, wf.col, wf.queue[0]);
+		k_begin_batch<<<1, 1, 0, st>>>(wf.counters, rp.n_active);
+		k_raygen<<<grid_256, 256, 0, st>>>(rp, wf.ray_o, wf.ray_d, wf.thr, wf.col, wf.queue[0], wf.trace_queue, wf.stats);
 		ctx->stats.kernel_launches += 2;
 		if (prof) {
 			cudaEventRecord(ctx->ev[2], st);
@@ -415,30 +481,38 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 			cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
 			ctx->stats.ms_film += ms;
 		}
+		const WavefrontSource src{wf.trace_queue, wf.ray_o, wf.ray_d, wf.nee, wf.hit, wf.probe_hit, wf.shadow_occ, wf.n_slots};
 		int q = 0;
 		for (int depth = 0; depth < std::max(pc.max_depth, 1); depth++) {
 			if (prof) cudaEventRecord(ctx->ev[1], st);
-			k_extend<<<grid_wide, 128, 0, st>>>(bvh, wf.counters, q, wf.queue[q], wf.ray_o, wf.ray_d, wf.hit, wf.stats);
+			k_trace<<<grid_trace, LMB_TRACE_THREADS, 0, st>>>(bvh, src, wf.counters, wf.stats);
 			if (prof) cudaEventRecord(ctx->ev[2], st);
-			k_zero_counters<<<1, 1, 0, st>>>(wf.counters, q ^ 1, CNT_NEE);  // next continuation queue and NEE queue start empty
-			k_shade<<<grid_wide, 128, 0, st>>>(rp, ctx->scene, depth, wf.counters, q, wf.queue[q], wf.queue[q ^ 1], wf.nee_queue, wf.ray_o, wf.ray_d,
-											   wf.hit, wf.thr, wf.col, wf.nee, wf.n_slots);
+			if (depth > 0) {
+				k_connect<<<grid_wide, 128, 0, st>>>(rp, ctx->scene, wf.counters, wf.nee_queue, wf.nee, wf.probe_hit, wf.shadow_occ, wf.col, wf.n_slots);
+				ctx->stats.kernel_launches += 1;
+			}
 			if (prof) cudaEventRecord(ctx->ev[3], st);
-			k_connect<<<grid_wide, 128, 0, st>>>(rp, ctx->scene, bvh, wf.counters, wf.nee_queue, wf.nee, wf.hit, wf.col, wf.n_slots, wf.stats);
-			ctx->stats.kernel_launches += 4;
+			k_begin_shade<<<1, 1, 0, st>>>(wf.counters, q ^ 1);
+			k_shade<<<grid_wide, 128, 0, st>>>(rp, ctx->scene, depth, wf.counters, q, wf.queue[q], wf.queue[q ^ 1], wf.nee_queue, wf.miss_queue,
+											   wf.trace_queue, wf.ray_o, wf.ray_d, wf.hit, wf.thr, wf.col, wf.nee, wf.n_slots, wf.stats);
+			ctx->stats.kernel_launches += 3;
 			if (prof) {
 				cudaEventRecord(ctx->ev[4], st);
 				cudaEventSynchronize(ctx->ev[4]);
 				cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
 				ctx->stats.ms_extend += ms;
 				cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
-				ctx->stats.ms_shade += ms;
-				cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
 				ctx->stats.ms_connect += ms;
+				cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
+				ctx->stats.ms_shade += ms;
 			}
 			q ^= 1;
 		}
 		if (prof) cudaEventRecord(ctx->ev[1], st);
+		if (pc.dir_light_idx != 0xFFFFFFFFu) {
+			k_miss<<<grid_wide, 128, 0, st>>>(rp, ctx->scene, wf.counters, wf.miss_queue, wf.ray_o, wf.ray_d, wf.thr, wf.col);
+			ctx->stats.kernel_launches += 1;
+		}
 		k_film<<<grid_256, 256, 0, st>>>(rp, nb, film_mode, wf.col, ctx->film, wf.stats);
 		ctx->stats.kernel_launches += 1;
 		if (prof) {
@@ -458,14 +532,19 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 	return 0;
 }
 
-int launch_trace_closest(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits) {
-	k_trace_closest<<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(view_of(ctx), d_rays, n, d_hits, ctx->wf.stats);
-	return check_cuda(ctx, cudaGetLastError(), "k_trace_closest");
+static int launch_trace_array(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits, uint8_t* d_occ, bool any) {
+	uint32_t* cursor = ctx->wf.trace_cursor;
+	if (!cursor) {
+		LMB_CUDA(ctx, cudaMalloc((void**)&ctx->wf.trace_cursor, 4));
+		cursor = ctx->wf.trace_cursor;
+	}
+	LMB_CUDA(ctx, cudaMemsetAsync(cursor, 0, 4, ctx->stream));
+	const ArraySource src{d_rays, d_hits, d_occ, any};
+	k_trace_array<<<ctx->sm_count * 7, LMB_TRACE_THREADS, 0, ctx->stream>>>(view_of(ctx), src, n, cursor, ctx->wf.stats);
+	return check_cuda(ctx, cudaGetLastError(), "k_trace_array");
 }
-int launch_trace_any(lmb_ctx* ctx, const float4* d_rays, uint32_t n, uint8_t* d_occ) {
-	k_trace_any<<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(view_of(ctx), d_rays, n, d_occ, ctx->wf.stats);
-	return check_cuda(ctx, cudaGetLastError(), "k_trace_any");
-}
+int launch_trace_closest(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits) { return launch_trace_array(ctx, d_rays, n, d_hits, nullptr, false); }
+int launch_trace_any(lmb_ctx* ctx, const float4* d_rays, uint32_t n, uint8_t* d_occ) { return launch_trace_array(ctx, d_rays, n, nullptr, d_occ, true); }
 int launch_resolve(lmb_ctx* ctx) {
 	k_resolve<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->width * ctx->height, ctx->film);
 	return check_cuda(ctx, cudaGetLastError(), "k_resolve");

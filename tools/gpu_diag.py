@@ -93,7 +93,7 @@ def scene_checks(path, W, H, depth, frames, force_lights=None):
     t = time.time(); cimg, cs = orc.render(pc, ubo, 0, frames); tc = time.time() - t
     print(f"gpu rays {gs.rays} ({gs.rays_closest},{gs.rays_shadow},{gs.rays_probe}) cpu rays {cs.rays} ({cs.rays_closest},{cs.rays_shadow},{cs.rays_probe}) nan gpu {gs.nan_samples} cpu {cs.nan_pixels}")
     print(f"gpu nodes/ray {gs.nodes_visited/max(gs.rays,1):.2f} tris/ray {gs.tris_tested/max(gs.rays,1):.2f} | cpu {cs.nodes_visited/max(cs.rays,1):.2f} {cs.tris_tested/max(cs.rays,1):.2f}")
-    print(f"gpu {gs.ms_render:.1f} ms ({gs.rays/gs.ms_render/1e3:.1f} Mrays/s; extend {gs.ms_extend:.1f} shade {gs.ms_shade:.1f} connect {gs.ms_connect:.1f} film {gs.ms_film:.1f}) wall {tg:.2f}s | cpu {tc:.2f}s ({cs.rays/cs.seconds/1e6:.2f} Mrays/s, {cs.threads} thr)")
+    print(f"gpu {gs.ms_render:.1f} ms ({gs.rays/gs.ms_render/1e3:.1f} Mrays/s; trace {gs.ms_extend:.1f} shade {gs.ms_shade:.1f} connect {gs.ms_connect:.1f} raygen+sky+film {gs.ms_film:.1f}) wall {tg:.2f}s | cpu {tc:.2f}s ({cs.rays/cs.seconds/1e6:.2f} Mrays/s, {cs.threads} thr)")
     a, b = gimg[..., :3], cimg[..., :3]
     exact = (a.view(np.uint32) == b.view(np.uint32)).all(axis=2)
     rel = np.abs(a - b) <= 1e-4 * np.maximum(np.abs(b), 1e-6)
