@@ -129,6 +129,13 @@ int lmb_upload_scene(lmb_ctx* ctx, const lmb_scene_desc* sd) {
 		lut[i] = (float)(c <= 0.04045 ? c / 12.92 : pow((c + 0.055) / 1.055, 2.4));
 	}
 	if ((rc = upload(ctx, lut, 256, &sc.srgb_lut))) return rc;
+	ctx->mat_queue_mask = 0;
+	for (uint32_t i = 0; i < sd->n_materials; i++) {
+		int q = 6;
+		for (int m = 0; m < 6; m++)
+			if (sd->materials[i].bsdf_type == (1u << m)) q = m;
+		ctx->mat_queue_mask |= 1u << q;
+	}
 	sc.n_tris = (uint32_t)tri_mesh.size();
 	sc.n_prim_meshes = sd->n_prim_meshes;
 	sc.n_lights = sd->n_lights;

@@ -58,9 +58,11 @@ struct Wavefront {
 	float4* thr = nullptr;     // throughput.xyz, rng counter (bits)
 	float4* col = nullptr;     // radiance.xyz, flags (bits): bit0 last_specular
 	float4* nee = nullptr;     // 8 float4 per slot, see wavefront.cu
+	float4* surf = nullptr;    // 4 float4 per slot: surface record k_surface -> k_nee / k_bsdf
 	uint32_t* queue[2] = {nullptr, nullptr};
 	uint32_t* nee_queue = nullptr;
 	uint32_t* miss_queue = nullptr;  // escaped rays awaiting the sky march (k_miss)
+	uint32_t* mat_queues = nullptr;  // 7 x n_slots: live paths sorted by the BSDF type they hit (k_classify -> k_shade<TYPE>)
 	uint32_t* trace_queue = nullptr; // typed ray entries for k_trace: slot | type << 30 (up to 3 per slot)
 	float4* probe_hit = nullptr;     // MIS-probe closest hit per slot
 	uint32_t* shadow_occ = nullptr;  // shadow-ray result per slot
@@ -81,6 +83,7 @@ struct lmb_ctx {
 	std::string err;
 	// scene
 	bool scene_loaded = false;
+	uint32_t mat_queue_mask = 0;  // bit m: some material maps to shade queue m (0..5 = log2(bsdf_type), 6 = unknown type)
 	lmb::DeviceScene scene{};
 	std::vector<void*> scene_allocs;
 	std::vector<lmb_prim_mesh_info> h_prim_infos;

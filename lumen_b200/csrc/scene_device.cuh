@@ -19,7 +19,7 @@ struct HitPayload {
 
 // Bilinear, REPEAT, LOD 0, sRGB-decoded texel fetch; texel centres at integer + 0.5, fp32 weights (same definition as the
 // CPU oracle; the fixed-function sampler's sub-texel precision is not specified by Vulkan).
-LMB_D V3 sample_texture(const DeviceScene& sc, uint32_t id, const V2& uv) {
+LMB_DN V3 sample_texture(const DeviceScene& sc, uint32_t id, const V2& uv) {
 	const uint2 dim = sc.tex_dims[id];
 	const uint8_t* __restrict__ px = sc.tex_data[id];
 	const int W = (int)dim.x, H = (int)dim.y;
@@ -52,7 +52,7 @@ LMB_D lmb_material load_material(const DeviceScene& sc, uint32_t material_idx, c
 LMB_D V3 vtx_pos(const lmb_vertex& v) { return v3(v.pos[0], v.pos[1], v.pos[2]); }
 LMB_D V3 vtx_nrm(const lmb_vertex& v) { return v3(v.normal[0], v.normal[1], v.normal[2]); }
 
-LMB_D HitPayload build_hit(const DeviceScene& sc, uint32_t prim_global, float b1, float b2) {
+LMB_DN HitPayload build_hit(const DeviceScene& sc, uint32_t prim_global, float b1, float b2) {
 	HitPayload p;
 	const uint32_t mesh = sc.tri_mesh[prim_global], prim = sc.tri_local[prim_global];
 	const lmb_prim_mesh_info& pinfo = sc.prim_infos[mesh];
@@ -86,7 +86,7 @@ struct LightSample {
 	uint32_t flags, triangle_idx, instance_idx;
 };
 
-LMB_D LightSample sample_light_Li(const DeviceScene& sc, const V4& rands, const V3& p, int num_lights) {
+LMB_DN LightSample sample_light_Li(const DeviceScene& sc, const V4& rands, const V3& p, int num_lights) {
 	LightSample o;
 	o.Le = v3(0.0f), o.wi = v3(0.0f);
 	o.wi_len = 0, o.pdf_w = 0, o.pdf_a = 0, o.cos_from_light = 0;

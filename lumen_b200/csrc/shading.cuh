@@ -25,11 +25,23 @@ namespace lmb {
 #define LMB_INV_PI (1.0f / LMB_PI)
 #define LMB_EPS 0.001f
 
+// Out-of-line copies of the deterministic transcendentals and of the hash: the shade kernels are instruction-fetch bound
+// (ncu: 83 % of stall samples were "no instruction" with everything inlined, 341 KB of SASS), so anything called from many
+// sites is a real function on the device.
+#define LMB_DN static __device__ __noinline__
+LMB_DN float d_powf(float x, float y) { return lmb_powf(x, y); }
+LMB_DN float d_expf(float x) { return lmb_expf(x); }
+LMB_DN float2 d_sincosf(float x) {
+	float s, c;
+	lmb_sincosf(x, &s, &c);
+	return make_float2(s, c);
+}
+
 // ------------------------------------------------------------------------------------------------ RNG
 struct Rng {
 	uint32_t x, y, z, w;
 };
-LMB_D uint32_t pcg4d_x(uint32_t vx, uint32_t vy, uint32_t vz, uint32_t vw) {
+LMB_DN uint32_t pcg4d_x(uint32_t vx, uint32_t vy, uint32_t vz, uint32_t vw) {
 	vx = vx * 1664525u + 1013904223u;
 	vy = vy * 1664525u + 1013904223u;
 	vz = vz * 1664525u + 1013904223u;
@@ -118,9 +130,8 @@ LMB_D V2 concentric_sample_disk(const V2& rands) {
 		r = offset.y;
 		theta = LMB_PI * (0.5f - 0.25f * offset.x / offset.y);
 	}
-	float s, c;
-	lmb_sincosf(theta, &s, &c);
-	return r * v2(c, s);
+	const float2 sc = d_sincosf(theta);
+	return r * v2(sc.y, sc.x);
 }
 LMB_D bool has_prop(uint32_t props, uint32_t flag) { return (props & flag) != 0; }
 
@@ -141,7 +152,7 @@ LMB_D void refract_dir(const V3& n_s, const V3& wo, bool forward_facing, float e
 	f = mode == 1 ? v3(inv_eta * inv_eta) : v3(1.0f);
 }
 
-LMB_D float fresnel_dielectric(float cos_i, float eta, bool forward_facing) {
+LMB_DN float fresnel_dielectric(float cos_i, float eta, bool forward_facing) {
 	cos_i = gclamp(cos_i, -1.0f, 1.0f);
 	if (!forward_facing) eta = 1.0f / eta;
 	if (cos_i < 0) {
@@ -157,7 +168,7 @@ LMB_D float fresnel_dielectric(float cos_i, float eta, bool forward_facing) {
 	return 0.5f * (r_parallel * r_parallel + r_perp * r_perp);
 }
 
-LMB_D float fresnel_conductor(float cos_i, float eta, float k) {
+LMB_DN float fresnel_conductor(float cos_i, float eta, float k) {
 	const float cos_sqr = cos_i * cos_i;
 	const float sin_sqr = gmax(1.0f - cos_sqr, 0.0f);
 	const float sin_4 = sin_sqr * sin_sqr;
@@ -171,8 +182,8 @@ LMB_D float fresnel_conductor(float cos_i, float eta, float k) {
 LMB_D V3 fresnel_conductor(float cos_i, const V3& eta, const V3& k) {
 	return v3(fresnel_conductor(cos_i, eta.x, k.x), fresnel_conductor(cos_i, eta.y, k.y), fresnel_conductor(cos_i, eta.z, k.z));
 }
-LMB_D float fresnel_schlick(float f0, float f90, float ns) { return f0 + (f90 - f0) * lmb_powf(gmax(1.0f - ns, 0.0f), 5.0f); }
-LMB_D V3 fresnel_schlick(const V3& f0, const V3& f90, float ns) { return f0 + (f90 - f0) * lmb_powf(gmax(1.0f - ns, 0.0f), 5.0f); }
+LMB_D float fresnel_schlick(float f0, float f90, float ns) { return f0 + (f90 - f0) * d_powf(gmax(1.0f - ns, 0.0f), 5.0f); }
+LMB_D V3 fresnel_schlick(const V3& f0, const V3& f90, float ns) { return f0 + (f90 - f0) * d_powf(gmax(1.0f - ns, 0.0f), 5.0f); }
 LMB_D float eta_to_schlick_R0(float eta) {
 	const float val = (eta - 1.0f) / (eta + 1.0f);
 	return val * val;
@@ -199,7 +210,7 @@ LMB_D V3 disney_fresnel(const lmb_material& mat, const V3& wo, const V3& h, floa
 	const V3 fr_metallic = fresnel_schlick(R0, v3(1.0f), wo_dot_h);
 	return mix(v3(fr_dielectric), fr_metallic, mat.metallic);
 }
-LMB_D V3 sample_hemisphere(const V2& xi) {
+LMB_DN V3 sample_hemisphere(const V2& xi) {
 	const V2 d = concentric_sample_disk(xi);
 	const float z = sqrtf(gmax(0.f, 1.f - dot(d, d)));
 	return v3(d.x, d.y, z);
@@ -265,15 +276,14 @@ LMB_D float vndf_pdf_aniso(const V2& alpha, const V3& wo, const V3& h, float& D)
 	D = d_ggx_aniso(alpha, h);
 	return G1 * D * gmax(0.0f, dot(wo, h)) / fabsf(wo.z);
 }
-LMB_D V3 sample_ggx_vndf_common(const V2& alpha, const V3& wo, const V2& xi) {
+LMB_DN V3 sample_ggx_vndf_common(const V2& alpha, const V3& wo, const V2& xi) {
 	const V3 wo_hemisphere = normalize(v3(alpha.x * wo.x, alpha.y * wo.y, wo.z));
 	const float phi = 2.0f * LMB_PI * xi.x;
 	const float z = ((1.0f - xi.y) * (1.0f + wo_hemisphere.z)) - wo_hemisphere.z;
 	const float sin_theta = sqrtf(gclamp(1.0f - z * z, 0.0f, 1.0f));
-	float sp, cp;
-	lmb_sincosf(phi, &sp, &cp);
-	const float x = sin_theta * cp;
-	const float y = sin_theta * sp;
+	const float2 scp = d_sincosf(phi);
+	const float x = sin_theta * scp.y;
+	const float y = sin_theta * scp.x;
 	const V3 n_h = v3(x, y, z) + wo_hemisphere;
 	return normalize(v3(alpha.x * n_h.x, alpha.y * n_h.y, gmax(0.0f, n_h.z)));
 }
@@ -567,12 +577,11 @@ LMB_D BsdfSample sample_principled_brdf(const lmb_material& mat, const V3& wo, c
 LMB_D BsdfSample sample_clearcoat(const lmb_material& mat, const V3& wo, const V2& xi) {
 	BsdfSample s = zero_sample();
 	const float alpha_2 = 0.25f * 0.25f;
-	const float cos_t = sqrtf(gmax(0.0f, (1.0f - lmb_powf(alpha_2, 1.0f - xi.x)) / (1.0f - alpha_2)));
+	const float cos_t = sqrtf(gmax(0.0f, (1.0f - d_powf(alpha_2, 1.0f - xi.x)) / (1.0f - alpha_2)));
 	const float sin_t = sqrtf(gmax(0.0f, 1.0f - s.cos_theta * s.cos_theta));  // Q2: stale inout cos_theta (= 0)
 	const float phi = LMB_TWO_PI * xi.y;
-	float sp, cp;
-	lmb_sincosf(phi, &sp, &cp);
-	V3 h = v3(sin_t * cp, sin_t * sp, cos_t);
+	const float2 scp = d_sincosf(phi);
+	V3 h = v3(sin_t * scp.y, sin_t * scp.x, cos_t);
 	if (dot(h, wo) < 0.0f) h *= -1.0f;
 	s.wi = reflect(-wo, h);
 	if (dot(s.wi, wo) < 0.0f) return s;
@@ -662,13 +671,17 @@ static __device__ __noinline__ V3 eval_principled(const lmb_material& mat, const
 }
 
 // ------------------------------------------------------------------------------------------------ dispatch
-LMB_D BsdfSample sample_bsdf(const V3& n_s, const V3& wo_world, const lmb_material& mat, uint32_t mode, bool forward_facing, const V3& rands) {
+// TYPE = LMB_BSDF_ANY dispatches on mat.bsdf_type at run time; a concrete LMB_BSDF_* constant folds the switch away so
+// that the per-material shade kernels carry only their own lobe code (material-sorted queues, wavefront.cu).
+#define LMB_BSDF_ANY 0xFFFFFFFFu
+template <uint32_t TYPE>
+LMB_D BsdfSample sample_bsdf_t(const V3& n_s, const V3& wo_world, const lmb_material& mat, uint32_t mode, bool forward_facing, const V3& rands) {
 	V3 T, B;
 	branchless_onb(n_s, T, B);
 	const V3 wo = to_local(wo_world, T, B, n_s);
 	BsdfSample s = zero_sample();
 	const V2 xy = v2(rands.x, rands.y);
-	switch (mat.bsdf_type) {
+	switch (TYPE == LMB_BSDF_ANY ? mat.bsdf_type : TYPE) {
 		case LMB_BSDF_DIFFUSE:
 			s = sample_lambertian(mat, wo, xy);
 			break;
@@ -693,13 +706,17 @@ LMB_D BsdfSample sample_bsdf(const V3& n_s, const V3& wo_world, const lmb_materi
 	s.wi = to_world(s.wi, T, B, n_s);
 	return s;
 }
-LMB_D V3 eval_bsdf(const V3& n_s, const V3& wo_world, const lmb_material& mat, bool forward_facing, const V3& wi_world, float& pdf_w) {
+LMB_D BsdfSample sample_bsdf(const V3& n_s, const V3& wo_world, const lmb_material& mat, uint32_t mode, bool forward_facing, const V3& rands) {
+	return sample_bsdf_t<LMB_BSDF_ANY>(n_s, wo_world, mat, mode, forward_facing, rands);
+}
+template <uint32_t TYPE>
+LMB_D V3 eval_bsdf_t(const V3& n_s, const V3& wo_world, const lmb_material& mat, bool forward_facing, const V3& wi_world, float& pdf_w) {
 	pdf_w = 0;
 	V3 T, B;
 	branchless_onb(n_s, T, B);
 	const V3 wo = to_local(wo_world, T, B, n_s);
 	const V3 wi = to_local(wi_world, T, B, n_s);
-	switch (mat.bsdf_type) {
+	switch (TYPE == LMB_BSDF_ANY ? mat.bsdf_type : TYPE) {
 		case LMB_BSDF_DIFFUSE:
 			return eval_lambertian(mat, wo, wi, pdf_w);
 		case LMB_BSDF_DIELECTRIC:
@@ -712,6 +729,10 @@ LMB_D V3 eval_bsdf(const V3& n_s, const V3& wo_world, const lmb_material& mat, b
 			break;
 	}
 	return v3(0.0f);
+}
+
+LMB_D V3 eval_bsdf(const V3& n_s, const V3& wo_world, const lmb_material& mat, bool forward_facing, const V3& wi_world, float& pdf_w) {
+	return eval_bsdf_t<LMB_BSDF_ANY>(n_s, wo_world, mat, forward_facing, wi_world, pdf_w);
 }
 
 // ------------------------------------------------------------------------------------------------ sky
@@ -747,10 +768,10 @@ LMB_D float phase_mie(float costh, float g) {
 }
 LMB_D float height(const V3& p) { return length(planet_center() - p) - LMB_PLANET_RADIUS; }
 LMB_D V3 density(float h) {
-	return v3(lmb_expf(-gmax(0.0f, h / LMB_RAYLEIGH_HEIGHT)), lmb_expf(-gmax(0.0f, h / LMB_MIE_HEIGHT)),
+	return v3(d_expf(-gmax(0.0f, h / LMB_RAYLEIGH_HEIGHT)), d_expf(-gmax(0.0f, h / LMB_MIE_HEIGHT)),
 			  gmax(0.0f, 1 - fabsf(h - 25000.0f) / 15000.0f));
 }
-LMB_D V3 vexp(const V3& a) { return v3(lmb_expf(a.x), lmb_expf(a.y), lmb_expf(a.z)); }
+LMB_D V3 vexp(const V3& a) { return v3(d_expf(a.x), d_expf(a.y), d_expf(a.z)); }
 LMB_D V3 absorb(const V3& od) { return vexp(-(od.x * c_rayleigh() + od.y * c_mie() * 1.1f + od.z * c_ozone()) * 1.0f); }
 LMB_D V3 optical_depth(const V3& ray_start, const V3& ray_dir) {
 	const V2 isect = atmosphere_intersection(ray_start, ray_dir);
@@ -781,7 +802,7 @@ static __device__ __noinline__ V3 integrate_scattering(V3 ray_start, const V3& r
 	V3 od = v3(0.0f), rayleigh = v3(0.0f), mie = v3(0.0f);
 	float prev_ray_time = 0;
 	for (int i = 0; i < sample_count; i++) {
-		const float ray_time = lmb_powf(float(i) / sample_count, exponent) * ray_length;
+		const float ray_time = d_powf(float(i) / sample_count, exponent) * ray_length;
 		const float step = (ray_time - prev_ray_time);
 		const V3 local_pos = ray_start + ray_dir * ray_time;
 		const V3 local_density = density(height(local_pos));
