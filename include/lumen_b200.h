@@ -50,7 +50,7 @@ typedef struct lmb_stats {
 	uint64_t rays_closest; /* continuation rays (path.rgen:48) */
 	uint64_t rays_shadow;  /* any-hit rays (pt_commons.glsl:21) */
 	uint64_t rays_probe;   /* MIS BSDF-probe rays (pt_commons.glsl:32) */
-	uint64_t nodes_visited;
+	uint64_t nodes_visited; /* traversal steps: 80-byte 8-wide nodes (LMB_TRAVERSAL=bvh2: 64-byte binary nodes) */
 	uint64_t tris_tested;
 	uint64_t nan_samples;  /* samples dropped by the NaN guard */
 	uint64_t frames;       /* frames rendered since lmb_init / lmb_reset_stats */
@@ -65,6 +65,10 @@ typedef struct lmb_stats {
 	float ms_build_sort;   /* radix sort */
 	float ms_build_tree;   /* Karras hierarchy */
 	float ms_build_refit;  /* bottom-up AABB refit + node packing */
+	float ms_build_wide;   /* collapse of the LBVH into the compressed 8-wide traversal BVH (included in ms_build_accel) */
+	uint32_t wide_nodes;   /* nodes of the 8-wide BVH (80 B each) */
+	uint32_t wide_levels;  /* depth of the 8-wide BVH */
+	uint32_t pad_;
 } lmb_stats;
 
 typedef struct lmb_hit {

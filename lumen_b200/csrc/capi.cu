@@ -2,6 +2,7 @@
 // ray-query entry points). No CPU fallback: every entry point needs a CUDA device and says so when there is none.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -73,6 +74,8 @@ int lmb_create(lmb_ctx** out, int device_id) {
 	}
 	cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_id);
 	for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+	const char* trav = getenv("LMB_TRAVERSAL");
+	ctx->use_bvh2 = trav && strcmp(trav, "bvh2") == 0;
 	*out = ctx;
 	return LMB_OK;
 }
@@ -253,7 +256,8 @@ int lmb_reset_stats(lmb_ctx* ctx) {
 	ctx->stats = lmb_stats{};
 	ctx->stats.ms_build_accel = keep.ms_build_accel, ctx->stats.ms_build_morton = keep.ms_build_morton;
 	ctx->stats.ms_build_sort = keep.ms_build_sort, ctx->stats.ms_build_tree = keep.ms_build_tree;
-	ctx->stats.ms_build_refit = keep.ms_build_refit;
+	ctx->stats.ms_build_refit = keep.ms_build_refit, ctx->stats.ms_build_wide = keep.ms_build_wide;
+	ctx->stats.wide_nodes = keep.wide_nodes, ctx->stats.wide_levels = keep.wide_levels;
 	if (ctx->wf.stats) {
 		LMB_CUDA(ctx, cudaMemsetAsync(ctx->wf.stats, 0, ST_COUNT * 8, ctx->stream));
 		LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -45,8 +45,19 @@ struct DeviceBvh {
 	float4* nodes = nullptr;  // 4*(n-1)
 	float4* tris = nullptr;   // 3n, leaf order
 	uint32_t* radix_hist = nullptr;
+	uint32_t* span_first = nullptr;  // n-1: first / last sorted leaf position under each internal node (Karras range)
+	uint32_t* span_last = nullptr;
 	uint32_t n = 0;
 	bool built = false;
+};
+
+// Compressed 8-wide BVH derived from the canonical LBVH (wide_bvh.cu); what k_trace walks.
+struct DeviceWideBvh {
+	float4* nodes = nullptr;  // 5 per node (80 B)
+	float4* tris = nullptr;   // 3 per triangle, contiguous per node
+	uint2* items[2] = {nullptr, nullptr};  // build scratch
+	uint32_t* counters = nullptr;
+	uint32_t n_nodes = 0, n_tris = 0, levels = 0;
 };
 
 // Wavefront state, struct-of-arrays over path slots (slot = frame_in_batch * W*H + y*W + x).
@@ -89,6 +100,8 @@ struct lmb_ctx {
 	std::vector<lmb_prim_mesh_info> h_prim_infos;
 	std::vector<uint32_t> h_idx_counts;
 	lmb::DeviceBvh bvh;
+	lmb::DeviceWideBvh wide;
+	bool use_bvh2 = false;  // LMB_TRAVERSAL=bvh2: walk the binary LBVH instead of the 8-wide BVH (A/B measurements)
 	// film / wavefront
 	uint32_t width = 0, height = 0;
 	float4* film = nullptr;
@@ -104,6 +117,8 @@ int set_error(lmb_ctx* ctx, int code, const std::string& msg);
 int check_cuda(lmb_ctx* ctx, cudaError_t e, const char* what);
 int build_lbvh(lmb_ctx* ctx);
 void free_bvh(lmb_ctx* ctx);
+int build_wide_bvh(lmb_ctx* ctx);
+void free_wide_bvh(lmb_ctx* ctx);
 int wavefront_alloc(lmb_ctx* ctx, uint32_t frames_in_flight);
 void wavefront_free(lmb_ctx* ctx);
 int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& ubo, uint32_t first_frame, uint32_t n_frames, uint32_t stride,

@@ -23,6 +23,7 @@
 #include "context.h"
 #include "scene_device.cuh"
 #include "trace_persistent.cuh"
+#include "trace_wide.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -149,7 +150,11 @@ struct WavefrontSource {
 	}
 };
 
-__global__ void __launch_bounds__(LMB_TRACE_THREADS) k_trace(BvhView bvh, WavefrontSource src, uint32_t* counters, unsigned long long* stats) {
+__global__ void __launch_bounds__(LMB_TRACE_THREADS, 6) k_trace(WideBvhView bvh, WavefrontSource src, uint32_t* counters, unsigned long long* stats) {
+	trace_wide_persistent(bvh, src, counters[CNT_TRACE], &counters[CNT_CURSOR], stats, -1, -1);
+}
+// the same rays over the binary LBVH (LMB_TRAVERSAL=bvh2; A/B measurements and the canonical node counts)
+__global__ void __launch_bounds__(LMB_TRACE_THREADS) k_trace_bvh2(BvhView bvh, WavefrontSource src, uint32_t* counters, unsigned long long* stats) {
 	trace_persistent(bvh, src, counters[CNT_TRACE], &counters[CNT_CURSOR], stats, -1, -1);
 }
 
@@ -477,11 +482,15 @@ struct ArraySource {
 	}
 };
 
-__global__ void __launch_bounds__(LMB_TRACE_THREADS) k_trace_array(BvhView bvh, ArraySource src, uint32_t n, uint32_t* cursor, unsigned long long* stats) {
+__global__ void __launch_bounds__(LMB_TRACE_THREADS, 6) k_trace_array(WideBvhView bvh, ArraySource src, uint32_t n, uint32_t* cursor, unsigned long long* stats) {
+	trace_wide_persistent(bvh, src, n, cursor, stats, ST_CLOSEST, ST_SHADOW);
+}
+__global__ void __launch_bounds__(LMB_TRACE_THREADS) k_trace_array_bvh2(BvhView bvh, ArraySource src, uint32_t n, uint32_t* cursor, unsigned long long* stats) {
 	trace_persistent(bvh, src, n, cursor, stats, ST_CLOSEST, ST_SHADOW);
 }
 
 BvhView view_of(const lmb_ctx* ctx) { return BvhView{ctx->bvh.nodes, ctx->bvh.tris, ctx->bvh.n}; }
+WideBvhView wide_view_of(const lmb_ctx* ctx) { return WideBvhView{ctx->wide.nodes, ctx->wide.tris, ctx->wide.n_tris}; }
 
 }  // namespace
 
@@ -545,9 +554,11 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 	rp.num_lights = pc.num_lights, rp.max_depth = pc.max_depth, rp.light_triangle_count = pc.light_triangle_count;
 	rp.dir_light_idx = pc.dir_light_idx, rp.direct_lighting = pc.direct_lighting;
 	const BvhView bvh = view_of(ctx);
+	const WideBvhView wide = wide_view_of(ctx);
 	const int grid_wide = ctx->sm_count * 16;
 	const int grid_256 = ctx->sm_count * 8;
 	const int grid_trace = ctx->sm_count * 7;  // persistent: 7 blocks x 32 KB stack fit one SM's shared memory
+	const int grid_trace_wide = ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM;
 	float ms;
 	const bool prof = ctx->profile_stages;  // per-stage timing serialises the bounce loop; off by default
 	cudaEventRecord(ctx->ev[0], st);
@@ -569,7 +580,10 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 		int q = 0;
 		for (int depth = 0; depth < std::max(pc.max_depth, 1); depth++) {
 			if (prof) cudaEventRecord(ctx->ev[1], st);
-			k_trace<<<grid_trace, LMB_TRACE_THREADS, 0, st>>>(bvh, src, wf.counters, wf.stats);
+			if (ctx->use_bvh2)
+				k_trace_bvh2<<<grid_trace, LMB_TRACE_THREADS, 0, st>>>(bvh, src, wf.counters, wf.stats);
+			else
+				k_trace<<<grid_trace_wide, LMB_TRACE_THREADS, 0, st>>>(wide, src, wf.counters, wf.stats);
 			if (prof) cudaEventRecord(ctx->ev[2], st);
 			if (depth > 0) {
 				k_connect<<<grid_wide, 128, 0, st>>>(rp, ctx->scene, wf.counters, wf.nee_queue, wf.nee, wf.probe_hit, wf.shadow_occ, wf.col, wf.n_slots);
@@ -648,7 +662,10 @@ static int launch_trace_array(lmb_ctx* ctx, const float4* d_rays, uint32_t n, fl
 	}
 	LMB_CUDA(ctx, cudaMemsetAsync(cursor, 0, 4, ctx->stream));
 	const ArraySource src{d_rays, d_hits, d_occ, any};
-	k_trace_array<<<ctx->sm_count * 7, LMB_TRACE_THREADS, 0, ctx->stream>>>(view_of(ctx), src, n, cursor, ctx->wf.stats);
+	if (ctx->use_bvh2)
+		k_trace_array_bvh2<<<ctx->sm_count * 7, LMB_TRACE_THREADS, 0, ctx->stream>>>(view_of(ctx), src, n, cursor, ctx->wf.stats);
+	else
+		k_trace_array<<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n, cursor, ctx->wf.stats);
 	return check_cuda(ctx, cudaGetLastError(), "k_trace_array");
 }
 int launch_trace_closest(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits) { return launch_trace_array(ctx, d_rays, n, d_hits, nullptr, false); }

@@ -24,7 +24,8 @@ class Stats(C.Structure):
                 ("tris_tested", C.c_uint64), ("nan_samples", C.c_uint64), ("frames", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("ms_render", C.c_float), ("ms_extend", C.c_float), ("ms_shade", C.c_float), ("ms_connect", C.c_float), ("ms_film", C.c_float),
                 ("ms_build_accel", C.c_float), ("ms_build_morton", C.c_float), ("ms_build_sort", C.c_float), ("ms_build_tree", C.c_float),
-                ("ms_build_refit", C.c_float)]
+                ("ms_build_refit", C.c_float), ("ms_build_wide", C.c_float), ("wide_nodes", C.c_uint32), ("wide_levels", C.c_uint32),
+                ("pad_", C.c_uint32)]
 
     @property
     def rays(self):
