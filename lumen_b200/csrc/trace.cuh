@@ -85,6 +85,36 @@ LMB_D bool tri_intersect(const RayPre& r, const V3& v0, const V3& v1, const V3& 
 	return true;
 }
 
+// Same arithmetic as tri_intersect up to t; the barycentric divisions are left to the caller (b1 = V / det, b2 = W / det),
+// who needs them only for an accepted closest hit.
+LMB_D bool tri_intersect_t(const RayPre& r, const float4& p0, const float4& p1, const float4& p2, float& t, float& V_out, float& W_out, float& det_out) {
+	const bool x0 = r.kx == 0, x1 = r.kx == 1, y0 = r.ky == 0, y1 = r.ky == 1, z0 = r.kz == 0, z1 = r.kz == 1;
+	const float Ax_ = p0.x - r.o.x, Ay_ = p0.y - r.o.y, Az_ = p0.z - r.o.z;
+	const float Bx_ = p1.x - r.o.x, By_ = p1.y - r.o.y, Bz_ = p1.z - r.o.z;
+	const float Cx_ = p2.x - r.o.x, Cy_ = p2.y - r.o.y, Cz_ = p2.z - r.o.z;
+	const float Akz = z0 ? Ax_ : (z1 ? Ay_ : Az_), Bkz = z0 ? Bx_ : (z1 ? By_ : Bz_), Ckz = z0 ? Cx_ : (z1 ? Cy_ : Cz_);
+	const float Akx = x0 ? Ax_ : (x1 ? Ay_ : Az_), Bkx = x0 ? Bx_ : (x1 ? By_ : Bz_), Ckx = x0 ? Cx_ : (x1 ? Cy_ : Cz_);
+	const float Aky = y0 ? Ax_ : (y1 ? Ay_ : Az_), Bky = y0 ? Bx_ : (y1 ? By_ : Bz_), Cky = y0 ? Cx_ : (y1 ? Cy_ : Cz_);
+	const float Ax = fmaf(-r.Sx, Akz, Akx), Ay = fmaf(-r.Sy, Akz, Aky);
+	const float Bx = fmaf(-r.Sx, Bkz, Bkx), By = fmaf(-r.Sy, Bkz, Bky);
+	const float Cx = fmaf(-r.Sx, Ckz, Ckx), Cy = fmaf(-r.Sy, Ckz, Cky);
+	float U = Cx * By - Cy * Bx;
+	float V = Ax * Cy - Ay * Cx;
+	float W = Bx * Ay - By * Ax;
+	if (U == 0.0f || V == 0.0f || W == 0.0f) {
+		U = (float)__dsub_rn(__dmul_rn((double)Cx, (double)By), __dmul_rn((double)Cy, (double)Bx));
+		V = (float)__dsub_rn(__dmul_rn((double)Ax, (double)Cy), __dmul_rn((double)Ay, (double)Cx));
+		W = (float)__dsub_rn(__dmul_rn((double)Bx, (double)Ay), __dmul_rn((double)By, (double)Ax));
+	}
+	if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+	const float det = U + V + W;
+	if (det == 0.0f) return false;
+	const float T = U * (r.Sz * Akz) + V * (r.Sz * Bkz) + W * (r.Sz * Ckz);
+	t = T / det;
+	V_out = V, W_out = W, det_out = det;
+	return true;
+}
+
 LMB_D bool box_intersect(const RayPre& r, float lox, float loy, float loz, float hix, float hiy, float hiz, float tmin, float tmax, float& tnear) {
 	const float t0x = (lox - r.o.x) * r.inv.x, t1x = (hix - r.o.x) * r.inv.x;
 	const float t0y = (loy - r.o.y) * r.inv.y, t1y = (hiy - r.o.y) * r.inv.y;

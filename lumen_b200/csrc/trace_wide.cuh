@@ -22,6 +22,7 @@ struct WideBvhView {
 	const float4* nodes;  // 5 per node
 	const float4* tris;   // 3 per triangle
 	uint32_t n_tris;
+	uint32_t one_bits;  // 0x3F800000, passed as DATA: keeps the PRMT byte selectors of the slab test immediates (no MOV per plane)
 };
 
 #ifndef LMB_TRACE_THREADS
@@ -31,23 +32,76 @@ struct WideBvhView {
 #define LMB_WSTACK_LOCAL 52
 #define LMB_WIDE_REFILL_LANES 20
 #define LMB_WIDE_BLOCKS_PER_SM 6
+#ifndef LMB_TRI_ROUND_LANES
+#define LMB_TRI_ROUND_LANES 8
+#endif
+
+// Ray constants of the triangle test as one lane publishes them for the whole warp (see the triangle phase below).
+struct TriRay {
+	V3 o;
+	float tmin, Sx, Sy, Sz;
+	uint32_t k;  // kx | ky << 2 | kz << 4
+};
+
+// tri_intersect (trace.cuh) on a TriRay: same expressions, same order; returns t only, the caller divides V / det, W / det.
+LMB_D bool tri_test(const TriRay& r, const float4& p0, const float4& p1, const float4& p2, float& t, float& V_out, float& W_out, float& det_out) {
+	const uint32_t kx = r.k & 3u, ky = (r.k >> 2) & 3u, kz = r.k >> 4;
+	const bool x0 = kx == 0, x1 = kx == 1, y0 = ky == 0, y1 = ky == 1, z0 = kz == 0, z1 = kz == 1;
+	const float Ax_ = p0.x - r.o.x, Ay_ = p0.y - r.o.y, Az_ = p0.z - r.o.z;
+	const float Bx_ = p1.x - r.o.x, By_ = p1.y - r.o.y, Bz_ = p1.z - r.o.z;
+	const float Cx_ = p2.x - r.o.x, Cy_ = p2.y - r.o.y, Cz_ = p2.z - r.o.z;
+	const float Akz = z0 ? Ax_ : (z1 ? Ay_ : Az_), Bkz = z0 ? Bx_ : (z1 ? By_ : Bz_), Ckz = z0 ? Cx_ : (z1 ? Cy_ : Cz_);
+	const float Akx = x0 ? Ax_ : (x1 ? Ay_ : Az_), Bkx = x0 ? Bx_ : (x1 ? By_ : Bz_), Ckx = x0 ? Cx_ : (x1 ? Cy_ : Cz_);
+	const float Aky = y0 ? Ax_ : (y1 ? Ay_ : Az_), Bky = y0 ? Bx_ : (y1 ? By_ : Bz_), Cky = y0 ? Cx_ : (y1 ? Cy_ : Cz_);
+	const float Ax = fmaf(-r.Sx, Akz, Akx), Ay = fmaf(-r.Sy, Akz, Aky);
+	const float Bx = fmaf(-r.Sx, Bkz, Bkx), By = fmaf(-r.Sy, Bkz, Bky);
+	const float Cx = fmaf(-r.Sx, Ckz, Ckx), Cy = fmaf(-r.Sy, Ckz, Cky);
+	float U = Cx * By - Cy * Bx;
+	float V = Ax * Cy - Ay * Cx;
+	float W = Bx * Ay - By * Ax;
+	if (U == 0.0f || V == 0.0f || W == 0.0f) {
+		U = (float)__dsub_rn(__dmul_rn((double)Cx, (double)By), __dmul_rn((double)Cy, (double)Bx));
+		V = (float)__dsub_rn(__dmul_rn((double)Ax, (double)Cy), __dmul_rn((double)Ay, (double)Cx));
+		W = (float)__dsub_rn(__dmul_rn((double)Bx, (double)Ay), __dmul_rn((double)By, (double)Ax));
+	}
+	if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+	const float det = U + V + W;
+	if (det == 0.0f) return false;
+	const float T = U * (r.Sz * Akz) + V * (r.Sz * Bkz) + W * (r.Sz * Ckz);
+	t = T / det;
+	V_out = V, W_out = W, det_out = det;
+	return true;
+}
+
+// Shared memory of one traversal block.
+struct TraceSmem {
+	uint2 stack[LMB_WSTACK_SM][LMB_TRACE_THREADS];
+	float4 ray_a[LMB_TRACE_THREADS];  // o.xyz, tmin            } TriRay of the ray each lane owns, written once per ray
+	float4 ray_b[LMB_TRACE_THREADS];  // Sx, Sy, Sz, k (bits)   }
+	uint32_t pair[LMB_TRACE_THREADS]; // owner lane << 27 | triangle index: one triangle test of this round
+	float4 res[LMB_TRACE_THREADS];    // t (or -1), V, W, det
+	uint32_t res_prim[LMB_TRACE_THREADS];
+};
 
 template <typename Source>
 __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, Source& src, uint32_t count, uint32_t* cursor, unsigned long long* stats,
 													  int stat_closest, int stat_any) {
-	__shared__ uint2 s_stack[LMB_WSTACK_SM][LMB_TRACE_THREADS];
+	__shared__ TraceSmem sm;
 	uint2 l_stack[LMB_WSTACK_LOCAL];
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
+	const int wbase = tid & ~31;
 	const uint32_t lt_mask = (1u << lane) - 1u;
+	const uint32_t one_bits = bvh.one_bits;
 
 	bool has = false;        // this lane owns a ray
 	bool exhausted = false;  // warp-uniform: the queue ran dry
 	bool any = false;
 	uint32_t item = 0;
-	RayPre r;
+	V3 ro = v3(0.0f), rinv = v3(1.0f);
 	float tmin = 0.0f;
 	Hit h{0.0f, 0.0f, 0.0f, 0xFFFFFFFFu};
+	float det = 1.0f;  // h.b1, h.b2 hold V, W of the current best hit until the ray is done
 	uint2 ng = make_uint2(0u, 0u);  // node group: (child_base, hits << 24 | imask)
 	uint2 tg = make_uint2(0u, 0u);  // triangle group: (tri_base, mask)
 	uint32_t oct_inv4 = 0;
@@ -70,10 +124,13 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 						float tmax;
 						src.load(i, o, d, tmin, tmax, any);
 						item = i;
-						r = ray_prepare(o, d);
+						const RayPre r = ray_prepare(o, d);
+						ro = r.o, rinv = r.inv;
+						sm.ray_a[tid] = make_float4(o.x, o.y, o.z, tmin);
+						sm.ray_b[tid] = make_float4(r.Sx, r.Sy, r.Sz, __uint_as_float((uint32_t)r.kx | ((uint32_t)r.ky << 2) | ((uint32_t)r.kz << 4)));
 						h = Hit{tmax, 0.0f, 0.0f, 0xFFFFFFFFu};
 						sp = 0;
-						oct_inv4 = ((r.inv.x < 0.0f ? 0u : 4u) | (r.inv.y < 0.0f ? 0u : 2u) | (r.inv.z < 0.0f ? 0u : 1u)) * 0x01010101u;
+						oct_inv4 = ((rinv.x < 0.0f ? 0u : 4u) | (rinv.y < 0.0f ? 0u : 2u) | (rinv.z < 0.0f ? 0u : 1u)) * 0x01010101u;
 						ng = make_uint2(0u, bvh.n_tris ? 0x80000000u : 0u);
 						tg = make_uint2(0u, 0u);
 						has = true;
@@ -82,20 +139,21 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 					}
 				}
 				if (base + (uint32_t)__popc(need) >= count) exhausted = true;
+				__syncwarp();
 			}
 		}
 		if (__ballot_sync(0xFFFFFFFFu, has) == 0) break;
 
 		for (;;) {
 			// ---- one node step
-			if (has && ng.y > 0x00FFFFFFu) {
+			if (has && tg.y == 0u && ng.y > 0x00FFFFFFu) {
 				const uint32_t hits = ng.y;
 				const int bit = 31 - __clz(hits);
 				ng.y = hits & ~(1u << bit);
 				const uint32_t slot = (uint32_t)(bit - 24) ^ (oct_inv4 & 7u);
 				const uint32_t node = ng.x + __popc(hits & 0xFFu & ((1u << slot) - 1u));
 				if (ng.y > 0x00FFFFFFu) {  // siblings still to visit
-					if (sp < LMB_WSTACK_SM) s_stack[sp][tid] = ng;
+					if (sp < LMB_WSTACK_SM) sm.stack[sp][tid] = ng;
 					else l_stack[sp - LMB_WSTACK_SM] = ng;
 					sp++;
 				}
@@ -103,13 +161,13 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 				const float4* np = bvh.nodes + 5 * (size_t)node;
 				const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
 				const uint32_t ew = __float_as_uint(n0.w);
-				const float ax = __uint_as_float(((ew & 0xFFu) + 15u) << 23) * r.inv.x;
-				const float ay = __uint_as_float((((ew >> 8) & 0xFFu) + 15u) << 23) * r.inv.y;
-				const float az = __uint_as_float((((ew >> 16) & 0xFFu) + 15u) << 23) * r.inv.z;
-				const float bx = fmaf(n0.x - r.o.x, r.inv.x, -ax);
-				const float by = fmaf(n0.y - r.o.y, r.inv.y, -ay);
-				const float bz = fmaf(n0.z - r.o.z, r.inv.z, -az);
-				const bool sx = r.inv.x < 0.0f, sy = r.inv.y < 0.0f, sz = r.inv.z < 0.0f;
+				const float ax = __uint_as_float(((ew & 0xFFu) + 15u) << 23) * rinv.x;
+				const float ay = __uint_as_float((((ew >> 8) & 0xFFu) + 15u) << 23) * rinv.y;
+				const float az = __uint_as_float((((ew >> 16) & 0xFFu) + 15u) << 23) * rinv.z;
+				const float bx = fmaf(n0.x - ro.x, rinv.x, -ax);
+				const float by = fmaf(n0.y - ro.y, rinv.y, -ay);
+				const float bz = fmaf(n0.z - ro.z, rinv.z, -az);
+				const bool sx = rinv.x < 0.0f, sy = rinv.y < 0.0f, sz = rinv.z < 0.0f;
 				const uint32_t qlx[2] = {__float_as_uint(n2.x), __float_as_uint(n2.y)}, qly[2] = {__float_as_uint(n2.z), __float_as_uint(n2.w)};
 				const uint32_t qlz[2] = {__float_as_uint(n3.x), __float_as_uint(n3.y)}, qhx[2] = {__float_as_uint(n3.z), __float_as_uint(n3.w)};
 				const uint32_t qhy[2] = {__float_as_uint(n4.x), __float_as_uint(n4.y)}, qhz[2] = {__float_as_uint(n4.z), __float_as_uint(n4.w)};
@@ -127,12 +185,12 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 #pragma unroll
 					for (int j = 0; j < 4; j++) {
 						const uint32_t sel = 0x7604u + (uint32_t)(j << 4);  // bytes (3F, 80, q_j, 00) = 1 + q_j * 2^-15
-						const float tx0 = fmaf(__uint_as_float(__byte_perm(nx, 0x3F800000u, sel)), ax, bx);
-						const float ty0 = fmaf(__uint_as_float(__byte_perm(ny, 0x3F800000u, sel)), ay, by);
-						const float tz0 = fmaf(__uint_as_float(__byte_perm(nz, 0x3F800000u, sel)), az, bz);
-						const float tx1 = fmaf(__uint_as_float(__byte_perm(fx, 0x3F800000u, sel)), ax, bx);
-						const float ty1 = fmaf(__uint_as_float(__byte_perm(fy, 0x3F800000u, sel)), ay, by);
-						const float tz1 = fmaf(__uint_as_float(__byte_perm(fz, 0x3F800000u, sel)), az, bz);
+						const float tx0 = fmaf(__uint_as_float(__byte_perm(nx, one_bits, sel)), ax, bx);
+						const float ty0 = fmaf(__uint_as_float(__byte_perm(ny, one_bits, sel)), ay, by);
+						const float tz0 = fmaf(__uint_as_float(__byte_perm(nz, one_bits, sel)), az, bz);
+						const float tx1 = fmaf(__uint_as_float(__byte_perm(fx, one_bits, sel)), ax, bx);
+						const float ty1 = fmaf(__uint_as_float(__byte_perm(fy, one_bits, sel)), ay, by);
+						const float tz1 = fmaf(__uint_as_float(__byte_perm(fz, one_bits, sel)), az, bz);
 						const float tn = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, tmin));
 						const float tf = fminf(fminf(tx1, ty1), fminf(tz1, h.t)) * 1.000001f;
 						if (tn <= tf) hitmask |= ((child_bits >> (8 * j)) & 0xFFu) << ((bit_index >> (8 * j)) & 0xFFu);
@@ -141,28 +199,64 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 				ng = make_uint2(__float_as_uint(n1.x), (hitmask & 0xFF000000u) | (ew >> 24));
 				tg = make_uint2(__float_as_uint(n1.y), hitmask & 0x00FFFFFFu);
 			}
-			// ---- the node's leaf triangles
-			while (tg.y != 0u) {
-				const int bit = __ffs((int)tg.y) - 1;
-				tg.y &= tg.y - 1u;
-				const float4* tp = bvh.tris + 3 * (size_t)(tg.x + (uint32_t)bit);
-				const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
-				n_tris++;
-				float t, b1, b2;
-				if (tri_intersect(r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, b1, b2) && t > tmin) {
-					const uint32_t p = __float_as_uint(a.w);
-					if (t < h.t || (t == h.t && p < h.prim && h.prim != 0xFFFFFFFFu)) {
-						h.t = t, h.b1 = b1, h.b2 = b2, h.prim = p;
-						if (any) tg.y = 0u, ng.y = 0u, sp = 0;  // first accepted hit ends a shadow ray
+			// ---- triangle phase, warp-cooperative: the (owner lane, triangle) pairs of all lanes are spread over the 32 lanes,
+			// tested once each (any lane tests for any owner: the owner's ray constants sit in shared memory), and every owner
+			// folds the results of its own pairs into its hit. A node step leaves only a few lanes with 1..3 triangles each;
+			// testing them lane-by-owner ran the ~150-instruction test at 3 of 32 lanes (profiles/r01b).
+			// A round is worth its fixed cost only with enough pairs: lanes holding triangles sit out node steps until
+			// LMB_TRI_ROUND_LANES lanes hold some, or nobody else can step.
+			uint32_t tri_lanes = __ballot_sync(0xFFFFFFFFu, tg.y != 0u);
+			if (__popc(tri_lanes) < LMB_TRI_ROUND_LANES && __ballot_sync(0xFFFFFFFFu, has && tg.y == 0u && ng.y > 0x00FFFFFFu) != 0u) tri_lanes = 0u;
+			while (tri_lanes) {
+				const uint32_t cnt = (uint32_t)__popc(tg.y);
+				uint32_t incl = cnt;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) {
+					const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+					if (lane >= o) incl += v;
+				}
+				const uint32_t excl = incl - cnt;
+				const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+				uint32_t wrote = 0;
+				while (tg.y != 0u && excl + wrote < 32u) {
+					const int bit = __ffs((int)tg.y) - 1;
+					tg.y &= tg.y - 1u;
+					sm.pair[wbase + excl + wrote] = ((uint32_t)lane << 27) | (tg.x + (uint32_t)bit);
+					wrote++;
+				}
+				__syncwarp();
+				if ((uint32_t)lane < min(total, 32u)) {
+					const uint32_t pr = sm.pair[wbase + lane];
+					const int owner = wbase + (int)(pr >> 27);
+					const float4 ra = sm.ray_a[owner], rb = sm.ray_b[owner];
+					const float4* tp = bvh.tris + 3 * (size_t)(pr & 0x07FFFFFFu);
+					const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+					const TriRay tr{v3(ra.x, ra.y, ra.z), ra.w, rb.x, rb.y, rb.z, __float_as_uint(rb.w)};
+					n_tris++;
+					float t, V = 0.0f, W = 0.0f, det = 1.0f;
+					if (!(tri_test(tr, a, b, c, t, V, W, det) && t > tr.tmin)) t = -1.0f;
+					sm.res[wbase + lane] = make_float4(t, V, W, det);
+					sm.res_prim[wbase + lane] = __float_as_uint(a.w);
+				}
+				__syncwarp();
+				for (uint32_t k = 0; k < wrote; k++) {
+					const float4 rs = sm.res[wbase + excl + k];
+					const uint32_t p = sm.res_prim[wbase + excl + k];
+					if (rs.x >= 0.0f && (rs.x < h.t || (rs.x == h.t && p < h.prim && h.prim != 0xFFFFFFFFu))) {
+						h.t = rs.x, h.prim = p, h.b1 = rs.y, h.b2 = rs.z, det = rs.w;  // b1 = V / det, b2 = W / det at the end
 					}
 				}
+				if (any && h.prim != 0xFFFFFFFFu) tg.y = 0u, ng.y = 0u, sp = 0;  // first accepted hit ends a shadow ray
+				__syncwarp();
+				tri_lanes = __ballot_sync(0xFFFFFFFFu, tg.y != 0u);
 			}
 			// ---- next group, or done
-			if (has && ng.y <= 0x00FFFFFFu) {
+			if (has && tg.y == 0u && ng.y <= 0x00FFFFFFu) {
 				if (sp > 0) {
 					sp--;
-					ng = sp < LMB_WSTACK_SM ? s_stack[sp][tid] : l_stack[sp - LMB_WSTACK_SM];
+					ng = sp < LMB_WSTACK_SM ? sm.stack[sp][tid] : l_stack[sp - LMB_WSTACK_SM];
 				} else {
+					if (!any && h.prim != 0xFFFFFFFFu) h.b1 = h.b1 / det, h.b2 = h.b2 / det;
 					src.store(item, h, any);
 					has = false;
 				}

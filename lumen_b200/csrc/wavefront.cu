@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(LMB_TRACE_THREADS) k_trace_array_bvh2(BvhView 
 }
 
 BvhView view_of(const lmb_ctx* ctx) { return BvhView{ctx->bvh.nodes, ctx->bvh.tris, ctx->bvh.n}; }
-WideBvhView wide_view_of(const lmb_ctx* ctx) { return WideBvhView{ctx->wide.nodes, ctx->wide.tris, ctx->wide.n_tris}; }
+WideBvhView wide_view_of(const lmb_ctx* ctx) { return WideBvhView{ctx->wide.nodes, ctx->wide.tris, ctx->wide.n_tris, 0x3F800000u}; }
 
 }  // namespace
 

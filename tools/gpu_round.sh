@@ -8,5 +8,5 @@ python bench.py --steps 10 --warmup 3 2> gpurun_out/bench_err.log | tee gpurun_o
 tail -5 gpurun_out/bench_err.log
 python bench.py --impl reference --steps 3 --warmup 1 | tee gpurun_out/bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/ncu_target.py 4 2 | tail -2
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_trace|k_shade|k_miss" -s 4 -c 6 -f -o gpurun_out/prof_trav python tools/ncu_target.py 4 2 | tail -2
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_trace" -s 2 -c 3 -f -o gpurun_out/prof_trav python tools/ncu_target.py 4 2 | tail -2
 ls -la gpurun_out
