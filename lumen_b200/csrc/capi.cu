@@ -133,12 +133,21 @@ int lmb_upload_scene(lmb_ctx* ctx, const lmb_scene_desc* sd) {
 	}
 	if ((rc = upload(ctx, lut, 256, &sc.srgb_lut))) return rc;
 	ctx->mat_queue_mask = 0;
+	std::vector<uint8_t> mat_q(sd->n_materials);
 	for (uint32_t i = 0; i < sd->n_materials; i++) {
 		int q = 6;
 		for (int m = 0; m < 6; m++)
 			if (sd->materials[i].bsdf_type == (1u << m)) q = m;
 		ctx->mat_queue_mask |= 1u << q;
+		mat_q[i] = (uint8_t)q;
 	}
+	// per triangle: which shade queue its material's BSDF type maps to (k_classify reads one byte per path)
+	std::vector<uint8_t> tri_matq(tri_mesh.size());
+	for (size_t t = 0; t < tri_mesh.size(); t++) {
+		const uint32_t mi = sd->prim_infos[tri_mesh[t]].material_index;
+		tri_matq[t] = mi < sd->n_materials ? mat_q[mi] : (uint8_t)6;
+	}
+	if ((rc = upload(ctx, tri_matq.data(), tri_matq.size(), &sc.tri_matq))) return rc;
 	sc.n_tris = (uint32_t)tri_mesh.size();
 	sc.n_prim_meshes = sd->n_prim_meshes;
 	sc.n_lights = sd->n_lights;

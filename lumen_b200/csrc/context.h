@@ -22,6 +22,7 @@ struct DeviceScene {
 	const lmb_light* lights;
 	const uint32_t* tri_mesh;   // global triangle id -> prim mesh index
 	const uint32_t* tri_local;  // global triangle id -> mesh-local triangle number
+	const uint8_t* tri_matq;    // global triangle id -> shade queue of its material's BSDF type (0..5 = log2(bsdf_type), 6 = unknown)
 	const uint8_t* const* tex_data;  // per texture: RGBA8 texels
 	const uint2* tex_dims;
 	const float* srgb_lut;  // 256 entries
@@ -69,7 +70,6 @@ struct Wavefront {
 	float4* thr = nullptr;     // throughput.xyz, rng counter (bits)
 	float4* col = nullptr;     // radiance.xyz, flags (bits): bit0 last_specular
 	float4* nee = nullptr;     // 8 float4 per slot, see wavefront.cu
-	float4* surf = nullptr;    // 4 float4 per slot: surface record k_surface -> k_nee / k_bsdf
 	uint32_t* queue[2] = {nullptr, nullptr};
 	uint32_t* nee_queue = nullptr;
 	uint32_t* miss_queue = nullptr;  // escaped rays awaiting the sky march (k_miss)

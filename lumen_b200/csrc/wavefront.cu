@@ -158,19 +158,12 @@ __global__ void __launch_bounds__(LMB_TRACE_THREADS) k_trace_bvh2(BvhView bvh, W
 	trace_persistent(bvh, src, counters[CNT_TRACE], &counters[CNT_CURSOR], stats, -1, -1);
 }
 
-// Surface record written by k_surface for the two per-material kernels: 4 float4 planes of n_slots each
-enum SurfPlane { SURF_POS = 0, SURF_NS, SURF_ORIGIN, SURF_ALBEDO, SURF_PLANES };
-constexpr uint32_t SURF_FLAG_SIDE = 1u;
-
-// k_surface: the material-independent part of a bounce (path.rgen:49-74) for every live path -- retire escaped rays, build
-// the hit record (ray.rchit), fetch the material (+ texture), add emission, apply the depth cut, orient the normals, offset
-// the next origin -- and sort the survivors by BSDF type into one queue per type, so that k_nee<TYPE> / k_bsdf<TYPE> run a
-// single lobe's code on full warps. Splitting the bounce into small kernels is what keeps them out of the instruction
-// cache wall the monolithic shade kernel hit (341 KB of SASS, 83 % "no instruction" stalls; profiles/r01_*.md).
-__global__ void __launch_bounds__(256) k_surface(RenderParams rp, DeviceScene sc, int depth, uint32_t* __restrict__ counters, int q,
-												  const uint32_t* __restrict__ queue, uint32_t* __restrict__ mat_queues, uint32_t* __restrict__ miss_queue,
-												  const float4* __restrict__ hit, const float4* __restrict__ ray_d, const float4* __restrict__ thr,
-												  float4* __restrict__ colb, float4* __restrict__ surf, uint32_t n_slots) {
+// k_classify: sorts the live paths by the BSDF type of the surface they hit (one queue per type), so that k_shade<TYPE>
+// runs a single lobe's code on full warps; retires escaped rays (path.rgen:49-55). Reads 4 B queue + 16 B hit + one byte of
+// the L2-resident per-triangle queue table per path.
+__global__ void __launch_bounds__(256) k_classify(RenderParams rp, DeviceScene sc, int depth, uint32_t* __restrict__ counters, int q,
+													   const uint32_t* __restrict__ queue, uint32_t* __restrict__ mat_queues, uint32_t* __restrict__ miss_queue,
+													   const float4* __restrict__ hit, const float4* __restrict__ thr, float4* __restrict__ colb, uint32_t n_slots) {
 	const uint32_t count = counters[q];
 	const int lane = threadIdx.x & 31;
 	const uint32_t stride = gridDim.x * blockDim.x;
@@ -180,49 +173,19 @@ __global__ void __launch_bounds__(256) k_surface(RenderParams rp, DeviceScene sc
 		int dest = -1;  // 0..6 material queue, 7 miss queue, -1 retired
 		if (i < count) {
 			slot = queue[i];
-			const float4 h4 = hit[slot];
-			const float4 c4 = colb[slot];
-			const V3 throughput = xyz(thr[slot]);
-			V3 col = xyz(c4);
-			const uint32_t prim = __float_as_uint(h4.w);
+			const uint32_t prim = __float_as_uint(hit[slot].w);
 			if (prim == 0xFFFFFFFFu) {  // path.rgen:49-55
 				if (depth > 0 || rp.direct_lighting == 1) {
 					if (rp.dir_light_idx == 0xFFFFFFFFu) {
-						col += throughput * rp.sky_col;  // shade_atmosphere's constant-sky branch (commons.glsl:157-159)
+						const float4 c4 = colb[slot];
+						const V3 col = xyz(c4) + xyz(thr[slot]) * rp.sky_col;  // shade_atmosphere's constant-sky branch (commons.glsl:157-159)
 						colb[slot] = f4(col, c4.w);
 					} else {
 						dest = 7;  // 64 x 8 step sky march: deferred to k_miss (ray_o / ray_d / thr / col of a dead path stay put)
 					}
 				}
 			} else {
-				const bool last_specular_in = (__float_as_uint(c4.w) & 1u) != 0;
-				const HitPayload payload = build_hit(sc, prim, h4.y, h4.z);
-				const lmb_material hit_mat = load_material(sc, payload.material_idx, payload.uv);
-				if ((depth == 0 && rp.direct_lighting == 1) || last_specular_in) col += throughput * v3(hit_mat.emissive_factor);
-				if (depth >= rp.max_depth - 1) {
-					colb[slot] = f4(col, c4.w);
-				} else {
-					const V3 wo = -xyz(ray_d[slot]);
-					V3 n_s = payload.n_s;
-					bool side = true;
-					V3 n_g = payload.n_g;
-					if (dot(payload.n_g, wo) < 0.0f) n_g = -n_g;
-					if (dot(n_g, payload.n_s) < 0) {
-						n_s = -n_s;
-						side = false;
-					}
-					const V3 origin = offset_ray(payload.pos, n_g);
-					const bool last_specular = (hit_mat.bsdf_props & LMB_FLAG_SPECULAR) != 0;
-					colb[slot] = f4(col, __uint_as_float(last_specular ? 1u : 0u));
-					surf[SURF_POS * (size_t)n_slots + slot] = f4(payload.pos, __uint_as_float(side ? SURF_FLAG_SIDE : 0u));
-					surf[SURF_NS * (size_t)n_slots + slot] = f4(n_s, __uint_as_float(payload.material_idx));
-					surf[SURF_ORIGIN * (size_t)n_slots + slot] = f4(origin, 0.0f);
-					surf[SURF_ALBEDO * (size_t)n_slots + slot] = f4(v3(hit_mat.albedo), 0.0f);
-					dest = 6;
-#pragma unroll
-					for (int m = 0; m < 6; m++)
-						if (hit_mat.bsdf_type == (1u << m)) dest = m;
-				}
+				dest = sc.tri_matq[prim];
 			}
 		}
 		const uint32_t peers = __match_any_sync(0xFFFFFFFFu, dest);
@@ -239,33 +202,55 @@ __global__ void __launch_bounds__(256) k_surface(RenderParams rp, DeviceScene sc
 	}
 }
 
-// material as k_surface saw it: table entry with the textured albedo
-__device__ __forceinline__ lmb_material surf_material(const DeviceScene& sc, const float4& ns4, const float4& alb4) {
-	lmb_material m = sc.materials[__float_as_uint(ns4.w)];
-	m.albedo[0] = alb4.x, m.albedo[1] = alb4.y, m.albedo[2] = alb4.z;
-	return m;
-}
-
-// k_nee<TYPE>: uniform_sample_light up to its two traceRayEXT calls (pt_commons.glsl:3-20, 28-30; gate at path.rgen:75-80)
-template <uint32_t TYPE>
-__global__ void __launch_bounds__(128) k_nee(RenderParams rp, DeviceScene sc, int depth, uint32_t* __restrict__ counters, int mat_q,
-											  const uint32_t* __restrict__ queue, uint32_t* __restrict__ nee_queue, uint32_t* __restrict__ trace_queue,
-											  const float4* __restrict__ ray_d, const float4* __restrict__ hit, float4* __restrict__ thr,
-											  const float4* __restrict__ surf, float4* __restrict__ nee, uint32_t n_slots, unsigned long long* stats) {
-	const uint32_t count = counters[CNT_MAT + mat_q];
-	uint32_t n_shadow = 0, n_probe = 0;
-	if (depth > 0 || rp.direct_lighting == 1) {
-		for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-			const uint32_t slot = queue[i];
-			const float4 ns4 = surf[SURF_NS * (size_t)n_slots + slot];
-			const lmb_material hit_mat = surf_material(sc, ns4, surf[SURF_ALBEDO * (size_t)n_slots + slot]);
-			if (hit_mat.bsdf_props & LMB_FLAG_SPECULAR) continue;
-			const float4 pos4 = surf[SURF_POS * (size_t)n_slots + slot];
-			const float4 t4 = thr[slot];
-			const V3 pos = xyz(pos4), n_s = xyz(ns4), wo = -xyz(ray_d[slot]), throughput = xyz(t4);
-			const bool side = (__float_as_uint(pos4.w) & SURF_FLAG_SIDE) != 0;
-			const uint32_t fb = slot / rp.n_pix, pix = slot - fb * rp.n_pix;
-			Rng seed{pix % rp.width, pix / rp.width, rp.first_frame + fb * rp.frame_stride, __float_as_uint(t4.w)};
+// k_shade<TYPE>: one whole bounce for the paths that hit a surface of BSDF type TYPE (path.rgen:56-100): hit record
+// (ray.rchit), material (+texture), emission, depth cut, normal orientation; NEE up to its two traceRayEXT calls
+// (pt_commons.glsl:3-20, 28-30); continuation sample, throughput update and Russian roulette. The path state stays in
+// registers across the three stages: per path-bounce the kernel reads hit + ray direction + throughput + radiance (64 B,
+// plus L2-resident scene data) and writes radiance, throughput, the next ray, the NEE record and three queue entries.
+// LAST = true is the bounce at depth max_depth - 1, which only collects emission (path.rgen:57-62) for any BSDF type.
+template <uint32_t TYPE, bool LAST>
+__global__ void __launch_bounds__(128) k_shade(RenderParams rp, DeviceScene sc, int depth, uint32_t* __restrict__ counters, int q, int count_idx,
+													const uint32_t* __restrict__ queue, uint32_t* __restrict__ queue_next, uint32_t* __restrict__ nee_queue,
+													uint32_t* __restrict__ trace_queue, const float4* __restrict__ hit, float4* __restrict__ ray_o,
+													float4* __restrict__ ray_d, float4* __restrict__ thr, float4* __restrict__ colb, float4* __restrict__ nee,
+													uint32_t n_slots, unsigned long long* stats) {
+	const uint32_t count = counters[count_idx];
+	uint32_t n_shadow = 0, n_probe = 0, n_cont = 0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+		const uint32_t slot = queue[i];
+		const float4 h4 = hit[slot];
+		const float4 c4 = colb[slot];
+		const float4 t4 = thr[slot];
+		const float4 d4 = ray_d[slot];
+		const uint32_t prim = __float_as_uint(h4.w);
+		if (LAST && prim == 0xFFFFFFFFu) continue;  // (escaped rays of the last bounce were retired by k_classify)
+		V3 throughput = xyz(t4);
+		V3 col = xyz(c4);
+		const bool last_specular_in = (__float_as_uint(c4.w) & 1u) != 0;
+		const HitPayload payload = build_hit(sc, prim, h4.y, h4.z);
+		const lmb_material hit_mat = load_material(sc, payload.material_idx, payload.uv);
+		if ((depth == 0 && rp.direct_lighting == 1) || last_specular_in) col += throughput * v3(hit_mat.emissive_factor);
+		if (LAST || depth >= rp.max_depth - 1) {
+			colb[slot] = f4(col, c4.w);
+			continue;
+		}
+		const V3 wo = -xyz(d4);
+		V3 n_s = payload.n_s;
+		bool side = true;
+		V3 n_g = payload.n_g;
+		if (dot(payload.n_g, wo) < 0.0f) n_g = -n_g;
+		if (dot(n_g, payload.n_s) < 0) {
+			n_s = -n_s;
+			side = false;
+		}
+		const V3 origin = offset_ray(payload.pos, n_g);
+		const bool last_specular = (hit_mat.bsdf_props & LMB_FLAG_SPECULAR) != 0;
+		colb[slot] = f4(col, __uint_as_float(last_specular ? 1u : 0u));
+		const V3 pos = payload.pos;
+		const uint32_t fb = slot / rp.n_pix, pix = slot - fb * rp.n_pix;
+		Rng seed{pix % rp.width, pix / rp.width, rp.first_frame + fb * rp.frame_stride, __float_as_uint(t4.w)};
+		// ---- next-event estimation (path.rgen:75-80, pt_commons.glsl:3-20, 28-30)
+		if (!last_specular && (depth > 0 || rp.direct_lighting == 1)) {
 			const V4 r4 = rand4(seed);
 			const LightSample ls = sample_light_Li(sc, r4, pos, rp.num_lights);
 			const V3 p = offset_ray2(pos, n_s);
@@ -294,12 +279,10 @@ __global__ void __launch_bounds__(128) k_nee(RenderParams rp, DeviceScene sc, in
 					// payload left by the previous trace, i.e. of the surface being shaded, and then uses its pos / n_s
 					// (wi_len = |pos - pos| = 0). That can only match when this surface is the sampled light triangle.
 					float g_stale = 0.0f;
-					const uint32_t prim = __float_as_uint(hit[slot].w);
-					if (sc.tri_local[prim] == ls.triangle_idx && sc.tri_mesh[prim] == ls.instance_idx) {
+					if (payload.triangle_idx == ls.triangle_idx && payload.instance_idx == ls.instance_idx) {
 						flags |= NEE_FLAG_STALE_MATCH;
-						const V3 payload_n_s = side ? n_s : -n_s;  // ray.rchit's un-flipped shading normal
 						const float wi_len = length(pos - pos);
-						g_stale = fabsf(dot(payload_n_s, -bs.wi)) / (wi_len * wi_len);
+						g_stale = fabsf(dot(payload.n_s, -bs.wi)) / (wi_len * wi_len);  // ray.rchit's un-flipped shading normal
 					}
 					nee[NEE_PROBE_WI * (size_t)n_slots + slot] = f4(bs.wi, bs.pdf);
 					nee[NEE_F2 * (size_t)n_slots + slot] = f4(bs.f, fabsf(bs.cos_theta));
@@ -310,32 +293,8 @@ __global__ void __launch_bounds__(128) k_nee(RenderParams rp, DeviceScene sc, in
 				}
 			}
 			nee[NEE_WI * (size_t)n_slots + slot] = f4(ls.wi, __uint_as_float(flags));
-			thr[slot].w = __uint_as_float(seed.w);  // RNG draw counter carries on into k_bsdf
 		}
-	}
-	flush_stats(stats, ST_SHADOW, n_shadow);
-	flush_stats(stats, ST_PROBE, n_probe);
-}
-
-// k_bsdf<TYPE>: continuation sample, throughput update and Russian roulette (path.rgen:81-100)
-template <uint32_t TYPE>
-__global__ void __launch_bounds__(128) k_bsdf(RenderParams rp, DeviceScene sc, int depth, uint32_t* __restrict__ counters, int q, int mat_q,
-											   const uint32_t* __restrict__ queue, uint32_t* __restrict__ queue_next, uint32_t* __restrict__ trace_queue,
-											   float4* __restrict__ ray_o, float4* __restrict__ ray_d, float4* __restrict__ thr, const float4* __restrict__ surf,
-											   uint32_t n_slots, unsigned long long* stats) {
-	const uint32_t count = counters[CNT_MAT + mat_q];
-	uint32_t n_cont = 0;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-		const uint32_t slot = queue[i];
-		const float4 ns4 = surf[SURF_NS * (size_t)n_slots + slot];
-		const lmb_material hit_mat = surf_material(sc, ns4, surf[SURF_ALBEDO * (size_t)n_slots + slot]);
-		const float4 pos4 = surf[SURF_POS * (size_t)n_slots + slot];
-		const float4 t4 = thr[slot];
-		const V3 n_s = xyz(ns4), wo = -xyz(ray_d[slot]);
-		V3 throughput = xyz(t4);
-		const bool side = (__float_as_uint(pos4.w) & SURF_FLAG_SIDE) != 0;
-		const uint32_t fb = slot / rp.n_pix, pix = slot - fb * rp.n_pix;
-		Rng seed{pix % rp.width, pix / rp.width, rp.first_frame + fb * rp.frame_stride, __float_as_uint(t4.w)};
+		// ---- continuation (path.rgen:81-100)
 		const V3 r3 = rand3(seed);
 		const BsdfSample bs = sample_bsdf_t<TYPE>(n_s, wo, hit_mat, 1, side, r3);
 		bool alive = bs.pdf != 0;
@@ -353,13 +312,15 @@ __global__ void __launch_bounds__(128) k_bsdf(RenderParams rp, DeviceScene sc, i
 		}
 		if (alive) {
 			thr[slot] = f4(throughput, __uint_as_float(seed.w));
-			ray_o[slot] = f4(xyz(surf[SURF_ORIGIN * (size_t)n_slots + slot]), T_MIN);
+			ray_o[slot] = f4(origin, T_MIN);
 			ray_d[slot] = f4(bs.wi, T_MAX);
 			queue_next[queue_push(&counters[q ^ 1])] = slot;
 			trace_queue[queue_push(&counters[CNT_TRACE])] = slot | (RAY_CONTINUE << 30);
 			n_cont++;
 		}
 	}
+	flush_stats(stats, ST_SHADOW, n_shadow);
+	flush_stats(stats, ST_PROBE, n_probe);
 	flush_stats(stats, ST_CLOSEST, n_cont);
 }
 
@@ -514,7 +475,6 @@ int wavefront_alloc(lmb_ctx* ctx, uint32_t frames_in_flight) {
 	if ((rc = alloc((void**)&wf.thr, n_slots * 16))) return rc;
 	if ((rc = alloc((void**)&wf.col, n_slots * 16))) return rc;
 	if ((rc = alloc((void**)&wf.nee, n_slots * 16 * NEE_PLANES))) return rc;
-	if ((rc = alloc((void**)&wf.surf, n_slots * 16 * SURF_PLANES))) return rc;
 	if ((rc = alloc((void**)&wf.queue[0], n_slots * 4))) return rc;
 	if ((rc = alloc((void**)&wf.queue[1], n_slots * 4))) return rc;
 	if ((rc = alloc((void**)&wf.nee_queue, n_slots * 4))) return rc;
@@ -531,7 +491,7 @@ int wavefront_alloc(lmb_ctx* ctx, uint32_t frames_in_flight) {
 
 void wavefront_free(lmb_ctx* ctx) {
 	Wavefront& wf = ctx->wf;
-	cudaFree(wf.ray_o), cudaFree(wf.ray_d), cudaFree(wf.hit), cudaFree(wf.thr), cudaFree(wf.col), cudaFree(wf.nee), cudaFree(wf.surf);
+	cudaFree(wf.ray_o), cudaFree(wf.ray_d), cudaFree(wf.hit), cudaFree(wf.thr), cudaFree(wf.col), cudaFree(wf.nee);
 	cudaFree(wf.queue[0]), cudaFree(wf.queue[1]), cudaFree(wf.nee_queue), cudaFree(wf.miss_queue), cudaFree(wf.mat_queues), cudaFree(wf.trace_queue), cudaFree(wf.probe_hit), cudaFree(wf.shadow_occ), cudaFree(wf.trace_cursor), cudaFree(wf.counters), cudaFree(wf.stats);
 	wf = Wavefront{};
 }
@@ -584,6 +544,7 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 				k_trace_bvh2<<<grid_trace, LMB_TRACE_THREADS, 0, st>>>(bvh, src, wf.counters, wf.stats);
 			else
 				k_trace<<<grid_trace_wide, LMB_TRACE_THREADS, 0, st>>>(wide, src, wf.counters, wf.stats);
+			ctx->stats.kernel_launches += 1;
 			if (prof) cudaEventRecord(ctx->ev[2], st);
 			if (depth > 0) {
 				k_connect<<<grid_wide, 128, 0, st>>>(rp, ctx->scene, wf.counters, wf.nee_queue, wf.nee, wf.probe_hit, wf.shadow_occ, wf.col, wf.n_slots);
@@ -591,33 +552,36 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 			}
 			if (prof) cudaEventRecord(ctx->ev[3], st);
 			k_begin_shade<<<1, 1, 0, st>>>(wf.counters, q ^ 1);
-			k_surface<<<grid_256, 256, 0, st>>>(rp, ctx->scene, depth, wf.counters, q, wf.queue[q], wf.mat_queues, wf.miss_queue, wf.hit, wf.ray_d, wf.thr,
-												wf.col, wf.surf, wf.n_slots);
-			ctx->stats.kernel_launches += 3;
-			if (depth < pc.max_depth - 1) {  // the last bounce only collects emission (path.rgen:60-62)
+			ctx->stats.kernel_launches += 1;
+#define LMB_SHADE_ARGS(mq, cidx) rp, ctx->scene, depth, wf.counters, q, cidx, mq, wf.queue[q ^ 1], wf.nee_queue, wf.trace_queue, wf.hit, wf.ray_o, wf.ray_d, wf.thr, wf.col, wf.nee, wf.n_slots, wf.stats
+			if (depth >= pc.max_depth - 1) {  // the last bounce only collects emission (path.rgen:57-62)
+				if (depth > 0 || pc.direct_lighting == 1) {
+					k_classify<<<grid_256, 256, 0, st>>>(rp, ctx->scene, depth, wf.counters, q, wf.queue[q], wf.mat_queues, wf.miss_queue, wf.hit, wf.thr, wf.col,
+														 wf.n_slots);
+					ctx->stats.kernel_launches += 1;
+				}
+				k_shade<0u, true><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(wf.queue[q], q));
+				ctx->stats.kernel_launches += 1;
+			} else {
+				k_classify<<<grid_256, 256, 0, st>>>(rp, ctx->scene, depth, wf.counters, q, wf.queue[q], wf.mat_queues, wf.miss_queue, wf.hit, wf.thr, wf.col,
+													 wf.n_slots);
+				ctx->stats.kernel_launches += 1;
 				for (int m = 0; m < N_MAT_QUEUES; m++) {
 					if (!(ctx->mat_queue_mask & (1u << m))) continue;  // BSDF type absent from the scene (ENABLE_* macros, LumenScene.cpp:217-228)
 					const uint32_t* mq = wf.mat_queues + (size_t)m * wf.n_slots;
-#define LMB_SHADE(T)                                                                                                                              \
-	do {                                                                                                                                          \
-		k_nee<T><<<grid_wide, 128, 0, st>>>(rp, ctx->scene, depth, wf.counters, m, mq, wf.nee_queue, wf.trace_queue, wf.ray_d, wf.hit, wf.thr, wf.surf, \
-											wf.nee, wf.n_slots, wf.stats);                                                                        \
-		k_bsdf<T><<<grid_wide, 128, 0, st>>>(rp, ctx->scene, depth, wf.counters, q, m, mq, wf.queue[q ^ 1], wf.trace_queue, wf.ray_o, wf.ray_d, wf.thr,    \
-											 wf.surf, wf.n_slots, wf.stats);                                                                     \
-	} while (0)
 					switch (m) {
-						case 0: LMB_SHADE(LMB_BSDF_DIFFUSE); break;
-						case 1: LMB_SHADE(LMB_BSDF_MIRROR); break;
-						case 2: LMB_SHADE(LMB_BSDF_GLASS); break;
-						case 3: LMB_SHADE(LMB_BSDF_DIELECTRIC); break;
-						case 4: LMB_SHADE(LMB_BSDF_CONDUCTOR); break;
-						case 5: LMB_SHADE(LMB_BSDF_PRINCIPLED); break;
-						default: LMB_SHADE(0u); break;
+						case 0: k_shade<LMB_BSDF_DIFFUSE, false><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m)); break;
+						case 1: k_shade<LMB_BSDF_MIRROR, false><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m)); break;
+						case 2: k_shade<LMB_BSDF_GLASS, false><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m)); break;
+						case 3: k_shade<LMB_BSDF_DIELECTRIC, false><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m)); break;
+						case 4: k_shade<LMB_BSDF_CONDUCTOR, false><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m)); break;
+						case 5: k_shade<LMB_BSDF_PRINCIPLED, false><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m)); break;
+						default: k_shade<0u, false><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m)); break;
 					}
-#undef LMB_SHADE
-					ctx->stats.kernel_launches += 2;
+					ctx->stats.kernel_launches += 1;
 				}
 			}
+#undef LMB_SHADE_ARGS
 			if (prof) {
 				cudaEventRecord(ctx->ev[4], st);
 				cudaEventSynchronize(ctx->ev[4]);
