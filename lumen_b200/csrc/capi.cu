@@ -148,6 +148,13 @@ int lmb_upload_scene(lmb_ctx* ctx, const lmb_scene_desc* sd) {
 		tri_matq[t] = mi < sd->n_materials ? mat_q[mi] : (uint8_t)6;
 	}
 	if ((rc = upload(ctx, tri_matq.data(), tri_matq.size(), &sc.tri_matq))) return rc;
+	std::vector<uint4> tri_rec(tri_mesh.size());
+	for (size_t t = 0; t < tri_mesh.size(); t++) {
+		const lmb_prim_mesh_info& pi = sd->prim_infos[tri_mesh[t]];
+		const uint32_t* ix = sd->indices + pi.index_offset + 3 * (size_t)tri_local[t];
+		tri_rec[t] = make_uint4(ix[0] + pi.vertex_offset, ix[1] + pi.vertex_offset, ix[2] + pi.vertex_offset, tri_mesh[t]);
+	}
+	if ((rc = upload(ctx, tri_rec.data(), tri_rec.size(), &sc.tri_rec))) return rc;
 	sc.n_tris = (uint32_t)tri_mesh.size();
 	sc.n_prim_meshes = sd->n_prim_meshes;
 	sc.n_lights = sd->n_lights;

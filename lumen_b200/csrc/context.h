@@ -22,6 +22,7 @@ struct DeviceScene {
 	const lmb_light* lights;
 	const uint32_t* tri_mesh;   // global triangle id -> prim mesh index
 	const uint32_t* tri_local;  // global triangle id -> mesh-local triangle number
+	const uint4* tri_rec;       // global triangle id -> (vertex index of corner 0, 1, 2, prim mesh index)
 	const uint8_t* tri_matq;    // global triangle id -> shade queue of its material's BSDF type (0..5 = log2(bsdf_type), 6 = unknown)
 	const uint8_t* const* tex_data;  // per texture: RGBA8 texels
 	const uint2* tex_dims;
@@ -70,8 +71,8 @@ struct Wavefront {
 	float4* thr = nullptr;     // throughput.xyz, rng counter (bits)
 	float4* col = nullptr;     // radiance.xyz, flags (bits): bit0 last_specular
 	float4* nee = nullptr;     // 8 float4 per slot, see wavefront.cu
-	uint32_t* queue[2] = {nullptr, nullptr};
-	uint32_t* nee_queue = nullptr;
+	uint32_t* path_queue = nullptr;  // live paths entering the bounce (slots)
+	uint32_t* nee_queue = nullptr;   // paths with a light sample awaiting its shadow / probe result
 	uint32_t* miss_queue = nullptr;  // escaped rays awaiting the sky march (k_miss)
 	uint32_t* mat_queues = nullptr;  // 7 x n_slots: live paths sorted by the BSDF type they hit (k_classify -> k_shade<TYPE>)
 	uint32_t* trace_queue = nullptr; // typed ray entries for k_trace: slot | type << 30 (up to 3 per slot)

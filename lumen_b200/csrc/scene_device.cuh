@@ -52,15 +52,16 @@ LMB_D lmb_material load_material(const DeviceScene& sc, uint32_t material_idx, c
 LMB_D V3 vtx_pos(const lmb_vertex& v) { return v3(v.pos[0], v.pos[1], v.pos[2]); }
 LMB_D V3 vtx_nrm(const lmb_vertex& v) { return v3(v.normal[0], v.normal[1], v.normal[2]); }
 
+// `tri_rec[prim]` = (absolute vertex index of each corner, prim mesh index): the PrimMeshInfo -> index buffer -> vertex chain
+// of ray.rchit:27-33 resolved once at upload, so the hit record costs one dependent fetch before the vertices instead of three.
+// payload.triangle_idx (gl_PrimitiveID) is only compared by the area-light MIS probe: callers read sc.tri_local[prim] there.
 LMB_DN HitPayload build_hit(const DeviceScene& sc, uint32_t prim_global, float b1, float b2) {
 	HitPayload p;
-	const uint32_t mesh = sc.tri_mesh[prim_global], prim = sc.tri_local[prim_global];
-	const lmb_prim_mesh_info& pinfo = sc.prim_infos[mesh];
-	const uint32_t index_offset = pinfo.index_offset + 3 * prim;
-	const uint32_t vo = pinfo.vertex_offset;
-	const lmb_vertex a0 = sc.vertices[sc.indices[index_offset + 0] + vo];
-	const lmb_vertex a1 = sc.vertices[sc.indices[index_offset + 1] + vo];
-	const lmb_vertex a2 = sc.vertices[sc.indices[index_offset + 2] + vo];
+	const uint4 rec = __ldg(&sc.tri_rec[prim_global]);
+	const uint32_t mesh = rec.w;
+	const lmb_vertex a0 = sc.vertices[rec.x];
+	const lmb_vertex a1 = sc.vertices[rec.y];
+	const lmb_vertex a2 = sc.vertices[rec.z];
 	const V3 q0 = vtx_pos(a0), q1 = vtx_pos(a1), q2 = vtx_pos(a2);
 	const V3 n0 = vtx_nrm(a0), n1 = vtx_nrm(a1), n2 = vtx_nrm(a2);
 	const V3 bary = v3(1.0f - b1 - b2, b1, b2);
@@ -74,8 +75,8 @@ LMB_DN HitPayload build_hit(const DeviceScene& sc, uint32_t prim_global, float b
 	const V3 e0 = q2 - q0;
 	const V3 e1 = q1 - q0;
 	p.n_g = normalize(mul_row(cross(e0, e1), w2o));
-	p.material_idx = pinfo.material_index;
-	p.triangle_idx = prim;
+	p.material_idx = sc.prim_infos[mesh].material_index;
+	p.triangle_idx = 0xFFFFFFFFu;
 	p.instance_idx = mesh;
 	return p;
 }

@@ -31,6 +31,9 @@ namespace lmb {
 
 namespace {
 
+#ifndef LMB_SHADE_MIN_BLOCKS
+#define LMB_SHADE_MIN_BLOCKS 4
+#endif
 constexpr float T_MIN = 0.001f;    // path.rgen:19
 constexpr float T_MAX = 10000.0f;  // path.rgen:20
 
@@ -44,11 +47,16 @@ struct RenderParams {
 	uint32_t dir_light_idx, direct_lighting;
 };
 
-enum Counter { CNT_Q0 = 0, CNT_Q1 = 1, CNT_NEE = 2, CNT_MISS = 3, CNT_TRACE = 4, CNT_CURSOR = 5, CNT_MAT = 8, CNT_COUNT = 16 };
+// Work counters, double-buffered by bounce parity: launch d reads [d & 1] while k_shade(d) fills [(d + 1) & 1], which
+// k_trace(d) zeroed when it started (together with the per-material counters). A shading warp appends to three lists per
+// trip -- the typed ray queue, the light-sample (NEE) list and the next path list -- with two atomics issued back to back:
+// one 32-bit add on the ray-queue size and one 64-bit add on the packed (path count << 32 | NEE count) pair.
+enum Counter { CNT_TRACE = 0, CNT_CURSOR = 2, CNT_MISS = 4, CNT_PAIR = 6 /* 6,7 | 8,9: lo = NEE count, hi = path count */, CNT_MAT = 10, CNT_COUNT = 20 };
+__device__ __forceinline__ uint32_t nee_count(const uint32_t* counters, int parity) { return counters[CNT_PAIR + 2 * parity]; }
+__device__ __forceinline__ uint32_t path_count(const uint32_t* counters, int parity) { return counters[CNT_PAIR + 2 * parity + 1]; }
 
 // material-sorted shade queues: index = log2(bsdf_type) for the six known types, 6 = unknown type (bsdf_type 0, quirk Q8)
 constexpr int N_MAT_QUEUES = 7;
-__host__ __device__ constexpr uint32_t mat_queue_type(int q) { return q < 6 ? (1u << q) : 0u; }
 
 // trace queue entry = slot | type << 30
 constexpr uint32_t RAY_CONTINUE = 0u, RAY_SHADOW = 1u, RAY_PROBE = 2u, SLOT_MASK = 0x3FFFFFFFu;
@@ -62,40 +70,31 @@ constexpr uint32_t NEE_FLAG_STALE_MATCH = 4u;     // the surface being shaded IS
 __device__ __forceinline__ float4 f4(const V3& v, float w) { return make_float4(v.x, v.y, v.z, w); }
 __device__ __forceinline__ V3 xyz(const float4& v) { return V3{v.x, v.y, v.z}; }
 
-// warp-aggregated append; callable from divergent code
-__device__ __forceinline__ uint32_t queue_push(uint32_t* counter) {
-	cg::coalesced_group g = cg::coalesced_threads();
-	uint32_t base = 0;
-	if (g.thread_rank() == 0) base = atomicAdd(counter, g.size());
-	return g.shfl(base, 0) + g.thread_rank();
-}
-
 __device__ __forceinline__ void flush_stats(unsigned long long* stats, int slot, uint32_t v) {
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
 	if ((threadIdx.x & 31) == 0 && v) atomicAdd(&stats[slot], (unsigned long long)v);
 }
 
 __global__ void k_begin_batch(uint32_t* counters, uint32_t n_active) {
-	counters[CNT_Q0] = n_active;
-	counters[CNT_Q1] = 0;
-	counters[CNT_NEE] = 0;
+	counters[CNT_TRACE] = n_active, counters[CNT_TRACE + 1] = 0;
+	counters[CNT_CURSOR] = 0, counters[CNT_CURSOR + 1] = 0;
 	counters[CNT_MISS] = 0;
-	counters[CNT_TRACE] = n_active;
-	counters[CNT_CURSOR] = 0;
+	counters[CNT_PAIR] = 0, counters[CNT_PAIR + 1] = n_active;
+	counters[CNT_PAIR + 2] = 0, counters[CNT_PAIR + 3] = 0;
 }
-// before k_shade(d): the next path queue, the NEE queue and the trace queue start empty
-__global__ void k_begin_shade(uint32_t* counters, int q_next) {
-	counters[q_next] = 0;
-	counters[CNT_NEE] = 0;
-	counters[CNT_TRACE] = 0;
-	counters[CNT_CURSOR] = 0;
-	for (int m = 0; m < N_MAT_QUEUES; m++) counters[CNT_MAT + m] = 0;
+// first thing k_trace(d) does: the lists k_classify(d) / k_shade(d) are about to fill start empty
+__device__ __forceinline__ void reset_next_counters(uint32_t* counters, int parity) {
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		counters[CNT_TRACE + (parity ^ 1)] = 0;
+		counters[CNT_CURSOR + (parity ^ 1)] = 0;
+		counters[CNT_PAIR + 2 * (parity ^ 1)] = 0, counters[CNT_PAIR + 2 * (parity ^ 1) + 1] = 0;
+		for (int m = 0; m < N_MAT_QUEUES; m++) counters[CNT_MAT + m] = 0;
+	}
 }
 
 // path.rgen:23-45 + sample_camera (commons.glsl:30-33)
 __global__ void __launch_bounds__(256) k_raygen(RenderParams rp, float4* __restrict__ ray_o, float4* __restrict__ ray_d, float4* __restrict__ thr,
-												 float4* __restrict__ col, uint32_t* __restrict__ queue, uint32_t* __restrict__ trace_queue,
-												 unsigned long long* stats) {
+												 float4* __restrict__ col, uint32_t* __restrict__ path_queue, uint32_t* __restrict__ trace_queue, unsigned long long* stats) {
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_CLOSEST], (unsigned long long)rp.n_active);
 	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < rp.n_active; slot += gridDim.x * blockDim.x) {
 		const uint32_t fb = slot / rp.n_pix, pix = slot - fb * rp.n_pix;
@@ -114,7 +113,7 @@ __global__ void __launch_bounds__(256) k_raygen(RenderParams rp, float4* __restr
 		ray_d[slot] = f4(direction, T_MAX);
 		thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed.w));
 		col[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
-		queue[slot] = slot;
+		path_queue[slot] = slot;
 		trace_queue[slot] = slot | (RAY_CONTINUE << 30);
 	}
 }
@@ -150,54 +149,67 @@ struct WavefrontSource {
 	}
 };
 
-__global__ void __launch_bounds__(LMB_TRACE_THREADS, 6) k_trace(WideBvhView bvh, WavefrontSource src, uint32_t* counters, unsigned long long* stats) {
-	trace_wide_persistent(bvh, src, counters[CNT_TRACE], &counters[CNT_CURSOR], stats, -1, -1);
+__global__ void __launch_bounds__(LMB_TRACE_THREADS, 6) k_trace(WideBvhView bvh, WavefrontSource src, uint32_t* counters, int parity, unsigned long long* stats) {
+	reset_next_counters(counters, parity);
+	trace_wide_persistent(bvh, src, counters[CNT_TRACE + parity], &counters[CNT_CURSOR + parity], stats, -1, -1);
 }
 // the same rays over the binary LBVH (LMB_TRAVERSAL=bvh2; A/B measurements and the canonical node counts)
-__global__ void __launch_bounds__(LMB_TRACE_THREADS) k_trace_bvh2(BvhView bvh, WavefrontSource src, uint32_t* counters, unsigned long long* stats) {
-	trace_persistent(bvh, src, counters[CNT_TRACE], &counters[CNT_CURSOR], stats, -1, -1);
+__global__ void __launch_bounds__(LMB_TRACE_THREADS) k_trace_bvh2(BvhView bvh, WavefrontSource src, uint32_t* counters, int parity, unsigned long long* stats) {
+	reset_next_counters(counters, parity);
+	trace_persistent(bvh, src, counters[CNT_TRACE + parity], &counters[CNT_CURSOR + parity], stats, -1, -1);
 }
 
 // k_classify: sorts the live paths by the BSDF type of the surface they hit (one queue per type), so that k_shade<TYPE>
 // runs a single lobe's code on full warps; retires escaped rays (path.rgen:49-55). Reads 4 B queue + 16 B hit + one byte of
 // the L2-resident per-triangle queue table per path.
-__global__ void __launch_bounds__(256) k_classify(RenderParams rp, DeviceScene sc, int depth, uint32_t* __restrict__ counters, int q,
+__global__ void __launch_bounds__(256) k_classify(RenderParams rp, DeviceScene sc, int depth, uint32_t* __restrict__ counters, int parity,
 													   const uint32_t* __restrict__ queue, uint32_t* __restrict__ mat_queues, uint32_t* __restrict__ miss_queue,
 													   const float4* __restrict__ hit, const float4* __restrict__ thr, float4* __restrict__ colb, uint32_t n_slots) {
-	const uint32_t count = counters[q];
+	const uint32_t count = path_count(counters, parity);
 	const int lane = threadIdx.x & 31;
-	const uint32_t stride = gridDim.x * blockDim.x;
-	for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride) {  // warp-uniform trip count
-		const uint32_t i = base + lane;
-		uint32_t slot = 0;
-		int dest = -1;  // 0..6 material queue, 7 miss queue, -1 retired
-		if (i < count) {
-			slot = queue[i];
-			const uint32_t prim = __float_as_uint(hit[slot].w);
-			if (prim == 0xFFFFFFFFu) {  // path.rgen:49-55
+	constexpr int U = 4;  // entries per lane and trip: four independent queue -> hit -> table chains in flight
+	const uint32_t stride = gridDim.x * blockDim.x * U;
+	for (uint32_t base = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * U; base < count; base += stride) {  // warp-uniform trip count
+		uint32_t slot[U], prim[U];
+		int dest[U];  // 0..6 material queue, 7 miss queue, -1 retired
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			const uint32_t i = base + u * 32 + lane;
+			slot[u] = i < count ? queue[i] : 0xFFFFFFFFu;
+		}
+#pragma unroll
+		for (int u = 0; u < U; u++) prim[u] = slot[u] != 0xFFFFFFFFu ? __float_as_uint(hit[slot[u]].w) : 0xFFFFFFFFu;
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			dest[u] = -1;
+			if (slot[u] == 0xFFFFFFFFu) continue;
+			if (prim[u] == 0xFFFFFFFFu) {  // path.rgen:49-55
 				if (depth > 0 || rp.direct_lighting == 1) {
 					if (rp.dir_light_idx == 0xFFFFFFFFu) {
-						const float4 c4 = colb[slot];
-						const V3 col = xyz(c4) + xyz(thr[slot]) * rp.sky_col;  // shade_atmosphere's constant-sky branch (commons.glsl:157-159)
-						colb[slot] = f4(col, c4.w);
+						const float4 c4 = colb[slot[u]];
+						const V3 col = xyz(c4) + xyz(thr[slot[u]]) * rp.sky_col;  // shade_atmosphere's constant-sky branch (commons.glsl:157-159)
+						colb[slot[u]] = f4(col, c4.w);
 					} else {
-						dest = 7;  // 64 x 8 step sky march: deferred to k_miss (ray_o / ray_d / thr / col of a dead path stay put)
+						dest[u] = 7;  // 64 x 8 step sky march: deferred to k_miss (ray_o / ray_d / thr / col of a dead path stay put)
 					}
 				}
 			} else {
-				dest = sc.tri_matq[prim];
+				dest[u] = sc.tri_matq[prim[u]];
 			}
 		}
-		const uint32_t peers = __match_any_sync(0xFFFFFFFFu, dest);
-		if (dest >= 0) {
-			const int leader = __ffs(peers) - 1;
-			uint32_t at = 0;
-			if (lane == leader) at = atomicAdd(dest == 7 ? &counters[CNT_MISS] : &counters[CNT_MAT + dest], (uint32_t)__popc(peers));
-			at = __shfl_sync(peers, at, leader) + __popc(peers & ((1u << lane) - 1u));
-			if (dest == 7)
-				miss_queue[at] = slot;
-			else
-				mat_queues[(size_t)dest * n_slots + at] = slot;
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			const uint32_t peers = __match_any_sync(0xFFFFFFFFu, dest[u]);
+			if (dest[u] >= 0) {
+				const int leader = __ffs(peers) - 1;
+				uint32_t at = 0;
+				if (lane == leader) at = atomicAdd(dest[u] == 7 ? &counters[CNT_MISS] : &counters[CNT_MAT + dest[u]], (uint32_t)__popc(peers));
+				at = __shfl_sync(peers, at, leader) + __popc(peers & ((1u << lane) - 1u));
+				if (dest[u] == 7)
+					miss_queue[at] = slot[u];
+				else
+					mat_queues[(size_t)dest[u] * n_slots + at] = slot[u];
+			}
 		}
 	}
 }
@@ -209,21 +221,29 @@ __global__ void __launch_bounds__(256) k_classify(RenderParams rp, DeviceScene s
 // plus L2-resident scene data) and writes radiance, throughput, the next ray, the NEE record and three queue entries.
 // LAST = true is the bounce at depth max_depth - 1, which only collects emission (path.rgen:57-62) for any BSDF type.
 template <uint32_t TYPE, bool LAST>
-__global__ void __launch_bounds__(128) k_shade(RenderParams rp, DeviceScene sc, int depth, uint32_t* __restrict__ counters, int q, int count_idx,
-													const uint32_t* __restrict__ queue, uint32_t* __restrict__ queue_next, uint32_t* __restrict__ nee_queue,
+__global__ void __launch_bounds__(128, LAST ? 8 : LMB_SHADE_MIN_BLOCKS) k_shade(RenderParams rp, DeviceScene sc, int depth, uint32_t* __restrict__ counters, int parity, int count_idx,
+													const uint32_t* __restrict__ queue, uint32_t* __restrict__ path_queue, uint32_t* __restrict__ nee_queue,
 													uint32_t* __restrict__ trace_queue, const float4* __restrict__ hit, float4* __restrict__ ray_o,
 													float4* __restrict__ ray_d, float4* __restrict__ thr, float4* __restrict__ colb, float4* __restrict__ nee,
 													uint32_t n_slots, unsigned long long* stats) {
-	const uint32_t count = counters[count_idx];
+	const uint32_t count = LAST ? path_count(counters, parity) : counters[count_idx];
+	const int lane = threadIdx.x & 31;
+	const uint32_t lt_mask = (1u << lane) - 1u;
 	uint32_t n_shadow = 0, n_probe = 0, n_cont = 0;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-		const uint32_t slot = queue[i];
+	const uint32_t stride = gridDim.x * blockDim.x;
+	for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride) {  // warp-uniform trip count
+		const uint32_t i = base + lane;
+		uint32_t slot = 0;
+		bool do_shadow = false, do_probe = false, alive = false;
+		do {
+		if (i >= count) break;
+		slot = queue[i];
 		const float4 h4 = hit[slot];
 		const float4 c4 = colb[slot];
 		const float4 t4 = thr[slot];
 		const float4 d4 = ray_d[slot];
 		const uint32_t prim = __float_as_uint(h4.w);
-		if (LAST && prim == 0xFFFFFFFFu) continue;  // (escaped rays of the last bounce were retired by k_classify)
+		if (LAST && prim == 0xFFFFFFFFu) break;  // (escaped rays of the last bounce were retired by k_classify)
 		V3 throughput = xyz(t4);
 		V3 col = xyz(c4);
 		const bool last_specular_in = (__float_as_uint(c4.w) & 1u) != 0;
@@ -232,7 +252,7 @@ __global__ void __launch_bounds__(128) k_shade(RenderParams rp, DeviceScene sc, 
 		if ((depth == 0 && rp.direct_lighting == 1) || last_specular_in) col += throughput * v3(hit_mat.emissive_factor);
 		if (LAST || depth >= rp.max_depth - 1) {
 			colb[slot] = f4(col, c4.w);
-			continue;
+			break;
 		}
 		const V3 wo = -xyz(d4);
 		V3 n_s = payload.n_s;
@@ -264,8 +284,7 @@ __global__ void __launch_bounds__(128) k_shade(RenderParams rp, DeviceScene sc, 
 				const float mis_weight = ((ls.flags >> 5) & 1u) ? 1.0f : 1.0f / (1.0f + bsdf_pdf / ls.pdf_w);
 				ldir = mis_weight * f * fabsf(cos_x) * ls.Le / ls.pdf_w;
 			}
-			nee_queue[queue_push(&counters[CNT_NEE])] = slot;
-			trace_queue[queue_push(&counters[CNT_TRACE])] = slot | (RAY_SHADOW << 30);
+			do_shadow = true;
 			n_shadow++;
 			nee[NEE_P * (size_t)n_slots + slot] = f4(p, ls.wi_len - LMB_EPS);
 			nee[NEE_LDIR * (size_t)n_slots + slot] = f4(ldir, ls.pdf_a);
@@ -279,7 +298,7 @@ __global__ void __launch_bounds__(128) k_shade(RenderParams rp, DeviceScene sc, 
 					// payload left by the previous trace, i.e. of the surface being shaded, and then uses its pos / n_s
 					// (wi_len = |pos - pos| = 0). That can only match when this surface is the sampled light triangle.
 					float g_stale = 0.0f;
-					if (payload.triangle_idx == ls.triangle_idx && payload.instance_idx == ls.instance_idx) {
+					if (payload.instance_idx == ls.instance_idx && sc.tri_local[prim] == ls.triangle_idx) {
 						flags |= NEE_FLAG_STALE_MATCH;
 						const float wi_len = length(pos - pos);
 						g_stale = fabsf(dot(payload.n_s, -bs.wi)) / (wi_len * wi_len);  // ray.rchit's un-flipped shading normal
@@ -288,7 +307,7 @@ __global__ void __launch_bounds__(128) k_shade(RenderParams rp, DeviceScene sc, 
 					nee[NEE_F2 * (size_t)n_slots + slot] = f4(bs.f, fabsf(bs.cos_theta));
 					nee[NEE_LE * (size_t)n_slots + slot] = f4(ls.Le, __uint_as_float(ls.triangle_idx));
 					nee[NEE_POS * (size_t)n_slots + slot] = f4(pos, g_stale);
-					trace_queue[queue_push(&counters[CNT_TRACE])] = slot | (RAY_PROBE << 30);
+					do_probe = true;
 					n_probe++;
 				}
 			}
@@ -297,7 +316,7 @@ __global__ void __launch_bounds__(128) k_shade(RenderParams rp, DeviceScene sc, 
 		// ---- continuation (path.rgen:81-100)
 		const V3 r3 = rand3(seed);
 		const BsdfSample bs = sample_bsdf_t<TYPE>(n_s, wo, hit_mat, 1, side, r3);
-		bool alive = bs.pdf != 0;
+		alive = bs.pdf != 0;
 		if (alive) {
 			throughput *= bs.f * fabsf(bs.cos_theta) / bs.pdf;
 			float rr_scale = 1.0f;
@@ -314,9 +333,35 @@ __global__ void __launch_bounds__(128) k_shade(RenderParams rp, DeviceScene sc, 
 			thr[slot] = f4(throughput, __uint_as_float(seed.w));
 			ray_o[slot] = f4(origin, T_MIN);
 			ray_d[slot] = f4(bs.wi, T_MAX);
-			queue_next[queue_push(&counters[q ^ 1])] = slot;
-			trace_queue[queue_push(&counters[CNT_TRACE])] = slot | (RAY_CONTINUE << 30);
 			n_cont++;
+		}
+		} while (0);
+		if (!LAST) {
+			// ---- the rays this warp generated go to the typed queue of the next launch: one atomic per warp and trip
+			const uint32_t b_sh = __ballot_sync(0xFFFFFFFFu, do_shadow), b_pr = __ballot_sync(0xFFFFFFFFu, do_probe);
+			const uint32_t b_ct = __ballot_sync(0xFFFFFFFFu, alive);
+			const uint32_t n_sh = __popc(b_sh), n_pr = __popc(b_pr), n_ct = __popc(b_ct), total = n_sh + n_pr + n_ct;
+			if (total) {
+				uint32_t at = 0;
+				unsigned long long at2 = 0;
+				if (lane == 0) {
+					at = atomicAdd(&counters[CNT_TRACE + (parity ^ 1)], total);
+					at2 = atomicAdd(reinterpret_cast<unsigned long long*>(&counters[CNT_PAIR + 2 * (parity ^ 1)]), ((unsigned long long)n_ct << 32) | n_sh);
+				}
+				at = __shfl_sync(0xFFFFFFFFu, at, 0);
+				const uint32_t at_nee = __shfl_sync(0xFFFFFFFFu, (uint32_t)at2, 0), at_path = __shfl_sync(0xFFFFFFFFu, (uint32_t)(at2 >> 32), 0);
+				if (do_shadow) {
+					const uint32_t r = __popc(b_sh & lt_mask);
+					trace_queue[at + r] = slot | (RAY_SHADOW << 30);
+					nee_queue[at_nee + r] = slot;
+				}
+				if (do_probe) trace_queue[at + n_sh + __popc(b_pr & lt_mask)] = slot | (RAY_PROBE << 30);
+				if (alive) {
+					const uint32_t r = __popc(b_ct & lt_mask);
+					trace_queue[at + n_sh + n_pr + r] = slot | (RAY_CONTINUE << 30);
+					path_queue[at_path + r] = slot;
+				}
+			}
 		}
 	}
 	flush_stats(stats, ST_SHADOW, n_shadow);
@@ -325,10 +370,10 @@ __global__ void __launch_bounds__(128) k_shade(RenderParams rp, DeviceScene sc, 
 }
 
 // pt_commons.glsl:23-27, 33-39 and the accumulation of path.rgen:78, once both rays of the light sample are traced
-__global__ void __launch_bounds__(128) k_connect(RenderParams rp, DeviceScene sc, const uint32_t* __restrict__ counters,
+__global__ void __launch_bounds__(128) k_connect(RenderParams rp, DeviceScene sc, const uint32_t* __restrict__ counters, int parity,
 												  const uint32_t* __restrict__ nee_queue, const float4* __restrict__ nee, const float4* __restrict__ probe_hit,
 												  const uint32_t* __restrict__ shadow_occ, float4* __restrict__ colb, uint32_t n_slots) {
-	const uint32_t count = counters[CNT_NEE];
+	const uint32_t count = nee_count(counters, parity);
 	const float light_pick_pdf = 1.0f / (float)rp.light_triangle_count;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
 		const uint32_t slot = nee_queue[i];
@@ -475,8 +520,7 @@ int wavefront_alloc(lmb_ctx* ctx, uint32_t frames_in_flight) {
 	if ((rc = alloc((void**)&wf.thr, n_slots * 16))) return rc;
 	if ((rc = alloc((void**)&wf.col, n_slots * 16))) return rc;
 	if ((rc = alloc((void**)&wf.nee, n_slots * 16 * NEE_PLANES))) return rc;
-	if ((rc = alloc((void**)&wf.queue[0], n_slots * 4))) return rc;
-	if ((rc = alloc((void**)&wf.queue[1], n_slots * 4))) return rc;
+	if ((rc = alloc((void**)&wf.path_queue, n_slots * 4))) return rc;
 	if ((rc = alloc((void**)&wf.nee_queue, n_slots * 4))) return rc;
 	if ((rc = alloc((void**)&wf.miss_queue, n_slots * 4))) return rc;
 	if ((rc = alloc((void**)&wf.mat_queues, n_slots * 4 * N_MAT_QUEUES))) return rc;
@@ -492,7 +536,7 @@ int wavefront_alloc(lmb_ctx* ctx, uint32_t frames_in_flight) {
 void wavefront_free(lmb_ctx* ctx) {
 	Wavefront& wf = ctx->wf;
 	cudaFree(wf.ray_o), cudaFree(wf.ray_d), cudaFree(wf.hit), cudaFree(wf.thr), cudaFree(wf.col), cudaFree(wf.nee);
-	cudaFree(wf.queue[0]), cudaFree(wf.queue[1]), cudaFree(wf.nee_queue), cudaFree(wf.miss_queue), cudaFree(wf.mat_queues), cudaFree(wf.trace_queue), cudaFree(wf.probe_hit), cudaFree(wf.shadow_occ), cudaFree(wf.trace_cursor), cudaFree(wf.counters), cudaFree(wf.stats);
+	cudaFree(wf.path_queue), cudaFree(wf.nee_queue), cudaFree(wf.miss_queue), cudaFree(wf.mat_queues), cudaFree(wf.trace_queue), cudaFree(wf.probe_hit), cudaFree(wf.shadow_occ), cudaFree(wf.trace_cursor), cudaFree(wf.counters), cudaFree(wf.stats);
 	wf = Wavefront{};
 }
 
@@ -528,7 +572,7 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 		rp.n_active = nb * rp.n_pix;
 		if (prof) cudaEventRecord(ctx->ev[1], st);
 		k_begin_batch<<<1, 1, 0, st>>>(wf.counters, rp.n_active);
-		k_raygen<<<grid_256, 256, 0, st>>>(rp, wf.ray_o, wf.ray_d, wf.thr, wf.col, wf.queue[0], wf.trace_queue, wf.stats);
+		k_raygen<<<grid_256, 256, 0, st>>>(rp, wf.ray_o, wf.ray_d, wf.thr, wf.col, wf.path_queue, wf.trace_queue, wf.stats);
 		ctx->stats.kernel_launches += 2;
 		if (prof) {
 			cudaEventRecord(ctx->ev[2], st);
@@ -537,35 +581,31 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 			ctx->stats.ms_film += ms;
 		}
 		const WavefrontSource src{wf.trace_queue, wf.ray_o, wf.ray_d, wf.nee, wf.hit, wf.probe_hit, wf.shadow_occ, wf.n_slots};
-		int q = 0;
 		for (int depth = 0; depth < std::max(pc.max_depth, 1); depth++) {
+			const int par = depth & 1;
 			if (prof) cudaEventRecord(ctx->ev[1], st);
 			if (ctx->use_bvh2)
-				k_trace_bvh2<<<grid_trace, LMB_TRACE_THREADS, 0, st>>>(bvh, src, wf.counters, wf.stats);
+				k_trace_bvh2<<<grid_trace, LMB_TRACE_THREADS, 0, st>>>(bvh, src, wf.counters, par, wf.stats);
 			else
-				k_trace<<<grid_trace_wide, LMB_TRACE_THREADS, 0, st>>>(wide, src, wf.counters, wf.stats);
+				k_trace<<<grid_trace_wide, LMB_TRACE_THREADS, 0, st>>>(wide, src, wf.counters, par, wf.stats);
 			ctx->stats.kernel_launches += 1;
 			if (prof) cudaEventRecord(ctx->ev[2], st);
 			if (depth > 0) {
-				k_connect<<<grid_wide, 128, 0, st>>>(rp, ctx->scene, wf.counters, wf.nee_queue, wf.nee, wf.probe_hit, wf.shadow_occ, wf.col, wf.n_slots);
+				k_connect<<<grid_wide, 128, 0, st>>>(rp, ctx->scene, wf.counters, par, wf.nee_queue, wf.nee, wf.probe_hit, wf.shadow_occ, wf.col, wf.n_slots);
 				ctx->stats.kernel_launches += 1;
 			}
 			if (prof) cudaEventRecord(ctx->ev[3], st);
-			k_begin_shade<<<1, 1, 0, st>>>(wf.counters, q ^ 1);
-			ctx->stats.kernel_launches += 1;
-#define LMB_SHADE_ARGS(mq, cidx) rp, ctx->scene, depth, wf.counters, q, cidx, mq, wf.queue[q ^ 1], wf.nee_queue, wf.trace_queue, wf.hit, wf.ray_o, wf.ray_d, wf.thr, wf.col, wf.nee, wf.n_slots, wf.stats
-			if (depth >= pc.max_depth - 1) {  // the last bounce only collects emission (path.rgen:57-62)
-				if (depth > 0 || pc.direct_lighting == 1) {
-					k_classify<<<grid_256, 256, 0, st>>>(rp, ctx->scene, depth, wf.counters, q, wf.queue[q], wf.mat_queues, wf.miss_queue, wf.hit, wf.thr, wf.col,
-														 wf.n_slots);
-					ctx->stats.kernel_launches += 1;
-				}
-				k_shade<0u, true><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(wf.queue[q], q));
-				ctx->stats.kernel_launches += 1;
-			} else {
-				k_classify<<<grid_256, 256, 0, st>>>(rp, ctx->scene, depth, wf.counters, q, wf.queue[q], wf.mat_queues, wf.miss_queue, wf.hit, wf.thr, wf.col,
+#define LMB_SHADE_ARGS(mq, cidx) rp, ctx->scene, depth, wf.counters, par, cidx, mq, wf.path_queue, wf.nee_queue, wf.trace_queue, wf.hit, wf.ray_o, wf.ray_d, wf.thr, wf.col, wf.nee, wf.n_slots, wf.stats
+			const bool last = depth >= pc.max_depth - 1;  // the last bounce only collects emission (path.rgen:57-62)
+			if (!last || depth > 0 || pc.direct_lighting == 1) {
+				k_classify<<<grid_256, 256, 0, st>>>(rp, ctx->scene, depth, wf.counters, par, wf.path_queue, wf.mat_queues, wf.miss_queue, wf.hit, wf.thr, wf.col,
 													 wf.n_slots);
 				ctx->stats.kernel_launches += 1;
+			}
+			if (last) {
+				k_shade<0u, true><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(wf.path_queue, 0));
+				ctx->stats.kernel_launches += 1;
+			} else {
 				for (int m = 0; m < N_MAT_QUEUES; m++) {
 					if (!(ctx->mat_queue_mask & (1u << m))) continue;  // BSDF type absent from the scene (ENABLE_* macros, LumenScene.cpp:217-228)
 					const uint32_t* mq = wf.mat_queues + (size_t)m * wf.n_slots;
@@ -592,7 +632,6 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 				cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
 				ctx->stats.ms_shade += ms;
 			}
-			q ^= 1;
 		}
 		if (prof) cudaEventRecord(ctx->ev[1], st);
 		if (pc.dir_light_idx != 0xFFFFFFFFu) {
