@@ -22,6 +22,10 @@ int lmb_kat_atmosphere(lmb_ctx* ctx, const float* origin3, const float* dir3, co
 					   float* out3);                                                                  /* atmosphere.glsl:148-204 */
 int lmb_kat_sample_light(lmb_ctx* ctx, int32_t num_lights, const float* rands4, const float* p3, uint32_t n, float* out16); /* commons.glsl:224-300 */
 int lmb_kat_texture(lmb_ctx* ctx, uint32_t tex, const float* uv2, uint32_t n, float* out3);          /* bsdf_commons.glsl:19 */
+/* Structural check of the 8-wide traversal BVH on the host: out8 = nodes allocated, nodes reachable from the root, depth,
+ * errors (child box not containing its subtree, bad meta / imask), duplicate + missing triangles, internal children,
+ * leaf children, leaf triangles. A valid tree has out8[0] == out8[1], out8[3] == out8[4] == 0, out8[7] == triangle count. */
+int lmb_kat_wide_bvh_check(lmb_ctx* ctx, uint64_t* out8);
 #ifdef __cplusplus
 }
 #endif

@@ -213,3 +213,90 @@ int lmb_kat_texture(lmb_ctx* ctx, uint32_t tex, const float* uv2, uint32_t n, fl
 }
 
 }  // extern "C"
+
+// ---- structural check of the 8-wide traversal BVH (wide_bvh.cu), done on the host from a device read-back ----------
+namespace {
+struct WideCheck {
+	const std::vector<float4>& nodes;
+	const std::vector<float4>& tris;
+	std::vector<uint8_t> seen;
+	uint64_t errors = 0, dup = 0, max_depth = 0, internal = 0, leaves = 0, leaf_tris = 0, visited = 0;
+	// returns the exact bounds of everything below `node`
+	void walk(uint32_t node, uint64_t depth, double lo[3], double hi[3]) {
+		visited++;
+		max_depth = std::max(max_depth, depth);
+		const float4* n = &nodes[5 * (size_t)node];
+		const uint32_t ew = __builtin_bit_cast(uint32_t, n[0].w);
+		const double p[3] = {n[0].x, n[0].y, n[0].z};
+		double step[3];
+		for (int a = 0; a < 3; a++) step[a] = ldexp(1.0, (int)((ew >> (8 * a)) & 0xFFu) - 127);
+		const uint32_t imask = ew >> 24;
+		const uint32_t child_base = __builtin_bit_cast(uint32_t, n[1].x), tri_base = __builtin_bit_cast(uint32_t, n[1].y);
+		const uint32_t w[12] = {__builtin_bit_cast(uint32_t, n[2].x), __builtin_bit_cast(uint32_t, n[2].y), __builtin_bit_cast(uint32_t, n[2].z),
+								__builtin_bit_cast(uint32_t, n[2].w), __builtin_bit_cast(uint32_t, n[3].x), __builtin_bit_cast(uint32_t, n[3].y),
+								__builtin_bit_cast(uint32_t, n[3].z), __builtin_bit_cast(uint32_t, n[3].w), __builtin_bit_cast(uint32_t, n[4].x),
+								__builtin_bit_cast(uint32_t, n[4].y), __builtin_bit_cast(uint32_t, n[4].z), __builtin_bit_cast(uint32_t, n[4].w)};
+		auto q = [&](int plane /*0..5 = lo xyz, hi xyz*/, int slot) { return (double)((w[2 * plane + (slot >> 2)] >> (8 * (slot & 3))) & 0xFFu); };
+		for (int a = 0; a < 3; a++) lo[a] = 1e300, hi[a] = -1e300;
+		for (int s = 0; s < 8; s++) {
+			const uint32_t meta = (__builtin_bit_cast(uint32_t, s < 4 ? n[1].z : n[1].w) >> (8 * (s & 3))) & 0xFFu;
+			if (meta == 0) continue;
+			double blo[3], bhi[3], clo[3], chi[3];
+			for (int a = 0; a < 3; a++) blo[a] = p[a] + q(a, s) * step[a], bhi[a] = p[a] + q(3 + a, s) * step[a];
+			const bool inner = (meta & 0x18u) == 0x18u && (meta >> 5) == 1u;
+			if (inner) {
+				if ((meta & 7u) != (uint32_t)s || !(imask & (1u << s))) errors++;
+				internal++;
+				const uint32_t rel = (uint32_t)__builtin_popcount(imask & ((1u << s) - 1u));
+				walk(child_base + rel, depth + 1, clo, chi);
+			} else {
+				if (imask & (1u << s)) errors++;
+				leaves++;
+				const uint32_t bits = meta >> 5, off = meta & 31u;
+				const uint32_t cnt = bits == 1 ? 1 : (bits == 3 ? 2 : (bits == 7 ? 3 : 0));
+				if (cnt == 0) errors++;
+				for (int a = 0; a < 3; a++) clo[a] = 1e300, chi[a] = -1e300;
+				for (uint32_t t = 0; t < cnt; t++) {
+					const size_t ti = (size_t)tri_base + off + t;
+					if (3 * ti + 2 >= tris.size()) {
+						errors++;
+						continue;
+					}
+					leaf_tris++;
+					const uint32_t prim = __builtin_bit_cast(uint32_t, tris[3 * ti].w);
+					if (prim >= seen.size() || seen[prim]) dup++;
+					else seen[prim] = 1;
+					for (int v = 0; v < 3; v++) {
+						const float4& P = tris[3 * ti + v];
+						const double c[3] = {P.x, P.y, P.z};
+						for (int a = 0; a < 3; a++) clo[a] = std::min(clo[a], c[a]), chi[a] = std::max(chi[a], c[a]);
+					}
+				}
+			}
+			for (int a = 0; a < 3; a++) {
+				if (!(blo[a] <= clo[a] && bhi[a] >= chi[a])) errors++;  // quantised child box must contain everything below it
+				lo[a] = std::min(lo[a], clo[a]), hi[a] = std::max(hi[a], chi[a]);
+			}
+		}
+	}
+};
+}  // namespace
+
+extern "C" int lmb_kat_wide_bvh_check(lmb_ctx* ctx, uint64_t* out8) {
+	if (!ctx || !out8 || !ctx->bvh.built) return LMB_ERR_INVALID;
+	cudaSetDevice(ctx->device);
+	const DeviceWideBvh& wb = ctx->wide;
+	for (int i = 0; i < 8; i++) out8[i] = 0;
+	if (wb.n_tris == 0) return LMB_OK;
+	std::vector<float4> nodes(5 * (size_t)wb.n_nodes), tris(3 * (size_t)wb.n_tris);
+	LMB_CUDA(ctx, cudaMemcpy(nodes.data(), wb.nodes, nodes.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+	LMB_CUDA(ctx, cudaMemcpy(tris.data(), wb.tris, tris.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+	WideCheck wc{nodes, tris, std::vector<uint8_t>(wb.n_tris, 0)};
+	double lo[3], hi[3];
+	wc.walk(0, 1, lo, hi);
+	uint64_t missing = 0;
+	for (uint8_t f : wc.seen) missing += f ? 0 : 1;
+	out8[0] = wb.n_nodes, out8[1] = wc.visited, out8[2] = wc.max_depth, out8[3] = wc.errors, out8[4] = wc.dup + missing, out8[5] = wc.internal,
+	out8[6] = wc.leaves, out8[7] = wc.leaf_tris;
+	return LMB_OK;
+}

@@ -72,6 +72,7 @@ def lib():
         L.lmb_kat_atmosphere.argtypes = [vp, vp, vp, vp, vp, u32, vp]
         L.lmb_kat_sample_light.argtypes = [vp, i32, vp, vp, u32, vp]
         L.lmb_kat_texture.argtypes = [vp, u32, vp, u32, vp]
+        L.lmb_kat_wide_bvh_check.argtypes = [vp, vp]
         _LIB = L
     return _LIB
 
@@ -80,7 +81,7 @@ EXPORTS = ["lmb_create", "lmb_destroy", "lmb_last_error", "lmb_upload_scene", "l
            "lmb_resolve", "lmb_download", "lmb_upload_film", "lmb_film_device_ptr", "lmb_stream", "lmb_set_profile_stages", "lmb_get_stats",
            "lmb_reset_stats", "lmb_trace_closest", "lmb_trace_any", "lmb_trace_closest_device", "lmb_accel_num_tris", "lmb_accel_download"]
 TESTHOOK_EXPORTS = ["lmb_kat_pcg4d", "lmb_kat_rand", "lmb_kat_detmath", "lmb_kat_offset_ray", "lmb_kat_sample_bsdf", "lmb_kat_eval_bsdf",
-                    "lmb_kat_atmosphere", "lmb_kat_sample_light", "lmb_kat_texture"]
+                    "lmb_kat_atmosphere", "lmb_kat_sample_light", "lmb_kat_texture", "lmb_kat_wide_bvh_check"]
 
 
 def _f32(a):
@@ -258,6 +259,13 @@ class Device:
         out = np.zeros((uv.shape[0], 3), dtype=np.float32)
         self._ck(lib().lmb_kat_texture(self._h, int(tex), uv.ctypes.data, uv.shape[0], out.ctypes.data), "lmb_kat_texture")
         return out
+
+    def wide_bvh_check(self):
+        """Host-side structural validation of the 8-wide traversal BVH (see lumen_b200_testhooks.h)."""
+        out = np.zeros(8, dtype=np.uint64)
+        self._ck(lib().lmb_kat_wide_bvh_check(self._h, out.ctypes.data), "lmb_kat_wide_bvh_check")
+        keys = ("nodes", "reachable", "depth", "errors", "dup_or_missing", "internal_children", "leaf_children", "leaf_tris")
+        return dict(zip(keys, (int(v) for v in out)))
 
 
 class PathB200:
