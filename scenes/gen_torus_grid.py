@@ -79,9 +79,9 @@ def make_scene(K=10, nu=100, nv=50, width=1024, height=1024):
     sun.to[:] = (0.0, 0.0, 0.0)
     sun.L[:] = (3.0, 3.0, 3.0)
     sun.light_flags = 3 | (1 << 5)  # directional, delta (LumenScene.cpp:500-510)
-    ext = K * PITCH
+    ext = K * PITCH  # Lumen's camera quirk (Camera.h:67-85, see cornell_box_path.json): "dir" +z looks down -z
     return host.Scene.from_arrays(verts, np.full(n_inst, tris_per, np.uint32), np.zeros(n_inst, np.uint32), mats, [sun], fov=45.0,
-                                  cam_pos=(0.0, 0.0, 1.6 * ext), cam_dir=(0.0, 0.0, -1.0), path_length=4, sky_col=(0.5, 0.6, 0.8), width=width,
+                                  cam_pos=(0.0, 0.0, 1.6 * ext), cam_dir=(0.0, 0.0, 1.0), path_length=4, sky_col=(0.5, 0.6, 0.8), width=width,
                                   height=height)
 
 

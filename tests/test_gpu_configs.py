@@ -143,7 +143,7 @@ def test_torus_grid_config5_small(device):
     device.init(128, 128, 2)
     device.render(pc, ubo, 0, 2)
     cpu, cs = orc.render(pc, ubo, 0, 2)
-    assert device.stats().rays == cs.rays
+    assert device.stats().rays == cs.rays and cs.rays_shadow > 0.3 * 128 * 128 * 2  # the camera does see the grid
     assert bits_equal(device.download(), cpu).mean() >= 0.999
 
 
