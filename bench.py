@@ -109,17 +109,17 @@ def run_reference(args, rank):
     scene = load_scene()
     orc = po.OracleScene(scene)
     pc, ubo = scene.make_pc(MAX_DEPTH, True), scene.make_ubo()
-    threads = po.max_threads()
+    threads = len(os.sched_getaffinity(0))  # every host thread this process may use (torchrun exports OMP_NUM_THREADS=1: do not inherit it)
     # bounded sample: a strip of scanlines would bias the ray mix, so the sample is the full view at half resolution
     pc.size_x, pc.size_y = WIDTH // 2, HEIGHT // 2
     frame = 0
     for _ in range(args.warmup):
-        orc.render_frame_raw(pc, ubo, frame)
+        orc.render_frame_raw(pc, ubo, frame, threads)
         frame += 1
     rays, secs = 0, 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, st = orc.render_frame_raw(pc, ubo, frame)
+        _, st = orc.render_frame_raw(pc, ubo, frame, threads)
         rays += st.rays
         secs += st.seconds
         frame += 1
@@ -264,11 +264,12 @@ def main():
             orc = po.OracleScene(scene)
             pcs = scene.make_pc(MAX_DEPTH, True)
             pcs.size_x, pcs.size_y = WIDTH // 2, HEIGHT // 2
-            orc.render_frame_raw(pcs, ubo, 0)  # warm-up (page-in, thread pool)
-            _, cst = orc.render_frame_raw(pcs, ubo, 1)
+            host_threads = len(os.sched_getaffinity(0))
+            orc.render_frame_raw(pcs, ubo, 0, host_threads)  # warm-up (page-in, thread pool)
+            _, cst = orc.render_frame_raw(pcs, ubo, 1, host_threads)
             n = 1
             while cst.seconds < 12.0 and n < 400:  # bounded sample: about 12 s of CPU work on all host threads
-                _, c2 = orc.render_frame_raw(pcs, ubo, 1 + n)
+                _, c2 = orc.render_frame_raw(pcs, ubo, 1 + n, host_threads)
                 cst.rays_closest += c2.rays_closest
                 cst.rays_shadow += c2.rays_shadow
                 cst.rays_probe += c2.rays_probe

@@ -230,8 +230,8 @@ struct WideCheck {
 		const double p[3] = {n[0].x, n[0].y, n[0].z};
 		double step[3];
 		for (int a = 0; a < 3; a++) step[a] = ldexp(1.0, (int)((ew >> (8 * a)) & 0xFFu) - 127);
-		const uint32_t imask = ew >> 24;
 		const uint32_t child_base = __builtin_bit_cast(uint32_t, n[1].x), tri_base = __builtin_bit_cast(uint32_t, n[1].y);
+		const uint32_t mw = __builtin_bit_cast(uint32_t, n[1].z), imask = mw >> 24, leaf24 = mw & 0xFFFFFFu;
 		const uint32_t w[12] = {__builtin_bit_cast(uint32_t, n[2].x), __builtin_bit_cast(uint32_t, n[2].y), __builtin_bit_cast(uint32_t, n[2].z),
 								__builtin_bit_cast(uint32_t, n[2].w), __builtin_bit_cast(uint32_t, n[3].x), __builtin_bit_cast(uint32_t, n[3].y),
 								__builtin_bit_cast(uint32_t, n[3].z), __builtin_bit_cast(uint32_t, n[3].w), __builtin_bit_cast(uint32_t, n[4].x),
@@ -239,20 +239,22 @@ struct WideCheck {
 		auto q = [&](int plane /*0..5 = lo xyz, hi xyz*/, int slot) { return (double)((w[2 * plane + (slot >> 2)] >> (8 * (slot & 3))) & 0xFFu); };
 		for (int a = 0; a < 3; a++) lo[a] = 1e300, hi[a] = -1e300;
 		for (int s = 0; s < 8; s++) {
-			const uint32_t meta = (__builtin_bit_cast(uint32_t, s < 4 ? n[1].z : n[1].w) >> (8 * (s & 3))) & 0xFFu;
-			if (meta == 0) continue;
+			const bool inner = (imask >> s) & 1u;
+			const uint32_t bits = (leaf24 >> (3 * s)) & 7u;
+			if (!inner && bits == 0) {  // empty slot: must carry an inverted box
+				if (!(q(0, s) > q(3, s))) errors++;
+				continue;
+			}
 			double blo[3], bhi[3], clo[3], chi[3];
 			for (int a = 0; a < 3; a++) blo[a] = p[a] + q(a, s) * step[a], bhi[a] = p[a] + q(3 + a, s) * step[a];
-			const bool inner = (meta & 0x18u) == 0x18u && (meta >> 5) == 1u;
 			if (inner) {
-				if ((meta & 7u) != (uint32_t)s || !(imask & (1u << s))) errors++;
+				if (bits != 0) errors++;
 				internal++;
 				const uint32_t rel = (uint32_t)__builtin_popcount(imask & ((1u << s) - 1u));
 				walk(child_base + rel, depth + 1, clo, chi);
 			} else {
-				if (imask & (1u << s)) errors++;
 				leaves++;
-				const uint32_t bits = meta >> 5, off = meta & 31u;
+				const uint32_t off = (uint32_t)__builtin_popcount(leaf24 & ((1u << (3 * s)) - 1u));
 				const uint32_t cnt = bits == 1 ? 1 : (bits == 3 ? 2 : (bits == 7 ? 3 : 0));
 				if (cnt == 0) errors++;
 				for (int a = 0; a < 3; a++) clo[a] = 1e300, chi[a] = -1e300;

@@ -8,8 +8,8 @@
 //   PRMT + FFMA and no int->float conversion. Rounding of this form is < 1/256 grid step; the builder rounds boxes out by
 //   >= 1/32 step on every side and the far side is padded by 8 ulp (the binary walk of trace.cuh pads by 3), so boxes stay
 //   conservative.
-// Hit children are collected in one 32-bit mask: bits 24..31 internal children in front-to-back order for this ray's
-// octant (bit 24 + (slot ^ octant)), bits 0..23 the node's leaf triangles. The traversal stack holds (child_base, mask)
+// The eight box tests give one 8-bit mask in slot order; a handful of bit operations per NODE (not per child) turn it into
+// the internal-children group (bit 24 + (slot ^ octant): highest bit = nearest child) and the 24-bit leaf-triangle mask. The traversal stack holds (child_base, mask)
 // groups: <= 1 push per level, LMB_WSTACK_SM entries per thread in shared memory laid out [entry][thread] (conflict free),
 // deeper levels spill to local memory. Triangle tests, the definition of a hit and the tie-break are those of trace.cuh,
 // bit for bit -- results are identical to the binary LBVH walk and to the CPU oracle.
@@ -31,7 +31,9 @@ struct WideBvhView {
 #define LMB_WSTACK_SM 12
 #define LMB_WSTACK_LOCAL 52
 #define LMB_WIDE_REFILL_LANES 20
-#define LMB_WIDE_BLOCKS_PER_SM 6
+#ifndef LMB_WIDE_BLOCKS_PER_SM
+#define LMB_WIDE_BLOCKS_PER_SM 8
+#endif
 #ifndef LMB_TRI_ROUND_LANES
 #define LMB_TRI_ROUND_LANES 8
 #endif
@@ -103,7 +105,8 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 	Hit h{0.0f, 0.0f, 0.0f, 0xFFFFFFFFu};
 	float det = 1.0f;  // h.b1, h.b2 hold V, W of the current best hit until the ray is done
 	uint2 ng = make_uint2(0u, 0u);  // node group: (child_base, hits << 24 | imask)
-	uint2 tg = make_uint2(0u, 0u);  // triangle group: (tri_base, mask)
+	uint2 tg = make_uint2(0u, 0u);  // triangle group: (tri_base, mask over the node's 24 leaf-triangle bits)
+	uint32_t tl = 0;                // leaf24 of the node tg came from: triangle of bit b = tg.x + popc(tl & ((1 << b) - 1))
 	uint32_t oct_inv4 = 0;
 	int sp = 0;
 	uint32_t n_nodes = 0, n_tris = 0, n_closest = 0, n_any = 0;
@@ -160,7 +163,7 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 				n_nodes++;
 				const float4* np = bvh.nodes + 5 * (size_t)node;
 				const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-				const uint32_t ew = __float_as_uint(n0.w);
+				const uint32_t ew = __float_as_uint(n0.w);  // ex | ey << 8 | ez << 16
 				const float ax = __uint_as_float(((ew & 0xFFu) + 15u) << 23) * rinv.x;
 				const float ay = __uint_as_float((((ew >> 8) & 0xFFu) + 15u) << 23) * rinv.y;
 				const float az = __uint_as_float((((ew >> 16) & 0xFFu) + 15u) << 23) * rinv.z;
@@ -171,14 +174,9 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 				const uint32_t qlx[2] = {__float_as_uint(n2.x), __float_as_uint(n2.y)}, qly[2] = {__float_as_uint(n2.z), __float_as_uint(n2.w)};
 				const uint32_t qlz[2] = {__float_as_uint(n3.x), __float_as_uint(n3.y)}, qhx[2] = {__float_as_uint(n3.z), __float_as_uint(n3.w)};
 				const uint32_t qhy[2] = {__float_as_uint(n4.x), __float_as_uint(n4.y)}, qhz[2] = {__float_as_uint(n4.z), __float_as_uint(n4.w)};
-				uint32_t hitmask = 0;
+				uint32_t hits8 = 0;  // bit s: the ray enters the box of slot s
 #pragma unroll
 				for (int hf = 0; hf < 2; hf++) {
-					const uint32_t meta = __float_as_uint(hf ? n1.w : n1.z);
-					const uint32_t is_inner = (meta & (meta << 1)) & 0x10101010u;
-					const uint32_t inner_mask = (is_inner >> 4) * 0xFFu;
-					const uint32_t bit_index = (meta ^ (oct_inv4 & inner_mask)) & 0x1F1F1F1Fu;
-					const uint32_t child_bits = (meta >> 5) & 0x07070707u;
 					const uint32_t nx = sx ? qhx[hf] : qlx[hf], fx = sx ? qlx[hf] : qhx[hf];
 					const uint32_t ny = sy ? qhy[hf] : qly[hf], fy = sy ? qly[hf] : qhy[hf];
 					const uint32_t nz = sz ? qhz[hf] : qlz[hf], fz = sz ? qlz[hf] : qhz[hf];
@@ -193,11 +191,25 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 						const float tz1 = fmaf(__uint_as_float(__byte_perm(fz, one_bits, sel)), az, bz);
 						const float tn = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, tmin));
 						const float tf = fminf(fminf(tx1, ty1), fminf(tz1, h.t)) * 1.000001f;
-						if (tn <= tf) hitmask |= ((child_bits >> (8 * j)) & 0xFFu) << ((bit_index >> (8 * j)) & 0xFFu);
+						if (tn <= tf) hits8 |= 1u << (4 * hf + j);
 					}
 				}
-				ng = make_uint2(__float_as_uint(n1.x), (hitmask & 0xFF000000u) | (ew >> 24));
-				tg = make_uint2(__float_as_uint(n1.y), hitmask & 0x00FFFFFFu);
+				// empty slots carry an inverted box (qlo 255, qhi 0) and can never be entered
+				const uint32_t mw = __float_as_uint(n1.z);
+				const uint32_t imask = mw >> 24;
+				// internal children: bit (slot ^ octant) so that the highest set bit is the nearest child (front to back)
+				uint32_t ih = hits8 & imask;
+				if (oct_inv4 & 1u) ih = ((ih & 0xAAu) >> 1) | ((ih & 0x55u) << 1);
+				if (oct_inv4 & 2u) ih = ((ih & 0xCCu) >> 2) | ((ih & 0x33u) << 2);
+				if (oct_inv4 & 4u) ih = ((ih & 0xF0u) >> 4) | ((ih & 0x0Fu) << 4);
+				// leaf children: bit s -> bits 3s..3s+2, masked by the node's per-slot triangle counts
+				uint32_t lh = hits8 & ~imask;
+				lh = (lh | (lh << 8)) & 0x0000F00Fu;
+				lh = (lh | (lh << 4)) & 0x000C30C3u;
+				lh = (lh | (lh << 2)) & 0x00249249u;
+				tl = mw & 0x00FFFFFFu;
+				ng = make_uint2(__float_as_uint(n1.x), (ih << 24) | imask);
+				tg = make_uint2(__float_as_uint(n1.y), (lh * 7u) & tl);
 			}
 			// ---- triangle phase, warp-cooperative: the (owner lane, triangle) pairs of all lanes are spread over the 32 lanes,
 			// tested once each (any lane tests for any owner: the owner's ray constants sit in shared memory), and every owner
@@ -221,7 +233,7 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 				while (tg.y != 0u && excl + wrote < 32u) {
 					const int bit = __ffs((int)tg.y) - 1;
 					tg.y &= tg.y - 1u;
-					sm.pair[wbase + excl + wrote] = ((uint32_t)lane << 27) | (tg.x + (uint32_t)bit);
+					sm.pair[wbase + excl + wrote] = ((uint32_t)lane << 27) | (tg.x + (uint32_t)__popc(tl & ((1u << bit) - 1u)));
 					wrote++;
 				}
 				__syncwarp();

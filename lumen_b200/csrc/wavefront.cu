@@ -149,7 +149,7 @@ struct WavefrontSource {
 	}
 };
 
-__global__ void __launch_bounds__(LMB_TRACE_THREADS, 6) k_trace(WideBvhView bvh, WavefrontSource src, uint32_t* counters, int parity, unsigned long long* stats) {
+__global__ void __launch_bounds__(LMB_TRACE_THREADS, LMB_WIDE_BLOCKS_PER_SM) k_trace(WideBvhView bvh, WavefrontSource src, uint32_t* counters, int parity, unsigned long long* stats) {
 	reset_next_counters(counters, parity);
 	trace_wide_persistent(bvh, src, counters[CNT_TRACE + parity], &counters[CNT_CURSOR + parity], stats, -1, -1);
 }
@@ -488,7 +488,7 @@ struct ArraySource {
 	}
 };
 
-__global__ void __launch_bounds__(LMB_TRACE_THREADS, 6) k_trace_array(WideBvhView bvh, ArraySource src, uint32_t n, uint32_t* cursor, unsigned long long* stats) {
+__global__ void __launch_bounds__(LMB_TRACE_THREADS, LMB_WIDE_BLOCKS_PER_SM) k_trace_array(WideBvhView bvh, ArraySource src, uint32_t n, uint32_t* cursor, unsigned long long* stats) {
 	trace_wide_persistent(bvh, src, n, cursor, stats, ST_CLOSEST, ST_SHADOW);
 }
 __global__ void __launch_bounds__(LMB_TRACE_THREADS) k_trace_array_bvh2(BvhView bvh, ArraySource src, uint32_t n, uint32_t* cursor, unsigned long long* stats) {

@@ -15,10 +15,11 @@
 //   Children are placed in slots by a greedy assignment on  dot(child centre - node centre, octant direction of slot),
 //   so that visiting slots in order of (slot XOR ray octant) is front to back.
 // Node, 80 bytes = 5 x 128-bit loads:
-//   n0 = (p.x, p.y, p.z, ex | ey << 8 | ez << 16 | imask << 24)       p = node box min - step/16, e* = biased exponents of the grid step
-//   n1 = (child_base, tri_base, meta[0..3], meta[4..7])               meta: internal 001sssss with sssss = 24 + slot;
-//                                                                           leaf  ccc ooooo, ccc = 1/3/7 for 1/2/3 tris,
-//                                                                           ooooo = first triangle - tri_base; empty 0
+//   n0 = (p.x, p.y, p.z, ex | ey << 8 | ez << 16)                    p = node box min - step/16, e* = biased exponents of the grid step
+//   n1 = (child_base, tri_base, imask << 24 | leaf24, 0)              imask bit s: slot s is an internal child; leaf24 bits 3s..3s+2 =
+//                                                                     1/3/7 for a leaf child with 1/2/3 triangles (0: internal or empty).
+//                                                                     Leaf triangles are stored compactly in slot order, so triangle
+//                                                                     (s, k) sits at tri_base + popc(leaf24 & ((1 << (3s + k)) - 1))
 //   n2 = (qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7])        child box = p + q * 2^(e-127), q in 0..255,
 //   n3 = (qlo.z[0..3], qlo.z[4..7], qhi.x[0..3], qhi.x[4..7])        rounded outwards by at least 1/32 grid step on every side
 //   n4 = (qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7])
@@ -137,11 +138,10 @@ __global__ void __launch_bounds__(128) k_collapse(uint32_t n, const uint32_t* __
 		P[a] = nb[a] - step * 0.0625f;
 		if (!(P[a] < nb[a])) P[a] = nextafterf(nb[a], -3.402823466e+38f);  // step/16 below the ulp of the coordinate
 	}
-	uint32_t meta[8], qlo[3][8], qhi[3][8];
+	uint32_t leaf24 = 0, qlo[3][8], qhi[3][8];
 	uint32_t rank = 0, tri_off = 0;
 	for (int s = 0; s < 8; s++) {
 		if (who[s] < 0) {
-			meta[s] = 0;
 			for (int a = 0; a < 3; a++) qlo[a][s] = 255u, qhi[a][s] = 0u;
 			continue;
 		}
@@ -157,11 +157,10 @@ __global__ void __launch_bounds__(128) k_collapse(uint32_t n, const uint32_t* __
 		}
 		const uint32_t nt = ntris(c);
 		if (imask & (1u << s)) {
-			meta[s] = (1u << 5) | (24u + (uint32_t)s);
 			items_out[item_base + rank] = make_uint2(child_base + rank, c);
 			rank++;
 		} else {
-			meta[s] = (((1u << nt) - 1u) << 5) | tri_off;
+			leaf24 |= ((1u << nt) - 1u) << (3 * s);
 			const uint32_t src = c >= first_leaf ? c - first_leaf : span_first[c];
 			for (uint32_t t = 0; t < nt; t++) {
 				const size_t d = 3 * (size_t)(tri_base + tri_off + t), q = 3 * (size_t)(src + t);
@@ -173,8 +172,8 @@ __global__ void __launch_bounds__(128) k_collapse(uint32_t n, const uint32_t* __
 	auto pack4 = [](const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); };
 	auto f = [](uint32_t u) { return __uint_as_float(u); };
 	float4* o = wnodes + 5 * (size_t)w;
-	o[0] = make_float4(P[0], P[1], P[2], f(E[0] | (E[1] << 8) | (E[2] << 16) | (imask << 24)));
-	o[1] = make_float4(f(child_base), f(tri_base), f(pack4(meta)), f(pack4(meta + 4)));
+	o[0] = make_float4(P[0], P[1], P[2], f(E[0] | (E[1] << 8) | (E[2] << 16)));
+	o[1] = make_float4(f(child_base), f(tri_base), f((imask << 24) | leaf24), 0.0f);
 	o[2] = make_float4(f(pack4(qlo[0])), f(pack4(qlo[0] + 4)), f(pack4(qlo[1])), f(pack4(qlo[1] + 4)));
 	o[3] = make_float4(f(pack4(qlo[2])), f(pack4(qlo[2] + 4)), f(pack4(qhi[0])), f(pack4(qhi[0] + 4)));
 	o[4] = make_float4(f(pack4(qhi[1])), f(pack4(qhi[1] + 4)), f(pack4(qhi[2])), f(pack4(qhi[2] + 4)));
