@@ -68,6 +68,8 @@ typedef struct lmb_stats {
 	float ms_build_wide;   /* collapse of the LBVH into the compressed 8-wide traversal BVH (included in ms_build_accel) */
 	uint32_t wide_nodes;   /* nodes of the 8-wide BVH (80 B each) */
 	uint32_t wide_levels;  /* depth of the 8-wide BVH */
+	uint32_t ploc_iterations; /* clustering iterations of the traversal tree (0: LMB_TREE=lbvh) */
+	float ms_build_ploc;   /* PLOC clustering over the sorted leaves (included in ms_build_accel) */
 	uint32_t pad_;
 } lmb_stats;
 

@@ -76,6 +76,8 @@ int lmb_create(lmb_ctx** out, int device_id) {
 	for (auto& ev : ctx->ev) cudaEventCreate(&ev);
 	const char* trav = getenv("LMB_TRAVERSAL");
 	ctx->use_bvh2 = trav && strcmp(trav, "bvh2") == 0;
+	const char* tree = getenv("LMB_TREE");
+	ctx->use_ploc = !(tree && strcmp(tree, "lbvh") == 0);
 	*out = ctx;
 	return LMB_OK;
 }
@@ -274,6 +276,7 @@ int lmb_reset_stats(lmb_ctx* ctx) {
 	ctx->stats.ms_build_sort = keep.ms_build_sort, ctx->stats.ms_build_tree = keep.ms_build_tree;
 	ctx->stats.ms_build_refit = keep.ms_build_refit, ctx->stats.ms_build_wide = keep.ms_build_wide;
 	ctx->stats.wide_nodes = keep.wide_nodes, ctx->stats.wide_levels = keep.wide_levels;
+	ctx->stats.ms_build_ploc = keep.ms_build_ploc, ctx->stats.ploc_iterations = keep.ploc_iterations;
 	if (ctx->wf.stats) {
 		LMB_CUDA(ctx, cudaMemsetAsync(ctx->wf.stats, 0, ST_COUNT * 8, ctx->stream));
 		LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -47,8 +47,12 @@ struct DeviceBvh {
 	float4* nodes = nullptr;  // 4*(n-1)
 	float4* tris = nullptr;   // 3n, leaf order
 	uint32_t* radix_hist = nullptr;
-	uint32_t* span_first = nullptr;  // n-1: first / last sorted leaf position under each internal node (Karras range)
-	uint32_t* span_last = nullptr;
+	uint32_t* span_count = nullptr;  // n-1: leaves under each internal node (size of its Karras range)
+	// quality tree for traversal (ploc.cu), same numbering as left/right/aabb; null when LMB_TREE=lbvh
+	uint32_t* q_left = nullptr;
+	uint32_t* q_right = nullptr;
+	uint32_t* q_count = nullptr;  // 2n-1
+	float* q_aabb = nullptr;      // 6*(2n-1)
 	uint32_t n = 0;
 	bool built = false;
 };
@@ -102,6 +106,7 @@ struct lmb_ctx {
 	std::vector<uint32_t> h_idx_counts;
 	lmb::DeviceBvh bvh;
 	lmb::DeviceWideBvh wide;
+	bool use_ploc = true;   // LMB_TREE=lbvh: collapse the canonical Karras tree instead of the PLOC tree
 	bool use_bvh2 = false;  // LMB_TRAVERSAL=bvh2: walk the binary LBVH instead of the 8-wide BVH (A/B measurements)
 	// film / wavefront
 	uint32_t width = 0, height = 0;
@@ -120,6 +125,8 @@ int build_lbvh(lmb_ctx* ctx);
 void free_bvh(lmb_ctx* ctx);
 int build_wide_bvh(lmb_ctx* ctx);
 void free_wide_bvh(lmb_ctx* ctx);
+int build_ploc(lmb_ctx* ctx);
+void free_ploc(lmb_ctx* ctx);
 int wavefront_alloc(lmb_ctx* ctx, uint32_t frames_in_flight);
 void wavefront_free(lmb_ctx* ctx);
 int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& ubo, uint32_t first_frame, uint32_t n_frames, uint32_t stride,

@@ -198,8 +198,7 @@ __device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, u
 }
 
 __global__ void __launch_bounds__(256) k_karras(const uint64_t* __restrict__ keys, int n, uint32_t* __restrict__ left, uint32_t* __restrict__ right,
-												 uint32_t* __restrict__ parent, uint32_t* __restrict__ leaf_prim, uint32_t* __restrict__ span_first,
-												 uint32_t* __restrict__ span_last) {
+												 uint32_t* __restrict__ parent, uint32_t* __restrict__ leaf_prim, uint32_t* __restrict__ span_count) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) leaf_prim[i] = (uint32_t)(keys[i] & 0xFFFFFFFFull);
 	if (i == 0) parent[0] = 0xFFFFFFFFu;
@@ -224,8 +223,7 @@ __global__ void __launch_bounds__(256) k_karras(const uint64_t* __restrict__ key
 	const uint32_t rc = (max(i, j) == gamma + 1) ? (uint32_t)(n - 1 + gamma + 1) : (uint32_t)(gamma + 1);
 	left[i] = lc;
 	right[i] = rc;
-	span_first[i] = (uint32_t)min(i, j);
-	span_last[i] = (uint32_t)max(i, j);
+	span_count[i] = (uint32_t)(max(i, j) - min(i, j) + 1);
 	parent[lc] = (uint32_t)i;
 	parent[rc] = (uint32_t)i;
 }
@@ -295,9 +293,10 @@ void free_bvh(lmb_ctx* ctx) {
 	DeviceBvh& b = ctx->bvh;
 	cudaFree(b.morton), cudaFree(b.keys), cudaFree(b.keys_tmp), cudaFree(b.leaf_prim), cudaFree(b.left), cudaFree(b.right);
 	cudaFree(b.parent), cudaFree(b.aabb), cudaFree(b.arrive), cudaFree(b.bounds_enc), cudaFree(b.tri_world), cudaFree(b.nodes);
-	cudaFree(b.tris), cudaFree(b.radix_hist), cudaFree(b.span_first), cudaFree(b.span_last);
+	cudaFree(b.tris), cudaFree(b.radix_hist), cudaFree(b.span_count);
 	b = DeviceBvh{};
 	free_wide_bvh(ctx);
+	free_ploc(ctx);
 }
 
 int build_lbvh(lmb_ctx* ctx) {
@@ -322,8 +321,7 @@ int build_lbvh(lmb_ctx* ctx) {
 	if ((rc = dmalloc(ctx, &b.nodes, 4 * (size_t)n))) return rc;
 	if ((rc = dmalloc(ctx, &b.tris, 3 * (size_t)n))) return rc;
 	if ((rc = dmalloc(ctx, &b.radix_hist, 256 * (size_t)std::max(radix_blocks, 1u)))) return rc;
-	if ((rc = dmalloc(ctx, &b.span_first, n))) return rc;
-	if ((rc = dmalloc(ctx, &b.span_last, n))) return rc;
+	if ((rc = dmalloc(ctx, &b.span_count, n))) return rc;
 	if (n == 0) {
 		b.built = true;
 		return 0;
@@ -346,7 +344,7 @@ int build_lbvh(lmb_ctx* ctx) {
 	// 4 passes: result is back in b.keys
 	cudaEventRecord(ctx->ev[2], st);
 	cudaMemsetAsync(b.arrive, 0, sizeof(uint32_t) * n, st);
-	k_karras<<<grid, 256, 0, st>>>(b.keys, (int)n, b.left, b.right, b.parent, b.leaf_prim, b.span_first, b.span_last);
+	k_karras<<<grid, 256, 0, st>>>(b.keys, (int)n, b.left, b.right, b.parent, b.leaf_prim, b.span_count);
 	cudaEventRecord(ctx->ev[3], st);
 	k_refit<<<grid, 256, 0, st>>>(n, b.tri_world, b.leaf_prim, b.left, b.right, b.parent, b.aabb, b.arrive);
 	k_pack<<<grid, 256, 0, st>>>(n, b.tri_world, b.leaf_prim, b.left, b.right, b.aabb, b.nodes, b.tris);
@@ -358,8 +356,16 @@ int build_lbvh(lmb_ctx* ctx) {
 	cudaEventElapsedTime(&ctx->stats.ms_build_tree, ctx->ev[2], ctx->ev[3]);
 	cudaEventElapsedTime(&ctx->stats.ms_build_refit, ctx->ev[3], ctx->ev[4]);
 	cudaEventElapsedTime(&ctx->stats.ms_build_accel, ctx->ev[0], ctx->ev[4]);
+	ctx->stats.ms_build_ploc = 0.0f, ctx->stats.ploc_iterations = 0;
+	if (ctx->use_ploc && n > 1 && (rc = build_ploc(ctx))) return rc;
 	if ((rc = build_wide_bvh(ctx))) return rc;
-	ctx->stats.ms_build_accel += ctx->stats.ms_build_wide;
+	if (b.q_left && ctx->wide.levels > 56) {
+		// the traversal stack holds one entry per level (64 in total): an adversarially deep clustering falls back to the
+		// canonical tree, whose depth is bounded by the 62 key bits
+		free_ploc(ctx);
+		if ((rc = build_wide_bvh(ctx))) return rc;
+	}
+	ctx->stats.ms_build_accel += ctx->stats.ms_build_wide + ctx->stats.ms_build_ploc;
 	ctx->stats.wide_nodes = ctx->wide.n_nodes, ctx->stats.wide_levels = ctx->wide.levels;
 	b.built = true;
 	return 0;

@@ -56,8 +56,7 @@ __device__ __forceinline__ uint32_t grid_exponent(float lo, float hi) {
 }
 
 __global__ void __launch_bounds__(128) k_collapse(uint32_t n, const uint32_t* __restrict__ left, const uint32_t* __restrict__ right,
-													  const uint32_t* __restrict__ span_first, const uint32_t* __restrict__ span_last,
-													  const float* __restrict__ aabb, const float4* __restrict__ leaf_tris, const uint2* __restrict__ items_in,
+													  const uint32_t* __restrict__ count, const float* __restrict__ aabb, const float4* __restrict__ leaf_tris, const uint2* __restrict__ items_in,
 													  uint32_t n_in, uint2* __restrict__ items_out, uint32_t* __restrict__ counters, float4* __restrict__ wnodes,
 													  float4* __restrict__ wtris) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -72,7 +71,7 @@ __global__ void __launch_bounds__(128) k_collapse(uint32_t n, const uint32_t* __
 	} else {
 		ch[0] = left[b], ch[1] = right[b], cnt = 2, nb = aabb + 6 * (size_t)b;
 	}
-	auto ntris = [&](uint32_t c) { return c >= first_leaf ? 1u : span_last[c] - span_first[c] + 1u; };
+	auto ntris = [&](uint32_t c) { return c >= first_leaf ? 1u : count[c]; };
 	for (int phase = 0; phase < 2 && n > 1; phase++) {
 		while (cnt < 8) {
 			int best = -1;
@@ -161,12 +160,20 @@ __global__ void __launch_bounds__(128) k_collapse(uint32_t n, const uint32_t* __
 			rank++;
 		} else {
 			leaf24 |= ((1u << nt) - 1u) << (3 * s);
-			const uint32_t src = c >= first_leaf ? c - first_leaf : span_first[c];
-			for (uint32_t t = 0; t < nt; t++) {
-				const size_t d = 3 * (size_t)(tri_base + tri_off + t), q = 3 * (size_t)(src + t);
-				wtris[d] = leaf_tris[q], wtris[d + 1] = leaf_tris[q + 1], wtris[d + 2] = leaf_tris[q + 2];
+			// the <= LMB_WIDE_LEAF_TRIS leaves below c, left to right
+			uint32_t todo[4] = {c, 0, 0, 0};
+			int sp2 = 1;
+			while (sp2 > 0) {
+				const uint32_t x = todo[--sp2];
+				if (x >= first_leaf) {
+					const size_t d = 3 * (size_t)(tri_base + tri_off), q = 3 * (size_t)(x - first_leaf);
+					wtris[d] = leaf_tris[q], wtris[d + 1] = leaf_tris[q + 1], wtris[d + 2] = leaf_tris[q + 2];
+					tri_off++;
+				} else {
+					todo[sp2++] = right[x];
+					todo[sp2++] = left[x];
+				}
 			}
-			tri_off += nt;
 		}
 	}
 	auto pack4 = [](const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); };
@@ -208,8 +215,12 @@ int build_wide_bvh(lmb_ctx* ctx) {
 	uint32_t n_in = 1, levels = 0;
 	int cur = 0;
 	while (n_in > 0) {
-		k_collapse<<<(n_in + 127) / 128, 128, 0, st>>>(n, b.left, b.right, b.span_first, b.span_last, b.aabb, b.tris, wb.items[cur], n_in, wb.items[cur ^ 1],
-													  wb.counters, wb.nodes, wb.tris);
+		if (b.q_left)  // quality tree (ploc.cu)
+			k_collapse<<<(n_in + 127) / 128, 128, 0, st>>>(n, b.q_left, b.q_right, b.q_count, b.q_aabb, b.tris, wb.items[cur], n_in, wb.items[cur ^ 1],
+														  wb.counters, wb.nodes, wb.tris);
+		else  // canonical Karras tree
+			k_collapse<<<(n_in + 127) / 128, 128, 0, st>>>(n, b.left, b.right, b.span_count, b.aabb, b.tris, wb.items[cur], n_in, wb.items[cur ^ 1],
+														  wb.counters, wb.nodes, wb.tris);
 		LMB_CUDA(ctx, cudaMemcpyAsync(&n_in, wb.counters + WC_ITEMS_OUT, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
 		LMB_CUDA(ctx, cudaStreamSynchronize(st));
 		LMB_CUDA(ctx, cudaMemsetAsync(wb.counters + WC_ITEMS_OUT, 0, sizeof(uint32_t), st));
