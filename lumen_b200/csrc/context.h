@@ -66,24 +66,30 @@ struct DeviceWideBvh {
 	uint32_t n_nodes = 0, n_tris = 0, levels = 0;
 };
 
-// Wavefront state, struct-of-arrays over path slots (slot = frame_in_batch * W*H + y*W + x).
+// Wavefront state (wavefront.cu). Path planes are indexed by POSITION in the bounce's dense path list and double-buffered by
+// bounce parity; acc / film are indexed by pixel slot (slot = frame_in_batch * W*H + y*W + x).
 struct Wavefront {
 	uint32_t n_slots = 0;
-	float4* ray_o = nullptr;   // origin.xyz, tmin
-	float4* ray_d = nullptr;   // direction.xyz, tmax
-	float4* hit = nullptr;     // t, b1, b2, prim (bits)
-	float4* thr = nullptr;     // throughput.xyz, rng counter (bits)
-	float4* col = nullptr;     // radiance.xyz, flags (bits): bit0 last_specular
-	float4* nee = nullptr;     // 8 float4 per slot, see wavefront.cu
-	uint32_t* path_queue = nullptr;  // live paths entering the bounce (slots)
-	uint32_t* nee_queue = nullptr;   // paths with a light sample awaiting its shadow / probe result
-	uint32_t* miss_queue = nullptr;  // escaped rays awaiting the sky march (k_miss)
-	uint32_t* mat_queues = nullptr;  // 7 x n_slots: live paths sorted by the BSDF type they hit (k_classify -> k_shade<TYPE>)
-	uint32_t* trace_queue = nullptr; // typed ray entries for k_trace: slot | type << 30 (up to 3 per slot)
-	float4* probe_hit = nullptr;     // MIS-probe closest hit per slot
-	uint32_t* shadow_occ = nullptr;  // shadow-ray result per slot
+	float4* ray_o[2] = {nullptr, nullptr};  // origin.xyz, tmin
+	float4* ray_d[2] = {nullptr, nullptr};  // direction.xyz, tmax
+	float4* thr[2] = {nullptr, nullptr};    // throughput.xyz, rng counter (bits)
+	float4* col[2] = {nullptr, nullptr};    // radiance.xyz, flags (bits): bit0 last_specular, bit1 ended (waits for its light sample)
+	uint32_t* pix[2] = {nullptr, nullptr};  // pixel slot of the path
+	float4* hit = nullptr;       // t, b1, b2, prim (bits) of the continuation ray, by path position
+	float4* acc = nullptr;       // radiance of finished paths, by pixel slot (written exactly once per path)
+	float4* nee = nullptr;       // 8 float4 planes, by position in the light-sample list
+	uint32_t* nee_path = nullptr;  // light sample -> position of its path in the next list
+	float4* probe_hit = nullptr;   // MIS-probe closest hit per light sample
+	uint32_t* shadow_occ = nullptr;  // shadow-ray result per light sample
+	float4* miss_ray_o = nullptr;  // escaped rays awaiting the sky march (k_miss): dense records
+	float4* miss_ray_d = nullptr;
+	float4* miss_thr = nullptr;
+	float4* miss_col = nullptr;
+	uint32_t* miss_pix = nullptr;
+	uint32_t* mat_queues = nullptr;  // 7 x n_slots: path positions sorted by the BSDF type they hit (k_classify -> k_shade<TYPE>)
+	uint32_t* trace_queue = nullptr; // typed ray entries for k_trace: index | type << 30 (up to 3 per path)
 	uint32_t* trace_cursor = nullptr;  // work-fetch cursor of the array ray queries
-	uint32_t* counters = nullptr;  // [0],[1]: queue sizes; [2]: nee queue size; [3..]: work-fetch cursors
+	uint32_t* counters = nullptr;  // see enum Counter in wavefront.cu
 	unsigned long long* stats = nullptr;  // device counters, see StatSlot
 	uint32_t frames_in_flight = 0;
 };

@@ -1,31 +1,30 @@
-// wavefront.cu -- the path integrator as wavefront kernels (replaces the single vkCmdTraceRaysKHR(W, H, 1) dispatch of
-// src/RayTracer/Path.cpp:39-58 / path.rgen main()).
+// wavefront.cu -- the path integrator as STREAMING wavefront kernels (replaces the single vkCmdTraceRaysKHR(W, H, 1)
+// dispatch of src/RayTracer/Path.cpp:39-58 / path.rgen main()).
 //
-// One path slot per (pixel, frame-in-batch). Per bounce d, in stream order:
-//   k_trace    ONE persistent traversal kernel for every ray in flight: continuation rays into bounce d (path.rgen:48),
-//              and the shadow any-hit + MIS-probe closest-hit rays bounce d-1 generated (pt_commons.glsl:21-22, 32)
-//   k_connect  MIS weights and radiance accumulation of bounce d-1's light samples (pt_commons.glsl:23-40, path.rgen:78)
-//   k_surface  hit record, material (+texture), emission, depth cut, normal orientation; sorts paths by BSDF type
-//              (path.rgen:49-74, ray.rchit, bsdf_commons.glsl:16-22)
-//   k_nee<T>   per BSDF type: light sample, BSDF eval, MIS probe sample; writes the NEE record and its two rays
-//              (path.rgen:75-80, pt_commons.glsl:3-20,28-30)
-//   k_bsdf<T>  per BSDF type: continuation sample, throughput, Russian roulette; writes the next ray (path.rgen:81-100)
-// then k_miss evaluates the sky for escaped rays (commons.glsl:156-168) and k_film applies the running-mean / sum film
-// update in frame order (path.rgen:102-112).
-// RNG state is a pure function of (x, y, frame, draw counter), so reordering paths across kernels cannot change any
-// sample; every float expression keeps the order of the GLSL (see vec.cuh).
-//
-// HBM bytes per path-bounce (algorithmic): ray 32 rd + hit 16 wr (extend); ray 32 + hit 16 + state 32 rd, state 32 +
-// ray 32 + NEE 128 wr, ~200 B scene gathers (shade); NEE 128 + col 16 rd, col 16 wr (connect). Film: 16 B per sample.
-#include <cooperative_groups.h>
+// Path state travels with the path: every bounce has a DENSE list of live paths (position i = 0 .. n-1) whose ray,
+// throughput, radiance and pixel id sit at position i of the planes of that bounce's parity; shading writes the survivors
+// to consecutive positions of the other parity. A slot-indexed layout (state at pixel slot, queues of slot numbers) loses
+// coalescing bounce by bounce as paths die and are regrouped by material -- DRAM bytes per shaded path grew 2.3x from
+// bounce 0 to bounce 2 (profiles/r01e_summary.md) -- here every plane access is a run of consecutive positions.
+// Per bounce d (parity p = d & 1), in stream order:
+//   k_trace     ONE persistent traversal kernel for every ray in flight: continuation rays of list d (path.rgen:48) and
+//               the shadow any-hit + MIS-probe rays of the light samples taken at bounce d-1 (pt_commons.glsl:21-22, 32)
+//   k_connect   MIS weights of bounce d-1's light samples, added to the radiance of their path at its position in list d
+//               (pt_commons.glsl:23-40, path.rgen:78) -- before bounce d adds emission, as in the reference
+//   k_classify  retires paths that only waited for that light sample, handles escaped rays (path.rgen:49-55), sorts the rest
+//               by the BSDF type they hit into one queue per type
+//   k_shade<T>  per BSDF type: hit record, material (+texture), emission, NEE sample + eval, continuation sample,
+//               throughput, Russian roulette (path.rgen:56-100); appends survivors to list d+1, light samples to the NEE list
+// then k_miss evaluates the sky for the escaped rays (commons.glsl:156-168) and k_film applies the running-mean / sum film
+// update in frame order (path.rgen:102-112). A path's radiance reaches acc[pixel slot] exactly once, when it ends.
+// RNG state is a pure function of (x, y, frame, draw counter), so reordering paths cannot change any sample; every float
+// expression keeps the order of the GLSL (see vec.cuh), including the order in which terms are added to a path's radiance.
 #include <stdio.h>
 
 #include "context.h"
 #include "scene_device.cuh"
 #include "trace_persistent.cuh"
 #include "trace_wide.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace lmb {
 
@@ -47,6 +46,17 @@ struct RenderParams {
 	uint32_t dir_light_idx, direct_lighting;
 };
 
+// Path state planes of one parity (position-indexed) and the lists shared by both.
+struct PathPlanes {
+	float4* ray_o;  // origin.xyz, tmin
+	float4* ray_d;  // direction.xyz, tmax
+	float4* thr;    // throughput.xyz, rng draw counter (bits)
+	float4* col;    // radiance.xyz, flags (bits)
+	uint32_t* pix;  // pixel slot = frame_in_batch * W*H + y*W + x
+};
+constexpr uint32_t COL_LAST_SPECULAR = 1u;  // path.rgen:73
+constexpr uint32_t COL_ENDED = 2u;          // no continuation ray: the path only waits for the light sample of its last bounce
+
 // Work counters, double-buffered by bounce parity: launch d reads [d & 1] while k_shade(d) fills [(d + 1) & 1], which
 // k_trace(d) zeroed when it started (together with the per-material counters). A shading warp appends to three lists per
 // trip -- the typed ray queue, the light-sample (NEE) list and the next path list -- with two atomics issued back to back:
@@ -58,10 +68,10 @@ __device__ __forceinline__ uint32_t path_count(const uint32_t* counters, int par
 // material-sorted shade queues: index = log2(bsdf_type) for the six known types, 6 = unknown type (bsdf_type 0, quirk Q8)
 constexpr int N_MAT_QUEUES = 7;
 
-// trace queue entry = slot | type << 30
-constexpr uint32_t RAY_CONTINUE = 0u, RAY_SHADOW = 1u, RAY_PROBE = 2u, SLOT_MASK = 0x3FFFFFFFu;
+// trace queue entry = index | type << 30: CONTINUE -> path position in the current list, SHADOW / PROBE -> NEE record
+constexpr uint32_t RAY_CONTINUE = 0u, RAY_SHADOW = 1u, RAY_PROBE = 2u, IDX_MASK = 0x3FFFFFFFu;
 
-// NEE record: 8 float4 planes of n_slots each
+// NEE record: float4 planes of n_slots each, indexed by position in the NEE list
 enum NeePlane { NEE_P = 0, NEE_WI, NEE_LDIR, NEE_PROBE_WI, NEE_F2, NEE_LE, NEE_T, NEE_POS, NEE_PLANES };
 constexpr uint32_t NEE_FLAG_SHADOW_CONTRIB = 1u;  // pdf_light_w > 0
 constexpr uint32_t NEE_FLAG_PROBE = 2u;           // area light and bsdf_pdf != 0
@@ -92,9 +102,8 @@ __device__ __forceinline__ void reset_next_counters(uint32_t* counters, int pari
 	}
 }
 
-// path.rgen:23-45 + sample_camera (commons.glsl:30-33)
-__global__ void __launch_bounds__(256) k_raygen(RenderParams rp, float4* __restrict__ ray_o, float4* __restrict__ ray_d, float4* __restrict__ thr,
-												 float4* __restrict__ col, uint32_t* __restrict__ path_queue, uint32_t* __restrict__ trace_queue, unsigned long long* stats) {
+// path.rgen:23-45 + sample_camera (commons.glsl:30-33): list 0 is the pixel slots in order
+__global__ void __launch_bounds__(256) k_raygen(RenderParams rp, PathPlanes pl, uint32_t* __restrict__ trace_queue, unsigned long long* stats) {
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_CLOSEST], (unsigned long long)rp.n_active);
 	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < rp.n_active; slot += gridDim.x * blockDim.x) {
 		const uint32_t fb = slot / rp.n_pix, pix = slot - fb * rp.n_pix;
@@ -109,16 +118,16 @@ __global__ void __launch_bounds__(256) k_raygen(RenderParams rp, float4* __restr
 		const V3 origin = lmb::xyz(mul(rp.inv_view, v4(0, 0, 0, 1)));
 		const V4 target = mul(rp.inv_proj, v4(d.x, d.y, 1, 1));
 		const V3 direction = lmb::xyz(mul(rp.inv_view, v4(normalize(lmb::xyz(target)), 0)));
-		ray_o[slot] = f4(origin, T_MIN);
-		ray_d[slot] = f4(direction, T_MAX);
-		thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed.w));
-		col[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
-		path_queue[slot] = slot;
+		pl.ray_o[slot] = f4(origin, T_MIN);
+		pl.ray_d[slot] = f4(direction, T_MAX);
+		pl.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed.w));
+		pl.col[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+		pl.pix[slot] = slot;
 		trace_queue[slot] = slot | (RAY_CONTINUE << 30);
 	}
 }
 
-// Ray source of the wavefront: typed queue entries over the path-state and NEE planes.
+// Ray source of the wavefront: typed queue entries over the path planes of the current parity and the NEE planes.
 struct WavefrontSource {
 	const uint32_t* __restrict__ queue;
 	const float4* __restrict__ ray_o;
@@ -129,23 +138,23 @@ struct WavefrontSource {
 	uint32_t* __restrict__ shadow_occ;
 	uint32_t n_slots;
 	__device__ __forceinline__ void load(uint32_t i, V3& o, V3& d, float& tmin, float& tmax, bool& any) const {
-		const uint32_t e = queue[i], type = e >> 30, slot = e & SLOT_MASK;
+		const uint32_t e = queue[i], type = e >> 30, idx = e & IDX_MASK;
 		if (type == RAY_CONTINUE) {
-			const float4 o4 = ray_o[slot], d4 = ray_d[slot];
+			const float4 o4 = ray_o[idx], d4 = ray_d[idx];
 			o = xyz(o4), d = xyz(d4), tmin = o4.w, tmax = d4.w, any = false;
 		} else if (type == RAY_SHADOW) {  // pt_commons.glsl:21-22: tmin 0, tmax = wi_len - EPS, terminate on first hit
-			const float4 p4 = nee[NEE_P * (size_t)n_slots + slot];
-			o = xyz(p4), d = xyz(nee[NEE_WI * (size_t)n_slots + slot]), tmin = 0.0f, tmax = p4.w, any = true;
+			const float4 p4 = nee[NEE_P * (size_t)n_slots + idx];
+			o = xyz(p4), d = xyz(nee[NEE_WI * (size_t)n_slots + idx]), tmin = 0.0f, tmax = p4.w, any = true;
 		} else {  // pt_commons.glsl:32
-			o = xyz(nee[NEE_P * (size_t)n_slots + slot]), d = xyz(nee[NEE_PROBE_WI * (size_t)n_slots + slot]), tmin = T_MIN, tmax = T_MAX, any = false;
+			o = xyz(nee[NEE_P * (size_t)n_slots + idx]), d = xyz(nee[NEE_PROBE_WI * (size_t)n_slots + idx]), tmin = T_MIN, tmax = T_MAX, any = false;
 		}
 	}
 	__device__ __forceinline__ void store(uint32_t i, const Hit& h, bool) const {
-		const uint32_t e = queue[i], type = e >> 30, slot = e & SLOT_MASK;
+		const uint32_t e = queue[i], type = e >> 30, idx = e & IDX_MASK;
 		if (type == RAY_SHADOW)
-			shadow_occ[slot] = h.prim != 0xFFFFFFFFu;
+			shadow_occ[idx] = h.prim != 0xFFFFFFFFu;
 		else
-			(type == RAY_CONTINUE ? hit : probe_hit)[slot] = make_float4(h.t, h.b1, h.b2, __uint_as_float(h.prim));
+			(type == RAY_CONTINUE ? hit : probe_hit)[idx] = make_float4(h.t, h.b1, h.b2, __uint_as_float(h.prim));
 	}
 };
 
@@ -159,39 +168,49 @@ __global__ void __launch_bounds__(LMB_TRACE_THREADS) k_trace_bvh2(BvhView bvh, W
 	trace_persistent(bvh, src, counters[CNT_TRACE + parity], &counters[CNT_CURSOR + parity], stats, -1, -1);
 }
 
-// k_classify: sorts the live paths by the BSDF type of the surface they hit (one queue per type), so that k_shade<TYPE>
-// runs a single lobe's code on full warps; retires escaped rays (path.rgen:49-55). Reads 4 B queue + 16 B hit + one byte of
-// the L2-resident per-triangle queue table per path.
-__global__ void __launch_bounds__(256) k_classify(RenderParams rp, DeviceScene sc, int depth, uint32_t* __restrict__ counters, int parity,
-													   const uint32_t* __restrict__ queue, uint32_t* __restrict__ mat_queues, uint32_t* __restrict__ miss_queue,
-													   const float4* __restrict__ hit, const float4* __restrict__ thr, float4* __restrict__ colb, uint32_t n_slots) {
+// Escaped rays of a sun + sky scene wait for k_miss in their own dense record (the path planes are recycled two bounces on).
+struct MissPlanes {
+	float4* ray_o;
+	float4* ray_d;
+	float4* thr;
+	float4* col;
+	uint32_t* pix;
+};
+
+// k_classify: walks list d. Paths that ended at bounce d-1 and only waited for k_connect hand their radiance to acc; escaped
+// rays get the constant sky or a miss record (path.rgen:49-55); the rest are sorted by the BSDF type of the surface they hit
+// (one byte per triangle, L2-resident) into one queue of POSITIONS per type, so that k_shade<TYPE> runs a single lobe's code.
+__global__ void __launch_bounds__(256) k_classify(RenderParams rp, DeviceScene sc, int depth, uint32_t* __restrict__ counters, int parity, PathPlanes pl,
+													   const float4* __restrict__ hit, uint32_t* __restrict__ mat_queues, MissPlanes ms, float4* __restrict__ acc,
+													   uint32_t n_slots) {
 	const uint32_t count = path_count(counters, parity);
 	const int lane = threadIdx.x & 31;
-	constexpr int U = 4;  // entries per lane and trip: four independent queue -> hit -> table chains in flight
+	constexpr int U = 4;  // positions per lane and trip: independent col -> hit -> table chains in flight
 	const uint32_t stride = gridDim.x * blockDim.x * U;
 	for (uint32_t base = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * U; base < count; base += stride) {  // warp-uniform trip count
-		uint32_t slot[U], prim[U];
-		int dest[U];  // 0..6 material queue, 7 miss queue, -1 retired
+		uint32_t pos[U], flags[U], prim[U];
+		int dest[U];  // 0..6 material queue, 7 miss record, -1 retired
 #pragma unroll
 		for (int u = 0; u < U; u++) {
-			const uint32_t i = base + u * 32 + lane;
-			slot[u] = i < count ? queue[i] : 0xFFFFFFFFu;
+			pos[u] = base + u * 32 + lane;
+			flags[u] = pos[u] < count ? __float_as_uint(pl.col[pos[u]].w) : COL_ENDED;
 		}
 #pragma unroll
-		for (int u = 0; u < U; u++) prim[u] = slot[u] != 0xFFFFFFFFu ? __float_as_uint(hit[slot[u]].w) : 0xFFFFFFFFu;
+		for (int u = 0; u < U; u++) prim[u] = (pos[u] < count && !(flags[u] & COL_ENDED)) ? __float_as_uint(hit[pos[u]].w) : 0xFFFFFFFFu;
 #pragma unroll
 		for (int u = 0; u < U; u++) {
 			dest[u] = -1;
-			if (slot[u] == 0xFFFFFFFFu) continue;
-			if (prim[u] == 0xFFFFFFFFu) {  // path.rgen:49-55
-				if (depth > 0 || rp.direct_lighting == 1) {
-					if (rp.dir_light_idx == 0xFFFFFFFFu) {
-						const float4 c4 = colb[slot[u]];
-						const V3 col = xyz(c4) + xyz(thr[slot[u]]) * rp.sky_col;  // shade_atmosphere's constant-sky branch (commons.glsl:157-159)
-						colb[slot[u]] = f4(col, c4.w);
-					} else {
-						dest[u] = 7;  // 64 x 8 step sky march: deferred to k_miss (ray_o / ray_d / thr / col of a dead path stay put)
-					}
+			if (pos[u] >= count) continue;
+			if (flags[u] & COL_ENDED) {
+				acc[pl.pix[pos[u]]] = pl.col[pos[u]];
+			} else if (prim[u] == 0xFFFFFFFFu) {  // path.rgen:49-55
+				if ((depth > 0 || rp.direct_lighting == 1) && rp.dir_light_idx != 0xFFFFFFFFu) {
+					dest[u] = 7;  // 64 x 8 step sky march: deferred to k_miss
+				} else {
+					const float4 c4 = pl.col[pos[u]];
+					V3 col = xyz(c4);
+					if (depth > 0 || rp.direct_lighting == 1) col += xyz(pl.thr[pos[u]]) * rp.sky_col;  // constant sky (commons.glsl:157-159)
+					acc[pl.pix[pos[u]]] = f4(col, 0.0f);
 				}
 			} else {
 				dest[u] = sc.tri_matq[prim[u]];
@@ -205,10 +224,12 @@ __global__ void __launch_bounds__(256) k_classify(RenderParams rp, DeviceScene s
 				uint32_t at = 0;
 				if (lane == leader) at = atomicAdd(dest[u] == 7 ? &counters[CNT_MISS] : &counters[CNT_MAT + dest[u]], (uint32_t)__popc(peers));
 				at = __shfl_sync(peers, at, leader) + __popc(peers & ((1u << lane) - 1u));
-				if (dest[u] == 7)
-					miss_queue[at] = slot[u];
-				else
-					mat_queues[(size_t)dest[u] * n_slots + at] = slot[u];
+				if (dest[u] == 7) {
+					ms.ray_o[at] = pl.ray_o[pos[u]], ms.ray_d[at] = pl.ray_d[pos[u]], ms.thr[at] = pl.thr[pos[u]], ms.col[at] = pl.col[pos[u]];
+					ms.pix[at] = pl.pix[pos[u]];
+				} else {
+					mat_queues[(size_t)dest[u] * n_slots + at] = pos[u];
+				}
 			}
 		}
 	}
@@ -217,15 +238,16 @@ __global__ void __launch_bounds__(256) k_classify(RenderParams rp, DeviceScene s
 // k_shade<TYPE>: one whole bounce for the paths that hit a surface of BSDF type TYPE (path.rgen:56-100): hit record
 // (ray.rchit), material (+texture), emission, depth cut, normal orientation; NEE up to its two traceRayEXT calls
 // (pt_commons.glsl:3-20, 28-30); continuation sample, throughput update and Russian roulette. The path state stays in
-// registers across the three stages: per path-bounce the kernel reads hit + ray direction + throughput + radiance (64 B,
-// plus L2-resident scene data) and writes radiance, throughput, the next ray, the NEE record and three queue entries.
-// LAST = true is the bounce at depth max_depth - 1, which only collects emission (path.rgen:57-62) for any BSDF type.
+// registers across the three stages: per path-bounce the kernel reads hit + ray direction + throughput + radiance + pixel id
+// at the path's position (68 B, plus L2-resident scene data) and writes the survivor's state to the next free position of the
+// other parity, the NEE record to the next free NEE position and <= 3 typed ray-queue entries.
+// LAST = true is the bounce at depth max_depth - 1, which only collects emission (path.rgen:57-62) for any BSDF type and
+// walks list d directly.
 template <uint32_t TYPE, bool LAST>
 __global__ void __launch_bounds__(128, LAST ? 8 : LMB_SHADE_MIN_BLOCKS) k_shade(RenderParams rp, DeviceScene sc, int depth, uint32_t* __restrict__ counters, int parity, int count_idx,
-													const uint32_t* __restrict__ queue, uint32_t* __restrict__ path_queue, uint32_t* __restrict__ nee_queue,
-													uint32_t* __restrict__ trace_queue, const float4* __restrict__ hit, float4* __restrict__ ray_o,
-													float4* __restrict__ ray_d, float4* __restrict__ thr, float4* __restrict__ colb, float4* __restrict__ nee,
-													uint32_t n_slots, unsigned long long* stats) {
+													const uint32_t* __restrict__ queue, PathPlanes pl, PathPlanes nx, const float4* __restrict__ hit,
+													uint32_t* __restrict__ trace_queue, float4* __restrict__ nee, uint32_t* __restrict__ nee_path,
+													float4* __restrict__ acc, uint32_t n_slots, unsigned long long* stats) {
 	const uint32_t count = LAST ? path_count(counters, parity) : counters[count_idx];
 	const int lane = threadIdx.x & 31;
 	const uint32_t lt_mask = (1u << lane) - 1u;
@@ -233,44 +255,63 @@ __global__ void __launch_bounds__(128, LAST ? 8 : LMB_SHADE_MIN_BLOCKS) k_shade(
 	const uint32_t stride = gridDim.x * blockDim.x;
 	for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride) {  // warp-uniform trip count
 		const uint32_t i = base + lane;
-		uint32_t slot = 0;
-		bool do_shadow = false, do_probe = false, alive = false;
-		do {
-		if (i >= count) break;
-		slot = queue[i];
-		const float4 h4 = hit[slot];
-		const float4 c4 = colb[slot];
-		const float4 t4 = thr[slot];
-		const float4 d4 = ray_d[slot];
-		const uint32_t prim = __float_as_uint(h4.w);
-		if (LAST && prim == 0xFFFFFFFFu) break;  // (escaped rays of the last bounce were retired by k_classify)
-		V3 throughput = xyz(t4);
-		V3 col = xyz(c4);
-		const bool last_specular_in = (__float_as_uint(c4.w) & 1u) != 0;
-		const HitPayload payload = build_hit(sc, prim, h4.y, h4.z);
-		const lmb_material hit_mat = load_material(sc, payload.material_idx, payload.uv);
-		if ((depth == 0 && rp.direct_lighting == 1) || last_specular_in) col += throughput * v3(hit_mat.emissive_factor);
-		if (LAST || depth >= rp.max_depth - 1) {
-			colb[slot] = f4(col, c4.w);
-			break;
+		// ---- stage 1: hit record, material, emission, depth cut, normal orientation (path.rgen:56-74)
+		bool active = i < count;
+		uint32_t slot = 0, prim = 0xFFFFFFFFu, out_flags = 0, rng_w = 0;
+		V3 col = v3(0.0f), throughput = v3(0.0f), origin = v3(0.0f), wo = v3(0.0f), n_s = v3(0.0f), pos = v3(0.0f), payload_n_s = v3(0.0f);
+		bool side = true, want_nee = false;
+		uint32_t payload_instance = 0;
+		lmb_material hit_mat;
+		if (active) {
+			const uint32_t at = LAST ? i : queue[i];
+			const float4 c4 = pl.col[at];
+			const float4 h4 = hit[at];
+			prim = __float_as_uint(h4.w);
+			// LAST walks list d itself: paths k_classify already handed to acc (ended, escaped) are skipped
+			if (LAST && ((__float_as_uint(c4.w) & COL_ENDED) || prim == 0xFFFFFFFFu)) active = false;
+			if (active) {
+				const float4 t4 = pl.thr[at];
+				const float4 d4 = pl.ray_d[at];
+				slot = pl.pix[at];
+				throughput = xyz(t4), rng_w = __float_as_uint(t4.w);
+				col = xyz(c4);
+				const bool last_specular_in = (__float_as_uint(c4.w) & COL_LAST_SPECULAR) != 0;
+				const HitPayload payload = build_hit(sc, prim, h4.y, h4.z);
+				hit_mat = load_material(sc, payload.material_idx, payload.uv);
+				if ((depth == 0 && rp.direct_lighting == 1) || last_specular_in) col += throughput * v3(hit_mat.emissive_factor);
+				if (LAST || depth >= rp.max_depth - 1) {
+					acc[slot] = f4(col, 0.0f);
+					active = false;
+				} else {
+					wo = -xyz(d4);
+					n_s = payload.n_s, payload_n_s = payload.n_s, payload_instance = payload.instance_idx;
+					V3 n_g = payload.n_g;
+					if (dot(payload.n_g, wo) < 0.0f) n_g = -n_g;
+					if (dot(n_g, payload.n_s) < 0) {
+						n_s = -n_s;
+						side = false;
+					}
+					origin = offset_ray(payload.pos, n_g);
+					const bool last_specular = (hit_mat.bsdf_props & LMB_FLAG_SPECULAR) != 0;
+					out_flags = last_specular ? COL_LAST_SPECULAR : 0u;
+					pos = payload.pos;
+					want_nee = !last_specular && (depth > 0 || rp.direct_lighting == 1);
+				}
+			}
 		}
-		const V3 wo = -xyz(d4);
-		V3 n_s = payload.n_s;
-		bool side = true;
-		V3 n_g = payload.n_g;
-		if (dot(payload.n_g, wo) < 0.0f) n_g = -n_g;
-		if (dot(n_g, payload.n_s) < 0) {
-			n_s = -n_s;
-			side = false;
-		}
-		const V3 origin = offset_ray(payload.pos, n_g);
-		const bool last_specular = (hit_mat.bsdf_props & LMB_FLAG_SPECULAR) != 0;
-		colb[slot] = f4(col, __uint_as_float(last_specular ? 1u : 0u));
-		const V3 pos = payload.pos;
+		if (LAST) continue;
 		const uint32_t fb = slot / rp.n_pix, pix = slot - fb * rp.n_pix;
-		Rng seed{pix % rp.width, pix / rp.width, rp.first_frame + fb * rp.frame_stride, __float_as_uint(t4.w)};
-		// ---- next-event estimation (path.rgen:75-80, pt_commons.glsl:3-20, 28-30)
-		if (!last_specular && (depth > 0 || rp.direct_lighting == 1)) {
+		Rng seed{pix % rp.width, pix / rp.width, rp.first_frame + fb * rp.frame_stride, rng_w};
+		// ---- stage 2: next-event estimation (path.rgen:75-80, pt_commons.glsl:3-20, 28-30). The NEE record goes straight to
+		// its position in the NEE list (one atomic per warp, its latency hidden behind the light sample)
+		const uint32_t b_sh = __ballot_sync(0xFFFFFFFFu, want_nee);
+		uint32_t k = 0;
+		if (b_sh) {
+			if (lane == 0) k = atomicAdd(&counters[CNT_PAIR + 2 * (parity ^ 1)], (uint32_t)__popc(b_sh));
+			k = __shfl_sync(0xFFFFFFFFu, k, 0) + __popc(b_sh & lt_mask);
+		}
+		bool do_probe = false;
+		if (want_nee) {
 			const V4 r4 = rand4(seed);
 			const LightSample ls = sample_light_Li(sc, r4, pos, rp.num_lights);
 			const V3 p = offset_ray2(pos, n_s);
@@ -284,11 +325,10 @@ __global__ void __launch_bounds__(128, LAST ? 8 : LMB_SHADE_MIN_BLOCKS) k_shade(
 				const float mis_weight = ((ls.flags >> 5) & 1u) ? 1.0f : 1.0f / (1.0f + bsdf_pdf / ls.pdf_w);
 				ldir = mis_weight * f * fabsf(cos_x) * ls.Le / ls.pdf_w;
 			}
-			do_shadow = true;
 			n_shadow++;
-			nee[NEE_P * (size_t)n_slots + slot] = f4(p, ls.wi_len - LMB_EPS);
-			nee[NEE_LDIR * (size_t)n_slots + slot] = f4(ldir, ls.pdf_a);
-			nee[NEE_T * (size_t)n_slots + slot] = f4(throughput, __uint_as_float(ls.instance_idx));
+			nee[NEE_P * (size_t)n_slots + k] = f4(p, ls.wi_len - LMB_EPS);
+			nee[NEE_LDIR * (size_t)n_slots + k] = f4(ldir, ls.pdf_a);
+			nee[NEE_T * (size_t)n_slots + k] = f4(throughput, __uint_as_float(ls.instance_idx));
 			if ((ls.flags & 0x7u) == LMB_LIGHT_AREA) {
 				const V3 r3 = rand3(seed);
 				const BsdfSample bs = sample_bsdf_t<TYPE>(n_s, wo, hit_mat, 1, side, r3);
@@ -298,68 +338,69 @@ __global__ void __launch_bounds__(128, LAST ? 8 : LMB_SHADE_MIN_BLOCKS) k_shade(
 					// payload left by the previous trace, i.e. of the surface being shaded, and then uses its pos / n_s
 					// (wi_len = |pos - pos| = 0). That can only match when this surface is the sampled light triangle.
 					float g_stale = 0.0f;
-					if (payload.instance_idx == ls.instance_idx && sc.tri_local[prim] == ls.triangle_idx) {
+					if (payload_instance == ls.instance_idx && sc.tri_local[prim] == ls.triangle_idx) {
 						flags |= NEE_FLAG_STALE_MATCH;
 						const float wi_len = length(pos - pos);
-						g_stale = fabsf(dot(payload.n_s, -bs.wi)) / (wi_len * wi_len);  // ray.rchit's un-flipped shading normal
+						g_stale = fabsf(dot(payload_n_s, -bs.wi)) / (wi_len * wi_len);  // ray.rchit's un-flipped shading normal
 					}
-					nee[NEE_PROBE_WI * (size_t)n_slots + slot] = f4(bs.wi, bs.pdf);
-					nee[NEE_F2 * (size_t)n_slots + slot] = f4(bs.f, fabsf(bs.cos_theta));
-					nee[NEE_LE * (size_t)n_slots + slot] = f4(ls.Le, __uint_as_float(ls.triangle_idx));
-					nee[NEE_POS * (size_t)n_slots + slot] = f4(pos, g_stale);
+					nee[NEE_PROBE_WI * (size_t)n_slots + k] = f4(bs.wi, bs.pdf);
+					nee[NEE_F2 * (size_t)n_slots + k] = f4(bs.f, fabsf(bs.cos_theta));
+					nee[NEE_LE * (size_t)n_slots + k] = f4(ls.Le, __uint_as_float(ls.triangle_idx));
+					nee[NEE_POS * (size_t)n_slots + k] = f4(pos, g_stale);
 					do_probe = true;
 					n_probe++;
 				}
 			}
-			nee[NEE_WI * (size_t)n_slots + slot] = f4(ls.wi, __uint_as_float(flags));
+			nee[NEE_WI * (size_t)n_slots + k] = f4(ls.wi, __uint_as_float(flags));
 		}
-		// ---- continuation (path.rgen:81-100)
-		const V3 r3 = rand3(seed);
-		const BsdfSample bs = sample_bsdf_t<TYPE>(n_s, wo, hit_mat, 1, side, r3);
-		alive = bs.pdf != 0;
-		if (alive) {
-			throughput *= bs.f * fabsf(bs.cos_theta) / bs.pdf;
-			float rr_scale = 1.0f;
-			if (has_prop(hit_mat.bsdf_props, LMB_FLAG_TRANSMISSION)) rr_scale *= side ? 1.0f / hit_mat.ior : hit_mat.ior;
-			if (depth > 3) {
-				const float rr_prob = gmin(0.95f, luminance(throughput) * rr_scale);
-				if (rr_prob == 0 || rr_prob < rand1(seed))
-					alive = false;
-				else
-					throughput /= rr_prob;
+		// ---- stage 3: continuation sample, throughput, Russian roulette (path.rgen:81-100)
+		bool alive = false;
+		V3 wi_next = v3(0.0f);
+		if (active) {
+			const V3 r3 = rand3(seed);
+			const BsdfSample bs = sample_bsdf_t<TYPE>(n_s, wo, hit_mat, 1, side, r3);
+			alive = bs.pdf != 0;
+			if (alive) {
+				throughput *= bs.f * fabsf(bs.cos_theta) / bs.pdf;
+				float rr_scale = 1.0f;
+				if (has_prop(hit_mat.bsdf_props, LMB_FLAG_TRANSMISSION)) rr_scale *= side ? 1.0f / hit_mat.ior : hit_mat.ior;
+				if (depth > 3) {
+					const float rr_prob = gmin(0.95f, luminance(throughput) * rr_scale);
+					if (rr_prob == 0 || rr_prob < rand1(seed))
+						alive = false;
+					else
+						throughput /= rr_prob;
+				}
 			}
+			wi_next = bs.wi;
+			if (alive) n_cont++;
+			else if (!want_nee) acc[slot] = f4(col, 0.0f);  // the path ends here with nothing pending
 		}
-		if (alive) {
-			thr[slot] = f4(throughput, __uint_as_float(seed.w));
-			ray_o[slot] = f4(origin, T_MIN);
-			ray_d[slot] = f4(bs.wi, T_MAX);
-			n_cont++;
-		}
-		} while (0);
-		if (!LAST) {
-			// ---- the rays this warp generated go to the typed queue of the next launch: one atomic per warp and trip
-			const uint32_t b_sh = __ballot_sync(0xFFFFFFFFu, do_shadow), b_pr = __ballot_sync(0xFFFFFFFFu, do_probe);
-			const uint32_t b_ct = __ballot_sync(0xFFFFFFFFu, alive);
-			const uint32_t n_sh = __popc(b_sh), n_pr = __popc(b_pr), n_ct = __popc(b_ct), total = n_sh + n_pr + n_ct;
-			if (total) {
-				uint32_t at = 0;
-				unsigned long long at2 = 0;
-				if (lane == 0) {
-					at = atomicAdd(&counters[CNT_TRACE + (parity ^ 1)], total);
-					at2 = atomicAdd(reinterpret_cast<unsigned long long*>(&counters[CNT_PAIR + 2 * (parity ^ 1)]), ((unsigned long long)n_ct << 32) | n_sh);
-				}
-				at = __shfl_sync(0xFFFFFFFFu, at, 0);
-				const uint32_t at_nee = __shfl_sync(0xFFFFFFFFu, (uint32_t)at2, 0), at_path = __shfl_sync(0xFFFFFFFFu, (uint32_t)(at2 >> 32), 0);
-				if (do_shadow) {
-					const uint32_t r = __popc(b_sh & lt_mask);
-					trace_queue[at + r] = slot | (RAY_SHADOW << 30);
-					nee_queue[at_nee + r] = slot;
-				}
-				if (do_probe) trace_queue[at + n_sh + __popc(b_pr & lt_mask)] = slot | (RAY_PROBE << 30);
+		// ---- one position in list d+1 per path that goes on (or waits for its light sample) and <= 3 typed ray-queue entries
+		const bool go_on = alive || want_nee;
+		const uint32_t b_pr = __ballot_sync(0xFFFFFFFFu, do_probe), b_ct = __ballot_sync(0xFFFFFFFFu, alive), b_go = __ballot_sync(0xFFFFFFFFu, go_on);
+		if (b_go) {
+			const uint32_t n_sh = __popc(b_sh), n_pr = __popc(b_pr);
+			uint32_t at = 0, at_path = 0;
+			if (lane == 0) {
+				at = atomicAdd(&counters[CNT_TRACE + (parity ^ 1)], n_sh + n_pr + (uint32_t)__popc(b_ct));
+				at_path = atomicAdd(&counters[CNT_PAIR + 2 * (parity ^ 1) + 1], (uint32_t)__popc(b_go));
+			}
+			at = __shfl_sync(0xFFFFFFFFu, at, 0), at_path = __shfl_sync(0xFFFFFFFFu, at_path, 0);
+			if (go_on) {
+				const uint32_t j = at_path + __popc(b_go & lt_mask);
+				nx.col[j] = f4(col, __uint_as_float(out_flags | (alive ? 0u : COL_ENDED)));
+				nx.pix[j] = slot;
 				if (alive) {
-					const uint32_t r = __popc(b_ct & lt_mask);
-					trace_queue[at + n_sh + n_pr + r] = slot | (RAY_CONTINUE << 30);
-					path_queue[at_path + r] = slot;
+					nx.thr[j] = f4(throughput, __uint_as_float(seed.w));
+					nx.ray_o[j] = f4(origin, T_MIN);
+					nx.ray_d[j] = f4(wi_next, T_MAX);
+					trace_queue[at + n_sh + n_pr + __popc(b_ct & lt_mask)] = j | (RAY_CONTINUE << 30);
+				}
+				if (want_nee) {
+					nee_path[k] = j;
+					trace_queue[at + __popc(b_sh & lt_mask)] = k | (RAY_SHADOW << 30);
+					if (do_probe) trace_queue[at + n_sh + __popc(b_pr & lt_mask)] = k | (RAY_PROBE << 30);
 				}
 			}
 		}
@@ -369,28 +410,28 @@ __global__ void __launch_bounds__(128, LAST ? 8 : LMB_SHADE_MIN_BLOCKS) k_shade(
 	flush_stats(stats, ST_CLOSEST, n_cont);
 }
 
-// pt_commons.glsl:23-27, 33-39 and the accumulation of path.rgen:78, once both rays of the light sample are traced
+// pt_commons.glsl:23-27, 33-39 and the accumulation of path.rgen:78, once both rays of the light sample are traced: the
+// result goes to the radiance of the path at its position in the current list (before this bounce adds emission)
 __global__ void __launch_bounds__(128) k_connect(RenderParams rp, DeviceScene sc, const uint32_t* __restrict__ counters, int parity,
-												  const uint32_t* __restrict__ nee_queue, const float4* __restrict__ nee, const float4* __restrict__ probe_hit,
+												  const uint32_t* __restrict__ nee_path, const float4* __restrict__ nee, const float4* __restrict__ probe_hit,
 												  const uint32_t* __restrict__ shadow_occ, float4* __restrict__ colb, uint32_t n_slots) {
 	const uint32_t count = nee_count(counters, parity);
 	const float light_pick_pdf = 1.0f / (float)rp.light_triangle_count;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-		const uint32_t slot = nee_queue[i];
-		const float4 wi4 = nee[NEE_WI * (size_t)n_slots + slot];
-		const float4 l4 = nee[NEE_LDIR * (size_t)n_slots + slot];
-		const float4 t4 = nee[NEE_T * (size_t)n_slots + slot];
+	for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+		const float4 wi4 = nee[NEE_WI * (size_t)n_slots + k];
+		const float4 l4 = nee[NEE_LDIR * (size_t)n_slots + k];
+		const float4 t4 = nee[NEE_T * (size_t)n_slots + k];
 		const uint32_t flags = __float_as_uint(wi4.w);
 		V3 res = v3(0.0f);
-		if (shadow_occ[slot] == 0u && (flags & NEE_FLAG_SHADOW_CONTRIB)) res += xyz(l4);
+		if (shadow_occ[k] == 0u && (flags & NEE_FLAG_SHADOW_CONTRIB)) res += xyz(l4);
 		if (flags & NEE_FLAG_PROBE) {
-			const float4 pw4 = nee[NEE_PROBE_WI * (size_t)n_slots + slot];
-			const float4 f4v = nee[NEE_F2 * (size_t)n_slots + slot];
-			const float4 le4 = nee[NEE_LE * (size_t)n_slots + slot];
-			const float4 pos4 = nee[NEE_POS * (size_t)n_slots + slot];
+			const float4 pw4 = nee[NEE_PROBE_WI * (size_t)n_slots + k];
+			const float4 f4v = nee[NEE_F2 * (size_t)n_slots + k];
+			const float4 le4 = nee[NEE_LE * (size_t)n_slots + k];
+			const float4 pos4 = nee[NEE_POS * (size_t)n_slots + k];
 			const V3 wi = xyz(pw4);
 			const float bsdf_pdf = pw4.w;
-			const float4 ph = probe_hit[slot];
+			const float4 ph = probe_hit[k];
 			const uint32_t prim = __float_as_uint(ph.w);
 			bool match = false;
 			float g = 0.0f;
@@ -410,25 +451,23 @@ __global__ void __launch_bounds__(128) k_connect(RenderParams rp, DeviceScene sc
 				res += xyz(f4v) * mis_weight * f4v.w * xyz(le4) / bsdf_pdf;
 			}
 		}
-		const float4 c4 = colb[slot];
+		const uint32_t j = nee_path[k];
+		const float4 c4 = colb[j];
 		const V3 col = xyz(c4) + xyz(t4) * res / light_pick_pdf;
-		colb[slot] = f4(col, c4.w);
+		colb[j] = f4(col, c4.w);
 	}
 }
 
 // Escaped rays with a sun + sky light: col += throughput * shade_atmosphere(...) (path.rgen:50-53, commons.glsl:156-168).
 // A path misses at most once and nothing is added to its radiance afterwards, so running this after the bounce loop keeps
 // the order of the float additions.
-__global__ void __launch_bounds__(128) k_miss(RenderParams rp, DeviceScene sc, const uint32_t* __restrict__ counters, const uint32_t* __restrict__ miss_queue,
-											   const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ thr,
-											   float4* __restrict__ colb) {
+__global__ void __launch_bounds__(128) k_miss(RenderParams rp, DeviceScene sc, const uint32_t* __restrict__ counters, MissPlanes ms, float4* __restrict__ acc) {
 	const uint32_t count = counters[CNT_MISS];
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-		const uint32_t slot = miss_queue[i];
-		const float4 c4 = colb[slot];
-		const V3 sky = shade_atmosphere(sc, rp.dir_light_idx, rp.sky_col, xyz(ray_o[slot]), xyz(ray_d[slot]), T_MAX);
-		const V3 col = xyz(c4) + xyz(thr[slot]) * sky;
-		colb[slot] = f4(col, c4.w);
+		const float4 c4 = ms.col[i];
+		const V3 sky = shade_atmosphere(sc, rp.dir_light_idx, rp.sky_col, xyz(ms.ray_o[i]), xyz(ms.ray_d[i]), T_MAX);
+		const V3 col = xyz(c4) + xyz(ms.thr[i]) * sky;
+		acc[ms.pix[i]] = f4(col, 0.0f);
 	}
 }
 
@@ -514,15 +553,22 @@ int wavefront_alloc(lmb_ctx* ctx, uint32_t frames_in_flight) {
 	wf.frames_in_flight = frames_in_flight;
 	auto alloc = [&](void** p, size_t bytes) { return check_cuda(ctx, cudaMalloc(p, bytes), "cudaMalloc(wavefront)"); };
 	int rc;
-	if ((rc = alloc((void**)&wf.ray_o, n_slots * 16))) return rc;
-	if ((rc = alloc((void**)&wf.ray_d, n_slots * 16))) return rc;
+	for (int p = 0; p < 2; p++) {
+		if ((rc = alloc((void**)&wf.ray_o[p], n_slots * 16))) return rc;
+		if ((rc = alloc((void**)&wf.ray_d[p], n_slots * 16))) return rc;
+		if ((rc = alloc((void**)&wf.thr[p], n_slots * 16))) return rc;
+		if ((rc = alloc((void**)&wf.col[p], n_slots * 16))) return rc;
+		if ((rc = alloc((void**)&wf.pix[p], n_slots * 4))) return rc;
+	}
 	if ((rc = alloc((void**)&wf.hit, n_slots * 16))) return rc;
-	if ((rc = alloc((void**)&wf.thr, n_slots * 16))) return rc;
-	if ((rc = alloc((void**)&wf.col, n_slots * 16))) return rc;
+	if ((rc = alloc((void**)&wf.acc, n_slots * 16))) return rc;
 	if ((rc = alloc((void**)&wf.nee, n_slots * 16 * NEE_PLANES))) return rc;
-	if ((rc = alloc((void**)&wf.path_queue, n_slots * 4))) return rc;
-	if ((rc = alloc((void**)&wf.nee_queue, n_slots * 4))) return rc;
-	if ((rc = alloc((void**)&wf.miss_queue, n_slots * 4))) return rc;
+	if ((rc = alloc((void**)&wf.nee_path, n_slots * 4))) return rc;
+	if ((rc = alloc((void**)&wf.miss_ray_o, n_slots * 16))) return rc;
+	if ((rc = alloc((void**)&wf.miss_ray_d, n_slots * 16))) return rc;
+	if ((rc = alloc((void**)&wf.miss_thr, n_slots * 16))) return rc;
+	if ((rc = alloc((void**)&wf.miss_col, n_slots * 16))) return rc;
+	if ((rc = alloc((void**)&wf.miss_pix, n_slots * 4))) return rc;
 	if ((rc = alloc((void**)&wf.mat_queues, n_slots * 4 * N_MAT_QUEUES))) return rc;
 	if ((rc = alloc((void**)&wf.trace_queue, n_slots * 4 * 3))) return rc;
 	if ((rc = alloc((void**)&wf.probe_hit, n_slots * 16))) return rc;
@@ -535,8 +581,10 @@ int wavefront_alloc(lmb_ctx* ctx, uint32_t frames_in_flight) {
 
 void wavefront_free(lmb_ctx* ctx) {
 	Wavefront& wf = ctx->wf;
-	cudaFree(wf.ray_o), cudaFree(wf.ray_d), cudaFree(wf.hit), cudaFree(wf.thr), cudaFree(wf.col), cudaFree(wf.nee);
-	cudaFree(wf.path_queue), cudaFree(wf.nee_queue), cudaFree(wf.miss_queue), cudaFree(wf.mat_queues), cudaFree(wf.trace_queue), cudaFree(wf.probe_hit), cudaFree(wf.shadow_occ), cudaFree(wf.trace_cursor), cudaFree(wf.counters), cudaFree(wf.stats);
+	for (int p = 0; p < 2; p++) cudaFree(wf.ray_o[p]), cudaFree(wf.ray_d[p]), cudaFree(wf.thr[p]), cudaFree(wf.col[p]), cudaFree(wf.pix[p]);
+	cudaFree(wf.hit), cudaFree(wf.acc), cudaFree(wf.nee), cudaFree(wf.nee_path);
+	cudaFree(wf.miss_ray_o), cudaFree(wf.miss_ray_d), cudaFree(wf.miss_thr), cudaFree(wf.miss_col), cudaFree(wf.miss_pix);
+	cudaFree(wf.mat_queues), cudaFree(wf.trace_queue), cudaFree(wf.probe_hit), cudaFree(wf.shadow_occ), cudaFree(wf.trace_cursor), cudaFree(wf.counters), cudaFree(wf.stats);
 	wf = Wavefront{};
 }
 
@@ -563,6 +611,8 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 	const int grid_256 = ctx->sm_count * 8;
 	const int grid_trace = ctx->sm_count * 7;  // persistent: 7 blocks x 32 KB stack fit one SM's shared memory
 	const int grid_trace_wide = ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM;
+	const PathPlanes planes[2] = {{wf.ray_o[0], wf.ray_d[0], wf.thr[0], wf.col[0], wf.pix[0]}, {wf.ray_o[1], wf.ray_d[1], wf.thr[1], wf.col[1], wf.pix[1]}};
+	const MissPlanes miss{wf.miss_ray_o, wf.miss_ray_d, wf.miss_thr, wf.miss_col, wf.miss_pix};
 	float ms;
 	const bool prof = ctx->profile_stages;  // per-stage timing serialises the bounce loop; off by default
 	cudaEventRecord(ctx->ev[0], st);
@@ -572,7 +622,7 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 		rp.n_active = nb * rp.n_pix;
 		if (prof) cudaEventRecord(ctx->ev[1], st);
 		k_begin_batch<<<1, 1, 0, st>>>(wf.counters, rp.n_active);
-		k_raygen<<<grid_256, 256, 0, st>>>(rp, wf.ray_o, wf.ray_d, wf.thr, wf.col, wf.path_queue, wf.trace_queue, wf.stats);
+		k_raygen<<<grid_256, 256, 0, st>>>(rp, planes[0], wf.trace_queue, wf.stats);
 		ctx->stats.kernel_launches += 2;
 		if (prof) {
 			cudaEventRecord(ctx->ev[2], st);
@@ -580,9 +630,9 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 			cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
 			ctx->stats.ms_film += ms;
 		}
-		const WavefrontSource src{wf.trace_queue, wf.ray_o, wf.ray_d, wf.nee, wf.hit, wf.probe_hit, wf.shadow_occ, wf.n_slots};
 		for (int depth = 0; depth < std::max(pc.max_depth, 1); depth++) {
 			const int par = depth & 1;
+			const WavefrontSource src{wf.trace_queue, wf.ray_o[par], wf.ray_d[par], wf.nee, wf.hit, wf.probe_hit, wf.shadow_occ, wf.n_slots};
 			if (prof) cudaEventRecord(ctx->ev[1], st);
 			if (ctx->use_bvh2)
 				k_trace_bvh2<<<grid_trace, LMB_TRACE_THREADS, 0, st>>>(bvh, src, wf.counters, par, wf.stats);
@@ -591,19 +641,16 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 			ctx->stats.kernel_launches += 1;
 			if (prof) cudaEventRecord(ctx->ev[2], st);
 			if (depth > 0) {
-				k_connect<<<grid_wide, 128, 0, st>>>(rp, ctx->scene, wf.counters, par, wf.nee_queue, wf.nee, wf.probe_hit, wf.shadow_occ, wf.col, wf.n_slots);
+				k_connect<<<grid_wide, 128, 0, st>>>(rp, ctx->scene, wf.counters, par, wf.nee_path, wf.nee, wf.probe_hit, wf.shadow_occ, wf.col[par], wf.n_slots);
 				ctx->stats.kernel_launches += 1;
 			}
 			if (prof) cudaEventRecord(ctx->ev[3], st);
-#define LMB_SHADE_ARGS(mq, cidx) rp, ctx->scene, depth, wf.counters, par, cidx, mq, wf.path_queue, wf.nee_queue, wf.trace_queue, wf.hit, wf.ray_o, wf.ray_d, wf.thr, wf.col, wf.nee, wf.n_slots, wf.stats
+#define LMB_SHADE_ARGS(mq, cidx) rp, ctx->scene, depth, wf.counters, par, cidx, mq, planes[par], planes[par ^ 1], wf.hit, wf.trace_queue, wf.nee, wf.nee_path, wf.acc, wf.n_slots, wf.stats
 			const bool last = depth >= pc.max_depth - 1;  // the last bounce only collects emission (path.rgen:57-62)
-			if (!last || depth > 0 || pc.direct_lighting == 1) {
-				k_classify<<<grid_256, 256, 0, st>>>(rp, ctx->scene, depth, wf.counters, par, wf.path_queue, wf.mat_queues, wf.miss_queue, wf.hit, wf.thr, wf.col,
-													 wf.n_slots);
-				ctx->stats.kernel_launches += 1;
-			}
+			k_classify<<<grid_256, 256, 0, st>>>(rp, ctx->scene, depth, wf.counters, par, planes[par], wf.hit, wf.mat_queues, miss, wf.acc, wf.n_slots);
+			ctx->stats.kernel_launches += 1;
 			if (last) {
-				k_shade<0u, true><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(wf.path_queue, 0));
+				k_shade<0u, true><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(wf.mat_queues, 0));
 				ctx->stats.kernel_launches += 1;
 			} else {
 				for (int m = 0; m < N_MAT_QUEUES; m++) {
@@ -635,10 +682,10 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 		}
 		if (prof) cudaEventRecord(ctx->ev[1], st);
 		if (pc.dir_light_idx != 0xFFFFFFFFu) {
-			k_miss<<<grid_wide, 128, 0, st>>>(rp, ctx->scene, wf.counters, wf.miss_queue, wf.ray_o, wf.ray_d, wf.thr, wf.col);
+			k_miss<<<grid_wide, 128, 0, st>>>(rp, ctx->scene, wf.counters, miss, wf.acc);
 			ctx->stats.kernel_launches += 1;
 		}
-		k_film<<<grid_256, 256, 0, st>>>(rp, nb, film_mode, wf.col, ctx->film, wf.stats);
+		k_film<<<grid_256, 256, 0, st>>>(rp, nb, film_mode, wf.acc, ctx->film, wf.stats);
 		ctx->stats.kernel_launches += 1;
 		if (prof) {
 			cudaEventRecord(ctx->ev[2], st);
