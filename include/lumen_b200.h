@@ -102,6 +102,21 @@ int lmb_resolve(lmb_ctx* ctx);
 /* Copies the film to `rgba` (host or device pointer, resolved by UVA): width*height*4 floats, row-major, pixel (x, y) at
  * 4*(y*width + x). */
 int lmb_download(lmb_ctx* ctx, float* rgba);
+/* lmb_download without the final wait: the copy is queued on the context's stream (pass pinned host memory for a truly
+ * asynchronous transfer); lmb_sync waits for everything queued so far. */
+int lmb_download_async(lmb_ctx* ctx, float* rgba);
+int lmb_sync(lmb_ctx* ctx);
+/* EXR payload made on the device: the film's R, G, B converted to HALF with tinyexr's float_to_half_full rounding
+ * (libs/tinyexr.h:898-934) and laid out as the three planes ImageUtils::save_exr writes (src/Framework/ImageUtils.cpp:22-89):
+ * planes[0 .. n) = B, [n .. 2n) = G, [2n .. 3n) = R, n = width*height. 6 bytes per pixel leave the device instead of 16. */
+int lmb_download_half_bgr(lmb_ctx* ctx, uint16_t* planes);
+/* Ground-truth image of the RMSE routine (RayTracer.cpp:117-126 load_reference / has_gt): width*height*4 floats, host or
+ * device pointer. Dropped by lmb_init. */
+int lmb_set_reference_image(lmb_ctx* ctx, const float* gt_rgba);
+/* RMSE of the film against the ground-truth image, on the device. *rmse_literal = Lumen's own routine
+ * (src/shaders/rmse/calc_rmse.comp + reduce_rmse.comp + output_rmse.comp as dispatched by RayTracer.cpp:215-241, with its
+ * subgroupMin and sqrt(S)/(3N) quirks); *rmse_true = sqrt(mean over RGB of (film - gt)^2) in fp64. Either may be NULL. */
+int lmb_rmse(lmb_ctx* ctx, float* rmse_literal, double* rmse_true);
 /* Copies an image (host or device pointer) into the film: resume an accumulation, or write back a reduced sum. */
 int lmb_upload_film(lmb_ctx* ctx, const float* rgba);
 /* Device pointer of the film and the CUDA stream (cudaStream_t) the context works on, for zero-copy consumers

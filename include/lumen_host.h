@@ -42,6 +42,12 @@ void lmh_scene_make_pc(const lmh_scene* s, int32_t max_depth, int32_t direct_lig
 /* Integrator::update_uniform_buffers (Integrator.cpp:60-72) */
 void lmh_scene_make_ubo(lmh_scene* s, lmb_scene_ubo* out);
 int lmh_save_exr(const float* rgba, int32_t width, int32_t height, const char* path);
+/* The same EXR from B, G, R planes already converted to HALF (lmb_download_half_bgr); file bytes equal lmh_save_exr's. */
+int lmh_save_exr_half_bgr(const uint16_t* planes, int32_t width, int32_t height, const char* path);
+/* Checkpoint of a progressive render (running-mean film + frames accumulated + path length); load allocates *rgba_out
+ * (free with lmh_free). Resuming = lmb_upload_film + continuing at frame `frames`: bit-identical to an uninterrupted run. */
+int lmh_save_checkpoint(const char* path, const float* rgba, uint32_t width, uint32_t height, uint32_t frames, uint32_t path_length);
+int lmh_load_checkpoint(const char* path, float** rgba_out, uint32_t* width, uint32_t* height, uint32_t* frames, uint32_t* path_length);
 int lmh_load_exr(const char* path, float** rgba_out, int32_t* width, int32_t* height); /* free with lmh_free */
 void lmh_free(void* p);
 const char* lmh_last_error(void);

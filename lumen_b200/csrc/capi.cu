@@ -41,6 +41,12 @@ int upload(lmb_ctx* ctx, const T* host, size_t count, const T** dev_out) {
 	return 0;
 }
 
+// buffers of the post steps (half planes, ground-truth image, RMSE scratch) are sized by the film
+void free_post(lmb_ctx* ctx) {
+	cudaFree(ctx->half_planes), cudaFree(ctx->gt_img), cudaFree(ctx->rmse_scratch);
+	ctx->half_planes = nullptr, ctx->gt_img = nullptr, ctx->rmse_scratch = nullptr, ctx->has_gt = false;
+}
+
 void free_scene(lmb_ctx* ctx) {
 	for (void* p : ctx->scene_allocs) cudaFree(p);
 	ctx->scene_allocs.clear();
@@ -88,6 +94,7 @@ void lmb_destroy(lmb_ctx* ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	wavefront_free(ctx);
 	cudaFree(ctx->film);
+	free_post(ctx);
 	free_scene(ctx);
 	for (auto& ev : ctx->ev) cudaEventDestroy(ev);
 	cudaStreamDestroy(ctx->stream);
@@ -107,14 +114,11 @@ int lmb_upload_scene(lmb_ctx* ctx, const lmb_scene_desc* sd) {
 	if ((rc = upload(ctx, sd->world_matrices, 16 * (size_t)sd->n_prim_meshes, &sc.world_matrices))) return rc;
 	if ((rc = upload(ctx, sd->inv_world_matrices, 16 * (size_t)sd->n_prim_meshes, &sc.inv_world_matrices))) return rc;
 	if ((rc = upload(ctx, sd->lights, sd->n_lights, &sc.lights))) return rc;
-	// global triangle numbering: prim meshes concatenated in order (one TLAS instance per mesh, Integrator.cpp:148-158)
-	std::vector<uint32_t> tri_mesh, tri_local;
-	for (uint32_t m = 0; m < sd->n_prim_meshes; m++) {
-		const uint32_t nt = sd->prim_idx_counts[m] / 3;
-		for (uint32_t t = 0; t < nt; t++) tri_mesh.push_back(m), tri_local.push_back(t);
-	}
-	if ((rc = upload(ctx, tri_mesh.data(), tri_mesh.size(), &sc.tri_mesh))) return rc;
-	if ((rc = upload(ctx, tri_local.data(), tri_local.size(), &sc.tri_local))) return rc;
+	// global triangle numbering: prim meshes concatenated in order (one TLAS instance per mesh, Integrator.cpp:148-158).
+	// The per-triangle tables are filled on the device (post.cu) from the arrays just uploaded.
+	std::vector<uint32_t> tri_first(sd->n_prim_meshes + 1, 0u);
+	for (uint32_t m = 0; m < sd->n_prim_meshes; m++) tri_first[m + 1] = tri_first[m] + sd->prim_idx_counts[m] / 3;
+	const uint32_t n_tris = tri_first[sd->n_prim_meshes];
 	// textures: RGBA8 texels + sRGB decode table (VK_FORMAT_R8G8B8A8_SRGB, LumenScene.cpp:204-213)
 	std::vector<const uint8_t*> tex_ptrs;
 	std::vector<uint2> tex_dims;
@@ -143,21 +147,27 @@ int lmb_upload_scene(lmb_ctx* ctx, const lmb_scene_desc* sd) {
 		ctx->mat_queue_mask |= 1u << q;
 		mat_q[i] = (uint8_t)q;
 	}
-	// per triangle: which shade queue its material's BSDF type maps to (k_classify reads one byte per path)
-	std::vector<uint8_t> tri_matq(tri_mesh.size());
-	for (size_t t = 0; t < tri_mesh.size(); t++) {
-		const uint32_t mi = sd->prim_infos[tri_mesh[t]].material_index;
-		tri_matq[t] = mi < sd->n_materials ? mat_q[mi] : (uint8_t)6;
-	}
-	if ((rc = upload(ctx, tri_matq.data(), tri_matq.size(), &sc.tri_matq))) return rc;
-	std::vector<uint4> tri_rec(tri_mesh.size());
-	for (size_t t = 0; t < tri_mesh.size(); t++) {
-		const lmb_prim_mesh_info& pi = sd->prim_infos[tri_mesh[t]];
-		const uint32_t* ix = sd->indices + pi.index_offset + 3 * (size_t)tri_local[t];
-		tri_rec[t] = make_uint4(ix[0] + pi.vertex_offset, ix[1] + pi.vertex_offset, ix[2] + pi.vertex_offset, tri_mesh[t]);
-	}
-	if ((rc = upload(ctx, tri_rec.data(), tri_rec.size(), &sc.tri_rec))) return rc;
-	sc.n_tris = (uint32_t)tri_mesh.size();
+	// per triangle: mesh, local id, vertex record and the shade queue its material's BSDF type maps to (k_classify reads one
+	// byte per path)
+	const uint32_t* d_tri_first = nullptr;
+	const uint8_t* d_mat_q = nullptr;
+	if ((rc = upload(ctx, tri_first.data(), tri_first.size(), &d_tri_first))) return rc;
+	if ((rc = upload(ctx, mat_q.data(), mat_q.size(), &d_mat_q))) return rc;
+	uint32_t *d_tri_mesh = nullptr, *d_tri_local = nullptr;
+	uint4* d_tri_rec = nullptr;
+	uint8_t* d_tri_matq = nullptr;
+	auto dev_alloc = [&](void** p, size_t bytes) -> int {
+		const int r = check_cuda(ctx, cudaMalloc(p, std::max<size_t>(bytes, 16)), "lmb_upload_scene: triangle tables");
+		if (!r) ctx->scene_allocs.push_back(*p);
+		return r;
+	};
+	if ((rc = dev_alloc((void**)&d_tri_mesh, (size_t)n_tris * 4))) return rc;
+	if ((rc = dev_alloc((void**)&d_tri_local, (size_t)n_tris * 4))) return rc;
+	if ((rc = dev_alloc((void**)&d_tri_rec, (size_t)n_tris * 16))) return rc;
+	if ((rc = dev_alloc((void**)&d_tri_matq, (size_t)n_tris))) return rc;
+	if ((rc = ingest_triangles(ctx, d_tri_first, d_mat_q, sd->n_prim_meshes, sd->n_materials, n_tris, d_tri_mesh, d_tri_local, d_tri_rec, d_tri_matq))) return rc;
+	sc.tri_mesh = d_tri_mesh, sc.tri_local = d_tri_local, sc.tri_rec = d_tri_rec, sc.tri_matq = d_tri_matq;
+	sc.n_tris = n_tris;
 	sc.n_prim_meshes = sd->n_prim_meshes;
 	sc.n_lights = sd->n_lights;
 	sc.n_textures = sd->n_textures;
@@ -178,6 +188,7 @@ int lmb_init(lmb_ctx* ctx, uint32_t width, uint32_t height, uint32_t frames_in_f
 	cudaSetDevice(ctx->device);
 	cudaFree(ctx->film);
 	ctx->film = nullptr;
+	free_post(ctx);
 	ctx->width = width, ctx->height = height;
 	LMB_CUDA(ctx, cudaMalloc((void**)&ctx->film, (size_t)width * height * 16));
 	LMB_CUDA(ctx, cudaMemsetAsync(ctx->film, 0, (size_t)width * height * 16, ctx->stream));
@@ -224,6 +235,51 @@ int lmb_download(lmb_ctx* ctx, float* rgba) {
 	LMB_CUDA(ctx, cudaMemcpyAsync(rgba, ctx->film, (size_t)ctx->width * ctx->height * 16, cudaMemcpyDefault, ctx->stream));
 	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return LMB_OK;
+}
+
+int lmb_download_async(lmb_ctx* ctx, float* rgba) {
+	if (!ctx || !ctx->film || !rgba) return LMB_ERR_INVALID;
+	cudaSetDevice(ctx->device);
+	LMB_CUDA(ctx, cudaMemcpyAsync(rgba, ctx->film, (size_t)ctx->width * ctx->height * 16, cudaMemcpyDefault, ctx->stream));
+	return LMB_OK;
+}
+
+int lmb_sync(lmb_ctx* ctx) {
+	if (!ctx) return LMB_ERR_INVALID;
+	cudaSetDevice(ctx->device);
+	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LMB_OK;
+}
+
+int lmb_download_half_bgr(lmb_ctx* ctx, uint16_t* planes) {
+	if (!ctx || !ctx->film || !planes) return LMB_ERR_INVALID;
+	cudaSetDevice(ctx->device);
+	const size_t bytes = (size_t)ctx->width * ctx->height * 3 * sizeof(uint16_t);
+	if (!ctx->half_planes) LMB_CUDA(ctx, cudaMalloc((void**)&ctx->half_planes, bytes));
+	const int rc = launch_film_to_half(ctx, ctx->half_planes);
+	if (rc) return rc;
+	LMB_CUDA(ctx, cudaMemcpyAsync(planes, ctx->half_planes, bytes, cudaMemcpyDefault, ctx->stream));
+	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LMB_OK;
+}
+
+int lmb_set_reference_image(lmb_ctx* ctx, const float* gt_rgba) {
+	if (!ctx || !ctx->film || !gt_rgba) return LMB_ERR_INVALID;
+	cudaSetDevice(ctx->device);
+	const size_t bytes = (size_t)ctx->width * ctx->height * 16;
+	if (!ctx->gt_img) LMB_CUDA(ctx, cudaMalloc((void**)&ctx->gt_img, bytes));
+	LMB_CUDA(ctx, cudaMemcpyAsync(ctx->gt_img, gt_rgba, bytes, cudaMemcpyDefault, ctx->stream));
+	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->has_gt = true;
+	return LMB_OK;
+}
+
+int lmb_rmse(lmb_ctx* ctx, float* rmse_literal, double* rmse_true) {
+	if (!ctx || !ctx->film) return LMB_ERR_INVALID;
+	if (!ctx->has_gt) return set_error(ctx, LMB_ERR_INVALID, "lmb_rmse: call lmb_set_reference_image first (has_gt, RayTracer.cpp:215)");
+	cudaSetDevice(ctx->device);
+	if (!ctx->rmse_scratch) LMB_CUDA(ctx, cudaMalloc(&ctx->rmse_scratch, rmse_scratch_bytes(ctx->width * ctx->height)));
+	return launch_rmse(ctx, ctx->gt_img, ctx->rmse_scratch, rmse_literal, rmse_true);
 }
 
 int lmb_upload_film(lmb_ctx* ctx, const float* rgba) {

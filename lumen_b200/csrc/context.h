@@ -118,6 +118,11 @@ struct lmb_ctx {
 	uint32_t width = 0, height = 0;
 	float4* film = nullptr;
 	lmb::Wavefront wf;
+	// post steps (post.cu)
+	uint16_t* half_planes = nullptr;  // 3 x W*H halves: B, G, R planes of the EXR writer
+	float4* gt_img = nullptr;         // ground-truth image of the RMSE routine ("gt_img_addr")
+	void* rmse_scratch = nullptr;
+	bool has_gt = false;
 	// stats
 	lmb_stats stats{};
 	bool profile_stages = false;
@@ -140,6 +145,11 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 int launch_trace_closest(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits);
 int launch_trace_any(lmb_ctx* ctx, const float4* d_rays, uint32_t n, uint8_t* d_occ);
 int launch_resolve(lmb_ctx* ctx);
+int ingest_triangles(lmb_ctx* ctx, const uint32_t* d_tri_first, const uint8_t* d_mat_q, uint32_t n_meshes, uint32_t n_materials, uint32_t n_tris,
+					 uint32_t* tri_mesh, uint32_t* tri_local, uint4* tri_rec, uint8_t* tri_matq);
+int launch_film_to_half(lmb_ctx* ctx, uint16_t* d_planes);
+size_t rmse_scratch_bytes(uint32_t n_pix);
+int launch_rmse(lmb_ctx* ctx, const float4* d_gt, void* d_scratch, float* h_literal, double* h_true);
 }  // namespace lmb
 
 #define LMB_CUDA(ctx, call)                                            \

@@ -23,6 +23,8 @@ struct WideBvhView {
 	const float4* tris;   // 3 per triangle
 	uint32_t n_tris;
 	uint32_t one_bits;  // 0x3F800000, passed as DATA: keeps the PRMT byte selectors of the slab test immediates (no MOV per plane)
+	uint32_t refill_lanes;     // lanes pop new rays once fewer than this many are busy (LMB_WIDE_REFILL_LANES)
+	uint32_t tri_round_lanes;  // a triangle round starts once this many lanes hold triangles (LMB_TRI_ROUND_LANES)
 };
 
 #ifndef LMB_TRACE_THREADS
@@ -30,7 +32,9 @@ struct WideBvhView {
 #endif
 #define LMB_WSTACK_SM 12
 #define LMB_WSTACK_LOCAL 52
-#define LMB_WIDE_REFILL_LANES 20
+#ifndef LMB_WIDE_REFILL_LANES
+#define LMB_WIDE_REFILL_LANES 28
+#endif
 #ifndef LMB_WIDE_BLOCKS_PER_SM
 #define LMB_WIDE_BLOCKS_PER_SM 8
 #endif
@@ -83,6 +87,11 @@ struct TraceSmem {
 	uint32_t pair[LMB_TRACE_THREADS]; // owner lane << 27 | triangle index: one triangle test of this round
 	float4 res[LMB_TRACE_THREADS];    // t (or -1), V, W, det
 	uint32_t res_prim[LMB_TRACE_THREADS];
+	// per-warp ready queue: 32 rays fetched and prepared by the whole warp at once, handed to lanes as they run dry
+	float4 rq_a[LMB_TRACE_THREADS];   // o.xyz, tmin
+	float4 rq_b[LMB_TRACE_THREADS];   // Sx, Sy, Sz, k (bits)
+	float4 rq_c[LMB_TRACE_THREADS];   // 1/d.xyz, tmax
+	uint32_t rq_i[LMB_TRACE_THREADS]; // queue index | any-hit << 31
 };
 
 template <typename Source>
@@ -96,8 +105,9 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	const uint32_t one_bits = bvh.one_bits;
 
-	bool has = false;        // this lane owns a ray
-	bool exhausted = false;  // warp-uniform: the queue ran dry
+	bool has = false;        // this lane owns a ray that is still being traced
+	bool exhausted = false;  // warp-uniform: the global queue ran dry
+	uint32_t rq_head = 0, rq_count = 0;  // warp-uniform: the ready queue holds entries [rq_head, rq_count)
 	bool any = false;
 	uint32_t item = 0;
 	V3 ro = v3(0.0f), rinv = v3(1.0f);
@@ -112,38 +122,54 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 	uint32_t n_nodes = 0, n_tris = 0, n_closest = 0, n_any = 0;
 
 	for (;;) {
-		// ---- refill: lanes without a ray take consecutive queue entries (one atomic per warp)
-		if (!exhausted) {
+		// ---- refill. Rays come out of the global queue 32 at a time: the whole warp fetches and prepares them (coalesced
+		// loads, ray_prepare at 32 of 32 lanes, one cursor atomic per 32 rays) into the warp's ready queue in shared memory;
+		// lanes that ran dry pop from it for the price of a few shared loads, so a refill is worth doing for a handful of
+		// idle lanes instead of a dozen (profiles/r01f: 20 of 32 lanes active with refill-in-place below 20 busy lanes).
+		for (;;) {
 			const uint32_t need = __ballot_sync(0xFFFFFFFFu, !has);
-			if (need) {
-				const int leader = __ffs(need) - 1;
+			if (need == 0u) break;
+			if (rq_head == rq_count) {
+				if (exhausted) break;
 				uint32_t base = 0;
-				if (lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(need));
-				base = __shfl_sync(0xFFFFFFFFu, base, leader);
-				if (!has) {
-					const uint32_t i = base + __popc(need & lt_mask);
-					if (i < count) {
-						V3 o, d;
-						float tmax;
-						src.load(i, o, d, tmin, tmax, any);
-						item = i;
-						const RayPre r = ray_prepare(o, d);
-						ro = r.o, rinv = r.inv;
-						sm.ray_a[tid] = make_float4(o.x, o.y, o.z, tmin);
-						sm.ray_b[tid] = make_float4(r.Sx, r.Sy, r.Sz, __uint_as_float((uint32_t)r.kx | ((uint32_t)r.ky << 2) | ((uint32_t)r.kz << 4)));
-						h = Hit{tmax, 0.0f, 0.0f, 0xFFFFFFFFu};
-						sp = 0;
-						oct_inv4 = ((rinv.x < 0.0f ? 0u : 4u) | (rinv.y < 0.0f ? 0u : 2u) | (rinv.z < 0.0f ? 0u : 1u)) * 0x01010101u;
-						ng = make_uint2(0u, bvh.n_tris ? 0x80000000u : 0u);
-						tg = make_uint2(0u, 0u);
-						has = true;
-						if (any) n_any++;
-						else n_closest++;
-					}
+				if (lane == 0) base = atomicAdd(cursor, 32u);
+				base = __shfl_sync(0xFFFFFFFFu, base, 0);
+				rq_head = 0, rq_count = base < count ? min(32u, count - base) : 0u;
+				if (base + 32u >= count) exhausted = true;
+				if ((uint32_t)lane < rq_count) {
+					V3 o, d;
+					float tmin_, tmax_;
+					bool any_;
+					src.load(base + lane, o, d, tmin_, tmax_, any_);
+					const RayPre r = ray_prepare(o, d);
+					sm.rq_a[tid] = make_float4(r.o.x, r.o.y, r.o.z, tmin_);
+					sm.rq_b[tid] = make_float4(r.Sx, r.Sy, r.Sz, __uint_as_float((uint32_t)r.kx | ((uint32_t)r.ky << 2) | ((uint32_t)r.kz << 4)));
+					sm.rq_c[tid] = make_float4(r.inv.x, r.inv.y, r.inv.z, tmax_);
+					sm.rq_i[tid] = (base + lane) | (any_ ? 0x80000000u : 0u);
 				}
-				if (base + (uint32_t)__popc(need) >= count) exhausted = true;
 				__syncwarp();
+				if (rq_count == 0u) break;
 			}
+			const uint32_t avail = rq_count - rq_head;
+			const uint32_t rank = (uint32_t)__popc(need & lt_mask);
+			if (!has && rank < avail) {
+				const int q = wbase + (int)(rq_head + rank);
+				const float4 qa = sm.rq_a[q], qb = sm.rq_b[q], qc = sm.rq_c[q];
+				const uint32_t qi = sm.rq_i[q];
+				item = qi & 0x7FFFFFFFu, any = (qi >> 31) != 0u;
+				ro = v3(qa.x, qa.y, qa.z), tmin = qa.w, rinv = v3(qc.x, qc.y, qc.z);
+				sm.ray_a[tid] = qa, sm.ray_b[tid] = qb;
+				h = Hit{qc.w, 0.0f, 0.0f, 0xFFFFFFFFu};
+				sp = 0;
+				oct_inv4 = ((rinv.x < 0.0f ? 0u : 4u) | (rinv.y < 0.0f ? 0u : 2u) | (rinv.z < 0.0f ? 0u : 1u)) * 0x01010101u;
+				ng = make_uint2(0u, bvh.n_tris ? 0x80000000u : 0u);
+				tg = make_uint2(0u, 0u);
+				has = true;
+				if (any) n_any++;
+				else n_closest++;
+			}
+			rq_head += min((uint32_t)__popc(need), avail);
+			__syncwarp();
 		}
 		if (__ballot_sync(0xFFFFFFFFu, has) == 0) break;
 
@@ -218,7 +244,7 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 			// A round is worth its fixed cost only with enough pairs: lanes holding triangles sit out node steps until
 			// LMB_TRI_ROUND_LANES lanes hold some, or nobody else can step.
 			uint32_t tri_lanes = __ballot_sync(0xFFFFFFFFu, tg.y != 0u);
-			if (__popc(tri_lanes) < LMB_TRI_ROUND_LANES && __ballot_sync(0xFFFFFFFFu, has && tg.y == 0u && ng.y > 0x00FFFFFFu) != 0u) tri_lanes = 0u;
+			if ((uint32_t)__popc(tri_lanes) < bvh.tri_round_lanes && __ballot_sync(0xFFFFFFFFu, has && tg.y == 0u && ng.y > 0x00FFFFFFu) != 0u) tri_lanes = 0u;
 			while (tri_lanes) {
 				const uint32_t cnt = (uint32_t)__popc(tg.y);
 				uint32_t incl = cnt;
@@ -274,7 +300,7 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 				}
 			}
 			const int busy = __popc(__ballot_sync(0xFFFFFFFFu, has));
-			if (busy == 0 || (!exhausted && busy < LMB_WIDE_REFILL_LANES)) break;
+			if (busy == 0 || ((!exhausted || rq_head != rq_count) && (uint32_t)busy < bvh.refill_lanes)) break;
 		}
 	}
 	// ---- statistics (one atomic per warp and counter)

@@ -20,6 +20,7 @@
 // RNG state is a pure function of (x, y, frame, draw counter), so reordering paths cannot change any sample; every float
 // expression keeps the order of the GLSL (see vec.cuh), including the order in which terms are added to a path's radiance.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "context.h"
 #include "scene_device.cuh"
@@ -186,9 +187,16 @@ __global__ void __launch_bounds__(256) k_classify(RenderParams rp, DeviceScene s
 	const uint32_t count = path_count(counters, parity);
 	const int lane = threadIdx.x & 31;
 	constexpr int U = 4;  // positions per lane and trip: independent col -> hit -> table chains in flight
-	const uint32_t stride = gridDim.x * blockDim.x * U;
-	for (uint32_t base = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * U; base < count; base += stride) {  // warp-uniform trip count
-		uint32_t pos[U], flags[U], prim[U];
+	// Queue space is claimed per BLOCK trip (256 x U positions): warps add their per-destination counts in shared memory and
+	// one thread per destination does the global atomic. One atomic per warp and destination serialised on a handful of
+	// L2 addresses (~0.85 cycles each, 0.55 M of them per launch) and WAS the kernel's run time (profiles/r01f).
+	__shared__ uint32_t s_cnt[8], s_base[8];
+	const uint32_t per_block = 256u * U;
+	for (uint32_t bbase = blockIdx.x * per_block; bbase < count; bbase += gridDim.x * per_block) {  // block-uniform trip count
+		if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+		__syncthreads();
+		const uint32_t base = bbase + (threadIdx.x >> 5) * (32u * U);
+		uint32_t pos[U], flags[U], prim[U], loc[U];
 		int dest[U];  // 0..6 material queue, 7 miss record, -1 retired
 #pragma unroll
 		for (int u = 0; u < U; u++) {
@@ -219,17 +227,26 @@ __global__ void __launch_bounds__(256) k_classify(RenderParams rp, DeviceScene s
 #pragma unroll
 		for (int u = 0; u < U; u++) {
 			const uint32_t peers = __match_any_sync(0xFFFFFFFFu, dest[u]);
+			loc[u] = 0;
 			if (dest[u] >= 0) {
 				const int leader = __ffs(peers) - 1;
 				uint32_t at = 0;
-				if (lane == leader) at = atomicAdd(dest[u] == 7 ? &counters[CNT_MISS] : &counters[CNT_MAT + dest[u]], (uint32_t)__popc(peers));
-				at = __shfl_sync(peers, at, leader) + __popc(peers & ((1u << lane) - 1u));
-				if (dest[u] == 7) {
-					ms.ray_o[at] = pl.ray_o[pos[u]], ms.ray_d[at] = pl.ray_d[pos[u]], ms.thr[at] = pl.thr[pos[u]], ms.col[at] = pl.col[pos[u]];
-					ms.pix[at] = pl.pix[pos[u]];
-				} else {
-					mat_queues[(size_t)dest[u] * n_slots + at] = pos[u];
-				}
+				if (lane == leader) at = atomicAdd(&s_cnt[dest[u]], (uint32_t)__popc(peers));
+				loc[u] = __shfl_sync(peers, at, leader) + __popc(peers & ((1u << lane) - 1u));
+			}
+		}
+		__syncthreads();
+		if (threadIdx.x < 8 && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(threadIdx.x == 7 ? &counters[CNT_MISS] : &counters[CNT_MAT + threadIdx.x], s_cnt[threadIdx.x]);
+		__syncthreads();
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			if (dest[u] < 0) continue;
+			const uint32_t at = s_base[dest[u]] + loc[u];
+			if (dest[u] == 7) {
+				ms.ray_o[at] = pl.ray_o[pos[u]], ms.ray_d[at] = pl.ray_d[pos[u]], ms.thr[at] = pl.thr[pos[u]], ms.col[at] = pl.col[pos[u]];
+				ms.pix[at] = pl.pix[pos[u]];
+			} else {
+				mat_queues[(size_t)dest[u] * n_slots + at] = pos[u];
 			}
 		}
 	}
@@ -535,7 +552,15 @@ __global__ void __launch_bounds__(LMB_TRACE_THREADS) k_trace_array_bvh2(BvhView 
 }
 
 BvhView view_of(const lmb_ctx* ctx) { return BvhView{ctx->bvh.nodes, ctx->bvh.tris, ctx->bvh.n}; }
-WideBvhView wide_view_of(const lmb_ctx* ctx) { return WideBvhView{ctx->wide.nodes, ctx->wide.tris, ctx->wide.n_tris, 0x3F800000u}; }
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+	const char* v = getenv(name);
+	return (v && *v) ? (uint32_t)atoi(v) : dflt;
+}
+WideBvhView wide_view_of(const lmb_ctx* ctx) {
+	// scheduling thresholds of k_trace (results do not depend on them): tuning overrides for A/B runs
+	static const uint32_t refill = env_u32("LMB_REFILL_LANES", LMB_WIDE_REFILL_LANES), round = env_u32("LMB_TRI_ROUND_LANES", LMB_TRI_ROUND_LANES);
+	return WideBvhView{ctx->wide.nodes, ctx->wide.tris, ctx->wide.n_tris, 0x3F800000u, refill, round};
+}
 
 }  // namespace
 

@@ -34,6 +34,9 @@ def lib():
         L.lmh_scene_make_pc.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(PCPath)]
         L.lmh_scene_make_ubo.argtypes = [C.c_void_p, C.POINTER(SceneUBO)]
         L.lmh_save_exr.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p]
+        L.lmh_save_exr_half_bgr.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p]
+        L.lmh_save_checkpoint.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.lmh_load_checkpoint.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)] + [C.POINTER(C.c_uint32)] * 4
         L.lmh_load_exr.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.lmh_free.argtypes = [C.c_void_p]
         _LIB = L
@@ -104,6 +107,32 @@ def save_exr(rgba, path):
     h, w = a.shape[0], a.shape[1]
     if lib().lmh_save_exr(a.ctypes.data, w, h, os.fsencode(path)) != 0:
         raise RuntimeError("lmh_save_exr: " + lib().lmh_last_error().decode())
+
+
+def save_exr_half_bgr(planes, path):
+    """planes: (3, H, W) uint16 = B, G, R half planes from Device.download_half_bgr()."""
+    a = np.ascontiguousarray(planes, dtype=np.uint16)
+    h, w = a.shape[1], a.shape[2]
+    if lib().lmh_save_exr_half_bgr(a.ctypes.data, w, h, os.fsencode(path)) != 0:
+        raise RuntimeError("lmh_save_exr_half_bgr: " + lib().lmh_last_error().decode())
+
+
+def save_checkpoint(path, rgba, frames, path_length):
+    a = np.ascontiguousarray(rgba, dtype=np.float32)
+    if lib().lmh_save_checkpoint(os.fsencode(path), a.ctypes.data, a.shape[1], a.shape[0], int(frames), int(path_length)) != 0:
+        raise RuntimeError("lmh_save_checkpoint: " + lib().lmh_last_error().decode())
+
+
+def load_checkpoint(path):
+    """-> (rgba (H, W, 4) float32, frames, path_length)"""
+    p = C.c_void_p()
+    w, h, fr, pl = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    if lib().lmh_load_checkpoint(os.fsencode(path), C.byref(p), C.byref(w), C.byref(h), C.byref(fr), C.byref(pl)) != 0:
+        raise RuntimeError("lmh_load_checkpoint: " + lib().lmh_last_error().decode())
+    n = w.value * h.value * 4
+    out = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n,)).copy().reshape(h.value, w.value, 4)
+    lib().lmh_free(p)
+    return out, fr.value, pl.value
 
 
 def load_exr(path):

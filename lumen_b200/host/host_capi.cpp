@@ -137,6 +137,33 @@ int lmh_save_exr(const float* rgba, int32_t width, int32_t height, const char* p
 	}
 	return 0;
 }
+int lmh_save_exr_half_bgr(const uint16_t* planes, int32_t width, int32_t height, const char* path) {
+	std::string err;
+	if (!lmh::save_exr_half_bgr(planes, width, height, path, &err)) {
+		g_err = err;
+		return -1;
+	}
+	return 0;
+}
+int lmh_save_checkpoint(const char* path, const float* rgba, uint32_t width, uint32_t height, uint32_t frames, uint32_t path_length) {
+	std::string err;
+	if (!lmh::save_checkpoint(path, rgba, width, height, frames, path_length, &err)) {
+		g_err = err;
+		return -1;
+	}
+	return 0;
+}
+int lmh_load_checkpoint(const char* path, float** rgba_out, uint32_t* width, uint32_t* height, uint32_t* frames, uint32_t* path_length) {
+	std::vector<float> px;
+	std::string err;
+	if (!lmh::load_checkpoint(path, px, *width, *height, *frames, *path_length, &err)) {
+		g_err = err;
+		return -1;
+	}
+	*rgba_out = (float*)std::malloc(px.size() * sizeof(float));
+	std::memcpy(*rgba_out, px.data(), px.size() * sizeof(float));
+	return 0;
+}
 int lmh_load_exr(const char* path, float** rgba_out, int32_t* width, int32_t* height) {
 	std::vector<float> px;
 	std::string err;

@@ -121,6 +121,11 @@ class Scene {
 // ImageUtils.cpp:22-89: RGBA fp32 -> 3-channel (B,G,R) HALF OpenEXR.
 bool save_exr(const float* rgba, int width, int height, const char* path, std::string* err);
 // ImageUtils.cpp:8-20
+bool save_exr_half_bgr(const uint16_t* planes, int width, int height, const char* path, std::string* err);
+// progressive-render checkpoint: header (magic, width, height, frames accumulated, path length) + RGBA32F film
+bool save_checkpoint(const char* path, const float* rgba, uint32_t width, uint32_t height, uint32_t frames, uint32_t path_length, std::string* err);
+bool load_checkpoint(const char* path, std::vector<float>& rgba, uint32_t& width, uint32_t& height, uint32_t& frames, uint32_t& path_length,
+					 std::string* err);
 bool load_exr(const char* path, std::vector<float>& rgba, int& width, int& height, std::string* err);
 
 }  // namespace lmh

@@ -4,11 +4,18 @@
 // -> cleanup (:491-499). The window size (hard-coded 1920x1080 in main.cpp:14-18) is a CLI option here.
 //
 //   lumen_headless scene.(json|xml) [--width W] [--height H] [--spp N] [--depth D] [--out out.exr] [--device i] [--batch F]
+//                  [--ref gt.exr [--target-rmse X]] [--checkpoint file [--checkpoint-every N] [--resume]]
+// Progressive service: with --ref the RMSE against the ground-truth image is computed on the device
+// after every batch (Lumen does it every 5 s, RayTracer.cpp:453-461, and prints rmse * 1e6) and rendering stops early once
+// the true RMSE falls to --target-rmse; --checkpoint writes film + frame count every N frames (and at the end), --resume
+// continues from it with results bit-identical to an uninterrupted run.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <regex>
 #include <string>
+#include <vector>
+#include <stdexcept>
 
 #include "path_b200.h"
 
@@ -16,7 +23,10 @@ int main(int argc, char** argv) {
 	std::string scene_name = "scenes/caustics.json";  // RayTracer.cpp:14-17 default
 	uint32_t width = 1920, height = 1080, spp = 64, batch = 8;
 	int depth = 0, device = 0;
-	std::string out = "out.exr";
+	std::string out = "out.exr", ref_path, ckpt_path;
+	double target_rmse = -1.0;
+	uint32_t ckpt_every = 0;
+	bool resume = false;
 	const std::regex fn("(.*).(.json|.xml)");  // RayTracer::parse_args, RayTracer.cpp:468-476
 	for (int i = 1; i < argc; i++) {
 		const std::string a = argv[i];
@@ -28,6 +38,11 @@ int main(int argc, char** argv) {
 		else if (a == "--out") out = next();
 		else if (a == "--device") device = atoi(next());
 		else if (a == "--batch") batch = (uint32_t)atoi(next());
+		else if (a == "--ref") ref_path = next();
+		else if (a == "--target-rmse") target_rmse = atof(next());
+		else if (a == "--checkpoint") ckpt_path = next();
+		else if (a == "--checkpoint-every") ckpt_every = (uint32_t)atoi(next());
+		else if (a == "--resume") resume = true;
 		else if (std::regex_match(a, fn)) scene_name = a;
 	}
 	try {
@@ -40,20 +55,41 @@ int main(int argc, char** argv) {
 		if (depth > 0) integrator.path_length = (uint32_t)depth;
 		integrator.init();
 		integrator.create_accel();
+		if (!ref_path.empty()) {
+			std::vector<float> gt;
+			int gw = 0, gh = 0;
+			std::string err;
+			if (!lmh::load_exr(ref_path.c_str(), gt, gw, gh, &err)) throw std::runtime_error("--ref: " + err);
+			if ((uint32_t)gw != width || (uint32_t)gh != height) throw std::runtime_error("--ref: image size differs from --width/--height");
+			integrator.set_reference(gt.data());
+		}
+		if (resume && !ckpt_path.empty()) {
+			integrator.load_checkpoint(ckpt_path.c_str());
+			printf("resumed %s at frame %u\n", ckpt_path.c_str(), integrator.frame_num);
+		}
+		uint32_t last_ckpt = integrator.frame_num;
 		while (integrator.frame_num + batch <= spp) {
 			integrator.render();
 			integrator.update();
+			if (!ref_path.empty()) {
+				float lit = 0;
+				double tru = 0;
+				integrator.rmse(&lit, &tru);
+				printf("frame %u: RMSE %g (Lumen's routine x 1e6), true RMSE %g\n", integrator.frame_num, (double)lit * 1e6, tru);
+				if (target_rmse >= 0 && tru <= target_rmse) break;
+			}
+			if (!ckpt_path.empty() && ckpt_every && integrator.frame_num - last_ckpt >= ckpt_every) {
+				integrator.save_checkpoint(ckpt_path.c_str());
+				last_ckpt = integrator.frame_num;
+			}
 		}
+		if (!ckpt_path.empty()) integrator.save_checkpoint(ckpt_path.c_str());
 		const lmb_stats st = integrator.stats();
 		const double rays = (double)(st.rays_closest + st.rays_shadow + st.rays_probe);
 		printf("%u x %u, %llu frames, depth %u: %.1f ms on device, %.1f Mrays/s, %.2f spp/s, LBVH build %.2f ms\n", width, height,
 			   (unsigned long long)st.frames, integrator.path_length, st.ms_render, rays / st.ms_render / 1e3, st.frames / (st.ms_render * 1e-3),
 			   st.ms_build_accel);
-		std::string err;
-		if (!lmh::save_exr(integrator.read_output().data(), (int)width, (int)height, out.c_str(), &err)) {
-			fprintf(stderr, "save_exr: %s\n", err.c_str());
-			return 1;
-		}
+		integrator.save_exr(out.c_str());
 		printf("wrote %s\n", out.c_str());
 		integrator.destroy();
 	} catch (const std::exception& e) {

@@ -51,6 +51,33 @@ class PathB200 final : public Integrator {
 		check(lmb_download(ctx, film.data()), "lmb_download");
 		return film;
 	}
+	// F10 -> save_exr("out.exr") (RayTracer.cpp:447-452): half conversion and B, G, R planes are made on the device.
+	void save_exr(const char* path) {
+		const size_t n = (size_t)lumen_scene->width * lumen_scene->height;
+		half_planes.resize(3 * n);
+		check(lmb_download_half_bgr(ctx, half_planes.data()), "lmb_download_half_bgr");
+		std::string err;
+		if (!lmh::save_exr_half_bgr(half_planes.data(), (int)lumen_scene->width, (int)lumen_scene->height, path, &err)) throw std::runtime_error("save_exr: " + err);
+	}
+	// load_reference / has_gt + calc_rmse (RayTracer.cpp:117-126, 215-241, 456-461)
+	void set_reference(const float* gt_rgba) { check(lmb_set_reference_image(ctx, gt_rgba), "lmb_set_reference_image"); }
+	void rmse(float* literal, double* true_rmse) { check(lmb_rmse(ctx, literal, true_rmse), "lmb_rmse"); }
+	// Checkpoint / resume of a progressive render: the running-mean film plus frame_num continue the accumulation exactly
+	// (path.rgen:106-109 reads the old value when frame_num > 0).
+	void save_checkpoint(const char* path) {
+		std::string err;
+		if (!lmh::save_checkpoint(path, read_output().data(), lumen_scene->width, lumen_scene->height, frame_num, path_length, &err))
+			throw std::runtime_error("save_checkpoint: " + err);
+	}
+	void load_checkpoint(const char* path) {
+		uint32_t w = 0, h = 0, frames = 0, depth = 0;
+		std::string err;
+		if (!lmh::load_checkpoint(path, film, w, h, frames, depth, &err)) throw std::runtime_error("load_checkpoint: " + err);
+		if (w != lumen_scene->width || h != lumen_scene->height || depth != path_length)
+			throw std::runtime_error("load_checkpoint: checkpoint is for another image size or path length");
+		check(lmb_upload_film(ctx, film.data()), "lmb_upload_film");
+		frame_num = frames;
+	}
 	lmb_stats stats() {
 		lmb_stats s{};
 		check(lmb_get_stats(ctx, &s), "lmb_get_stats");
@@ -69,4 +96,5 @@ class PathB200 final : public Integrator {
 	lmb_pc_path pc_ray{};
 	lmb_scene_ubo scene_ubo{};
 	std::vector<float> film;
+	std::vector<uint16_t> half_planes;
 };

@@ -53,6 +53,11 @@ def lib():
         L.lmb_resolve.argtypes = [vp]
         L.lmb_download.argtypes = [vp, vp]
         L.lmb_upload_film.argtypes = [vp, vp]
+        L.lmb_download_async.argtypes = [vp, vp]
+        L.lmb_sync.argtypes = [vp]
+        L.lmb_download_half_bgr.argtypes = [vp, vp]
+        L.lmb_set_reference_image.argtypes = [vp, vp]
+        L.lmb_rmse.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_double)]
         L.lmb_film_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
         L.lmb_stream.argtypes = [vp, C.POINTER(vp)]
         L.lmb_set_profile_stages.argtypes = [vp, i32]
@@ -79,7 +84,8 @@ def lib():
 
 EXPORTS = ["lmb_create", "lmb_destroy", "lmb_last_error", "lmb_upload_scene", "lmb_build_accel", "lmb_init", "lmb_render", "lmb_clear_film",
            "lmb_resolve", "lmb_download", "lmb_upload_film", "lmb_film_device_ptr", "lmb_stream", "lmb_set_profile_stages", "lmb_get_stats",
-           "lmb_reset_stats", "lmb_trace_closest", "lmb_trace_any", "lmb_trace_closest_device", "lmb_accel_num_tris", "lmb_accel_download"]
+           "lmb_reset_stats", "lmb_trace_closest", "lmb_trace_any", "lmb_trace_closest_device", "lmb_accel_num_tris", "lmb_accel_download",
+           "lmb_download_async", "lmb_sync", "lmb_download_half_bgr", "lmb_set_reference_image", "lmb_rmse"]
 TESTHOOK_EXPORTS = ["lmb_kat_pcg4d", "lmb_kat_rand", "lmb_kat_detmath", "lmb_kat_offset_ray", "lmb_kat_sample_bsdf", "lmb_kat_eval_bsdf",
                     "lmb_kat_atmosphere", "lmb_kat_sample_light", "lmb_kat_texture", "lmb_kat_wide_bvh_check"]
 
@@ -154,6 +160,29 @@ class Device:
 
     def download_into(self, host_ptr):
         self._ck(lib().lmb_download(self._h, host_ptr), "lmb_download")
+
+    def download_async(self, host_ptr):
+        self._ck(lib().lmb_download_async(self._h, host_ptr), "lmb_download_async")
+
+    def sync(self):
+        self._ck(lib().lmb_sync(self._h), "lmb_sync")
+
+    def download_half_bgr(self):
+        """(3, H, W) uint16: the B, G, R half planes of the EXR writer, converted on the device."""
+        out = np.empty((3, self.height, self.width), dtype=np.uint16)
+        self._ck(lib().lmb_download_half_bgr(self._h, out.ctypes.data), "lmb_download_half_bgr")
+        return out
+
+    def set_reference_image(self, rgba):
+        a = _f32(rgba)
+        assert a.size == self.width * self.height * 4
+        self._ck(lib().lmb_set_reference_image(self._h, a.ctypes.data), "lmb_set_reference_image")
+
+    def rmse(self):
+        """(literal, true): Lumen's RMSE routine and a true RMSE of the film against the reference image."""
+        lit, tru = C.c_float(), C.c_double()
+        self._ck(lib().lmb_rmse(self._h, C.byref(lit), C.byref(tru)), "lmb_rmse")
+        return lit.value, tru.value
 
     def upload_film(self, rgba):
         a = _f32(rgba)

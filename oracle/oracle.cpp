@@ -597,6 +597,40 @@ float orc_rmse_literal(const float* a, const float* b, uint32_t n_pixels) {
 	}
 	return std::sqrt(res.empty() ? 0.0f : res[0]) / ((float)n_pixels * 3.0f);
 }
+// ------------------------------------------------------------------------------------------------ EXR half conversion
+// ImageUtils::save_exr (src/Framework/ImageUtils.cpp:72-76) asks tinyexr for HALF channels; tinyexr converts with
+// float_to_half_full (libs/tinyexr.h:898-934): mantissa truncated to 10 bits plus one when the first dropped bit is set
+// (round half up in magnitude), NaN -> quiet NaN 0x200, overflow -> inf, fp32 subnormals -> signed zero, half subnormals
+// by shifting the mantissa with the hidden bit. Pinned against the real tinyexr in tests/test_post_cpu.py (EXR round trip).
+void orc_float_to_half(const float* in, uint32_t n, uint16_t* out) {
+	for (uint32_t i = 0; i < n; i++) {
+		uint32_t u;
+		memcpy(&u, &in[i], 4);
+		const uint32_t sign = u >> 31, exponent = (u >> 23) & 0xFFu, mantissa = u & 0x7FFFFFu;
+		uint32_t o = 0;  // exponent << 10 | mantissa of the half, carries of the rounding run into the exponent on purpose
+		if (exponent == 0) {
+			o = 0;
+		} else if (exponent == 255) {
+			o = (31u << 10) | (mantissa ? 0x200u : 0u);
+		} else {
+			const int newexp = (int)exponent - 127 + 15;
+			if (newexp >= 31) {
+				o = 31u << 10;
+			} else if (newexp <= 0) {
+				if ((14 - newexp) <= 24) {
+					const uint32_t mant = mantissa | 0x800000u;
+					o = mant >> (14 - newexp);
+					if ((mant >> (13 - newexp)) & 1u) o++;
+				}
+			} else {
+				o = ((uint32_t)newexp << 10) | (mantissa >> 13);
+				if (mantissa & 0x1000u) o++;
+			}
+		}
+		out[i] = (uint16_t)((sign << 15) | (o & 0x7FFFu));
+	}
+}
+
 double orc_rmse_true(const float* a, const float* b, uint32_t n_pixels) {
 	double acc = 0;
 	for (uint32_t i = 0; i < n_pixels; i++)

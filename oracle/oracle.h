@@ -86,6 +86,9 @@ void orc_kat_texture(const orc_scene* s, uint32_t tex, const float* uv2, uint32_
 float orc_rmse_literal(const float* rgba_a, const float* rgba_b, uint32_t n_pixels);
 double orc_rmse_true(const float* rgba_a, const float* rgba_b, uint32_t n_pixels);
 
+/* float -> half exactly as the EXR writer does it (tinyexr float_to_half_full, libs/tinyexr.h:898-934). */
+void orc_float_to_half(const float* in, uint32_t n, uint16_t* out);
+
 int orc_max_threads(void);
 
 #ifdef __cplusplus

@@ -58,6 +58,7 @@ def lib():
         L.orc_rmse_literal.restype = C.c_float
         L.orc_rmse_true.argtypes = [vp, vp, u32]
         L.orc_rmse_true.restype = C.c_double
+        L.orc_float_to_half.argtypes = [vp, u32, vp]
         L.orc_max_threads.restype = i32
         _LIB = L
     return _LIB
@@ -201,6 +202,14 @@ def atmosphere(origin, direction, light_dir, light_L):
 def rmse_literal(a, b):
     a, b = _f32(a).reshape(-1, 4), _f32(b).reshape(-1, 4)
     return float(lib().orc_rmse_literal(a.ctypes.data, b.ctypes.data, a.shape[0]))
+
+
+def float_to_half(x):
+    """tinyexr's float -> half conversion (what ImageUtils::save_exr stores); returns uint16 of x's shape."""
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty(a.shape, dtype=np.uint16)
+    lib().orc_float_to_half(a.ctypes.data, a.size, out.ctypes.data)
+    return out
 
 
 def rmse_true(a, b):

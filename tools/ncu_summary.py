@@ -3,7 +3,7 @@
 
     python tools/ncu_summary.py launches gpurun_out/launches.csv            # per-kernel totals and shares
     python tools/ncu_summary.py full gpurun_out/prof.ncu-rep [--traffic]    # key metrics per captured launch
-    python tools/ncu_summary.py sass gpurun_out/prof.ncu-rep k_trace        # instruction mix by SASS region
+    python tools/ncu_summary.py sass gpurun_out/prof.ncu-rep k_trace [skip] # instruction mix by SASS region of launch #skip
 
 `full --traffic` also writes profiles/ktrace_dram_traffic.json (mean dram bytes per k_trace launch), which bench.py
 reports as roofline.traffic.
@@ -88,8 +88,8 @@ def full(path, traffic):
         print("\nwrote profiles/ktrace_dram_traffic.json:", d)
 
 
-def sass(path, kernel, seg=20):
-    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass", "--kernel-name", f"regex:{kernel}", "--launch-count", "1"],
+def sass(path, kernel, seg=20, skip=0):
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass", "--kernel-name", f"regex:{kernel}", "--launch-skip", str(skip), "--launch-count", "1"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr = rows[1]
@@ -114,4 +114,4 @@ if __name__ == "__main__":
     elif mode == "full":
         full(sys.argv[2], "--traffic" in sys.argv)
     elif mode == "sass":
-        sass(sys.argv[2], sys.argv[3])
+        sass(sys.argv[2], sys.argv[3], skip=int(sys.argv[4]) if len(sys.argv) > 4 else 0)
