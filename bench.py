@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WIDTH, HEIGHT, MAX_DEPTH = 1920, 1080, 8
-WORKLOAD = "classroom-standin 1920x1080 depth 8 (procedural stand-in for scenes/classroom, whose meshes are not in the reference tree)"
+WORKLOAD = "classroom-standin {w}x{h} depth 8 (procedural stand-in for scenes/classroom, whose meshes are not in the reference tree)"
 NODE_BYTES, TRI_BYTES, RAY_BYTES, HIT_BYTES = 80, 48, 32, 16  # 8-wide compressed node, 3 x float4 triangle, ray in, hit out
 
 
@@ -129,7 +129,7 @@ def run_reference(args, rank):
     print(json.dumps({
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "max_depth": MAX_DEPTH, "sample": sample},
+        "config": {"workload": WORKLOAD.format(w=WIDTH, h=HEIGHT), "max_depth": MAX_DEPTH, "sample": sample},
         "spp_per_s": args.steps / wall * (pc.size_x * pc.size_y) / (WIDTH * HEIGHT),
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -145,7 +145,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pixel-shards", type=int, default=1, help="P: ranks form a P x (N/P) grid of interleaved-row pixel shards x sample shards (config 4)")
+    ap.add_argument("--width", type=int, default=WIDTH)
+    ap.add_argument("--height", type=int, default=HEIGHT)
     args = ap.parse_args()
+    globals().update(WIDTH=args.width, HEIGHT=args.height)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -171,6 +175,9 @@ def main():
     dev.upload_scene(scene.desc)
     dev.build_accel()
     fps = args.frames_per_step
+    from lumen_b200 import sharding
+    p_shard, s_shard, n_pshards, n_sshards = sharding.grid_of_rank(rank, world, args.pixel_shards)
+    dev.set_pixel_shard(p_shard, n_pshards)
     dev.init(WIDTH, HEIGHT, fps)
     pc, ubo = scene.make_pc(MAX_DEPTH, True), scene.make_ubo()
     build = dev.stats()
@@ -195,9 +202,9 @@ def main():
 
     def step(download):
         dev.clear_film()
-        first = state["frame"] + rank
-        dev.render(pc, ubo, first, fps, world, integrator.FILM_SUM)  # frames first, first + world, ...
-        state["frame"] += fps * world
+        first = state["frame"] + s_shard
+        dev.render(pc, ubo, first, fps, n_sshards, integrator.FILM_SUM)  # frames first, first + S, ... of this rank's rows
+        state["frame"] += fps * n_sshards
         if world > 1:
             dist.all_reduce(film_t)  # fp32 sum of rgb and of the per-pixel valid-sample count over NVLink
             torch.cuda.synchronize()
@@ -277,12 +284,13 @@ def main():
                 n += 1
             cpu_baseline = {"value": cst.rays / cst.seconds / 1e6, "unit": "Mrays/s", "cores": cst.threads, "kind": "port",
                             "sample": f"{n} frames at {pcs.size_x}x{pcs.size_y} (full view, half resolution), depth {MAX_DEPTH}, {cst.seconds:.1f} s"}
-        total_frames = args.steps * fps * world
+        total_frames = args.steps * fps * n_sshards  # whole-image frames: a pixel shard renders 1/P of each
         line = {
             "metric": "Mrays/s", "value": rays / dt / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "max_depth": MAX_DEPTH, "frames_per_step_per_gpu": fps, "triangles": int(scene.info.n_triangles),
-                       "sharding": f"frame index mod {world}, full scene + BVH replica per GPU, fp32 film all-reduce per step" if world > 1 else "single GPU",
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak" if n_pshards == 1 else "mixed (pixel shards split the image, sample shards add frames)", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD.format(w=WIDTH, h=HEIGHT), "max_depth": MAX_DEPTH, "frames_per_step_per_gpu": fps, "triangles": int(scene.info.n_triangles),
+                       "sharding": (f"{n_pshards} pixel shard(s) (interleaved rows) x {n_sshards} sample shard(s) (frame index mod {n_sshards}), full scene + BVH replica per GPU, fp32 film all-reduce per step"
+                                    if world > 1 else "single GPU"), "width": WIDTH, "height": HEIGHT,
                        "l2": "256 MB flush before the timed region; per-step wavefront state (~2 GB) exceeds the 126 MB L2, the 15 MB BVH stays L2-resident by design"},
             "spp_per_s": total_frames / dt,
             "rays_per_path": rays / (total_frames * WIDTH * HEIGHT),

@@ -91,6 +91,15 @@ int lmb_build_accel(lmb_ctx* ctx);
  * `frames_in_flight` = how many frames (samples per pixel) one wavefront batch carries; 0 picks a default. */
 int lmb_init(lmb_ctx* ctx, uint32_t width, uint32_t height, uint32_t frames_in_flight);
 
+/* Pixel sharding (secondary axis; BASELINE config 4 "tile + sample sharding"): this context renders only the
+ * image rows row_first, row_first + row_stride, ... (full-width tiles one row high, interleaved over the shards, so every
+ * shard sees the same mix of sky, walls and floor). Call BEFORE lmb_init: the wavefront state is sized for the shard's
+ * pixels (calling it afterwards with different values drops film + wavefront; run lmb_init again). The film keeps the full
+ * width x height; rows of other shards are never touched, so an LMB_FILM_SUM film of the shards adds up to the whole image
+ * with one all-reduce. RNG seeds stay (x, y, frame, 0) of the FULL image (path.rgen:23): a sharded render is bit-identical
+ * to the same rows of an unsharded one. Default (0, 1) = every row. Combine with frame_stride for tile x sample sharding. */
+int lmb_set_pixel_shard(lmb_ctx* ctx, uint32_t row_first, uint32_t row_stride);
+
 /* Renders frames first_frame, first_frame + frame_stride, ... (n_frames of them) and updates the film.
  * pc->frame_num is ignored; RNG seed of a sample is (x, y, frame, 0) exactly as path.rgen:23. Synchronous. */
 int lmb_render(lmb_ctx* ctx, const lmb_pc_path* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames,

@@ -190,11 +190,28 @@ int lmb_init(lmb_ctx* ctx, uint32_t width, uint32_t height, uint32_t frames_in_f
 	ctx->film = nullptr;
 	free_post(ctx);
 	ctx->width = width, ctx->height = height;
+	if (shard_rows(ctx) == 0) return set_error(ctx, LMB_ERR_INVALID, "lmb_init: the pixel shard owns no row of this image");
 	LMB_CUDA(ctx, cudaMalloc((void**)&ctx->film, (size_t)width * height * 16));
 	LMB_CUDA(ctx, cudaMemsetAsync(ctx->film, 0, (size_t)width * height * 16, ctx->stream));
 	const int rc = wavefront_alloc(ctx, frames_in_flight);
 	if (rc) return rc;
 	return lmb_reset_stats(ctx);
+}
+
+int lmb_set_pixel_shard(lmb_ctx* ctx, uint32_t row_first, uint32_t row_stride) {
+	if (!ctx) return LMB_ERR_INVALID;
+	if (row_stride == 0 || row_first >= row_stride) return set_error(ctx, LMB_ERR_INVALID, "lmb_set_pixel_shard: need row_first < row_stride, row_stride >= 1");
+	if (ctx->film && (row_first != ctx->row_first || row_stride != ctx->row_stride)) {
+		// the wavefront state is sized by the shard: drop it, the caller runs lmb_init again
+		cudaSetDevice(ctx->device);
+		cudaStreamSynchronize(ctx->stream);
+		wavefront_free(ctx);
+		cudaFree(ctx->film);
+		ctx->film = nullptr;
+		free_post(ctx);
+	}
+	ctx->row_first = row_first, ctx->row_stride = row_stride;
+	return LMB_OK;
 }
 
 int lmb_render(lmb_ctx* ctx, const lmb_pc_path* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames, uint32_t frame_stride,

@@ -116,6 +116,7 @@ struct lmb_ctx {
 	bool use_bvh2 = false;  // LMB_TRAVERSAL=bvh2: walk the binary LBVH instead of the 8-wide BVH (A/B measurements)
 	// film / wavefront
 	uint32_t width = 0, height = 0;
+	uint32_t row_first = 0, row_stride = 1;  // pixel shard: this context renders image rows row_first + k * row_stride
 	float4* film = nullptr;
 	lmb::Wavefront wf;
 	// post steps (post.cu)
@@ -139,6 +140,7 @@ void free_wide_bvh(lmb_ctx* ctx);
 int build_ploc(lmb_ctx* ctx);
 void free_ploc(lmb_ctx* ctx);
 int wavefront_alloc(lmb_ctx* ctx, uint32_t frames_in_flight);
+uint32_t shard_rows(const lmb_ctx* ctx);
 void wavefront_free(lmb_ctx* ctx);
 int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& ubo, uint32_t first_frame, uint32_t n_frames, uint32_t stride,
 					 int film_mode);

@@ -50,8 +50,8 @@ __device__ __forceinline__ void trace_persistent(const BvhView& bvh, Source& src
 					if (i < count) {
 						V3 o, d;
 						float tmax;
-						src.load(i, o, d, tmin, tmax, any);
-						item = i;
+						src.load(i, o, d, tmin, tmax, item);  // item = the source's tag of the ray
+						any = src.is_any(item);
 						r = ray_prepare(o, d);
 						h = Hit{tmax, 0.0f, 0.0f, 0xFFFFFFFFu};
 						sp = 0;
@@ -110,7 +110,7 @@ __device__ __forceinline__ void trace_persistent(const BvhView& bvh, Source& src
 				cur = (accepted && any) ? LMB_SENTINEL : (sp > 0 ? s_stack[--sp][tid] : LMB_SENTINEL);
 			}
 			if (has && cur == LMB_SENTINEL) {
-				src.store(item, h, any);
+				src.store(item, h);
 				has = false;
 			}
 			const int busy = __popc(__ballot_sync(0xFFFFFFFFu, has));

@@ -91,7 +91,7 @@ struct TraceSmem {
 	float4 rq_a[LMB_TRACE_THREADS];   // o.xyz, tmin
 	float4 rq_b[LMB_TRACE_THREADS];   // Sx, Sy, Sz, k (bits)
 	float4 rq_c[LMB_TRACE_THREADS];   // 1/d.xyz, tmax
-	uint32_t rq_i[LMB_TRACE_THREADS]; // queue index | any-hit << 31
+	uint32_t rq_i[LMB_TRACE_THREADS]; // the source's tag of the ray
 };
 
 template <typename Source>
@@ -139,13 +139,13 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 				if ((uint32_t)lane < rq_count) {
 					V3 o, d;
 					float tmin_, tmax_;
-					bool any_;
-					src.load(base + lane, o, d, tmin_, tmax_, any_);
+					uint32_t tag_;  // what the source needs to store the result (the queue ENTRY, not its index: no reload at the end)
+					src.load(base + lane, o, d, tmin_, tmax_, tag_);
 					const RayPre r = ray_prepare(o, d);
 					sm.rq_a[tid] = make_float4(r.o.x, r.o.y, r.o.z, tmin_);
 					sm.rq_b[tid] = make_float4(r.Sx, r.Sy, r.Sz, __uint_as_float((uint32_t)r.kx | ((uint32_t)r.ky << 2) | ((uint32_t)r.kz << 4)));
 					sm.rq_c[tid] = make_float4(r.inv.x, r.inv.y, r.inv.z, tmax_);
-					sm.rq_i[tid] = (base + lane) | (any_ ? 0x80000000u : 0u);
+					sm.rq_i[tid] = tag_;
 				}
 				__syncwarp();
 				if (rq_count == 0u) break;
@@ -295,7 +295,7 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 					ng = sp < LMB_WSTACK_SM ? sm.stack[sp][tid] : l_stack[sp - LMB_WSTACK_SM];
 				} else {
 					if (!any && h.prim != 0xFFFFFFFFu) h.b1 = h.b1 / det, h.b2 = h.b2 / det;
-					src.store(item, h, any);
+					src.store(item, h);
 					has = false;
 				}
 			}

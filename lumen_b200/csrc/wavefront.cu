@@ -40,7 +40,8 @@ constexpr float T_MAX = 10000.0f;  // path.rgen:20
 struct RenderParams {
 	M4 inv_view, inv_proj;
 	V3 sky_col;
-	uint32_t width, height, n_pix;
+	uint32_t width, height, n_pix;       // n_pix = pixels THIS context renders = width * (rows of its shard)
+	uint32_t row_first, row_stride;      // pixel shard (lmb_set_pixel_shard): local row r is image row row_first + r * row_stride
 	uint32_t first_frame, frame_stride;  // frame of batch slot fb = first_frame + fb * frame_stride
 	uint32_t n_active;                    // live slots this batch = n_batch_frames * n_pix
 	int32_t num_lights, max_depth, light_triangle_count;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(256) k_raygen(RenderParams rp, PathPlanes pl, 
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_CLOSEST], (unsigned long long)rp.n_active);
 	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < rp.n_active; slot += gridDim.x * blockDim.x) {
 		const uint32_t fb = slot / rp.n_pix, pix = slot - fb * rp.n_pix;
-		const uint32_t px = pix % rp.width, py = pix / rp.width;
+		const uint32_t px = pix % rp.width, py = rp.row_first + (pix / rp.width) * rp.row_stride;
 		Rng seed{px, py, rp.first_frame + fb * rp.frame_stride, 0u};
 		const float j0 = rand1(seed);
 		const float j1 = rand1(seed);
@@ -138,20 +139,23 @@ struct WavefrontSource {
 	float4* __restrict__ probe_hit;
 	uint32_t* __restrict__ shadow_occ;
 	uint32_t n_slots;
-	__device__ __forceinline__ void load(uint32_t i, V3& o, V3& d, float& tmin, float& tmax, bool& any) const {
-		const uint32_t e = queue[i], type = e >> 30, idx = e & IDX_MASK;
+	// the tag of a ray is its queue entry (index | type << 30)
+	__device__ __forceinline__ bool is_any(uint32_t e) const { return (e >> 30) == RAY_SHADOW; }
+	__device__ __forceinline__ void load(uint32_t i, V3& o, V3& d, float& tmin, float& tmax, uint32_t& e) const {
+		e = queue[i];
+		const uint32_t type = e >> 30, idx = e & IDX_MASK;
 		if (type == RAY_CONTINUE) {
 			const float4 o4 = ray_o[idx], d4 = ray_d[idx];
-			o = xyz(o4), d = xyz(d4), tmin = o4.w, tmax = d4.w, any = false;
+			o = xyz(o4), d = xyz(d4), tmin = o4.w, tmax = d4.w;
 		} else if (type == RAY_SHADOW) {  // pt_commons.glsl:21-22: tmin 0, tmax = wi_len - EPS, terminate on first hit
 			const float4 p4 = nee[NEE_P * (size_t)n_slots + idx];
-			o = xyz(p4), d = xyz(nee[NEE_WI * (size_t)n_slots + idx]), tmin = 0.0f, tmax = p4.w, any = true;
+			o = xyz(p4), d = xyz(nee[NEE_WI * (size_t)n_slots + idx]), tmin = 0.0f, tmax = p4.w;
 		} else {  // pt_commons.glsl:32
-			o = xyz(nee[NEE_P * (size_t)n_slots + idx]), d = xyz(nee[NEE_PROBE_WI * (size_t)n_slots + idx]), tmin = T_MIN, tmax = T_MAX, any = false;
+			o = xyz(nee[NEE_P * (size_t)n_slots + idx]), d = xyz(nee[NEE_PROBE_WI * (size_t)n_slots + idx]), tmin = T_MIN, tmax = T_MAX;
 		}
 	}
-	__device__ __forceinline__ void store(uint32_t i, const Hit& h, bool) const {
-		const uint32_t e = queue[i], type = e >> 30, idx = e & IDX_MASK;
+	__device__ __forceinline__ void store(uint32_t e, const Hit& h) const {
+		const uint32_t type = e >> 30, idx = e & IDX_MASK;
 		if (type == RAY_SHADOW)
 			shadow_occ[idx] = h.prim != 0xFFFFFFFFu;
 		else
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(128, LAST ? 8 : LMB_SHADE_MIN_BLOCKS) k_shade(
 		}
 		if (LAST) continue;
 		const uint32_t fb = slot / rp.n_pix, pix = slot - fb * rp.n_pix;
-		Rng seed{pix % rp.width, pix / rp.width, rp.first_frame + fb * rp.frame_stride, rng_w};
+		Rng seed{pix % rp.width, rp.row_first + (pix / rp.width) * rp.row_stride, rp.first_frame + fb * rp.frame_stride, rng_w};
 		// ---- stage 2: next-event estimation (path.rgen:75-80, pt_commons.glsl:3-20, 28-30). The NEE record goes straight to
 		// its position in the NEE list (one atomic per warp, its latency hidden behind the light sample)
 		const uint32_t b_sh = __ballot_sync(0xFFFFFFFFu, want_nee);
@@ -493,7 +497,8 @@ __global__ void __launch_bounds__(256) k_film(RenderParams rp, uint32_t n_batch_
 											   float4* __restrict__ film, unsigned long long* stats) {
 	uint32_t nan_count = 0;
 	for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < rp.n_pix; pix += gridDim.x * blockDim.x) {
-		float4 acc = film[pix];
+		const uint32_t gpix = (rp.row_first + (pix / rp.width) * rp.row_stride) * rp.width + pix % rp.width;  // position in the full image
+		float4 acc = film[gpix];
 		for (uint32_t fb = 0; fb < n_batch_frames; fb++) {
 			const V3 col = xyz(colb[(size_t)fb * rp.n_pix + pix]);
 			const float lum = luminance(col);
@@ -514,7 +519,7 @@ __global__ void __launch_bounds__(256) k_film(RenderParams rp, uint32_t n_batch_
 				acc = make_float4(acc.x + col.x, acc.y + col.y, acc.z + col.z, acc.w + 1.0f);
 			}
 		}
-		film[pix] = acc;
+		film[gpix] = acc;
 	}
 	flush_stats(stats, ST_NAN, nan_count);
 }
@@ -532,11 +537,12 @@ struct ArraySource {
 	float4* __restrict__ hits;
 	uint8_t* __restrict__ occ;
 	bool any_hit;
-	__device__ __forceinline__ void load(uint32_t i, V3& o, V3& d, float& tmin, float& tmax, bool& any) const {
+	__device__ __forceinline__ bool is_any(uint32_t) const { return any_hit; }
+	__device__ __forceinline__ void load(uint32_t i, V3& o, V3& d, float& tmin, float& tmax, uint32_t& tag) const {
 		const float4 o4 = rays[2 * (size_t)i], d4 = rays[2 * (size_t)i + 1];
-		o = xyz(o4), d = xyz(d4), tmin = o4.w, tmax = d4.w, any = any_hit;
+		o = xyz(o4), d = xyz(d4), tmin = o4.w, tmax = d4.w, tag = i;
 	}
-	__device__ __forceinline__ void store(uint32_t i, const Hit& h, bool) const {
+	__device__ __forceinline__ void store(uint32_t i, const Hit& h) const {
 		if (any_hit)
 			occ[i] = h.prim != 0xFFFFFFFFu;
 		else
@@ -564,10 +570,15 @@ WideBvhView wide_view_of(const lmb_ctx* ctx) {
 
 }  // namespace
 
+// rows of the image this context renders: row_first, row_first + row_stride, ... below height
+uint32_t shard_rows(const lmb_ctx* ctx) {
+	return ctx->row_first < ctx->height ? (ctx->height - ctx->row_first + ctx->row_stride - 1) / ctx->row_stride : 0u;
+}
+
 int wavefront_alloc(lmb_ctx* ctx, uint32_t frames_in_flight) {
 	wavefront_free(ctx);
 	Wavefront& wf = ctx->wf;
-	const uint64_t n_pix = (uint64_t)ctx->width * ctx->height;
+	const uint64_t n_pix = (uint64_t)ctx->width * shard_rows(ctx);
 	if (frames_in_flight == 0) {
 		// default: about 8 M path slots in flight (enough to fill 148 SMs many times over), at most 64 frames
 		frames_in_flight = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (8ull << 20) / std::max<uint64_t>(n_pix, 1)));
@@ -626,7 +637,8 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 	rp.inv_view = load(ubo.inv_view);
 	rp.inv_proj = load(ubo.inv_projection);
 	rp.sky_col = V3{pc.sky_col[0], pc.sky_col[1], pc.sky_col[2]};
-	rp.width = ctx->width, rp.height = ctx->height, rp.n_pix = ctx->width * ctx->height;
+	rp.width = ctx->width, rp.height = ctx->height, rp.n_pix = ctx->width * shard_rows(ctx);
+	rp.row_first = ctx->row_first, rp.row_stride = ctx->row_stride;
 	rp.frame_stride = stride;
 	rp.num_lights = pc.num_lights, rp.max_depth = pc.max_depth, rp.light_triangle_count = pc.light_triangle_count;
 	rp.dir_light_idx = pc.dir_light_idx, rp.direct_lighting = pc.direct_lighting;

@@ -50,6 +50,7 @@ def lib():
         L.lmb_init.argtypes = [vp, u32, u32, u32]
         L.lmb_render.argtypes = [vp, vp, vp, u32, u32, u32, i32]
         L.lmb_clear_film.argtypes = [vp]
+        L.lmb_set_pixel_shard.argtypes = [vp, C.c_uint32, C.c_uint32]
         L.lmb_resolve.argtypes = [vp]
         L.lmb_download.argtypes = [vp, vp]
         L.lmb_upload_film.argtypes = [vp, vp]
@@ -82,7 +83,7 @@ def lib():
     return _LIB
 
 
-EXPORTS = ["lmb_create", "lmb_destroy", "lmb_last_error", "lmb_upload_scene", "lmb_build_accel", "lmb_init", "lmb_render", "lmb_clear_film",
+EXPORTS = ["lmb_create", "lmb_destroy", "lmb_last_error", "lmb_upload_scene", "lmb_build_accel", "lmb_init", "lmb_render", "lmb_set_pixel_shard", "lmb_clear_film",
            "lmb_resolve", "lmb_download", "lmb_upload_film", "lmb_film_device_ptr", "lmb_stream", "lmb_set_profile_stages", "lmb_get_stats",
            "lmb_reset_stats", "lmb_trace_closest", "lmb_trace_any", "lmb_trace_closest_device", "lmb_accel_num_tris", "lmb_accel_download",
            "lmb_download_async", "lmb_sync", "lmb_download_half_bgr", "lmb_set_reference_image", "lmb_rmse"]
@@ -141,6 +142,10 @@ class Device:
     def init(self, width, height, frames_in_flight=0):
         self.width, self.height = int(width), int(height)
         self._ck(lib().lmb_init(self._h, self.width, self.height, int(frames_in_flight)), "lmb_init")
+
+    def set_pixel_shard(self, row_first, row_stride):
+        """This context renders only image rows row_first + k * row_stride. Call before init()."""
+        self._ck(lib().lmb_set_pixel_shard(self._h, int(row_first), int(row_stride)), "lmb_set_pixel_shard")
 
     def render(self, pc, ubo, first_frame, n_frames, frame_stride=1, film_mode=FILM_RUNNING_MEAN):
         self._ck(lib().lmb_render(self._h, C.addressof(pc), C.addressof(ubo), int(first_frame), int(n_frames), int(frame_stride), int(film_mode)),

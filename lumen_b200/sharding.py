@@ -5,6 +5,11 @@ per-pixel, so rank r of N renders frames {first + r + k*N}. Each rank holds a fu
 un-normalised SUM with a per-pixel valid-sample count in alpha (the reference skips NaN samples, path.rgen:102-104). The
 only exchange step is one all-reduce (sum, fp32) of the W*H*4 film, after which every rank divides rgb by the count.
 No other data-path collective exists.
+
+Secondary axis, pixel tiles (BASELINE config 4, "tile + sample sharding"): the N ranks form a grid of `pixel_shards` x
+`sample_shards`; pixel shard p renders image rows p, p + P, p + 2P, ... (lmb_set_pixel_shard: full-width tiles one row high,
+interleaved so every shard sees the same mix of content) and, inside it, sample shard s takes frames first + s + k*S. Every
+rank still writes into a full-size sum film whose foreign rows stay zero, so the exchange step is the same single all-reduce.
 """
 import numpy as np
 
@@ -17,6 +22,20 @@ def frames_of_rank(first_frame, frames_per_rank, rank, world):
 def shard_frame_list(first_frame, frames_per_rank, rank, world):
     f0, stride, n = frames_of_rank(first_frame, frames_per_rank, rank, world)
     return [f0 + k * stride for k in range(n)]
+
+
+def grid_of_rank(rank, world, pixel_shards):
+    """(pixel shard p, sample shard s, P, S) of `rank` in a P x S grid, P * S == world. Ranks that share a pixel shard are
+    consecutive, so they differ only in the frames they render."""
+    if pixel_shards < 1 or world % pixel_shards:
+        raise ValueError(f"pixel_shards={pixel_shards} does not divide world={world}")
+    sample_shards = world // pixel_shards
+    return rank // sample_shards, rank % sample_shards, pixel_shards, sample_shards
+
+
+def rows_of_shard(height, row_first, row_stride):
+    """Image rows a pixel shard owns."""
+    return np.arange(row_first, height, row_stride)
 
 
 def accumulate_sum(film_rgba, sample_rgb):

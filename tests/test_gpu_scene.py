@@ -162,6 +162,51 @@ def test_sum_film_and_resolve_match_mean(device, loaded):
     assert np.allclose(merged[..., :3][full], mean[..., :3][full], rtol=2e-5, atol=1e-6)
 
 
+def test_pixel_shard_rows_are_bit_identical_and_sum_to_the_image(device, loaded):
+    """lmb_set_pixel_shard (SURVEY.md 8e secondary axis, BASELINE config 4): a shard renders exactly its interleaved rows,
+    bit-identical to the same rows of the unsharded render (seeds are those of the full image), leaves the other rows
+    untouched, traces exactly its share of the rays, and 3 pixel shards x 2 sample shards add up to the whole image."""
+    sc, orc = loaded("materials", 96, 50)  # 50 rows over 3 shards: 17 + 17 + 16
+    pc, ubo = sc.make_pc(8, True), sc.make_ubo()
+    try:
+        device.set_pixel_shard(0, 1)
+        device.init(96, 50, 2)
+        device.reset_stats()
+        device.render(pc, ubo, 0, 4)
+        full, full_rays = device.download(), device.stats().rays
+        device.clear_film()
+        device.render(pc, ubo, 0, 4, 1, integrator.FILM_SUM)
+        full_sum = device.download()
+        total, rays = np.zeros_like(full), 0
+        for p in range(3):
+            device.set_pixel_shard(p, 3)
+            device.init(96, 50, 3)  # a batch size that does not divide the frame count
+            device.reset_stats()
+            device.render(pc, ubo, 0, 4)
+            part = device.download()
+            rays += device.stats().rays
+            own = np.zeros(50, bool)
+            own[p::3] = True
+            assert part[own].tobytes() == full[own].tobytes()
+            assert not part[~own].any()
+            for s in range(2):  # sample shards inside the pixel shard: frames {0, 2} and {1, 3}
+                device.clear_film()
+                device.render(pc, ubo, s, 2, 2, integrator.FILM_SUM)
+                shard = device.download()
+                assert not shard[~own].any()
+                total += shard
+        assert rays == full_rays
+        assert (total[..., 3] == full_sum[..., 3]).all()
+        assert np.allclose(total[..., :3], full_sum[..., :3], rtol=2e-6, atol=1e-7)
+        with pytest.raises(RuntimeError):
+            device.set_pixel_shard(3, 3)
+        device.set_pixel_shard(60, 64)  # owns no row of a 50-row image
+        with pytest.raises(RuntimeError):
+            device.init(96, 50, 1)
+    finally:
+        device.set_pixel_shard(0, 1)
+
+
 def test_render_without_accel_fails_cleanly(device):
     sc = host.Scene(scene_path("cornell"), 32, 32)
     dev2 = integrator.Device(0)
