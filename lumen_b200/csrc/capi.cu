@@ -335,6 +335,10 @@ int lmb_get_stats(lmb_ctx* ctx, lmb_stats* out) {
 		LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 		ctx->stats.rays_closest = h[ST_CLOSEST], ctx->stats.rays_shadow = h[ST_SHADOW], ctx->stats.rays_probe = h[ST_PROBE];
 		ctx->stats.nodes_visited = h[ST_NODES], ctx->stats.tris_tested = h[ST_TRIS], ctx->stats.nan_samples = h[ST_NAN];
+#ifdef LMB_TRACE_PROFILE
+		fprintf(stderr, "k_trace profile: iters %llu node_trips %llu node_lanes %llu has_lanes %llu parked_lanes %llu rounds %llu pairs %llu refills %llu\n",
+				h[ST_P_ITERS], h[ST_P_NODE_TRIPS], h[ST_P_NODE_LANES], h[ST_P_HAS_LANES], h[ST_P_PARKED_LANES], h[ST_P_ROUNDS], h[ST_P_PAIRS], h[ST_P_REFILLS]);
+#endif
 	}
 	*out = ctx->stats;
 	return LMB_OK;

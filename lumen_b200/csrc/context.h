@@ -94,7 +94,13 @@ struct Wavefront {
 	uint32_t frames_in_flight = 0;
 };
 
-enum StatSlot { ST_CLOSEST = 0, ST_SHADOW, ST_PROBE, ST_NODES, ST_TRIS, ST_NAN, ST_COUNT };
+enum StatSlot {
+	ST_CLOSEST = 0, ST_SHADOW, ST_PROBE, ST_NODES, ST_TRIS, ST_NAN,
+	// k_trace scheduling counters, filled only by a -DLMB_TRACE_PROFILE build (tools/gpu_variants.sh): warp trips of the inner
+	// loop, trips with a node step, lanes stepping, lanes owning a ray, lanes parked on triangles, rounds, pairs, refills
+	ST_P_ITERS, ST_P_NODE_TRIPS, ST_P_NODE_LANES, ST_P_HAS_LANES, ST_P_PARKED_LANES, ST_P_ROUNDS, ST_P_PAIRS, ST_P_REFILLS,
+	ST_COUNT
+};
 
 }  // namespace lmb
 

@@ -34,6 +34,10 @@ LMB_D float guard_inv(float d) {
 	return 1.0f / dk;
 }
 
+// Part of the hit definition (oracle/lbvh_cpu.h ray_finite): a ray with a NaN or infinite component in its origin or direction
+// hits nothing. Slab and edge tests on NaN would otherwise make the result depend on which nodes a walk happens to visit.
+LMB_D bool ray_finite(const V3& o, const V3& d) { return (o.x * 0.0f + o.y * 0.0f + o.z * 0.0f + d.x * 0.0f + d.y * 0.0f + d.z * 0.0f) == 0.0f; }
+
 LMB_D RayPre ray_prepare(const V3& o, const V3& d) {
 	RayPre r;
 	r.o = o;
@@ -138,7 +142,7 @@ struct Hit {
 template <bool ANY>
 LMB_D Hit trace_ray(const BvhView& bvh, const V3& o, const V3& d, float tmin, float tmax, uint32_t& nodes_visited, uint32_t& tris_tested) {
 	Hit h{tmax, 0.0f, 0.0f, 0xFFFFFFFFu};
-	if (bvh.n_tris == 0) return h;
+	if (bvh.n_tris == 0 || !ray_finite(o, d)) return h;
 	const RayPre r = ray_prepare(o, d);
 	auto leaf_test = [&](int leafpos) -> bool {
 		const float4 a = __ldg(&bvh.tris[3 * leafpos + 0]);

@@ -55,7 +55,7 @@ __device__ __forceinline__ void trace_persistent(const BvhView& bvh, Source& src
 						r = ray_prepare(o, d);
 						h = Hit{tmax, 0.0f, 0.0f, 0xFFFFFFFFu};
 						sp = 0;
-						cur = bvh.n_tris == 0 ? LMB_SENTINEL : (bvh.n_tris == 1 ? ~0 : 0);
+						cur = (bvh.n_tris == 0 || !ray_finite(o, d)) ? LMB_SENTINEL : (bvh.n_tris == 1 ? ~0 : 0);
 						has = true;
 						if (any) n_any++;
 						else n_closest++;

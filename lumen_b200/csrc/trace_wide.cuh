@@ -120,6 +120,9 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 	uint32_t oct_inv4 = 0;
 	int sp = 0;
 	uint32_t n_nodes = 0, n_tris = 0, n_closest = 0, n_any = 0;
+#ifdef LMB_TRACE_PROFILE
+	uint32_t p_iters = 0, p_node_trips = 0, p_node_lanes = 0, p_has = 0, p_parked = 0, p_rounds = 0, p_pairs = 0, p_refills = 0;  // lane 0 only
+#endif
 
 	for (;;) {
 		// ---- refill. Rays come out of the global queue 32 at a time: the whole warp fetches and prepares them (coalesced
@@ -132,6 +135,9 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 			if (rq_head == rq_count) {
 				if (exhausted) break;
 				uint32_t base = 0;
+#ifdef LMB_TRACE_PROFILE
+				p_refills++;
+#endif
 				if (lane == 0) base = atomicAdd(cursor, 32u);
 				base = __shfl_sync(0xFFFFFFFFu, base, 0);
 				rq_head = 0, rq_count = base < count ? min(32u, count - base) : 0u;
@@ -143,7 +149,8 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 					src.load(base + lane, o, d, tmin_, tmax_, tag_);
 					const RayPre r = ray_prepare(o, d);
 					sm.rq_a[tid] = make_float4(r.o.x, r.o.y, r.o.z, tmin_);
-					sm.rq_b[tid] = make_float4(r.Sx, r.Sy, r.Sz, __uint_as_float((uint32_t)r.kx | ((uint32_t)r.ky << 2) | ((uint32_t)r.kz << 4)));
+					// bit 6 of the axis word: non-finite ray, hits nothing by definition (ray_finite, trace.cuh)
+					sm.rq_b[tid] = make_float4(r.Sx, r.Sy, r.Sz, __uint_as_float((uint32_t)r.kx | ((uint32_t)r.ky << 2) | ((uint32_t)r.kz << 4) | (ray_finite(o, d) ? 0u : 64u)));
 					sm.rq_c[tid] = make_float4(r.inv.x, r.inv.y, r.inv.z, tmax_);
 					sm.rq_i[tid] = tag_;
 				}
@@ -156,13 +163,13 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 				const int q = wbase + (int)(rq_head + rank);
 				const float4 qa = sm.rq_a[q], qb = sm.rq_b[q], qc = sm.rq_c[q];
 				const uint32_t qi = sm.rq_i[q];
-				item = qi & 0x7FFFFFFFu, any = (qi >> 31) != 0u;
+				item = qi, any = src.is_any(qi);  // the source's tag travels with the ray
 				ro = v3(qa.x, qa.y, qa.z), tmin = qa.w, rinv = v3(qc.x, qc.y, qc.z);
 				sm.ray_a[tid] = qa, sm.ray_b[tid] = qb;
 				h = Hit{qc.w, 0.0f, 0.0f, 0xFFFFFFFFu};
 				sp = 0;
 				oct_inv4 = ((rinv.x < 0.0f ? 0u : 4u) | (rinv.y < 0.0f ? 0u : 2u) | (rinv.z < 0.0f ? 0u : 1u)) * 0x01010101u;
-				ng = make_uint2(0u, bvh.n_tris ? 0x80000000u : 0u);
+				ng = make_uint2(0u, (bvh.n_tris && !(__float_as_uint(qb.w) & 64u)) ? 0x80000000u : 0u);
 				tg = make_uint2(0u, 0u);
 				has = true;
 				if (any) n_any++;
@@ -174,6 +181,12 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 		if (__ballot_sync(0xFFFFFFFFu, has) == 0) break;
 
 		for (;;) {
+#ifdef LMB_TRACE_PROFILE
+			{
+				const uint32_t st = __ballot_sync(0xFFFFFFFFu, has && tg.y == 0u && ng.y > 0x00FFFFFFu);
+				p_iters++, p_node_trips += st != 0u, p_node_lanes += __popc(st), p_has += __popc(__ballot_sync(0xFFFFFFFFu, has));
+			}
+#endif
 			// ---- one node step
 			if (has && tg.y == 0u && ng.y > 0x00FFFFFFu) {
 				const uint32_t hits = ng.y;
@@ -186,7 +199,9 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 					else l_stack[sp - LMB_WSTACK_SM] = ng;
 					sp++;
 				}
+#ifndef LMB_TRACE_NO_STATS
 				n_nodes++;
+#endif
 				const float4* np = bvh.nodes + 5 * (size_t)node;
 				const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
 				const uint32_t ew = __float_as_uint(n0.w);  // ex | ey << 8 | ez << 16
@@ -244,7 +259,12 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 			// A round is worth its fixed cost only with enough pairs: lanes holding triangles sit out node steps until
 			// LMB_TRI_ROUND_LANES lanes hold some, or nobody else can step.
 			uint32_t tri_lanes = __ballot_sync(0xFFFFFFFFu, tg.y != 0u);
-			if ((uint32_t)__popc(tri_lanes) < bvh.tri_round_lanes && __ballot_sync(0xFFFFFFFFu, has && tg.y == 0u && ng.y > 0x00FFFFFFu) != 0u) tri_lanes = 0u;
+			if ((uint32_t)__popc(tri_lanes) < bvh.tri_round_lanes && __ballot_sync(0xFFFFFFFFu, has && tg.y == 0u && ng.y > 0x00FFFFFFu) != 0u) {
+#ifdef LMB_TRACE_PROFILE
+				p_parked += __popc(tri_lanes);
+#endif
+				tri_lanes = 0u;
+			}
 			while (tri_lanes) {
 				const uint32_t cnt = (uint32_t)__popc(tg.y);
 				uint32_t incl = cnt;
@@ -255,6 +275,9 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 				}
 				const uint32_t excl = incl - cnt;
 				const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+#ifdef LMB_TRACE_PROFILE
+				p_rounds++, p_pairs += min(total, 32u);
+#endif
 				uint32_t wrote = 0;
 				while (tg.y != 0u && excl + wrote < 32u) {
 					const int bit = __ffs((int)tg.y) - 1;
@@ -270,7 +293,9 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 					const float4* tp = bvh.tris + 3 * (size_t)(pr & 0x07FFFFFFu);
 					const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
 					const TriRay tr{v3(ra.x, ra.y, ra.z), ra.w, rb.x, rb.y, rb.z, __float_as_uint(rb.w)};
+#ifndef LMB_TRACE_NO_STATS
 					n_tris++;
+#endif
 					float t, V = 0.0f, W = 0.0f, det = 1.0f;
 					if (!(tri_test(tr, a, b, c, t, V, W, det) && t > tr.tmin)) t = -1.0f;
 					sm.res[wbase + lane] = make_float4(t, V, W, det);
@@ -310,6 +335,14 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 		n_closest += __shfl_xor_sync(0xFFFFFFFFu, n_closest, o);
 		n_any += __shfl_xor_sync(0xFFFFFFFFu, n_any, o);
 	}
+#ifdef LMB_TRACE_PROFILE
+	if (lane == 0 && stats) {
+		atomicAdd(&stats[ST_P_ITERS], (unsigned long long)p_iters), atomicAdd(&stats[ST_P_NODE_TRIPS], (unsigned long long)p_node_trips);
+		atomicAdd(&stats[ST_P_NODE_LANES], (unsigned long long)p_node_lanes), atomicAdd(&stats[ST_P_HAS_LANES], (unsigned long long)p_has);
+		atomicAdd(&stats[ST_P_PARKED_LANES], (unsigned long long)p_parked), atomicAdd(&stats[ST_P_ROUNDS], (unsigned long long)p_rounds);
+		atomicAdd(&stats[ST_P_PAIRS], (unsigned long long)p_pairs), atomicAdd(&stats[ST_P_REFILLS], (unsigned long long)p_refills);
+	}
+#endif
 	if (lane == 0 && stats) {
 		if (n_nodes) atomicAdd(&stats[ST_NODES], (unsigned long long)n_nodes);
 		if (n_tris) atomicAdd(&stats[ST_TRIS], (unsigned long long)n_tris);

@@ -36,7 +36,8 @@ def lib():
     """Loads the CUDA library; raises (never falls back) when it has not been built."""
     global _LIB
     if _LIB is None:
-        path = os.path.join(_HERE, "csrc", "liblumen_b200.so")
+        # LMB_LIB: another build of the same library (A/B runs of kernel variants, tools/gpu_variants.sh)
+        path = os.environ.get("LMB_LIB") or os.path.join(_HERE, "csrc", "liblumen_b200.so")
         if not os.path.exists(path):
             raise RuntimeError(f"{path} is missing: build it with `make -C lumen_b200/csrc` (nvcc, sm_100a). lumen_b200 has no CPU fallback.")
         L = C.CDLL(path)

@@ -185,6 +185,10 @@ struct RayPre {
 	vec3 inv;  // guarded reciprocal direction for slab tests
 };
 
+// Part of the hit definition: a ray with a NaN or infinite component in its origin or direction hits nothing (NaN in the slab and
+// edge tests would make the result depend on the nodes a particular walk visits; the Vulkan spec leaves such rays undefined).
+inline bool ray_finite(const vec3& o, const vec3& d) { return (o.x * 0.0f + o.y * 0.0f + o.z * 0.0f + d.x * 0.0f + d.y * 0.0f + d.z * 0.0f) == 0.0f; }
+
 inline RayPre ray_prepare(const vec3& o, const vec3& d) {
 	RayPre r;
 	r.o = o;
@@ -255,7 +259,7 @@ template <bool ANY>
 inline Hit trace(const Lbvh& b, const vec3& o, const vec3& d, float tmin, float tmax, TraceStats* st) {
 	Hit h{tmax, 0, 0, 0xFFFFFFFFu};
 	const uint32_t N = b.n_tris;
-	if (N == 0) return h;
+	if (N == 0 || !ray_finite(o, d)) return h;
 	const RayPre r = ray_prepare(o, d);
 	auto leaf_test = [&](uint32_t leafpos) -> bool {
 		const uint32_t p = b.leaf_prim[leafpos];

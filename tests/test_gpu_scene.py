@@ -81,6 +81,25 @@ def test_axis_aligned_and_degenerate_rays(device, loaded):
     assert gh["prim"][4000] == 0xFFFFFFFF and gh["prim"][4001] == 0xFFFFFFFF
 
 
+def test_non_finite_rays_hit_nothing(device, loaded, monkeypatch):
+    """Hit definition (oracle/lbvh_cpu.h ray_finite): a NaN / inf component anywhere in origin or direction is a miss, for the
+    wide walk, the binary walk and any-hit queries alike -- a partially NaN ray must not depend on the nodes a walk visits."""
+    sc, orc = loaded("cornell", 64, 64)
+    rng = np.random.default_rng(23)
+    n = 4096
+    rays = random_rays(rng, [-3, -1, -3], [3, 5, 3], n)
+    bad = np.array([np.nan, np.inf, -np.inf], np.float32)
+    cols = np.array([0, 1, 2, 4, 5, 6])
+    for i in range(0, n, 2):  # every other ray gets one non-finite component; its neighbours stay valid
+        rays[i, cols[rng.integers(0, 6)]] = bad[rng.integers(0, 3)]
+    gh, (ch, _) = device.trace_closest(rays), orc.trace_closest(rays)
+    assert (gh["prim"][0::2] == 0xFFFFFFFF).all() and (ch["prim"][0::2] == 0xFFFFFFFF).all()
+    assert (gh["prim"] == ch["prim"]).all() and bits_equal(gh["t"], ch["t"]).all()
+    assert (gh["prim"][1::2] != 0xFFFFFFFF).any()
+    assert (device.trace_any(rays) == orc.trace_any(rays)[0]).all()
+    assert not device.trace_any(rays)[0::2].any()
+
+
 def test_light_and_texture_sampling(device, loaded):
     rng = np.random.default_rng(23)
     for name in ("cornell", "caustics", "materials", "cornell_dir"):
