@@ -119,6 +119,23 @@ LMB_D bool tri_intersect_t(const RayPre& r, const float4& p0, const float4& p1, 
 	return true;
 }
 
+// Third part of the hit definition (oracle/lbvh_cpu.h tri_clamp_t, expression for expression): an accepted hit passes the slab
+// test of the triangle's exact bounding box and its t is clamped into [near, far * pad] of that box, so that no box test on
+// an enclosing box can cull a triangle that would beat the current best -- the closest hit does not depend on tree or order.
+LMB_D bool tri_clamp_t(const V3& o, const V3& inv, const float4& p0, const float4& p1, const float4& p2, float& t) {
+	const float lox = fminf(fminf(p0.x, p1.x), p2.x), hix = fmaxf(fmaxf(p0.x, p1.x), p2.x);
+	const float loy = fminf(fminf(p0.y, p1.y), p2.y), hiy = fmaxf(fmaxf(p0.y, p1.y), p2.y);
+	const float loz = fminf(fminf(p0.z, p1.z), p2.z), hiz = fmaxf(fmaxf(p0.z, p1.z), p2.z);
+	const float t0x = (lox - o.x) * inv.x, t1x = (hix - o.x) * inv.x;
+	const float t0y = (loy - o.y) * inv.y, t1y = (hiy - o.y) * inv.y;
+	const float t0z = (loz - o.z) * inv.z, t1z = (hiz - o.z) * inv.z;
+	const float n = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+	const float f = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z)) * 1.0000004f;
+	if (!(n <= f)) return false;
+	t = fminf(fmaxf(t, n), f);
+	return true;
+}
+
 LMB_D bool box_intersect(const RayPre& r, float lox, float loy, float loz, float hix, float hiy, float hiz, float tmin, float tmax, float& tnear) {
 	const float t0x = (lox - r.o.x) * r.inv.x, t1x = (hix - r.o.x) * r.inv.x;
 	const float t0y = (loy - r.o.y) * r.inv.y, t1y = (hiy - r.o.y) * r.inv.y;
@@ -151,6 +168,7 @@ LMB_D Hit trace_ray(const BvhView& bvh, const V3& o, const V3& d, float tmin, fl
 		tris_tested++;
 		float t, b1, b2;
 		if (!tri_intersect(r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, b1, b2)) return false;
+		if (!tri_clamp_t(r.o, r.inv, a, b, c, t)) return false;
 		if (!(t > tmin)) return false;
 		const uint32_t p = __float_as_uint(a.w);
 		if (t < h.t || (t == h.t && p < h.prim && h.prim != 0xFFFFFFFFu)) {

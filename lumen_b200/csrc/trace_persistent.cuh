@@ -100,7 +100,7 @@ __device__ __forceinline__ void trace_persistent(const BvhView& bvh, Source& src
 				n_tris++;
 				float t, b1, b2;
 				bool accepted = false;
-				if (tri_intersect(r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, b1, b2) && t > tmin) {
+				if (tri_intersect(r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, b1, b2) && tri_clamp_t(r.o, r.inv, a, b, c, t) && t > tmin) {
 					const uint32_t p = __float_as_uint(a.w);
 					if (t < h.t || (t == h.t && p < h.prim && h.prim != 0xFFFFFFFFu)) {
 						h.t = t, h.b1 = b1, h.b2 = b2, h.prim = p;

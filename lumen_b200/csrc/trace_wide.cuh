@@ -30,8 +30,8 @@ struct WideBvhView {
 #ifndef LMB_TRACE_THREADS
 #define LMB_TRACE_THREADS 128
 #endif
-#define LMB_WSTACK_SM 12
-#define LMB_WSTACK_LOCAL 52
+#define LMB_WSTACK_SM 11
+#define LMB_WSTACK_LOCAL 53
 #ifndef LMB_WIDE_REFILL_LANES
 #define LMB_WIDE_REFILL_LANES 28
 #endif
@@ -47,15 +47,24 @@ struct TriRay {
 	V3 o;
 	float tmin, Sx, Sy, Sz;
 	uint32_t k;  // kx | ky << 2 | kz << 4
+	V3 inv;      // guarded 1/d (tri_clamp_t)
 };
 
-// tri_intersect (trace.cuh) on a TriRay: same expressions, same order; returns t only, the caller divides V / det, W / det.
+// tri_intersect + tri_clamp_t (trace.cuh) on a TriRay: same expressions, same order; returns t only, the caller divides V / det,
+// W / det. The slab interval of the triangle's box is taken from the origin-relative vertices the edge test needs anyway:
+// min(a - o, b - o, c - o) == min(a, b, c) - o bit for bit (fp subtraction is monotone), so only (near, far) stay live.
 LMB_D bool tri_test(const TriRay& r, const float4& p0, const float4& p1, const float4& p2, float& t, float& V_out, float& W_out, float& det_out) {
 	const uint32_t kx = r.k & 3u, ky = (r.k >> 2) & 3u, kz = r.k >> 4;
 	const bool x0 = kx == 0, x1 = kx == 1, y0 = ky == 0, y1 = ky == 1, z0 = kz == 0, z1 = kz == 1;
 	const float Ax_ = p0.x - r.o.x, Ay_ = p0.y - r.o.y, Az_ = p0.z - r.o.z;
 	const float Bx_ = p1.x - r.o.x, By_ = p1.y - r.o.y, Bz_ = p1.z - r.o.z;
 	const float Cx_ = p2.x - r.o.x, Cy_ = p2.y - r.o.y, Cz_ = p2.z - r.o.z;
+	const float t0x = fminf(fminf(Ax_, Bx_), Cx_) * r.inv.x, t1x = fmaxf(fmaxf(Ax_, Bx_), Cx_) * r.inv.x;
+	const float t0y = fminf(fminf(Ay_, By_), Cy_) * r.inv.y, t1y = fmaxf(fmaxf(Ay_, By_), Cy_) * r.inv.y;
+	const float t0z = fminf(fminf(Az_, Bz_), Cz_) * r.inv.z, t1z = fmaxf(fmaxf(Az_, Bz_), Cz_) * r.inv.z;
+	const float box_n = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+	const float box_f = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z)) * 1.0000004f;
+	if (!(box_n <= box_f)) return false;
 	const float Akz = z0 ? Ax_ : (z1 ? Ay_ : Az_), Bkz = z0 ? Bx_ : (z1 ? By_ : Bz_), Ckz = z0 ? Cx_ : (z1 ? Cy_ : Cz_);
 	const float Akx = x0 ? Ax_ : (x1 ? Ay_ : Az_), Bkx = x0 ? Bx_ : (x1 ? By_ : Bz_), Ckx = x0 ? Cx_ : (x1 ? Cy_ : Cz_);
 	const float Aky = y0 ? Ax_ : (y1 ? Ay_ : Az_), Bky = y0 ? Bx_ : (y1 ? By_ : Bz_), Cky = y0 ? Cx_ : (y1 ? Cy_ : Cz_);
@@ -74,7 +83,7 @@ LMB_D bool tri_test(const TriRay& r, const float4& p0, const float4& p1, const f
 	const float det = U + V + W;
 	if (det == 0.0f) return false;
 	const float T = U * (r.Sz * Akz) + V * (r.Sz * Bkz) + W * (r.Sz * Ckz);
-	t = T / det;
+	t = fminf(fmaxf(T / det, box_n), box_f);
 	V_out = V, W_out = W, det_out = det;
 	return true;
 }
@@ -84,6 +93,7 @@ struct TraceSmem {
 	uint2 stack[LMB_WSTACK_SM][LMB_TRACE_THREADS];
 	float4 ray_a[LMB_TRACE_THREADS];  // o.xyz, tmin            } TriRay of the ray each lane owns, written once per ray
 	float4 ray_b[LMB_TRACE_THREADS];  // Sx, Sy, Sz, k (bits)   }
+	float4 ray_c[LMB_TRACE_THREADS];  // guarded 1/d.xyz (tri_clamp_t)
 	uint32_t pair[LMB_TRACE_THREADS]; // owner lane << 27 | triangle index: one triangle test of this round
 	float4 res[LMB_TRACE_THREADS];    // t (or -1), V, W, det
 	uint32_t res_prim[LMB_TRACE_THREADS];
@@ -165,7 +175,7 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 				const uint32_t qi = sm.rq_i[q];
 				item = qi, any = src.is_any(qi);  // the source's tag travels with the ray
 				ro = v3(qa.x, qa.y, qa.z), tmin = qa.w, rinv = v3(qc.x, qc.y, qc.z);
-				sm.ray_a[tid] = qa, sm.ray_b[tid] = qb;
+				sm.ray_a[tid] = qa, sm.ray_b[tid] = qb, sm.ray_c[tid] = qc;
 				h = Hit{qc.w, 0.0f, 0.0f, 0xFFFFFFFFu};
 				sp = 0;
 				oct_inv4 = ((rinv.x < 0.0f ? 0u : 4u) | (rinv.y < 0.0f ? 0u : 2u) | (rinv.z < 0.0f ? 0u : 1u)) * 0x01010101u;
@@ -292,7 +302,8 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 					const float4 ra = sm.ray_a[owner], rb = sm.ray_b[owner];
 					const float4* tp = bvh.tris + 3 * (size_t)(pr & 0x07FFFFFFu);
 					const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
-					const TriRay tr{v3(ra.x, ra.y, ra.z), ra.w, rb.x, rb.y, rb.z, __float_as_uint(rb.w)};
+					const float4 rc = sm.ray_c[owner];
+					const TriRay tr{v3(ra.x, ra.y, ra.z), ra.w, rb.x, rb.y, rb.z, __float_as_uint(rb.w), v3(rc.x, rc.y, rc.z)};
 #ifndef LMB_TRACE_NO_STATS
 					n_tris++;
 #endif

@@ -238,6 +238,26 @@ inline bool tri_intersect(const RayPre& r, const vec3& v0, const vec3& v1, const
 	return true;
 }
 
+// Third part of the hit definition. The watertight test decides WHETHER the ray hits the triangle; its t carries rounding error
+// of the order eps * (extent of the triangle along the ray), which can put t a few ulp outside the slab interval of the
+// triangle's own bounding box -- and then a walk that already holds a slightly larger t culls that box while another walk,
+// arriving in a different order, finds the triangle: the closest hit would depend on the tree. So an accepted hit must
+// also pass the slab test of the triangle's exact fp32 bounding box, and its t is clamped into [near, far * pad] of that
+// box, evaluated with box_intersect's own arithmetic. Every box that encloses the triangle then has near_B <= near_T <= t
+// and t <= far_T * pad <= far_B * pad (fp subtraction, multiplication by a fixed reciprocal, min and max are monotone),
+// so no box test can cull a triangle whose t is inside (tmin, best]: the result is independent of tree and order.
+inline bool tri_clamp_t(const RayPre& r, const vec3& v0, const vec3& v1, const vec3& v2, float& t) {
+	const vec3 lo = glm::min(glm::min(v0, v1), v2), hi = glm::max(glm::max(v0, v1), v2);
+	const float t0x = (lo.x - r.o.x) * r.inv.x, t1x = (hi.x - r.o.x) * r.inv.x;
+	const float t0y = (lo.y - r.o.y) * r.inv.y, t1y = (hi.y - r.o.y) * r.inv.y;
+	const float t0z = (lo.z - r.o.z) * r.inv.z, t1z = (hi.z - r.o.z) * r.inv.z;
+	const float n = std::max(std::max(std::min(t0x, t1x), std::min(t0y, t1y)), std::min(t0z, t1z));
+	const float f = std::min(std::min(std::max(t0x, t1x), std::max(t0y, t1y)), std::max(t0z, t1z)) * 1.0000004f;
+	if (!(n <= f)) return false;
+	t = std::min(std::max(t, n), f);
+	return true;
+}
+
 inline bool box_intersect(const RayPre& r, const float* bb, float tmin, float tmax, float& tnear) {
 	const float t0x = (bb[0] - r.o.x) * r.inv.x, t1x = (bb[3] - r.o.x) * r.inv.x;
 	const float t0y = (bb[1] - r.o.y) * r.inv.y, t1y = (bb[4] - r.o.y) * r.inv.y;
@@ -267,6 +287,7 @@ inline Hit trace(const Lbvh& b, const vec3& o, const vec3& d, float tmin, float 
 		float t, b1, b2;
 		if (!tri_intersect(r, b.tri_world[3 * (size_t)p], b.tri_world[3 * (size_t)p + 1], b.tri_world[3 * (size_t)p + 2], t, b1, b2))
 			return false;
+		if (!tri_clamp_t(r, b.tri_world[3 * (size_t)p], b.tri_world[3 * (size_t)p + 1], b.tri_world[3 * (size_t)p + 2], t)) return false;
 		if (!(t > tmin)) return false;
 		if (t < h.t || (t == h.t && p < h.prim && h.prim != 0xFFFFFFFFu)) {
 			h.t = t, h.b1 = b1, h.b2 = b2, h.prim = p;
@@ -315,6 +336,21 @@ inline Hit trace(const Lbvh& b, const vec3& o, const vec3& d, float tmin, float 
 			next = stack[--sp];
 		}
 		node = next;
+	}
+	return h;
+}
+
+// The hit definition evaluated with no tree at all: every triangle, same tests, same acceptance rule. trace<false> must return
+// exactly this (tests/test_oracle.py); it is what makes hits independent of tree shape and traversal order.
+inline Hit trace_brute(const Lbvh& b, const vec3& o, const vec3& d, float tmin, float tmax) {
+	Hit h{tmax, 0, 0, 0xFFFFFFFFu};
+	if (b.n_tris == 0 || !ray_finite(o, d)) return h;
+	const RayPre r = ray_prepare(o, d);
+	for (uint32_t p = 0; p < b.n_tris; p++) {
+		const vec3 &v0 = b.tri_world[3 * (size_t)p], &v1 = b.tri_world[3 * (size_t)p + 1], &v2 = b.tri_world[3 * (size_t)p + 2];
+		float t, b1, b2;
+		if (!tri_intersect(r, v0, v1, v2, t, b1, b2) || !tri_clamp_t(r, v0, v1, v2, t) || !(t > tmin)) continue;
+		if (t < h.t || (t == h.t && p < h.prim && h.prim != 0xFFFFFFFFu)) h.t = t, h.b1 = b1, h.b2 = b2, h.prim = p;
 	}
 	return h;
 }

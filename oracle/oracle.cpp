@@ -471,6 +471,17 @@ int orc_trace_closest(const orc_scene* s, const float* rays, uint32_t n, orc_hit
 	return 0;
 }
 
+int orc_trace_closest_brute(const orc_scene* s, const float* rays, uint32_t n, orc_hit* hits, int n_threads) {
+	const int nt = pick_threads(n_threads);
+#pragma omp parallel for num_threads(nt) schedule(dynamic, 64)
+	for (int64_t i = 0; i < (int64_t)n; i++) {
+		const float* r = rays + 8 * i;
+		const Hit h = trace_brute(s->bvh, vec3(r[0], r[1], r[2]), vec3(r[4], r[5], r[6]), r[3], r[7]);
+		hits[i] = {h.t, h.b1, h.b2, h.prim};
+	}
+	return 0;
+}
+
 int orc_trace_any(const orc_scene* s, const float* rays, uint32_t n, uint8_t* occluded, orc_stats* stats, int n_threads) {
 	const int nt = pick_threads(n_threads);
 	uint64_t nodes = 0, tris = 0;

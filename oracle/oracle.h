@@ -60,6 +60,8 @@ int orc_render_frame_raw(const orc_scene* s, const lmb_pc_path* pc, const lmb_sc
 
 /* Ray queries: rays = n x 8 floats (ox, oy, oz, tmin, dx, dy, dz, tmax). */
 int orc_trace_closest(const orc_scene* s, const float* rays, uint32_t n, orc_hit* hits, orc_stats* stats, int n_threads);
+/* the hit definition evaluated over ALL triangles, no tree: what orc_trace_closest must equal bit for bit */
+int orc_trace_closest_brute(const orc_scene* s, const float* rays, uint32_t n, orc_hit* hits, int n_threads);
 int orc_trace_any(const orc_scene* s, const float* rays, uint32_t n, uint8_t* occluded, orc_stats* stats, int n_threads);
 
 /* Known-answer probes for individual shader functions (all arrays are n-element, tightly packed). */

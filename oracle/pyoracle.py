@@ -45,6 +45,7 @@ def lib():
         L.orc_render_frame_raw.argtypes = [vp, vp, vp, u32, vp, vp, i32]
         L.orc_trace_closest.argtypes = [vp, vp, u32, vp, vp, i32]
         L.orc_trace_any.argtypes = [vp, vp, u32, vp, vp, i32]
+        L.orc_trace_closest_brute.argtypes = [vp, vp, u32, vp, i32]
         L.orc_kat_pcg4d.argtypes = [vp, u32, vp]
         L.orc_kat_rand.argtypes = [vp, u32, u32, vp]
         L.orc_kat_detmath.argtypes = [vp, vp, u32, vp, vp, vp, vp]
@@ -115,6 +116,13 @@ class OracleScene:
         st = Stats()
         lib().orc_trace_closest(self._h, rays.ctypes.data, rays.shape[0], hits.ctypes.data, C.addressof(st), threads)
         return hits, st
+
+    def trace_closest_brute(self, rays, threads=0):
+        """The hit definition over all triangles with no tree (O(rays x triangles))."""
+        rays = _f32(rays).reshape(-1, 8)
+        hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
+        lib().orc_trace_closest_brute(self._h, rays.ctypes.data, rays.shape[0], hits.ctypes.data, threads)
+        return hits
 
     def trace_any(self, rays, threads=0):
         rays = _f32(rays).reshape(-1, 8)
