@@ -111,8 +111,9 @@ int lmb_resolve(lmb_ctx* ctx);
 /* Copies the film to `rgba` (host or device pointer, resolved by UVA): width*height*4 floats, row-major, pixel (x, y) at
  * 4*(y*width + x). */
 int lmb_download(lmb_ctx* ctx, float* rgba);
-/* lmb_download without the final wait: the copy is queued on the context's stream (pass pinned host memory for a truly
- * asynchronous transfer); lmb_sync waits for everything queued so far. */
+/* lmb_download without the wait: the film is snapshotted in stream order and sent to `rgba` by a second stream, so the
+ * transfer overlaps the next lmb_render (pass pinned host memory for a truly asynchronous transfer). `rgba` holds the
+ * film as of this call once lmb_sync returns; lmb_sync waits for everything queued so far, transfers included. */
 int lmb_download_async(lmb_ctx* ctx, float* rgba);
 int lmb_sync(lmb_ctx* ctx);
 /* EXR payload made on the device: the film's R, G, B converted to HALF with tinyexr's float_to_half_full rounding

@@ -126,6 +126,10 @@ struct lmb_ctx {
 	float4* film = nullptr;
 	lmb::Wavefront wf;
 	// post steps (post.cu)
+	float4* film_snapshot = nullptr;  // lmb_download_async: copy of the film the copy stream sends home while rendering goes on
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t ev_snapshot = nullptr, ev_copied = nullptr;
+	bool copy_pending = false;
 	uint16_t* half_planes = nullptr;  // 3 x W*H halves: B, G, R planes of the EXR writer
 	float4* gt_img = nullptr;         // ground-truth image of the RMSE routine ("gt_img_addr")
 	void* rmse_scratch = nullptr;
