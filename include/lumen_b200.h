@@ -68,9 +68,9 @@ typedef struct lmb_stats {
 	float ms_build_wide;   /* collapse of the LBVH into the compressed 8-wide traversal BVH (included in ms_build_accel) */
 	uint32_t wide_nodes;   /* nodes of the 8-wide BVH (80 B each) */
 	uint32_t wide_levels;  /* depth of the 8-wide BVH */
-	uint32_t ploc_iterations; /* clustering iterations of the traversal tree (0: LMB_TREE=lbvh) */
+	uint32_t ploc_iterations; /* clustering iterations of the traversal tree (0: the Karras tree is walked) */
 	float ms_build_ploc;   /* PLOC clustering over the sorted leaves (included in ms_build_accel) */
-	uint32_t pad_;
+	float tree_cost_ratio; /* probe-ray traversal steps of the clustered 8-wide tree / of the Karras one (the cheaper is walked; 0: not compared) */
 } lmb_stats;
 
 typedef struct lmb_hit {

@@ -86,6 +86,7 @@ int lmb_create(lmb_ctx** out, int device_id) {
 	ctx->use_bvh2 = trav && strcmp(trav, "bvh2") == 0;
 	const char* tree = getenv("LMB_TREE");
 	ctx->use_ploc = !(tree && strcmp(tree, "lbvh") == 0);
+	ctx->tree_auto = !(tree && (strcmp(tree, "lbvh") == 0 || strcmp(tree, "ploc") == 0));
 	*out = ctx;
 	return LMB_OK;
 }

@@ -119,6 +119,7 @@ struct lmb_ctx {
 	lmb::DeviceBvh bvh;
 	lmb::DeviceWideBvh wide;
 	bool use_ploc = true;   // LMB_TREE=lbvh: collapse the canonical Karras tree instead of the PLOC tree
+	bool tree_auto = true;  // LMB_TREE unset: build both binary trees, walk the one with the lower surface-area cost
 	bool use_bvh2 = false;  // LMB_TRAVERSAL=bvh2: walk the binary LBVH instead of the 8-wide BVH (A/B measurements)
 	// film / wavefront
 	uint32_t width = 0, height = 0;
@@ -149,6 +150,7 @@ int build_wide_bvh(lmb_ctx* ctx);
 void free_wide_bvh(lmb_ctx* ctx);
 int build_ploc(lmb_ctx* ctx);
 void free_ploc(lmb_ctx* ctx);
+int probe_wide_tree(lmb_ctx* ctx, uint32_t n_rays, double* steps_per_ray);
 int wavefront_alloc(lmb_ctx* ctx, uint32_t frames_in_flight);
 uint32_t shard_rows(const lmb_ctx* ctx);
 void wavefront_free(lmb_ctx* ctx);

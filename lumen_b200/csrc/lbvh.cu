@@ -358,7 +358,43 @@ int build_lbvh(lmb_ctx* ctx) {
 	cudaEventElapsedTime(&ctx->stats.ms_build_accel, ctx->ev[0], ctx->ev[4]);
 	ctx->stats.ms_build_ploc = 0.0f, ctx->stats.ploc_iterations = 0;
 	if (ctx->use_ploc && n > 1 && (rc = build_ploc(ctx))) return rc;
-	if ((rc = build_wide_bvh(ctx))) return rc;
+	ctx->stats.tree_cost_ratio = 0.0f;
+	if (b.q_left && ctx->tree_auto) {
+		// Which binary tree to walk is MEASURED on the two collapsed 8-wide trees: 64 K probe rays that leave random surface points in
+		// random directions (wavefront.cu k_probe_rays), node steps + triangle tests counted by the traversal kernel itself. Clustering
+		// usually wins (classroom stand-in: 9.5 vs 11.5 nodes per ray); on a regular grid of small closed objects the Morton splits are
+		// already object-aligned and the Karras tree is the better one (10 M-triangle torus grid: 19.4 vs 21.4 nodes per ray) -- and
+		// neither the surface-area cost of the binary trees (0.90) nor that of the wide trees (0.95) sees that: both favour clustering
+		// there, because they price rays that never stop, while a closest-hit ray ends at the first surface.
+		double cost_ploc = 0.0, cost_karras = 0.0;
+		if ((rc = build_wide_bvh(ctx)) || (rc = probe_wide_tree(ctx, 1u << 16, &cost_ploc))) return rc;
+		const DeviceWideBvh wide_ploc = ctx->wide;
+		const float ms_ploc_wide = ctx->stats.ms_build_wide;
+		ctx->wide = DeviceWideBvh{};
+		uint32_t* const ql = b.q_left;
+		b.q_left = nullptr;  // build_wide_bvh collapses the canonical tree
+		rc = build_wide_bvh(ctx);
+		if (!rc) rc = probe_wide_tree(ctx, 1u << 16, &cost_karras);
+		b.q_left = ql;
+		ctx->stats.ms_build_wide += ms_ploc_wide;
+		ctx->stats.tree_cost_ratio = cost_karras > 0.0 ? (float)(cost_ploc / cost_karras) : 0.0f;
+		if (getenv("LMB_VERBOSE")) fprintf(stderr, "lumen_b200: probe steps per ray: karras %.3f clustered %.3f ratio %.4f\n", cost_karras, cost_ploc, ctx->stats.tree_cost_ratio);
+		// the probe is a stand-in for the real ray distribution, where clustering tends to do better than on the probe (classroom stand-in:
+		// probe 0.99, path tracing 0.875): the Karras tree has to win by 3 % to be taken
+		const bool keep_ploc = !rc && cost_ploc < 1.03 * cost_karras && wide_ploc.levels <= 56;
+		if (keep_ploc) {
+			free_wide_bvh(ctx);
+			ctx->wide = wide_ploc;
+		} else {
+			DeviceWideBvh loser = wide_ploc;
+			cudaFree(loser.nodes), cudaFree(loser.tris), cudaFree(loser.counters);
+			free_ploc(ctx);
+			ctx->stats.ploc_iterations = 0;
+		}
+		if (rc) return rc;
+	} else {
+		if ((rc = build_wide_bvh(ctx))) return rc;
+	}
 	if (b.q_left && ctx->wide.levels > 56) {
 		// the traversal stack holds one entry per level (64 in total): an adversarially deep clustering falls back to the
 		// canonical tree, whose depth is bounded by the 62 key bits

@@ -755,6 +755,51 @@ static int launch_trace_array(lmb_ctx* ctx, const float4* d_rays, uint32_t n, fl
 		k_trace_array<<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n, cursor, ctx->wf.stats);
 	return check_cuda(ctx, cudaGetLastError(), "k_trace_array");
 }
+// Probe rays for the choice of the traversal tree (lbvh.cu): they leave a random point of a random triangle in a uniformly random
+// direction, like the bounce rays of a path do. Pure integer hashing (pcg4d) + detmath: the same rays for both candidate trees.
+__global__ void __launch_bounds__(256) k_probe_rays(uint32_t n_tris, const float4* __restrict__ tris, uint32_t n_rays, float4* __restrict__ rays) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_rays) return;
+	Rng s{i, 0x9E3779B9u, 0x85EBCA6Bu, 0u};
+	const V4 r = rand4(s);
+	const float pick = rand1(s);
+	const uint32_t t = min((uint32_t)(pick * (float)n_tris), n_tris - 1u);
+	const float4 a = tris[3 * (size_t)t], b = tris[3 * (size_t)t + 1], c = tris[3 * (size_t)t + 2];
+	float u = r.x, v = r.y;
+	if (u + v > 1.0f) u = 1.0f - u, v = 1.0f - v;
+	const V3 p = v3(a.x, a.y, a.z) + u * (v3(b.x, b.y, b.z) - v3(a.x, a.y, a.z)) + v * (v3(c.x, c.y, c.z) - v3(a.x, a.y, a.z));
+	const float z = 1.0f - 2.0f * r.z, rad = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+	float sn, cs;
+	lmb_sincosf(LMB_TWO_PI * r.w, &sn, &cs);
+	rays[2 * (size_t)i] = make_float4(p.x, p.y, p.z, 1e-3f);
+	rays[2 * (size_t)i + 1] = make_float4(rad * cs, rad * sn, z, 1e30f);
+}
+
+// Mean traversal steps (wide nodes visited + triangles tested) of n_rays probe rays through the CURRENT wide tree.
+int probe_wide_tree(lmb_ctx* ctx, uint32_t n_rays, double* steps_per_ray) {
+	*steps_per_ray = 0.0;
+	if (ctx->bvh.n == 0 || n_rays == 0) return 0;
+	float4 *rays = nullptr, *hits = nullptr;
+	unsigned long long* st = nullptr;
+	uint32_t* cursor = nullptr;
+	LMB_CUDA(ctx, cudaMalloc((void**)&rays, (size_t)n_rays * 32));
+	LMB_CUDA(ctx, cudaMalloc((void**)&hits, (size_t)n_rays * 16));
+	LMB_CUDA(ctx, cudaMalloc((void**)&st, ST_COUNT * 8));
+	LMB_CUDA(ctx, cudaMalloc((void**)&cursor, 4));
+	LMB_CUDA(ctx, cudaMemsetAsync(st, 0, ST_COUNT * 8, ctx->stream));
+	LMB_CUDA(ctx, cudaMemsetAsync(cursor, 0, 4, ctx->stream));
+	k_probe_rays<<<(n_rays + 255) / 256, 256, 0, ctx->stream>>>(ctx->bvh.n, ctx->bvh.tris, n_rays, rays);
+	const ArraySource src{rays, hits, nullptr, false};
+	k_trace_array<<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n_rays, cursor, st);
+	unsigned long long h[ST_COUNT];
+	LMB_CUDA(ctx, cudaMemcpyAsync(h, st, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	const int rc = check_cuda(ctx, cudaGetLastError(), "probe_wide_tree");
+	cudaFree(rays), cudaFree(hits), cudaFree(st), cudaFree(cursor);
+	*steps_per_ray = (double)(h[ST_NODES] + h[ST_TRIS]) / n_rays;
+	return rc;
+}
+
 int launch_trace_closest(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits) { return launch_trace_array(ctx, d_rays, n, d_hits, nullptr, false); }
 int launch_trace_any(lmb_ctx* ctx, const float4* d_rays, uint32_t n, uint8_t* d_occ) { return launch_trace_array(ctx, d_rays, n, nullptr, d_occ, true); }
 int launch_resolve(lmb_ctx* ctx) {
