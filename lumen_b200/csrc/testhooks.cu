@@ -229,7 +229,7 @@ struct WideCheck {
 		const uint32_t ew = __builtin_bit_cast(uint32_t, n[0].w);
 		const double p[3] = {n[0].x, n[0].y, n[0].z};
 		double step[3];
-		for (int a = 0; a < 3; a++) step[a] = ldexp(1.0, (int)((ew >> (8 * a)) & 0xFFu) - 127);
+		for (int a = 0; a < 3; a++) step[a] = ldexp(1.0, (int)((ew >> (8 * a)) & 0xFFu) - 15 - 127);
 		const uint32_t child_base = __builtin_bit_cast(uint32_t, n[1].x), tri_base = __builtin_bit_cast(uint32_t, n[1].y);
 		const uint32_t mw = __builtin_bit_cast(uint32_t, n[1].z), imask = mw >> 24, leaf24 = mw & 0xFFFFFFu;
 		const uint32_t w[12] = {__builtin_bit_cast(uint32_t, n[2].x), __builtin_bit_cast(uint32_t, n[2].y), __builtin_bit_cast(uint32_t, n[2].z),

@@ -15,7 +15,7 @@
 //   Children are placed in slots by a greedy assignment on  dot(child centre - node centre, octant direction of slot),
 //   so that visiting slots in order of (slot XOR ray octant) is front to back.
 // Node, 80 bytes = 5 x 128-bit loads:
-//   n0 = (p.x, p.y, p.z, ex | ey << 8 | ez << 16)                    p = node box min - step/16, e* = biased exponents of the grid step
+//   n0 = (p.x, p.y, p.z, ex | ey << 8 | ez << 16)                    p = node box min - step/16, e* = biased exponents of the grid step + 15
 //   n1 = (child_base, tri_base, imask << 24 | leaf24, 0)              imask bit s: slot s is an internal child; leaf24 bits 3s..3s+2 =
 //                                                                     1/3/7 for a leaf child with 1/2/3 triangles (0: internal or empty).
 //                                                                     Leaf triangles are stored compactly in slot order, so triangle
@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(128) k_collapse(uint32_t n, const uint32_t* __
 	auto pack4 = [](const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); };
 	auto f = [](uint32_t u) { return __uint_as_float(u); };
 	float4* o = wnodes + 5 * (size_t)w;
-	o[0] = make_float4(P[0], P[1], P[2], f(E[0] | (E[1] << 8) | (E[2] << 16)));
+	// stored with the + 15 the slab test needs (A = 2^(e + 15) / d, trace_wide.cuh); E <= 239 for any scene below 1e36 in size
+	o[0] = make_float4(P[0], P[1], P[2], f(min(E[0] + 15u, 255u) | (min(E[1] + 15u, 255u) << 8) | (min(E[2] + 15u, 255u) << 16)));
 	o[1] = make_float4(f(child_base), f(tri_base), f((imask << 24) | leaf24), 0.0f);
 	o[2] = make_float4(f(pack4(qlo[0])), f(pack4(qlo[0] + 4)), f(pack4(qlo[1])), f(pack4(qlo[1] + 4)));
 	o[3] = make_float4(f(pack4(qlo[2])), f(pack4(qlo[2] + 4)), f(pack4(qhi[0])), f(pack4(qhi[0] + 4)));
