@@ -287,9 +287,11 @@ struct MBsdf {
 	float roughness = 0, ior = 1.0f;
 };
 struct MMesh {
-	std::string file;
+	std::string file, shape_type;
 	int bsdf_idx = -1;
 	glm::mat4 transform{1};
+	bool has_emitter = false;  // nested <emitter type="area">
+	glm::vec3 radiance{0};
 };
 struct MLight {
 	std::string type;
@@ -355,6 +357,18 @@ void Scene::load_mitsuba_scene(const std::string& path) {
 			} break;
 			case OT_SHAPE: {
 				MMesh m;
+				m.shape_type = obj->pluginType();
+				for (const auto& mc : obj->anonymousChildren()) {
+					if (mc->type() != OT_EMITTER || mc->pluginType() != "area") continue;
+					for (const auto& ep : mc->properties()) {
+						if (ep.first != "radiance") continue;
+						m.has_emitter = true;
+						if (ep.second.type() == PT_COLOR)
+							m.radiance = glm::vec3((float)ep.second.getColor().r, (float)ep.second.getColor().g, (float)ep.second.getColor().b);
+						else if (ep.second.type() == PT_NUMBER || ep.second.type() == PT_INTEGER)
+							m.radiance = glm::vec3((float)ep.second.getNumber());
+					}
+				}
 				for (const auto& prop : obj->properties()) {
 					if (prop.first == "filename") {
 						m.file = prop.second.getString();
@@ -410,8 +424,61 @@ void Scene::load_mitsuba_scene(const std::string& path) {
 	config.cam.pos = glm::vec3(0);
 	// Q11: shapes without a file (rectangle emitters etc.) are skipped. The reference keeps zero-sized trailing
 	// prim-mesh slots for them; they hold no triangles and are dropped here.
+	// SURVEY.md 8f-2, OPT-IN (LUMEN_B200_MITSUBA_AREA_EMITTERS=1; off by default because the reference drops them, LumenScene.cpp:
+	// 538-540, MitsubaParser.cpp:121-142): `rectangle` shapes become two triangles (Mitsuba's [-1,1]^2 in the XY plane, normal +Z)
+	// and a nested <emitter type="area"> makes the shape's material emissive, i.e. an area light of Lumen's own kind
+	// (LumenScene.cpp:83-95). Emitter geometry is baked to world space with an identity world matrix: sample_triangle puts
+	// w = 1 on edge vectors (quirk Q7), which is only right without a translation.
+	const char* opt = std::getenv("LUMEN_B200_MITSUBA_AREA_EMITTERS");
+	const bool area_emitters = opt && *opt && std::strcmp(opt, "0") != 0;
+	std::vector<std::pair<size_t, glm::vec3>> emissive;  // (material index, radiance)
+	auto bake_to_world = [&](PrimMesh& pm) {
+		const glm::mat3 nm = glm::transpose(glm::inverse(glm::mat3(pm.world_matrix)));
+		glm::vec3 mn(FLT_MAX), mx(-FLT_MAX);
+		for (uint32_t v = pm.vtx_offset; v < pm.vtx_offset + pm.idx_count; v++) {
+			positions[v] = glm::vec3(pm.world_matrix * glm::vec4(positions[v], 1.0f));
+			normals[v] = glm::normalize(nm * normals[v]);
+			mn = glm::min(mn, positions[v]), mx = glm::max(mx, positions[v]);
+		}
+		pm.min_pos = mn, pm.max_pos = mx;
+		pm.world_matrix = glm::mat4(1.0f);
+	};
+	auto emitter_material = [&](const MMesh& mesh) -> uint32_t {
+		MBsdf b = mesh.bsdf_idx >= 0 ? bsdfs[(size_t)mesh.bsdf_idx] : MBsdf{};
+		if (mesh.bsdf_idx < 0) b.type = "diffuse", b.albedo = glm::vec3(0.5f);  // Mitsuba's default bsdf
+		b.name += "#emitter" + std::to_string(emissive.size());
+		bsdfs.push_back(b);
+		emissive.emplace_back(bsdfs.size() - 1, mesh.radiance);
+		return (uint32_t)(bsdfs.size() - 1);
+	};
 	for (const auto& mesh : meshes) {
-		if (mesh.file.empty()) continue;
+		if (mesh.file.empty()) {
+			if (!area_emitters || mesh.shape_type != "rectangle") continue;
+			PrimMesh pm;
+			pm.name = "rectangle";
+			pm.first_idx = (uint32_t)indices.size();
+			pm.vtx_offset = (uint32_t)positions.size();
+			pm.idx_count = 6, pm.vtx_count = 2;
+			static const float q[4][2] = {{-1, -1}, {1, -1}, {1, 1}, {-1, 1}};
+			static const int tri[6] = {0, 1, 2, 0, 2, 3};
+			for (uint32_t k = 0; k < 6; k++) {
+				indices.push_back(k);
+				positions.emplace_back(q[tri[k]][0], q[tri[k]][1], 0.0f);
+				normals.emplace_back(0.0f, 0.0f, 1.0f);
+				texcoords0.emplace_back(0.5f * (q[tri[k]][0] + 1.0f), 0.5f * (q[tri[k]][1] + 1.0f));
+			}
+			pm.prim_idx = (uint32_t)prim_meshes.size();
+			pm.world_matrix = mesh.transform;
+			bake_to_world(pm);
+			if (mesh.has_emitter)
+				pm.material_idx = emitter_material(mesh);
+			else if (mesh.bsdf_idx >= 0)
+				pm.material_idx = (uint32_t)mesh.bsdf_idx;
+			else
+				throw std::runtime_error("rectangle shape without bsdf ref or area emitter");
+			prim_meshes.push_back(pm);
+			continue;
+		}
 		const std::string mesh_file = root + mesh.file;
 		tinyobj::ObjReaderConfig reader_config;
 		tinyobj::ObjReader reader;
@@ -422,8 +489,13 @@ void Scene::load_mitsuba_scene(const std::string& path) {
 		append_obj_shape(&reader.GetAttrib(), &shapes[0], pm);
 		pm.prim_idx = (uint32_t)prim_meshes.size();
 		pm.world_matrix = mesh.transform;
-		if (mesh.bsdf_idx < 0) throw std::runtime_error("shape without a resolvable bsdf ref: " + mesh_file);
-		pm.material_idx = (uint32_t)mesh.bsdf_idx;
+		if (area_emitters && mesh.has_emitter) {
+			bake_to_world(pm);
+			pm.material_idx = emitter_material(mesh);
+		} else {
+			if (mesh.bsdf_idx < 0) throw std::runtime_error("shape without a resolvable bsdf ref: " + mesh_file);
+			pm.material_idx = (uint32_t)mesh.bsdf_idx;
+		}
 		prim_meshes.push_back(pm);
 	}
 
@@ -476,6 +548,7 @@ void Scene::load_mitsuba_scene(const std::string& path) {
 			mat.ior = b.ior;
 		}
 	}
+	for (const auto& e : emissive) put3(materials[e.first].emissive_factor, e.second);
 	compute_scene_dimensions();
 	lights.assign(mlights.size(), AnalyticLight{});
 	for (size_t i = 0; i < mlights.size(); i++) {
