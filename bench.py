@@ -90,13 +90,18 @@ class ClockSampler:
         return out
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per k_trace launch, from the committed ncu --set full capture
-    (profiles/ktrace_dram_traffic.json, written by tools/ncu_summary.py from the capture of tools/gpu_prof.sh)."""
+def ncu_capture():
+    """The committed ncu --set full capture of k_trace (profiles/ktrace_dram_traffic.json, written by tools/ncu_summary.py
+    from the capture of tools/gpu_round.sh): dram bytes per launch and the issue / pipe utilisation of the same launches."""
     try:
-        return float(json.load(open(os.path.join(ROOT, "profiles", "ktrace_dram_traffic.json")))["dram_bytes_per_launch"])
+        return json.load(open(os.path.join(ROOT, "profiles", "ktrace_dram_traffic.json")))
     except Exception:
-        return None
+        return {}
+
+
+def ncu_traffic():
+    v = ncu_capture().get("dram_bytes_per_launch")
+    return float(v) if v is not None else None
 
 
 def run_reference(args, rank):
@@ -278,6 +283,8 @@ def main():
             "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic(), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": trav_bytes / n_trav_launches, "avg_launch_ms": trav_ms / n_trav_launches,
             "bytes_per_ray": trav_bytes / max(ps.rays, 1), "nodes_per_ray": ps.nodes_visited / max(ps.rays, 1), "tris_per_ray": ps.tris_tested / max(ps.rays, 1),
+            # second ceiling of SURVEY.md 8d, from the committed ncu capture (not re-measured in this run): instruction issue
+            "issue": {k: ncu_capture().get(k) for k in ("issue_active_pct", "alu_pipe_pct", "fma_pipe_pct", "active_lanes_per_instruction", "source")},
             "stage_ms": {"trace": ps.ms_extend, "shade": ps.ms_shade, "connect": ps.ms_connect, "raygen_sky_film": ps.ms_film, "total": ps.ms_render},
             "note": "algorithmic bytes = wide nodes visited*80 + triangles tested*48 + rays*48 (DESIGN.md); the ~18 MB wide BVH is L2-resident by design, so these bytes are served by L1/L2 and the kernel is issue bound, not DRAM bound: see traffic (ncu dram bytes per launch) against algorithmic_bytes_per_launch",
         }

@@ -62,7 +62,7 @@ def raw(path):
 def full(path, traffic):
     hdr, units, rows = raw(path)
     print("| kernel | " + " | ".join(METRICS) + " |\n|" + "---|" * (len(METRICS) + 1))
-    trace_bytes = []
+    trace_bytes, trace_pipe = [], []  # per k_trace launch: dram bytes; (ms, issue %, alu pipe %, fma pipe %, lanes per instruction)
     for r in rows:
         name = short(r[hdr.index("Kernel Name")])
         vals = []
@@ -81,9 +81,15 @@ def full(path, traffic):
         if name.startswith("k_trace"):
             i, j = hdr.index(METRICS["dram_rd_MB"]), hdr.index(METRICS["dram_wr_MB"])
             trace_bytes.append((float(r[i]) * SCALE[units[i]] + float(r[j]) * SCALE[units[j]]) * 1e6)
+            t = hdr.index(METRICS["ms"])
+            trace_pipe.append([float(r[t].replace(",", "")) * SCALE.get(units[t], 1.0)] + [float(r[hdr.index(METRICS[k])].replace(",", "")) for k in ("issue%", "alu%", "fma%", "lanes")])
     if traffic and trace_bytes:
+        w = sum(p[0] for p in trace_pipe)
         d = {"dram_bytes_per_launch": sum(trace_bytes) / len(trace_bytes), "launches": len(trace_bytes), "source": os.path.basename(path),
-             "how": "mean of dram__bytes_read.sum + dram__bytes_write.sum over the captured k_trace launches (ncu --set full)"}
+             "how": "mean of dram__bytes_read.sum + dram__bytes_write.sum over the captured k_trace launches (ncu --set full)",
+             # duration-weighted means over the same launches: what the kernel is actually bound by when the BVH is L2-resident
+             "issue_active_pct": sum(p[0] * p[1] for p in trace_pipe) / w, "alu_pipe_pct": sum(p[0] * p[2] for p in trace_pipe) / w,
+             "fma_pipe_pct": sum(p[0] * p[3] for p in trace_pipe) / w, "active_lanes_per_instruction": sum(p[0] * p[4] for p in trace_pipe) / w}
         json.dump(d, open(os.path.join(ROOT, "profiles", "ktrace_dram_traffic.json"), "w"), indent=1)
         print("\nwrote profiles/ktrace_dram_traffic.json:", d)
 
