@@ -1,7 +1,7 @@
-"""Diagnostic parity sweep CUDA vs oracle (prints, does not assert). Run on the GPU box: python tools/gpu_diag.py"""
+"""Diagnostic parity sweep CUDA vs oracle (prints, does not assert). Run on the GPU box: python tests/diag_gpu_vs_oracle.py"""
 import sys, os, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 from lumen_b200 import host, integrator
 from lumen_b200._ctypes_types import Material
 from oracle import pyoracle as po

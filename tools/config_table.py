@@ -1,12 +1,12 @@
 #!/usr/bin/env python
 """BASELINE.json configs 1-4 at their FULL sizes on one GPU (acceptance criterion 4): Mrays/s, spp/s, rays per
-path, traversal work per ray and the roofline figure of k_trace, each beside a bounded oracle run of the same config on the
-box's host threads (parity of the frames the oracle rendered: ray counts equal, film bit-equal / within 1e-4).
+path, traversal work per ray and the roofline figure of k_trace.
 
     python tools/config_table.py [--configs 1,2,3,4] [--frames4 4096] [--out gpurun_out/config_table.json]
 
-The oracle is the checker here (tools/ is measurement tooling, like bench.py's cpu_baseline leg); the product path is the
-C-ABI library only. Config 5 (10 M-triangle torus grid) is tools/torus_sweep.py.
+Product path only (the C-ABI library): parity of the same configs at full resolution against the oracle is
+tests/test_gpu_full_configs.py, the CPU baseline is `bench.py --impl reference`. Config 5 (10 M-triangle torus grid) is
+tools/torus_sweep.py.
 """
 import argparse
 import json
@@ -17,7 +17,6 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "scenes"))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
@@ -33,18 +32,16 @@ def classroom_path():
 
 
 CONFIGS = {
-    # id: (label, scene path fn, W, H, frames, depth, oracle frames, oracle scale)
-    1: ("cornell_box path, 512x512, 16 spp, depth 6", lambda: os.path.join(ROOT, "scenes/cornell_box/cornell_box_path.json"), 512, 512, 16, 6, 16, 1),
-    2: ("caustics, 1280x720, 64 spp, depth 12", lambda: os.path.join(ROOT, "scenes/caustics.json"), 1280, 720, 64, 12, 4, 1),
-    3: ("classroom stand-in, 1920x1080, 1024 spp, depth 8", classroom_path, 1920, 1080, 1024, 8, 1, 1),
-    4: ("bedroom slot (classroom stand-in geometry, assets absent), 3840x2160, 4096 spp, depth 8", classroom_path, 3840, 2160, 4096, 8, 1, 2),
+    # id: (label, scene path fn, W, H, frames, depth)
+    1: ("cornell_box path, 512x512, 16 spp, depth 6", lambda: os.path.join(ROOT, "scenes/cornell_box/cornell_box_path.json"), 512, 512, 16, 6),
+    2: ("caustics, 1280x720, 64 spp, depth 12", lambda: os.path.join(ROOT, "scenes/caustics.json"), 1280, 720, 64, 12),
+    3: ("classroom stand-in, 1920x1080, 1024 spp, depth 8", classroom_path, 1920, 1080, 1024, 8),
+    4: ("bedroom slot (classroom stand-in geometry, assets absent), 3840x2160, 4096 spp, depth 8", classroom_path, 3840, 2160, 4096, 8),
 }
 
 
 def run(cfg, dev, frames_override=None):
-    from helpers import bits_equal, pixel_agreement
-    from oracle import pyoracle as po
-    label, path_fn, W, H, frames, depth, o_frames, o_scale = CONFIGS[cfg]
+    label, path_fn, W, H, frames, depth = CONFIGS[cfg]
     if frames_override:
         frames = frames_override
     sc = host.Scene(path_fn(), W, H)
@@ -80,27 +77,6 @@ def run(cfg, dev, frames_override=None):
         "k_trace_algorithmic_GBps": trav_bytes / (ps.ms_extend * 1e-3) / 1e9 if ps.ms_extend > 0 else 0.0,
         "accel_build_ms": build.ms_build_accel, "film_mean_rgb": [float(x) for x in film[..., :3].reshape(-1, 3).mean(0)],
     }
-    # oracle on the box's host threads: the first o_frames frames, at 1/o_scale resolution when the full frame is too slow
-    # (a reduced-resolution oracle frame is a baseline timing only; parity is checked when o_scale == 1)
-    threads = len(os.sched_getaffinity(0))
-    if o_scale == 1:
-        osc, orc = sc, po.OracleScene(sc)
-    else:
-        osc = host.Scene(path_fn(), W // o_scale, H // o_scale)
-        orc = po.OracleScene(osc)
-    opc, oubo = osc.make_pc(depth, True), osc.make_ubo()
-    cpu, cs = orc.render(opc, oubo, 0, o_frames, threads=threads)
-    row["oracle"] = {"frames": o_frames, "width": W // o_scale, "height": H // o_scale, "threads": int(cs.threads), "seconds": cs.seconds,
-                     "mrays_per_s": cs.rays / cs.seconds / 1e6, "rays": int(cs.rays)}
-    if o_scale == 1:
-        dev.reset_stats()
-        dev.clear_film()
-        dev.render(pc, ubo, 0, o_frames)
-        g, gs = dev.download(), dev.stats()
-        row["parity"] = {"frames": o_frames, "ray_counts_equal": (gs.rays_closest, gs.rays_shadow, gs.rays_probe) == (cs.rays_closest, cs.rays_shadow, cs.rays_probe),
-                         "pixels_within_1e-4": pixel_agreement(g, cpu), "values_bit_equal": float(bits_equal(g, cpu).mean()),
-                         "nan_samples_equal": int(gs.nan_samples) == int(cs.nan_pixels)}
-    row["speedup_vs_oracle"] = row["mrays_per_s"] / row["oracle"]["mrays_per_s"]
     return row
 
 
@@ -124,14 +100,12 @@ def main():
         print(json.dumps(row), flush=True)
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump({"hbm_peak_GBps": float(peaks.get("hbm_gbs", 6650.0)), "rows": rows}, open(a.out, "w"), indent=1)
-    print("| config | Mrays/s | spp/s | rays/path | nodes/ray | tris/ray | k_trace GB/s (frac) | oracle Mrays/s (threads) | x | parity |")
-    print("|---|---|---|---|---|---|---|---|---|---|")
+    print("| config | Mrays/s | spp/s | rays/path | nodes/ray | tris/ray | k_trace GB/s (frac of HBM peak) | trace / shade / connect / sky+film ms per frame |")
+    print("|---|---|---|---|---|---|---|---|")
     for r in rows:
-        p = r.get("parity")
-        ptxt = (f"{p['frames']} frames: counts {'=' if p['ray_counts_equal'] else 'DIFFER'}, {p['pixels_within_1e-4']*100:.3f}% px within 1e-4, {p['values_bit_equal']*100:.3f}% bit-equal"
-                if p else "timing only (oracle at reduced resolution)")
+        st = r["stage_ms_per_frame"]
         print(f"| {r['config']}: {r['label']} | {r['mrays_per_s']:.0f} | {r['spp_per_s']:.1f} | {r['rays_per_path']:.2f} | {r['nodes_per_ray']:.2f} | {r['tris_per_ray']:.2f} | "
-              f"{r['k_trace_algorithmic_GBps']:.0f} ({r['k_trace_frac_of_hbm_peak']:.2f}) | {r['oracle']['mrays_per_s']:.1f} ({r['oracle']['threads']}) | {r['speedup_vs_oracle']:.0f} | {ptxt} |")
+              f"{r['k_trace_algorithmic_GBps']:.0f} ({r['k_trace_frac_of_hbm_peak']:.2f}) | {st['trace']:.2f} / {st['shade']:.2f} / {st['connect']:.2f} / {st['raygen_sky_film']:.2f} |")
 
 
 if __name__ == "__main__":
