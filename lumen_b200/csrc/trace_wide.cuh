@@ -108,7 +108,7 @@ struct TraceSmem {
 	uint32_t rq_i[LMB_TRACE_THREADS]; // the source's tag of the ray
 };
 
-template <typename Source>
+template <bool PIN, typename Source>
 __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, Source& src, uint32_t count, uint32_t* cursor, unsigned long long* stats,
 													  int stat_closest, int stat_any) {
 	__shared__ TraceSmem sm;
@@ -118,10 +118,14 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 	const int wbase = tid & ~31;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	const uint32_t one_bits = bvh.one_bits;
-	// The shared-memory address of this thread's stack column, pinned in a register: left to itself the compiler rebuilds it at every
-	// push and pop from two special-register reads (S2R SR_CgaCtaId, SR_TID.X: ~20 cycles each) to save that register.
-	uint32_t stack_base;
-	asm volatile("mov.u32 %0, %1;" : "=r"(stack_base) : "r"((uint32_t)__cvta_generic_to_shared(&sm.stack[0][tid])));
+	// PIN: the shared-memory address of this thread's stack column is pinned in a register; left to itself the compiler rebuilds it at
+	// every push and pop from two special-register reads (S2R SR_CgaCtaId, SR_TID.X) to save that register. Pinning takes ~10
+	// instructions off a node step, which pays when the kernel is issue bound (BVH resident in L2: classroom stand-in trace -2 %), and
+	// costs 11 % when it is bound by memory latency (10 M-triangle torus grid, 590 MB of nodes + triangles: 1455 -> 1290 Mrays/s with
+	// any way of pinning, inline PTX or an opaque C++ pointer -- the register it takes is then missed by loads in flight). The host
+	// picks the instantiation by the footprint of the BVH against the L2 (wavefront.cu trace_pinned).
+	uint32_t stack_base = 0;
+	if (PIN) asm volatile("mov.u32 %0, %1;" : "=r"(stack_base) : "r"((uint32_t)__cvta_generic_to_shared(&sm.stack[0][tid])));
 
 	bool has = false;        // this lane owns a ray that is still being traced
 	bool exhausted = false;  // warp-uniform: the global queue ran dry
@@ -214,7 +218,10 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 				const uint32_t slot = (uint32_t)(bit - 24) ^ (oct_inv4 & 7u);
 				const uint32_t node = ng.x + __popc(hits & 0xFFu & ((1u << slot) - 1u));
 				if (ng.y > 0x00FFFFFFu) {  // siblings still to visit
-					if (sp < LMB_WSTACK_SM) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(stack_base + (uint32_t)sp * (LMB_TRACE_THREADS * 8u)), "r"(ng.x), "r"(ng.y));
+					if (sp < LMB_WSTACK_SM) {
+						if (PIN) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(stack_base + (uint32_t)sp * (LMB_TRACE_THREADS * 8u)), "r"(ng.x), "r"(ng.y));
+						else sm.stack[sp][tid] = ng;
+					}
 					else l_stack[sp - LMB_WSTACK_SM] = ng;
 					sp++;
 				}
@@ -341,8 +348,9 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 			if (has && tg.y == 0u && ng.y <= 0x00FFFFFFu) {
 				if (sp > 0) {
 					sp--;
-					if (sp < LMB_WSTACK_SM) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ng.x), "=r"(ng.y) : "r"(stack_base + (uint32_t)sp * (LMB_TRACE_THREADS * 8u)));
-					else ng = l_stack[sp - LMB_WSTACK_SM];
+					if (sp >= LMB_WSTACK_SM) ng = l_stack[sp - LMB_WSTACK_SM];
+					else if (PIN) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ng.x), "=r"(ng.y) : "r"(stack_base + (uint32_t)sp * (LMB_TRACE_THREADS * 8u)));
+					else ng = sm.stack[sp][tid];
 				} else {
 					if (!any && h.prim != 0xFFFFFFFFu) h.b1 = h.b1 / det, h.b2 = h.b2 / det;
 					src.store(item, h);

@@ -168,9 +168,10 @@ struct WavefrontSource {
 	}
 };
 
+template <bool PIN>
 __global__ void __launch_bounds__(LMB_TRACE_THREADS, LMB_WIDE_BLOCKS_PER_SM) k_trace(WideBvhView bvh, WavefrontSource src, uint32_t* counters, int parity, unsigned long long* stats) {
 	reset_next_counters(counters, parity);
-	trace_wide_persistent(bvh, src, counters[CNT_TRACE + parity * CNT_LINE], &counters[CNT_CURSOR + parity * CNT_LINE], stats, -1, -1);
+	trace_wide_persistent<PIN>(bvh, src, counters[CNT_TRACE + parity * CNT_LINE], &counters[CNT_CURSOR + parity * CNT_LINE], stats, -1, -1);
 }
 // the same rays over the binary LBVH (LMB_TRAVERSAL=bvh2; A/B measurements and the canonical node counts)
 __global__ void __launch_bounds__(LMB_TRACE_THREADS) k_trace_bvh2(BvhView bvh, WavefrontSource src, uint32_t* counters, int parity, unsigned long long* stats) {
@@ -555,8 +556,9 @@ struct ArraySource {
 	}
 };
 
+template <bool PIN>
 __global__ void __launch_bounds__(LMB_TRACE_THREADS, LMB_WIDE_BLOCKS_PER_SM) k_trace_array(WideBvhView bvh, ArraySource src, uint32_t n, uint32_t* cursor, unsigned long long* stats) {
-	trace_wide_persistent(bvh, src, n, cursor, stats, ST_CLOSEST, ST_SHADOW);
+	trace_wide_persistent<PIN>(bvh, src, n, cursor, stats, ST_CLOSEST, ST_SHADOW);
 }
 __global__ void __launch_bounds__(LMB_TRACE_THREADS) k_trace_array_bvh2(BvhView bvh, ArraySource src, uint32_t n, uint32_t* cursor, unsigned long long* stats) {
 	trace_persistent(bvh, src, n, cursor, stats, ST_CLOSEST, ST_SHADOW);
@@ -566,6 +568,13 @@ BvhView view_of(const lmb_ctx* ctx) { return BvhView{ctx->bvh.nodes, ctx->bvh.tr
 static uint32_t env_u32(const char* name, uint32_t dflt) {
 	const char* v = getenv(name);
 	return (v && *v) ? (uint32_t)atoi(v) : dflt;
+}
+// Which instantiation of the wide walker to launch (trace_wide.cuh, PIN): the pinned one while nodes + triangles fit the L2 with room
+// to spare (issue bound), the unpinned one beyond that (latency bound). LMB_TRACE_PIN=0|1 overrides for A/B runs.
+bool trace_pinned(const lmb_ctx* ctx) {
+	static const int forced = getenv("LMB_TRACE_PIN") ? atoi(getenv("LMB_TRACE_PIN")) : -1;
+	if (forced >= 0) return forced != 0;
+	return (size_t)ctx->wide.n_nodes * 80 + (size_t)ctx->wide.n_tris * 48 <= (size_t)96 << 20;
 }
 WideBvhView wide_view_of(const lmb_ctx* ctx) {
 	// scheduling thresholds of k_trace (results do not depend on them): tuning overrides for A/B runs
@@ -649,6 +658,7 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 	rp.dir_light_idx = pc.dir_light_idx, rp.direct_lighting = pc.direct_lighting;
 	const BvhView bvh = view_of(ctx);
 	const WideBvhView wide = wide_view_of(ctx);
+	const bool pinned = trace_pinned(ctx);
 	const int grid_wide = ctx->sm_count * 16;
 	const int grid_256 = ctx->sm_count * 8;
 	const int grid_trace = ctx->sm_count * 7;  // persistent: 7 blocks x 32 KB stack fit one SM's shared memory
@@ -678,8 +688,10 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 			if (prof) cudaEventRecord(ctx->ev[1], st);
 			if (ctx->use_bvh2)
 				k_trace_bvh2<<<grid_trace, LMB_TRACE_THREADS, 0, st>>>(bvh, src, wf.counters, par, wf.stats);
+			else if (pinned)
+				k_trace<true><<<grid_trace_wide, LMB_TRACE_THREADS, 0, st>>>(wide, src, wf.counters, par, wf.stats);
 			else
-				k_trace<<<grid_trace_wide, LMB_TRACE_THREADS, 0, st>>>(wide, src, wf.counters, par, wf.stats);
+				k_trace<false><<<grid_trace_wide, LMB_TRACE_THREADS, 0, st>>>(wide, src, wf.counters, par, wf.stats);
 			ctx->stats.kernel_launches += 1;
 			if (prof) cudaEventRecord(ctx->ev[2], st);
 			if (depth > 0) {
@@ -756,8 +768,10 @@ static int launch_trace_array(lmb_ctx* ctx, const float4* d_rays, uint32_t n, fl
 	const ArraySource src{d_rays, d_hits, d_occ, any};
 	if (ctx->use_bvh2)
 		k_trace_array_bvh2<<<ctx->sm_count * 7, LMB_TRACE_THREADS, 0, ctx->stream>>>(view_of(ctx), src, n, cursor, ctx->wf.stats);
+	else if (trace_pinned(ctx))
+		k_trace_array<true><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n, cursor, ctx->wf.stats);
 	else
-		k_trace_array<<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n, cursor, ctx->wf.stats);
+		k_trace_array<false><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n, cursor, ctx->wf.stats);
 	return check_cuda(ctx, cudaGetLastError(), "k_trace_array");
 }
 // Probe rays for the choice of the traversal tree (lbvh.cu): they leave a random point of a random triangle in a uniformly random
@@ -795,7 +809,10 @@ int probe_wide_tree(lmb_ctx* ctx, uint32_t n_rays, double* steps_per_ray) {
 	LMB_CUDA(ctx, cudaMemsetAsync(cursor, 0, 4, ctx->stream));
 	k_probe_rays<<<(n_rays + 255) / 256, 256, 0, ctx->stream>>>(ctx->bvh.n, ctx->bvh.tris, n_rays, rays);
 	const ArraySource src{rays, hits, nullptr, false};
-	k_trace_array<<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n_rays, cursor, st);
+	if (trace_pinned(ctx))
+		k_trace_array<true><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n_rays, cursor, st);
+	else
+		k_trace_array<false><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n_rays, cursor, st);
 	unsigned long long h[ST_COUNT];
 	LMB_CUDA(ctx, cudaMemcpyAsync(h, st, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
 	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
