@@ -148,7 +148,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=4)
+    ap.add_argument("--frames-per-step", type=int, default=16, help="frames (samples per pixel) one step renders in one wavefront batch per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pixel-shards", type=int, default=1, help="P: ranks form a P x (N/P) grid of interleaved-row pixel shards x sample shards (config 4)")
     ap.add_argument("--width", type=int, default=WIDTH)
@@ -314,7 +314,7 @@ def main():
             "config": {"workload": WORKLOAD.format(w=WIDTH, h=HEIGHT), "max_depth": MAX_DEPTH, "frames_per_step_per_gpu": fps, "triangles": int(scene.info.n_triangles),
                        "sharding": (f"{n_pshards} pixel shard(s) (interleaved rows) x {n_sshards} sample shard(s) (frame index mod {n_sshards}), full scene + BVH replica per GPU, fp32 film all-reduce per step"
                                     if world > 1 else "single GPU"), "width": WIDTH, "height": HEIGHT,
-                       "l2": "256 MB flush before the timed region; per-step wavefront state (~2 GB) exceeds the 126 MB L2, the 15 MB BVH stays L2-resident by design"},
+                       "l2": f"256 MB flush before the timed region; per-step wavefront state (~{0.33 * fps * WIDTH * HEIGHT / 1e6 / 1e3:.1f} GB) exceeds the 126 MB L2, the 15 MB BVH stays L2-resident by design"},
             "spp_per_s": total_frames / dt,
             "rays_per_path": rays / (total_frames * WIDTH * HEIGHT),
             "device_ms_render_per_step": ms_render / args.steps,

@@ -9,6 +9,6 @@ python bench.py --steps 10 --warmup 3 2> gpurun_out/bench_err.log | tee gpurun_o
 tail -5 gpurun_out/bench_err.log
 python bench.py --impl reference --steps 3 --warmup 1 | tee gpurun_out/bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/ncu_target.py 4 2 | tail -2
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_trace" -s 0 -c 8 -f -o gpurun_out/prof_trace python tools/ncu_target.py 4 1 | tail -2
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^k_trace$" -s 0 -c 8 -f -o gpurun_out/prof_trace python tools/ncu_target.py 4 1 | tail -2
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_shade|k_classify|k_connect|k_miss" -s 0 -c 12 -f -o gpurun_out/prof_shade python tools/ncu_target.py 4 1 | tail -2
 ls -la gpurun_out

@@ -78,7 +78,7 @@ def full(path, traffic):
                 v /= 1e6
             vals.append(f"{v:.2f}" if k in ("ms", "st_long_sb", "st_wait", "st_branch", "st_not_sel", "st_no_inst") else f"{v:.1f}")
         print(f"| {name} | " + " | ".join(vals) + " |")
-        if name.startswith("k_trace"):
+        if name.startswith("k_trace") and not name.startswith("k_trace_array"):  # the two probe launches of the tree choice are not the wavefront
             i, j = hdr.index(METRICS["dram_rd_MB"]), hdr.index(METRICS["dram_wr_MB"])
             trace_bytes.append((float(r[i]) * SCALE[units[i]] + float(r[j]) * SCALE[units[j]]) * 1e6)
             t = hdr.index(METRICS["ms"])
