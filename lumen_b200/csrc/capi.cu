@@ -87,6 +87,8 @@ int lmb_create(lmb_ctx** out, int device_id) {
 	const char* tree = getenv("LMB_TREE");
 	ctx->use_ploc = !(tree && strcmp(tree, "lbvh") == 0);
 	ctx->tree_auto = !(tree && (strcmp(tree, "lbvh") == 0 || strcmp(tree, "ploc") == 0));
+	const char* pin = getenv("LMB_TRACE_PIN");
+	ctx->trace_pin = (pin && *pin) ? (atoi(pin) != 0) : -1;
 	*out = ctx;
 	return LMB_OK;
 }

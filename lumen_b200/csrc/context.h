@@ -119,6 +119,7 @@ struct lmb_ctx {
 	lmb::DeviceBvh bvh;
 	lmb::DeviceWideBvh wide;
 	bool use_ploc = true;   // LMB_TREE=lbvh: collapse the canonical Karras tree instead of the PLOC tree
+	int trace_pin = -1;     // LMB_TRACE_PIN=0|1 forces the unpinned / pinned instantiation of the wide walker (-1: by BVH footprint)
 	bool tree_auto = true;  // LMB_TREE unset: build both binary trees, walk the one with the lower surface-area cost
 	bool use_bvh2 = false;  // LMB_TRAVERSAL=bvh2: walk the binary LBVH instead of the 8-wide BVH (A/B measurements)
 	// film / wavefront

@@ -572,8 +572,7 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
 // Which instantiation of the wide walker to launch (trace_wide.cuh, PIN): the pinned one while nodes + triangles fit the L2 with room
 // to spare (issue bound), the unpinned one beyond that (latency bound). LMB_TRACE_PIN=0|1 overrides for A/B runs.
 bool trace_pinned(const lmb_ctx* ctx) {
-	static const int forced = getenv("LMB_TRACE_PIN") ? atoi(getenv("LMB_TRACE_PIN")) : -1;
-	if (forced >= 0) return forced != 0;
+	if (ctx->trace_pin >= 0) return ctx->trace_pin != 0;
 	return (size_t)ctx->wide.n_nodes * 80 + (size_t)ctx->wide.n_tris * 48 <= (size_t)96 << 20;
 }
 WideBvhView wide_view_of(const lmb_ctx* ctx) {

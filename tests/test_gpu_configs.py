@@ -61,6 +61,33 @@ def test_wide_walk_equals_binary_walk(device, monkeypatch):
         dev2.close()
 
 
+def test_pinned_and_unpinned_walkers_agree(monkeypatch):
+    """k_trace has two instantiations (stack column address pinned in a register or not), picked by the BVH footprint against the
+    L2; LMB_TRACE_PIN forces one. Same hits, same film, same traversal work."""
+    from oracle import pyoracle as po
+    sc = host.Scene(scene_path("cornell"), 96, 96)
+    pc, ubo = sc.make_pc(6, True), sc.make_ubo()
+    rays = random_rays(np.random.default_rng(9), [-3, -1, -3], [3, 5, 3], 50000)
+    out = []
+    for pin in ("0", "1"):
+        monkeypatch.setenv("LMB_TRACE_PIN", pin)
+        dev = integrator.Device(0)
+        try:
+            dev.upload_scene(sc.desc)
+            dev.build_accel()
+            dev.init(96, 96, 3)
+            dev.render(pc, ubo, 0, 5)
+            st = dev.stats()
+            out.append((dev.download(), dev.trace_closest(rays), dev.trace_any(rays), (st.rays_closest, st.rays_shadow, st.rays_probe, st.nodes_visited)))
+        finally:
+            dev.close()
+    assert out[0][0].tobytes() == out[1][0].tobytes()
+    assert out[0][1].tobytes() == out[1][1].tobytes() and (out[0][2] == out[1][2]).all()
+    assert out[0][3] == out[1][3]
+    cpu, _ = po.OracleScene(sc).render(pc, ubo, 0, 5)
+    assert bits_equal(out[0][0], cpu).mean() >= 0.999
+
+
 def test_tiny_and_degenerate_scenes(device):
     """1, 2 and 5 triangle scenes (root-only wide trees) and a scene of coplanar, axis-aligned triangles (flat boxes)."""
     from helpers import make_material
