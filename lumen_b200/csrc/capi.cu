@@ -109,8 +109,41 @@ void lmb_destroy(lmb_ctx* ctx) {
 	delete ctx;
 }
 
+// Every index the kernels will follow is checked here, once, on the host: the reference trusts its own loader, a C ABI cannot.
+static int validate_scene(lmb_ctx* ctx, const lmb_scene_desc* sd) {
+	auto bad = [&](const std::string& what) { return set_error(ctx, LMB_ERR_INVALID, "lmb_upload_scene: " + what); };
+	if ((sd->n_vertices && !sd->vertices) || (sd->n_indices && !sd->indices) || (sd->n_materials && !sd->materials) || (sd->n_lights && !sd->lights) ||
+		(sd->n_textures && !sd->textures) || (sd->n_prim_meshes && (!sd->prim_infos || !sd->prim_idx_counts || !sd->world_matrices || !sd->inv_world_matrices)))
+		return bad("null array with a non-zero count");
+	uint64_t total_tris = 0;
+	for (uint32_t m = 0; m < sd->n_prim_meshes; m++) {
+		const lmb_prim_mesh_info& pi = sd->prim_infos[m];
+		const uint32_t cnt = sd->prim_idx_counts[m];
+		if (cnt % 3) return bad("prim mesh " + std::to_string(m) + ": index count is not a multiple of 3");
+		if ((uint64_t)pi.index_offset + cnt > sd->n_indices) return bad("prim mesh " + std::to_string(m) + ": index range exceeds n_indices");
+		if (pi.material_index >= sd->n_materials) return bad("prim mesh " + std::to_string(m) + ": material_index out of range");
+		for (uint32_t i = 0; i < cnt; i++)
+			if ((uint64_t)sd->indices[pi.index_offset + i] + pi.vertex_offset >= sd->n_vertices)
+				return bad("prim mesh " + std::to_string(m) + ": vertex index out of range");
+		total_tris += cnt / 3;
+	}
+	if (total_tris > 0x07FFFFFFull) return bad("more than 2^27 - 1 triangles (the traversal packs triangle indices in 27 bits)");
+	for (uint32_t i = 0; i < sd->n_materials; i++)
+		if (sd->materials[i].texture_id >= (int32_t)sd->n_textures) return bad("material " + std::to_string(i) + ": texture_id out of range");
+	for (uint32_t i = 0; i < sd->n_textures; i++)
+		if (!sd->textures[i].rgba8 || sd->textures[i].width == 0 || sd->textures[i].height == 0) return bad("texture " + std::to_string(i) + ": empty");
+	for (uint32_t i = 0; i < sd->n_lights; i++) {
+		const lmb_light& l = sd->lights[i];
+		if ((l.light_flags & 0x7u) != LMB_LIGHT_AREA) continue;
+		if (l.prim_mesh_idx >= sd->n_prim_meshes) return bad("area light " + std::to_string(i) + ": prim_mesh_idx out of range");
+		if (l.num_triangles == 0 || l.num_triangles > sd->prim_idx_counts[l.prim_mesh_idx] / 3) return bad("area light " + std::to_string(i) + ": num_triangles does not fit its mesh");
+	}
+	return 0;
+}
+
 int lmb_upload_scene(lmb_ctx* ctx, const lmb_scene_desc* sd) {
 	if (!ctx || !sd) return LMB_ERR_INVALID;
+	if (const int bad = validate_scene(ctx, sd)) return bad;
 	cudaSetDevice(ctx->device);
 	free_scene(ctx);
 	DeviceScene& sc = ctx->scene;

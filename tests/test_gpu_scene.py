@@ -253,3 +253,35 @@ def test_integrator_lifecycle_mirror(device):
     cpu, _ = po.OracleScene(sc).render(sc.make_pc(6, True), sc.make_ubo(), 0, 3)
     integ.destroy()
     assert bits_equal(out, cpu).all()
+
+
+def test_upload_rejects_out_of_range_indices(device):
+    """The C ABI validates every index the kernels will follow (material, vertex, texture, light mesh) and reports it instead of
+    reading out of bounds on the device; the context stays usable."""
+    import ctypes as C
+    from lumen_b200._ctypes_types import SceneDesc, PrimMeshInfo
+    sc = host.Scene(scene_path("cornell"), 32, 32)
+    dev2 = integrator.Device(0)
+    try:
+        bad = SceneDesc.from_buffer_copy(sc.desc)
+        infos = (PrimMeshInfo * sc.desc.n_prim_meshes).from_address(sc.desc.prim_infos)
+        copy = (PrimMeshInfo * sc.desc.n_prim_meshes)(*infos)
+        copy[1].material_index = sc.desc.n_materials + 3
+        bad.prim_infos = C.addressof(copy)
+        with pytest.raises(RuntimeError, match="material_index out of range"):
+            dev2.upload_scene(bad)
+        bad = SceneDesc.from_buffer_copy(sc.desc)
+        bad.n_vertices = sc.desc.n_vertices - 5
+        with pytest.raises(RuntimeError, match="vertex index out of range"):
+            dev2.upload_scene(bad)
+        bad = SceneDesc.from_buffer_copy(sc.desc)
+        bad.n_indices = sc.desc.n_indices - 3
+        with pytest.raises(RuntimeError, match="index range exceeds"):
+            dev2.upload_scene(bad)
+        dev2.upload_scene(sc.desc)  # the context is still good
+        dev2.build_accel()
+        dev2.init(32, 32, 1)
+        dev2.render(sc.make_pc(6, True), sc.make_ubo(), 0, 1)
+        assert dev2.stats().rays > 0
+    finally:
+        dev2.close()

@@ -100,3 +100,25 @@ def test_opt_in_scene_gpu_equals_oracle(xml_scene, monkeypatch, device):
     cpu, cs = orc.render(pc, ubo, 0, 8)
     assert (gs.rays_closest, gs.rays_shadow, gs.rays_probe) == (cs.rays_closest, cs.rays_shadow, cs.rays_probe)
     assert pixel_agreement(gpu, cpu) >= 0.999 and bits_equal(gpu, cpu).mean() >= 0.999
+
+
+@pytest.mark.gpu
+def test_scene_without_any_light_is_sky_only_and_matches(xml_scene, monkeypatch, device):
+    """Default loading drops the rectangle emitter, which leaves a scene with NO light: the reference still takes a light sample
+    (of a zeroed Light: num_lights = 0, light_triangle_count = 0 -> a contribution of 0 / inf = 0) and a shadow ray per bounce.
+    Both sides do exactly that; only the constant sky lights the floor."""
+    from oracle import pyoracle as po
+    monkeypatch.delenv("LUMEN_B200_MITSUBA_AREA_EMITTERS", raising=False)
+    sc = host.Scene(xml_scene, 96, 72)
+    assert sc.info.n_lights == 0
+    pc, ubo = sc.make_pc(5, True), sc.make_ubo()
+    pc.sky_col[0], pc.sky_col[1], pc.sky_col[2] = 0.5, 0.6, 0.7
+    device.upload_scene(sc.desc)
+    device.build_accel()
+    device.init(96, 72, 2)
+    device.render(pc, ubo, 0, 4)
+    gpu, gs = device.download(), device.stats()
+    cpu, cs = po.OracleScene(sc).render(pc, ubo, 0, 4)
+    assert (gs.rays_closest, gs.rays_shadow, gs.rays_probe) == (cs.rays_closest, cs.rays_shadow, cs.rays_probe)
+    assert gs.rays_shadow > 0 and gpu[..., :3].mean() > 0.05
+    assert bits_equal(gpu, cpu).mean() >= 0.999
