@@ -129,6 +129,10 @@ int lmb_set_reference_image(lmb_ctx* ctx, const float* gt_rgba);
 int lmb_rmse(lmb_ctx* ctx, float* rmse_literal, double* rmse_true);
 /* Copies an image (host or device pointer) into the film: resume an accumulation, or write back a reduced sum. */
 int lmb_upload_film(lmb_ctx* ctx, const float* rgba);
+/* dst.film += src.film, element-wise: the reduce of the LMB_FILM_SUM films of a multi-GPU render (same image size; the two
+ * contexts may sit on different devices -- the copy goes device to device, over NVLink where the peers are connected).
+ * Synchronous on return. No reference equivalent (Lumen drives one GPU). */
+int lmb_film_add_from(lmb_ctx* dst, lmb_ctx* src);
 /* Device pointer of the film and the CUDA stream (cudaStream_t) the context works on, for zero-copy consumers
  * (e.g. an NCCL all-reduce issued by the caller). */
 int lmb_film_device_ptr(lmb_ctx* ctx, void** dptr, uint64_t* n_floats);

@@ -357,6 +357,29 @@ int lmb_rmse(lmb_ctx* ctx, float* rmse_literal, double* rmse_true) {
 	return launch_rmse(ctx, ctx->gt_img, ctx->rmse_scratch, rmse_literal, rmse_true);
 }
 
+// The reduce of the sum films of a multi-GPU render without leaving the devices: src's film is copied device to device
+// (cudaMemcpyPeerAsync: NVLink / NVSwitch where the peers are connected, through the host otherwise) into a staging buffer of dst
+// and added there. fp32 adds in call order: the caller fixes the order, so the result is reproducible.
+int lmb_film_add_from(lmb_ctx* dst, lmb_ctx* src) {
+	if (!dst || !src || !dst->film || !src->film) return LMB_ERR_INVALID;
+	if (dst == src) return set_error(dst, LMB_ERR_INVALID, "lmb_film_add_from: dst == src");
+	if (dst->width != src->width || dst->height != src->height) return set_error(dst, LMB_ERR_INVALID, "lmb_film_add_from: image sizes differ");
+	const size_t bytes = (size_t)dst->width * dst->height * 16;
+	cudaSetDevice(src->device);
+	LMB_CUDA(dst, cudaStreamSynchronize(src->stream));
+	cudaSetDevice(dst->device);
+	if (!dst->film_snapshot) LMB_CUDA(dst, cudaMalloc((void**)&dst->film_snapshot, bytes));
+	if (dst->copy_pending) {  // an lmb_download_async transfer may still read the staging buffer
+		LMB_CUDA(dst, cudaStreamSynchronize(dst->copy_stream));
+		dst->copy_pending = false;
+	}
+	LMB_CUDA(dst, cudaMemcpyPeerAsync(dst->film_snapshot, dst->device, src->film, src->device, bytes, dst->stream));
+	const int rc = launch_film_add(dst, dst->film_snapshot);
+	if (rc) return rc;
+	LMB_CUDA(dst, cudaStreamSynchronize(dst->stream));
+	return LMB_OK;
+}
+
 int lmb_upload_film(lmb_ctx* ctx, const float* rgba) {
 	if (!ctx || !ctx->film || !rgba) return LMB_ERR_INVALID;
 	cudaSetDevice(ctx->device);

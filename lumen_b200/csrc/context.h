@@ -163,6 +163,7 @@ int launch_resolve(lmb_ctx* ctx);
 int ingest_triangles(lmb_ctx* ctx, const uint32_t* d_tri_first, const uint8_t* d_mat_q, uint32_t n_meshes, uint32_t n_materials, uint32_t n_tris,
 					 uint32_t* tri_mesh, uint32_t* tri_local, uint4* tri_rec, uint8_t* tri_matq);
 int launch_film_to_half(lmb_ctx* ctx, uint16_t* d_planes);
+int launch_film_add(lmb_ctx* ctx, const float4* d_other);
 size_t rmse_scratch_bytes(uint32_t n_pix);
 int launch_rmse(lmb_ctx* ctx, const float4* d_gt, void* d_scratch, float* h_literal, double* h_true);
 }  // namespace lmb

@@ -154,6 +154,17 @@ int ingest_triangles(lmb_ctx* ctx, const uint32_t* d_tri_first, const uint8_t* d
 	return check_cuda(ctx, cudaGetLastError(), "k_ingest_triangles");
 }
 
+__global__ void __launch_bounds__(256) k_film_add(float4* __restrict__ film, const float4* __restrict__ other, uint32_t n_pix) {
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += gridDim.x * blockDim.x) {
+		const float4 a = film[i], b = other[i];
+		film[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+	}
+}
+int launch_film_add(lmb_ctx* ctx, const float4* d_other) {
+	k_film_add<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->film, d_other, ctx->width * ctx->height);
+	return check_cuda(ctx, cudaGetLastError(), "k_film_add");
+}
+
 int launch_film_to_half(lmb_ctx* ctx, uint16_t* d_planes) {
 	const uint32_t n_pix = ctx->width * ctx->height;
 	k_film_to_half_bgr<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->film, n_pix, d_planes);

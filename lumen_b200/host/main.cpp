@@ -5,6 +5,8 @@
 //
 //   lumen_headless scene.(json|xml) [--width W] [--height H] [--spp N] [--depth D] [--out out.exr] [--device i] [--batch F]
 //                  [--ref gt.exr [--target-rmse X]] [--checkpoint file [--checkpoint-every N] [--resume]]
+//                  [--devices 0,1,...]   several GPUs of one box: sample-index sharding, sum films reduced device to device
+//                                        (PathB200Multi; a device may be listed twice; not combined with --ref / --checkpoint)
 // Progressive service: with --ref the RMSE against the ground-truth image is computed on the device
 // after every batch (Lumen does it every 5 s, RayTracer.cpp:453-461, and prints rmse * 1e6) and rendering stops early once
 // the true RMSE falls to --target-rmse; --checkpoint writes film + frame count every N frames (and at the end), --resume
@@ -27,6 +29,7 @@ int main(int argc, char** argv) {
 	double target_rmse = -1.0;
 	uint32_t ckpt_every = 0;
 	bool resume = false;
+	std::vector<int> devices;
 	const std::regex fn("(.*).(.json|.xml)");  // RayTracer::parse_args, RayTracer.cpp:468-476
 	for (int i = 1; i < argc; i++) {
 		const std::string a = argv[i];
@@ -43,6 +46,15 @@ int main(int argc, char** argv) {
 		else if (a == "--checkpoint") ckpt_path = next();
 		else if (a == "--checkpoint-every") ckpt_every = (uint32_t)atoi(next());
 		else if (a == "--resume") resume = true;
+		else if (a == "--devices") {
+			const std::string list = next();
+			for (size_t b = 0; b < list.size();) {
+				const size_t e = list.find(',', b);
+				devices.push_back(atoi(list.substr(b, e == std::string::npos ? std::string::npos : e - b).c_str()));
+				if (e == std::string::npos) break;
+				b = e + 1;
+			}
+		}
 		else if (std::regex_match(a, fn)) scene_name = a;
 	}
 	try {
@@ -51,6 +63,26 @@ int main(int argc, char** argv) {
 		if (scene.config.integrator_name != "path")
 			fprintf(stderr, "note: scene asks for integrator '%s'; this build provides the Path integrator and uses it\n", scene.config.integrator_name.c_str());
 		batch = std::max(1u, std::min(batch, spp));
+		if (devices.size() > 1) {
+			if (!ref_path.empty() || !ckpt_path.empty()) throw std::runtime_error("--devices cannot be combined with --ref / --checkpoint");
+			const uint32_t n = (uint32_t)devices.size();
+			PathB200Multi multi(&scene, devices, batch);
+			if (depth > 0) multi.path_length = (uint32_t)depth;
+			multi.init();
+			multi.create_accel();
+			while (multi.frame_num + batch * n <= spp) {  // whole rounds of N x batch frames
+				multi.render();
+				multi.update();
+			}
+			const lmb_stats st = multi.stats();
+			const double rays = (double)(st.rays_closest + st.rays_shadow + st.rays_probe);
+			printf("%u x %u, %llu frames on %u devices, depth %u: %.1f ms on the slowest device, %.1f Mrays/s, %.2f spp/s\n", width, height,
+				   (unsigned long long)st.frames, n, multi.path_length, st.ms_render, rays / st.ms_render / 1e3, st.frames / (st.ms_render * 1e-3));
+			multi.save_exr(out.c_str());
+			printf("wrote %s\n", out.c_str());
+			multi.destroy();
+			return 0;
+		}
 		PathB200 integrator(&scene, device, batch);
 		if (depth > 0) integrator.path_length = (uint32_t)depth;
 		integrator.init();

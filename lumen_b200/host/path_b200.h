@@ -98,3 +98,119 @@ class PathB200 final : public Integrator {
 	std::vector<float> film;
 	std::vector<uint16_t> half_planes;
 };
+
+// PathB200Multi: the same integrator over several GPUs of one box. Every device holds a full scene + BVH replica
+// and renders the frames f with f mod N == its rank over the whole image (sample-index sharding: perfect balance, no seams)
+// into an un-normalised sum film with the per-pixel valid-sample count in alpha (LMB_FILM_SUM); read_output() adds the films
+// on device 0 (lmb_film_add_from: device-to-device copies, NVLink where the peers are connected) in rank order and resolves.
+// One host thread per device, because lmb_render is synchronous on return. render() advances frame_num by N * frames_per_call.
+#include <thread>
+
+class PathB200Multi final : public Integrator {
+  public:
+	PathB200Multi(lmh::Scene* scene, std::vector<int> devices, uint32_t frames_per_call = 1)
+		: Integrator(scene), devices(std::move(devices)), frames_per_call(frames_per_call), path_length((uint32_t)scene->config.path_length) {
+		if (this->devices.empty()) throw std::runtime_error("PathB200Multi: no device");
+	}
+	~PathB200Multi() override { destroy(); }
+
+	void init() override {
+		ctx.assign(devices.size(), nullptr);
+		const lmb_scene_desc desc = lumen_scene->desc();
+		each([&](size_t r) {
+			check(r, lmb_create(&ctx[r], devices[r]), "lmb_create");
+			check(r, lmb_upload_scene(ctx[r], &desc), "lmb_upload_scene");
+			check(r, lmb_init(ctx[r], lumen_scene->width, lumen_scene->height, frames_per_call), "lmb_init");
+		});
+		scene_ubo = lumen_scene->make_ubo();
+		frame_num = 0;
+		reduced = false;
+	}
+	void create_accel() override {
+		each([&](size_t r) { check(r, lmb_build_accel(ctx[r]), "lmb_build_accel"); });
+	}
+	void render() override {
+		if (reduced) throw std::runtime_error("PathB200Multi: render() after read_output() needs init() (device 0 holds the reduced film)");
+		pc_ray = lumen_scene->make_pc((int)path_length, direct_lighting);
+		pc_ray.frame_num = frame_num;
+		const uint32_t n = (uint32_t)ctx.size();
+		each([&](size_t r) { check(r, lmb_render(ctx[r], &pc_ray, &scene_ubo, frame_num + (uint32_t)r, frames_per_call, n, LMB_FILM_SUM), "lmb_render"); });
+	}
+	bool update() override {
+		frame_num += frames_per_call * (uint32_t)ctx.size();
+		return false;
+	}
+	void destroy() override {
+		for (auto& c : ctx)
+			if (c) lmb_destroy(c);
+		ctx.clear();
+	}
+	const std::vector<float>& read_output() override {
+		reduce();
+		film.resize((size_t)lumen_scene->width * lumen_scene->height * 4);
+		check(0, lmb_download(ctx[0], film.data()), "lmb_download");
+		return film;
+	}
+	void save_exr(const char* path) {
+		reduce();
+		const size_t n = (size_t)lumen_scene->width * lumen_scene->height;
+		half_planes.resize(3 * n);
+		check(0, lmb_download_half_bgr(ctx[0], half_planes.data()), "lmb_download_half_bgr");
+		std::string err;
+		if (!lmh::save_exr_half_bgr(half_planes.data(), (int)lumen_scene->width, (int)lumen_scene->height, path, &err)) throw std::runtime_error("save_exr: " + err);
+	}
+	// summed over the devices (ms_render: the slowest device)
+	lmb_stats stats() {
+		lmb_stats total{};
+		for (size_t r = 0; r < ctx.size(); r++) {
+			lmb_stats s{};
+			check(r, lmb_get_stats(ctx[r], &s), "lmb_get_stats");
+			if (r == 0) total = s;
+			else {
+				total.rays_closest += s.rays_closest, total.rays_shadow += s.rays_shadow, total.rays_probe += s.rays_probe;
+				total.nodes_visited += s.nodes_visited, total.tris_tested += s.tris_tested, total.nan_samples += s.nan_samples;
+				total.frames += s.frames, total.kernel_launches += s.kernel_launches;
+				total.ms_render = std::max(total.ms_render, s.ms_render);
+			}
+		}
+		return total;
+	}
+	uint32_t path_length;
+	bool direct_lighting = true;
+
+  private:
+	// sum films -> device 0, in rank order, then rgb /= valid-sample count
+	void reduce() {
+		if (reduced) return;
+		for (size_t r = 1; r < ctx.size(); r++) check(0, lmb_film_add_from(ctx[0], ctx[r]), "lmb_film_add_from");
+		check(0, lmb_resolve(ctx[0]), "lmb_resolve");
+		reduced = true;
+	}
+	template <typename F>
+	void each(F f) {
+		std::vector<std::thread> th;
+		std::vector<std::string> errs(devices.size());
+		for (size_t r = 0; r < devices.size(); r++)
+			th.emplace_back([&, r] {
+				try {
+					f(r);
+				} catch (const std::exception& e) {
+					errs[r] = e.what();
+				}
+			});
+		for (auto& t : th) t.join();
+		for (size_t r = 0; r < errs.size(); r++)
+			if (!errs[r].empty()) throw std::runtime_error("device " + std::to_string(devices[r]) + ": " + errs[r]);
+	}
+	void check(size_t r, int rc, const char* what) {
+		if (rc != 0) throw std::runtime_error(std::string(what) + ": " + lmb_last_error(r < ctx.size() ? ctx[r] : nullptr));
+	}
+	std::vector<int> devices;
+	uint32_t frames_per_call;
+	std::vector<lmb_ctx*> ctx;
+	bool reduced = false;
+	lmb_pc_path pc_ray{};
+	lmb_scene_ubo scene_ubo{};
+	std::vector<float> film;
+	std::vector<uint16_t> half_planes;
+};

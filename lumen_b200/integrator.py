@@ -55,6 +55,7 @@ def lib():
         L.lmb_resolve.argtypes = [vp]
         L.lmb_download.argtypes = [vp, vp]
         L.lmb_upload_film.argtypes = [vp, vp]
+        L.lmb_film_add_from.argtypes = [vp, vp]
         L.lmb_download_async.argtypes = [vp, vp]
         L.lmb_sync.argtypes = [vp]
         L.lmb_download_half_bgr.argtypes = [vp, vp]
@@ -85,7 +86,7 @@ def lib():
 
 
 EXPORTS = ["lmb_create", "lmb_destroy", "lmb_last_error", "lmb_upload_scene", "lmb_build_accel", "lmb_init", "lmb_render", "lmb_set_pixel_shard", "lmb_clear_film",
-           "lmb_resolve", "lmb_download", "lmb_upload_film", "lmb_film_device_ptr", "lmb_stream", "lmb_set_profile_stages", "lmb_get_stats",
+           "lmb_resolve", "lmb_download", "lmb_upload_film", "lmb_film_add_from", "lmb_film_device_ptr", "lmb_stream", "lmb_set_profile_stages", "lmb_get_stats",
            "lmb_reset_stats", "lmb_trace_closest", "lmb_trace_any", "lmb_trace_closest_device", "lmb_accel_num_tris", "lmb_accel_download",
            "lmb_download_async", "lmb_sync", "lmb_download_half_bgr", "lmb_set_reference_image", "lmb_rmse"]
 TESTHOOK_EXPORTS = ["lmb_kat_pcg4d", "lmb_kat_rand", "lmb_kat_detmath", "lmb_kat_offset_ray", "lmb_kat_sample_bsdf", "lmb_kat_eval_bsdf",
@@ -194,6 +195,10 @@ class Device:
         a = _f32(rgba)
         assert a.size == self.width * self.height * 4
         self._ck(lib().lmb_upload_film(self._h, a.ctypes.data), "lmb_upload_film")
+
+    def film_add_from(self, other):
+        """self.film += other.film (sum films of a multi-GPU render; device-to-device copy)."""
+        self._ck(lib().lmb_film_add_from(self._h, other._h), "lmb_film_add_from")
 
     def film_device_ptr(self):
         p, n = C.c_void_p(), C.c_uint64()

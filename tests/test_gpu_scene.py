@@ -285,3 +285,34 @@ def test_upload_rejects_out_of_range_indices(device):
         assert dev2.stats().rays > 0
     finally:
         dev2.close()
+
+
+def test_film_add_from_reduces_sum_films(device, loaded):
+    """lmb_film_add_from: dst.film += src.film, device to device -- the multi-GPU reduce of the C++ host (PathB200Multi). Two contexts
+    render the even and the odd frames in sum mode; added and resolved they give the mean of all frames."""
+    sc, orc = loaded("cornell", 64, 48)
+    pc, ubo = sc.make_pc(6, True), sc.make_ubo()
+    a, b = integrator.Device(0), integrator.Device(0)
+    try:
+        for d, first in ((a, 0), (b, 1)):
+            d.upload_scene(sc.desc)
+            d.build_accel()
+            d.init(64, 48, 2)
+            d.render(pc, ubo, first, 3, 2, integrator.FILM_SUM)  # frames first, first + 2, first + 4
+        sa, sb = a.download(), b.download()
+        a.film_add_from(b)
+        assert a.download().tobytes() == (sa + sb).tobytes()
+        a.resolve()
+        got = a.download()
+        device.init(64, 48, 3)
+        device.render(pc, ubo, 0, 6)
+        want = device.download()
+        assert np.allclose(got[..., :3], want[..., :3], rtol=3e-6, atol=1e-7) and (got[..., 3] == 1.0).all()
+        with pytest.raises(RuntimeError, match="dst == src"):
+            a.film_add_from(a)
+        b.init(32, 32, 1)
+        with pytest.raises(RuntimeError, match="image sizes differ"):
+            a.film_add_from(b)
+    finally:
+        a.close()
+        b.close()

@@ -60,3 +60,31 @@ def test_cli_checkpoint_resume_and_rmse(tmp_path):
     assert host.load_exr(str(part)).tobytes() == host.load_exr(str(full)).tobytes()
     r = _run(base + ["--spp", "8", "--out", str(part), "--ref", str(full), "--target-rmse", "1e9"])
     assert r.returncode == 0 and "true RMSE" in r.stdout
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices", ["0,0", "0,1"])
+def test_cli_multi_device_render_equals_single(tmp_path, devices):
+    """--devices: PathB200Multi shards the sample index over the listed devices (one host thread and one context each), reduces
+    the sum films device to device (lmb_film_add_from) and resolves. Same image as one device up to the order of fp32 adds."""
+    if devices == "0,1" and _n_gpus() < 2:
+        pytest.skip("needs two GPUs")
+    one, two = tmp_path / "one.exr", tmp_path / "two.exr"
+    base = [scene_path("cornell"), "--width", "80", "--height", "64", "--depth", "6", "--spp", "8", "--batch", "2"]
+    assert _run(base + ["--out", str(one)]).returncode == 0
+    r = _run(base + ["--out", str(two), "--devices", devices])
+    assert r.returncode == 0, r.stderr
+    assert "8 frames on 2 devices" in r.stdout
+    a, b = host.load_exr(str(one))[..., :3], host.load_exr(str(two))[..., :3]
+    close = np.abs(a - b) <= 2.0 ** -9 * np.maximum(np.abs(a), 1e-4)  # one half ulp either way
+    assert close.mean() > 0.999
+    r = _run(base + ["--devices", devices, "--checkpoint", str(tmp_path / "c.bin")])
+    assert r.returncode != 0 and "cannot be combined" in r.stderr
