@@ -102,6 +102,19 @@ typedef struct lmb_pc_path { /* 52 B, path_commons.h:3-14 */
 	uint32_t direct_lighting;
 } lmb_pc_path;
 
+typedef struct lmb_pc_bdpt { /* 48 B, integrators/bdpt/bdpt_commons.h:5-16 (PCPath without direct_lighting) */
+	float sky_col[3];
+	uint32_t frame_num;
+	uint32_t size_x;
+	uint32_t size_y;
+	int32_t num_lights;
+	uint32_t time; /* BDPT.cpp:57 rand() % UINT_MAX per frame; enters the RNG seed as frame_num ^ time (bdpt.rgen:36-37) */
+	int32_t max_depth;
+	float total_light_area;
+	int32_t light_triangle_count;
+	uint32_t dir_light_idx;
+} lmb_pc_bdpt;
+
 typedef struct lmb_scene_ubo { /* 492 B, commons.h:180-192; matrices column-major */
 	float projection[16];
 	float view[16];
@@ -153,6 +166,7 @@ static_assert(sizeof(lmb_light) == 128, "Light layout");
 static_assert(sizeof(lmb_material) == 104, "Material layout");
 static_assert(sizeof(lmb_prim_mesh_info) == 48, "PrimMeshInfo layout");
 static_assert(sizeof(lmb_pc_path) == 52, "PCPath layout");
+static_assert(sizeof(lmb_pc_bdpt) == 48, "PCBDPT layout");
 static_assert(sizeof(lmb_scene_ubo) == 492, "SceneUBO layout");
 #endif
 

@@ -104,6 +104,13 @@ int lmb_set_pixel_shard(lmb_ctx* ctx, uint32_t row_first, uint32_t row_stride);
  * pc->frame_num is ignored; RNG seed of a sample is (x, y, frame, 0) exactly as path.rgen:23. Synchronous. */
 int lmb_render(lmb_ctx* ctx, const lmb_pc_path* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames,
 			   uint32_t frame_stride, int film_mode);
+/* Lumen's BDPT integrator on the same scene, accel and film. Replaces BDPT::render
+ * (src/RayTracer/BDPT.cpp:55-95) = one dispatch of src/shaders/integrators/bdpt/bdpt.rgen per frame: renders frames
+ * first_frame .. first_frame + n_frames - 1 into the running-mean film (bdpt.rgen:79-89). pc->frame_num is ignored; the RNG
+ * seed of a sample is (x, y, frame ^ pc->time, 0) as bdpt.rgen:36-37 -- `time` is the caller's (BDPT.cpp:57 draws rand() per
+ * frame; pass a fresh value per call to do the same). Light-tracer splats of a frame land in that frame. Vertex storage
+ * (2 x (max_depth + 1) x 92 B per pixel) is allocated on first use. Not available with pixel shards. Synchronous. */
+int lmb_render_bdpt(lmb_ctx* ctx, const lmb_pc_bdpt* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames);
 /* Zeroes the film (Path::update resets frame_num to 0 on camera change; sum mode needs an explicit clear). */
 int lmb_clear_film(lmb_ctx* ctx);
 /* LMB_FILM_SUM epilogue: rgb /= alpha (pixels with alpha 0 stay 0), alpha = 1. */

@@ -26,6 +26,9 @@ int lmb_kat_texture(lmb_ctx* ctx, uint32_t tex, const float* uv2, uint32_t n, fl
  * errors (child box not containing its subtree, bad meta / imask), duplicate + missing triangles, internal children,
  * leaf children, leaf triangles. A valid tree has out8[0] == out8[1], out8[3] == out8[4] == 0, out8[7] == triangle count. */
 int lmb_kat_wide_bvh_check(lmb_ctx* ctx, uint64_t* out8);
+/* One BDPT frame (lmb_render_bdpt, film update included) that also hands back the two images the film is made of:
+ * col_rgba[W*H*4] = radiance of each pixel's own (s, t >= 2) strategies, splat_rgb[W*H*3] = the light-tracer image. */
+int lmb_kat_bdpt_frame_raw(lmb_ctx* ctx, const lmb_pc_bdpt* pc, const lmb_scene_ubo* ubo, uint32_t frame, float* col_rgba, float* splat_rgb);
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,20 @@ class PCPath(C.Structure):
                 ("direct_lighting", u32)]
 
 
+class PCBdpt(C.Structure):
+    """PCBDPT, integrators/bdpt/bdpt_commons.h:5-16 (48 B): PCPath without direct_lighting."""
+    _fields_ = [("sky_col", f32 * 3), ("frame_num", u32), ("size_x", u32), ("size_y", u32), ("num_lights", i32), ("time", u32),
+                ("max_depth", i32), ("total_light_area", f32), ("light_triangle_count", i32), ("dir_light_idx", u32)]
+
+    @classmethod
+    def from_path_pc(cls, pc, time=0):
+        """BDPT.cpp:55-66 fills the same fields Path.cpp:27-38 does (time is the caller's: oracle/bdpt.h quirk B1)."""
+        out = cls()
+        C.memmove(C.addressof(out), C.addressof(pc), C.sizeof(cls))
+        out.time = time
+        return out
+
+
 class SceneUBO(C.Structure):
     _fields_ = [("projection", f32 * 16), ("view", f32 * 16), ("model", f32 * 16), ("inv_view", f32 * 16),
                 ("inv_projection", f32 * 16), ("light_pos", f32 * 4), ("view_pos", f32 * 4), ("prev_view", f32 * 16),

@@ -1,0 +1,899 @@
+// bdpt.cu -- Lumen's bidirectional path tracer on the Path integrator's scene, BVH and BSDF code.
+//
+// Replaces: BDPT::render (src/RayTracer/BDPT.cpp:55-95) = one vkCmdTraceRaysKHR of src/shaders/integrators/bdpt/bdpt.rgen:39-90
+// with src/shaders/integrators/bdpt_commons.glsl:13-641 (random walks, calc_mis_weight, bdpt_connect_cam, bdpt_connect),
+// sample_light_Le / light_pdf / light_pdf_a_to_w (src/shaders/commons.glsl:40-111, 335-406) and the stand-alone bsdf_pdf
+// functions (bsdf_commons.glsl:26-66, diffuse.glsl:85-90, dielectric.glsl:191-240, conductor.glsl:74-90,
+// principled.glsl:177-181, 226-251, 338-360).
+//
+// Frozen where the reference is undefined (the same definitions as the CPU oracle, oracle/bdpt.h B1-B6): the RNG seed is
+// (x, y, frame ^ pc.time, 0) with `time` an input; vertex storage is zeroed before every frame exactly as BDPT.cpp:79-80 does;
+// the light tracer's splats (t == 1) of frame f all land in frame f: k_bdpt adds them to a splat image with float atomics and
+// k_bdpt_film, a second launch, adds that image to the pixel's own strategies before the film update (the reference reads and
+// clears the splat buffer inside the same dispatch that is still writing it).
+//
+// Layout: one thread per pixel per frame. The two sub-paths of a pixel live in HBM as a struct of arrays over pixels -- word w
+// of vertex i of pixel p at verts[((i * 23 + w) * n_pix) + p] -- so every vertex field access of a warp is one coalesced
+// 128-byte transaction; 2 x (max_depth + 1) x 92 B per pixel (2.7 GB at 1080p, depth 6). Rays walk the binary LBVH with the
+// per-thread walker of trace.cuh (hits do not depend on the tree: DESIGN.md section 2). This is the first correct state of the
+// BDPT row -- a megakernel, divergent by construction; the wavefront split the Path integrator has is the next step.
+#include <stdio.h>
+
+#include "context.h"
+#include "scene_device.cuh"
+#include "trace.cuh"
+
+namespace lmb {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ bsdf_pdf
+// diffuse.glsl:85-90
+LMB_D float lambertian_diffuse_pdf(const V3& wo, const V3& wi) {
+	if (gmin(wi.z, wo.z) <= 0.0f) return 0.0f;
+	return wi.z * LMB_INV_PI;
+}
+// dielectric.glsl:191-240
+LMB_DN float dielectric_pdf(const lmb_material& mat, const V3& wo, const V3& wi, bool forward_facing) {
+	const float roughness = mat.thin == 1 ? modify_thin_roughness(mat.ior, mat.roughness) : mat.roughness;
+	const float alpha = roughness * roughness;
+	if (alpha == 0 || mat.ior == 1) return 0.0f;
+	const bool has_reflection = has_prop(mat.bsdf_props, LMB_FLAG_REFLECTION);
+	const bool has_transmission = has_prop(mat.bsdf_props, LMB_FLAG_TRANSMISSION);
+	if (!has_reflection && !has_transmission) return 0.0f;
+	const bool is_reflection = wi.z * wo.z > 0;
+	float eta = 1.0f;
+	if (!is_reflection) eta = forward_facing ? mat.ior : 1.0f / mat.ior;
+	V3 h = normalize(wo + wi * eta);
+	h *= gsign(h.z);
+	if (wi.z == 0 || wo.z == 0 || dot(h, h) == 0) return 0.0f;
+	if (dot(wi, h) * wi.z < 0 || dot(wo, h) * wo.z < 0) return 0.0f;
+	const float F = fresnel_dielectric(dot(wo, h), mat.ior, forward_facing);
+	const float pr = has_reflection ? F : 0.0f;
+	const float pt = has_transmission ? (1.0f - F) : 0.0f;
+	float D;
+	float pdf_w = vndf_pdf_iso(alpha, wo, h, D);
+	if (is_reflection) {
+		const float jacobian = 1.0f / (4.0f * fabsf(dot(wo, h)));
+		const float prob_reflection = pr / (pr + pt);
+		pdf_w = pdf_w * jacobian * prob_reflection;
+	} else {
+		float jacobian_denom = dot(wi, h) + dot(wo, h) / eta;
+		jacobian_denom = jacobian_denom * jacobian_denom;
+		const float jacobian = fabsf(dot(wi, h)) / jacobian_denom;
+		const float prob_refraction = pt / (pr + pt);
+		pdf_w = pdf_w * jacobian * prob_refraction;
+	}
+	return pdf_w;
+}
+// conductor.glsl:74-90
+LMB_DN float conductor_pdf(const lmb_material& mat, const V3& wo, const V3& wi) {
+	const float alpha = mat.roughness * mat.roughness;
+	if (effectively_delta(alpha)) return 0.0f;
+	if (wo.z * wi.z < 0) return 0.0f;
+	if (wo.z == 0 || wi.z == 0) return 0.0f;
+	V3 h = normalize(wo + wi);
+	h *= gsign(h.z);
+	float D;
+	return vndf_pdf_iso(alpha, wo, h, D) / (4.0f * dot(wo, h));
+}
+// principled.glsl:177-181
+LMB_D float clearcoat_pdf(const lmb_material& mat, const V3& wo, const V3& wi) {
+	const V3 h = normalize(wo + wi);
+	const float D = d_ggx_iso(mix(0.1f, 0.001f, mat.clearcoat_gloss), h.z);
+	return D / (4.0f * dot(wo, h));
+}
+// principled.glsl:226-251
+LMB_DN float principled_brdf_pdf(const lmb_material& mat, const V3& wo, const V3& wi) {
+	const V2 alpha = calc_anisotropy(mat.roughness, mat.anisotropy);
+	if (effectively_delta(alpha)) return 0.0f;
+	if (wo.z * wi.z < 0) return 0.0f;
+	if (wo.z == 0 || wi.z == 0) return 0.0f;
+	V3 h = normalize(wo + wi);
+	h *= gsign(h.z);
+	float D;
+	return vndf_pdf_aniso(alpha, wo, h, D) / (4.0f * dot(wo, h));
+}
+// principled.glsl:338-360
+LMB_DN float principled_pdf(const lmb_material& mat, const V3& wo, const V3& wi, bool forward_facing) {
+	float pdf = 0.0f;
+	const float F = fresnel_dielectric(wo.z, mat.ior, forward_facing);
+	const LobeProbs p = sampling_probs(mat, F, forward_facing);
+	if (p.spec > 0) pdf += p.spec * principled_brdf_pdf(mat, wo, wi);
+	const bool upper = gmin(wi.z, wo.z) > 0;
+	if (upper) {
+		if (p.diff > 0) pdf += p.diff * lambertian_diffuse_pdf(wo, wi);
+		if (p.clearcoat > 0) pdf += p.clearcoat * clearcoat_pdf(mat, wo, wi);
+	}
+	if (p.spec_trans > 0) pdf += p.spec_trans * dielectric_pdf(mat, wo, wi, forward_facing);
+	return pdf;
+}
+// bsdf_commons.glsl:26-66
+LMB_DN float bsdf_pdf(const lmb_material& mat, const V3& n_s, const V3& wo_world, const V3& wi_world, bool forward_facing) {
+	V3 T, B;
+	branchless_onb(n_s, T, B);
+	const V3 wo = to_local(wo_world, T, B, n_s);
+	const V3 wi = to_local(wi_world, T, B, n_s);
+	switch (mat.bsdf_type) {
+		case LMB_BSDF_DIFFUSE:
+			return lambertian_diffuse_pdf(wo, wi);
+		case LMB_BSDF_DIELECTRIC:
+			return dielectric_pdf(mat, wo, wi, forward_facing);
+		case LMB_BSDF_CONDUCTOR:
+			return conductor_pdf(mat, wo, wi);
+		case LMB_BSDF_PRINCIPLED:
+			return principled_pdf(mat, wo, wi, forward_facing);
+		default:
+			break;
+	}
+	return 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------ lights
+LMB_D bool is_light_finite(uint32_t f) { return ((f >> 4) & 1u) != 0; }  // commons.glsl:42
+LMB_D bool is_light_delta(uint32_t f) { return ((f >> 5) & 1u) != 0; }   // commons.glsl:44
+LMB_D float uniform_cone_pdf(float cos_max) { return 1.0f / (LMB_TWO_PI * (1 - cos_max)); }  // commons.glsl:40
+LMB_D bool same_hemisphere(const V3& wi, const V3& wo, const V3& n) { return dot(wi, n) > 0 && dot(wo, n) > 0; }
+LMB_D bool is_zero(const V3& f) { return f.x == 0 && f.y == 0 && f.z == 0; }
+
+// commons.glsl:81-95
+LMB_D float light_pdf(uint32_t light_flags, const V3& n_s, const V3& wi) {
+	const float cos_width = lmb_cosf(30 * LMB_PI / 180);
+	switch (light_flags & 0x7u) {
+		case LMB_LIGHT_AREA:
+			return gmax(dot(n_s, wi) / LMB_PI, 0.0f);
+		case LMB_LIGHT_SPOT:
+			return uniform_cone_pdf(cos_width);
+		default:
+			break;
+	}
+	return 0.0f;
+}
+// commons.glsl:64-79
+LMB_D float light_pdf_a_to_w(uint32_t light_flags, float pdf_a, float wi_len_sqr, float cos_from_light) {
+	switch (light_flags & 0x7u) {
+		case LMB_LIGHT_AREA:
+			return pdf_a * wi_len_sqr / cos_from_light;
+		case LMB_LIGHT_SPOT:
+			return wi_len_sqr / cos_from_light;
+		case LMB_LIGHT_DIRECTIONAL:
+			return 1.0f;
+		default:
+			break;
+	}
+	return 0.0f;
+}
+// utils.glsl:157-173
+LMB_D V4 to_local_quat(const V3& v) {
+	if (v.z < -0.99999f) return v4(1, 0, 0, 0);
+	const V4 q = v4(v.y, -v.x, 0.0f, 1.0f + v.z);
+	const float inv = 1.0f / sqrtf((q.x * q.x + q.y * q.y) + (q.z * q.z + q.w * q.w));
+	return v4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+}
+LMB_D V3 rot_quat(const V4& q, const V3& v) {
+	const V3 q_axis = v3(q.x, q.y, q.z);
+	return (2.0f * dot(q_axis, v)) * q_axis + (q.w * q.w - dot(q_axis, q_axis)) * v + (2.0f * q.w) * cross(q_axis, v);
+}
+// utils.glsl:175-182
+LMB_D void make_coord_system(const V3& v1, V3& v2o, V3& v3o) {
+	if (fabsf(v1.x) > fabsf(v1.y))
+		v2o = normalize(v3(-v1.z, 0, v1.x));
+	else
+		v2o = normalize(v3(0, v1.z, -v1.y));
+	v3o = cross(v1, v2o);
+}
+// commons.glsl:217-222
+LMB_D V3 uniform_sample_cone(const V2& uv, float cos_max) {
+	const float cos_theta = (1.0f - uv.x) + uv.x * cos_max;
+	const float sin_theta = sqrtf(1 - cos_theta * cos_theta);
+	const float phi = uv.y * LMB_TWO_PI;
+	return v3(lmb_cosf(phi) * sin_theta, lmb_sinf(phi) * sin_theta, cos_theta);
+}
+// sampling_commons.glsl:147-161 (concentric-disk mode), explicit normal
+LMB_D V3 sample_hemisphere_n(const V2& xi, const V3& n) {
+	V3 T, B;
+	branchless_onb(n, T, B);
+	const V2 d = concentric_sample_disk(xi);
+	const float z = sqrtf(gmax(0.f, 1.f - dot(d, d)));
+	return to_world(v3(d.x, d.y, z), T, B, n);
+}
+
+struct TriangleRecord {
+	V3 pos, n_s;
+	float triangle_pdf;
+};
+// commons.glsl:112-149 (Q7: w = 1 on the edge vectors and on the normal); same expressions as the AREA branch of sample_light_Li
+LMB_DN TriangleRecord sample_triangle(const DeviceScene& sc, const lmb_light& light, float r_tri, float r_u, float r_v, V2& uv, uint32_t& material_idx) {
+	TriangleRecord r;
+	const uint32_t pm = light.prim_mesh_idx;
+	const lmb_prim_mesh_info& pinfo = sc.prim_infos[pm];
+	material_idx = pinfo.material_index;
+	const uint32_t triangle_idx = (uint32_t)(r_tri * (float)light.num_triangles);
+	const M4 wm = load_m4(light.world_matrix);
+	const M4 inv_tr = transpose(load_m4(sc.inv_world_matrices + 16 * pm));
+	const uint32_t index_offset = pinfo.index_offset + 3 * triangle_idx;
+	const uint32_t vo = pinfo.vertex_offset;
+	const lmb_vertex a0 = sc.vertices[sc.indices[index_offset + 0] + vo];
+	const lmb_vertex a1 = sc.vertices[sc.indices[index_offset + 1] + vo];
+	const lmb_vertex a2 = sc.vertices[sc.indices[index_offset + 2] + vo];
+	const V3 q0 = vtx_pos(a0), q1 = vtx_pos(a1), q2 = vtx_pos(a2);
+	const V3 n0 = vtx_nrm(a0), n1 = vtx_nrm(a1), n2 = vtx_nrm(a2);
+	const float sq = sqrtf(r_u);
+	uv = v2(1 - sq, r_v * sq);
+	const V3 bary = v3(1.0f - uv.x - uv.y, uv.x, uv.y);
+	const V4 etmp0 = mul(wm, v4(q1 - q0, 1.0f));
+	const V4 etmp1 = mul(wm, v4(q2 - q0, 1.0f));
+	const V3 pos = q0 * bary.x + q1 * bary.y + q2 * bary.z;
+	const V3 nrm = normalize(n0 * bary.x + n1 * bary.y + n2 * bary.z);
+	const V4 world_pos = mul(wm, v4(pos, 1.0f));
+	r.n_s = normalize(xyz(mul(inv_tr, v4(nrm, 1.0f))));
+	r.triangle_pdf = 2.0f / length(cross(xyz(etmp0), xyz(etmp1)));
+	r.pos = xyz(world_pos);
+	return r;
+}
+
+// `out vec3 n, out vec3 pos` of sample_light_Li (commons.glsl:224-300), which scene_device.cuh's version (shared with the Path
+// kernels) does not return: recomputed from the same inputs with the same expressions.
+LMB_DN void light_sample_n_pos(const DeviceScene& sc, const V4& rands, const V3& p, int num_lights, const LightSample& ls, V3& n, V3& pos) {
+	n = v3(0.0f), pos = v3(0.0f);
+	const uint32_t light_idx = (uint32_t)(rands.x * (float)num_lights);
+	const lmb_light& light = sc.lights[light_idx];
+	switch (light.light_flags & 0x7u) {
+		case LMB_LIGHT_AREA: {
+			V2 uv;
+			uint32_t material_idx;
+			const TriangleRecord rec = sample_triangle(sc, light, rands.y, rands.z, rands.w, uv, material_idx);
+			n = rec.n_s;
+			pos = rec.pos;
+		} break;
+		case LMB_LIGHT_SPOT:
+			n = -ls.wi;
+			pos = v3(light.pos);
+			break;
+		case LMB_LIGHT_DIRECTIONAL: {
+			const V3 dir = normalize(v3(light.pos) - v3(light.to));
+			n = -ls.wi;
+			pos = p + dir * (2 * light.world_radius);
+		} break;
+		default:
+			break;
+	}
+}
+
+struct LightEmission {
+	V3 L, pos, wi, n;
+	float cos_from_light, pdf_pos_a, pdf_dir_w;
+	uint32_t flags;
+};
+// commons.glsl:335-406
+LMB_DN LightEmission sample_light_Le(const DeviceScene& sc, const V4& rands_pos, const V2& rands_dir, int num_lights, int total_light) {
+	LightEmission o;
+	o.L = v3(0.0f), o.pos = v3(0.0f), o.wi = v3(0.0f), o.n = v3(0.0f);
+	o.cos_from_light = 0, o.pdf_pos_a = 0, o.pdf_dir_w = 0;
+	const uint32_t light_idx = (uint32_t)(rands_pos.x * (float)num_lights);
+	const lmb_light& light = sc.lights[light_idx];
+	o.flags = light.light_flags;
+	switch (light.light_flags & 0x7u) {
+		case LMB_LIGHT_AREA: {
+			V2 bary;
+			uint32_t material_idx;
+			const TriangleRecord rec = sample_triangle(sc, light, rands_pos.y, rands_pos.z, rands_pos.w, bary, material_idx);
+			const lmb_material light_mat = load_material(sc, material_idx, bary);
+			o.pos = rec.pos;
+			o.wi = sample_hemisphere_n(rands_dir, rec.n_s);
+			o.L = v3(light_mat.emissive_factor);
+			o.cos_from_light = gmax(dot(rec.n_s, o.wi), 0.0f);
+			o.pdf_pos_a = rec.triangle_pdf;
+			o.pdf_dir_w = dot(o.wi, rec.n_s) / LMB_PI;
+			o.n = rec.n_s;
+		} break;
+		case LMB_LIGHT_SPOT: {
+			const float cos_width = lmb_cosf(30 * LMB_PI / 180);
+			const float cos_faloff = lmb_cosf(25 * LMB_PI / 180);
+			const V3 light_dir = normalize(v3(light.to) - v3(light.pos));
+			const V4 lq = to_local_quat(light_dir);
+			o.wi = rot_quat(v4(-lq.x, -lq.y, -lq.z, lq.w), uniform_sample_cone(rands_dir, cos_width));
+			o.pos = v3(light.pos);
+			o.cos_from_light = dot(o.wi, light_dir);
+			float faloff;
+			if (o.cos_from_light < cos_width) {
+				faloff = 0;
+			} else if (o.cos_from_light >= cos_faloff) {
+				faloff = 1;
+			} else {
+				const float d = (o.cos_from_light - cos_width) / (cos_faloff - cos_width);
+				faloff = (d * d) * (d * d);
+			}
+			o.L = v3(light.L) * faloff;
+			o.pdf_pos_a = 1.0f;
+			o.pdf_dir_w = uniform_cone_pdf(cos_width);
+			o.n = o.wi;
+		} break;
+		case LMB_LIGHT_DIRECTIONAL: {
+			const V3 dir = -normalize(v3(light.to) - v3(light.pos));
+			V3 v1, v2_;
+			make_coord_system(dir, v1, v2_);
+			const V2 uv = concentric_sample_disk(rands_dir);
+			const V3 l_pos = v3(light.world_center) + light.world_radius * (uv.x * v1 + uv.y * v2_);
+			o.pos = l_pos + dir * light.world_radius;
+			o.wi = -dir;
+			o.L = v3(light.L);
+			o.pdf_pos_a = 1.0f / (LMB_PI * light.world_radius * light.world_radius);
+			o.pdf_dir_w = 1;
+			o.cos_from_light = 1;
+			o.n = o.wi;
+		} break;
+		default:
+			break;
+	}
+	o.pdf_pos_a /= (float)total_light;
+	return o;
+}
+
+// payload.area of ray.rchit:76-83 (the Path kernels' build_hit leaves it out: path.rgen never reads it)
+LMB_DN float hit_area(const DeviceScene& sc, uint32_t prim_global) {
+	const uint4 rec = __ldg(&sc.tri_rec[prim_global]);
+	const V3 q0 = vtx_pos(sc.vertices[rec.x]), q1 = vtx_pos(sc.vertices[rec.y]), q2 = vtx_pos(sc.vertices[rec.z]);
+	const M4 o2w = load_m4(sc.world_matrices + 16 * rec.w);
+	const V3 e0t = xyz(mul(o2w, v4(q2 - q0, 0.0f)));
+	const V3 e1t = xyz(mul(o2w, v4(q1 - q0, 0.0f)));
+	return 0.5f * length(cross(e0t, e1t));
+}
+
+// ------------------------------------------------------------------------------------------------ vertex storage
+// PathVertex (bdpt_commons.h:18-33), 23 words, struct of arrays over pixels.
+enum VertexWord { W_DIR = 0, W_NS = 3, W_POS = 6, W_UV = 9, W_THR = 11, W_LFLAGS = 14, W_LIDX = 15, W_MAT = 16, W_DELTA = 17, W_SIDE = 18, W_MODE = 19,
+				  W_AREA = 20, W_PFWD = 21, W_PREV = 22, W_COUNT = 23 };
+
+struct Verts {
+	float* base;    // word 0 of vertex 0 of this pixel
+	size_t stride;  // pixels
+	LMB_D float& f(int i, int w) const { return base[((size_t)i * W_COUNT + w) * stride]; }
+	LMB_D uint32_t u(int i, int w) const { return __float_as_uint(f(i, w)); }
+	LMB_D void su(int i, int w, uint32_t v) const { f(i, w) = __uint_as_float(v); }
+	LMB_D V3 v(int i, int w) const { return v3(f(i, w), f(i, w + 1), f(i, w + 2)); }
+	LMB_D void sv(int i, int w, const V3& a) const { f(i, w) = a.x, f(i, w + 1) = a.y, f(i, w + 2) = a.z; }
+	LMB_D V2 uv(int i) const { return v2(f(i, W_UV), f(i, W_UV + 1)); }
+};
+
+struct Sampled {  // the fields of `PathVertex sampled` that calc_mis_weight reads (oracle/bdpt.h B4: zero unless a strategy writes them)
+	V3 pos, n_s;
+	float pdf_fwd;
+};
+
+struct BdptParams {
+	M4 inv_view, inv_proj, view, neg_proj;
+	uint32_t width, height, n_pix, frame, seed_z;
+	int32_t num_lights, max_depth, light_triangle_count;
+	float* light_verts;
+	float* camera_verts;
+	float4* col;    // per pixel: radiance of the pixel's own strategies (t >= 2)
+	float* splat;   // 3 floats per pixel: light-tracer image of this frame
+	unsigned long long* stats;
+};
+
+struct Kctx {  // per-thread state of one pixel
+	const BdptParams& P;
+	const DeviceScene& sc;
+	const BvhView& bvh;
+	Rng seed;
+	Verts lig, cam;
+	float light_pdf_pos;
+	float screen_size;
+	uint32_t n_closest, n_shadow, n_nodes, n_tris;
+};
+
+constexpr float BDPT_T_MIN = 0.001f;  // bdpt_commons.glsl:24-25
+constexpr float BDPT_T_MAX = 1e6f;
+
+LMB_DN Hit trace_closest(Kctx& k, const V3& o, const V3& d, float tmin, float tmax) {
+	k.n_closest++;
+	return trace_ray<false>(k.bvh, o, d, tmin, tmax, k.n_nodes, k.n_tris);
+}
+LMB_DN bool occluded(Kctx& k, const V3& o, const V3& d, float tmax) {
+	k.n_shadow++;
+	return trace_ray<true>(k.bvh, o, d, 0.0f, tmax, k.n_nodes, k.n_tris).prim != 0xFFFFFFFFu;
+}
+
+// bdpt_commons.glsl:13-111 (EYE = false), :113-216 (EYE = true). V.x(i + 1, ..) is the GLSL's vtx(i, ..).
+template <bool EYE>
+LMB_DN int random_walk(Kctx& k, const Verts& V, int max_depth, V3 throughput, float pdf) {
+	if (max_depth == 0) return 0;
+	int b = 0;
+	int prev = 0;
+	V3 ray_pos = V.v(0, W_POS);
+	float pdf_fwd = pdf;
+	float pdf_rev = 0.0f;
+	V3 wi = V.v(0, W_DIR);
+	const bool finite_light = is_light_finite(V.u(0, W_LFLAGS));
+	while (true) {
+		prev = b - 1;
+		const Hit h = trace_closest(k, ray_pos, wi, BDPT_T_MIN, BDPT_T_MAX);
+		if (h.prim == 0xFFFFFFFFu) {
+			if (EYE) {
+				V.sv(b + 1, W_THR, throughput);
+				V.f(b + 1, W_PFWD) = pdf_fwd;
+				b++;
+			}
+			break;
+		}
+		const HitPayload payload = build_hit(k.sc, h.prim, h.b1, h.b2);
+		V3 wo = V.v(prev + 1, W_POS) - payload.pos;
+		const float wo_len = length(wo);
+		wo /= wo_len;
+		V3 n_s = payload.n_s;
+		bool side = true;
+		V3 n_g = payload.n_g;
+		if (dot(payload.n_g, wo) < 0.0f) n_g = -n_g;
+		if (dot(n_g, n_s) < 0) {
+			n_s *= -1.0f;
+			side = false;
+		}
+		V.f(b + 1, W_PFWD) = pdf_fwd * fabsf(dot(wo, n_s)) / (wo_len * wo_len);
+		V.sv(b + 1, W_NS, n_s);
+		V.f(b + 1, W_AREA) = hit_area(k.sc, h.prim);
+		V.sv(b + 1, W_POS, payload.pos);
+		V.f(b + 1, W_UV) = payload.uv.x, V.f(b + 1, W_UV + 1) = payload.uv.y;
+		V.su(b + 1, W_MAT, payload.material_idx);
+		V.sv(b + 1, W_THR, throughput);
+		V.su(b + 1, W_SIDE, side ? 1u : 0u);
+		V.su(b + 1, W_MODE, EYE ? 1u : 0u);
+		const lmb_material mat = load_material(k.sc, payload.material_idx, payload.uv);
+		const bool mat_specular = (mat.bsdf_props & LMB_FLAG_SPECULAR) == LMB_FLAG_SPECULAR;
+		const bool mat_transmissive = (mat.bsdf_props & LMB_FLAG_TRANSMISSION) == LMB_FLAG_TRANSMISSION;
+		V.su(b + 1, W_DELTA, mat_specular ? 1u : 0u);
+		if (++b >= max_depth) break;
+		const V3 r3 = rand3(k.seed);
+		const BsdfSample bs = sample_bsdf(n_s, wo, mat, EYE ? 1u : 0u, side, r3);
+		wi = bs.wi;
+		pdf_fwd = bs.pdf;
+		const bool same_hem = same_hemisphere(wi, wo, n_s);
+		if (is_zero(bs.f) || pdf_fwd == 0 || (!same_hem && !mat_transmissive)) break;
+		throughput *= bs.f * fabsf(bs.cos_theta) / pdf_fwd;
+		pdf_rev = pdf_fwd;
+		if (!mat_specular) pdf_rev = bsdf_pdf(mat, n_s, wi, wo, side);
+		const bool g_term = EYE ? true : (prev > -1 || finite_light);
+		if (g_term) pdf_rev *= fabsf(dot(V.v(prev + 1, W_NS), wo)) / (wo_len * wo_len);
+		V.f(prev + 1, W_PREV) = pdf_rev;
+		ray_pos = offset_ray(payload.pos, n_g);
+	}
+	return b;
+}
+
+// bdpt_commons.glsl:218-260
+LMB_DN int generate_light_subpath(Kctx& k, int max_depth) {
+	const V4 rands_pos = rand4(k.seed);
+	const float d0 = rand1(k.seed);
+	const float d1 = rand1(k.seed);
+	const LightEmission le = sample_light_Le(k.sc, rands_pos, v2(d0, d1), k.P.num_lights, k.P.light_triangle_count);
+	if (le.pdf_dir_w <= 0) return 0;
+	k.light_pdf_pos = le.pdf_pos_a;
+	const Verts& L = k.lig;
+	L.sv(0, W_POS, le.pos);
+	L.su(0, W_LFLAGS, le.flags);
+	L.su(0, W_DELTA, 0);
+	L.sv(0, W_DIR, le.wi);
+	L.f(0, W_PFWD) = le.pdf_pos_a;
+	L.sv(0, W_NS, le.n);
+	L.su(0, W_SIDE, 1);
+	L.su(0, W_MODE, 0);
+	const V3 throughput = le.L * le.cos_from_light / (le.pdf_dir_w * le.pdf_pos_a);
+	L.sv(0, W_THR, le.L);
+	const int num_light_verts = random_walk<false>(k, L, max_depth - 1, throughput, le.pdf_dir_w) + 1;
+	if (!is_light_finite(le.flags)) L.f(1, W_PFWD) = le.pdf_pos_a * fabsf(dot(le.wi, L.v(1, W_NS)));
+	if (is_light_delta(le.flags)) L.f(0, W_PFWD) = 0.0f;
+	return num_light_verts;
+}
+
+LMB_D M4 neg_m4(const M4& m) {
+	M4 r;
+#pragma unroll
+	for (int c = 0; c < 4; c++) r.c[c] = v4(-m.c[c].x, -m.c[c].y, -m.c[c].z, -m.c[c].w);
+	return r;
+}
+
+// bdpt_commons.glsl:262-286
+LMB_DN int generate_camera_subpath(Kctx& k, const V2& d, const V3& origin, int max_depth, float cam_area) {
+	const Verts& C = k.cam;
+	C.sv(0, W_POS, origin);
+	const V4 target = mul(k.P.inv_proj, v4(d.x, d.y, 1, 1));
+	const V3 dir = xyz(mul(k.P.inv_view, v4(normalize(xyz(target)), 0)));  // sample_camera, commons.glsl:30-33
+	C.sv(0, W_DIR, dir);
+	C.f(0, W_AREA) = cam_area;
+	C.sv(0, W_THR, v3(1.0f));
+	C.su(0, W_DELTA, 0);
+	const V3 n_s = xyz(mul(neg_m4(k.P.inv_view), v4(0, 0, 1, 0)));
+	C.sv(0, W_NS, n_s);
+	C.su(0, W_SIDE, 1);
+	k.lig.su(0, W_MODE, 1);  // sic, :272
+	const float cos_theta = dot(dir, n_s);
+	const float pdf = 1 / (cam_area * k.screen_size * cos_theta * cos_theta * cos_theta);
+	return random_walk<true>(k, C, max_depth - 1, v3(1.0f), pdf) + 1;
+}
+
+LMB_D float remap0(float v) { return v != 0.0f ? v : 1.0f; }
+
+// bdpt_commons.glsl:288-470. The GLSL patches vertices in place and restores them afterwards; so does this.
+LMB_DN float calc_mis_weight(Kctx& k, int s, int t, const Sampled& sampled) {
+	const Verts& cam = k.cam;
+	const Verts& lig = k.lig;
+	bool s_0_changed = false, t_0_changed = false;
+	float s_0_pdf = 0;
+	V3 s_0_pdf_pos = v3(0.0f), s_0_pdf_nrm = v3(0.0f);
+	uint32_t idx_1 = 0xFFFFFFFFu, idx_2 = 0xFFFFFFFFu, idx_3 = 0xFFFFFFFFu, idx_4 = 0xFFFFFFFFu;
+	float idx_1_val = 0, idx_2_val = 0, idx_3_val = 0, idx_4_val = 0;
+	uint32_t delta_t_old = 0, delta_s_old = 0;
+	if (s + t == 2) return 1.0f;
+	if (s == 1) {
+		s_0_pdf = lig.f(0, W_PFWD), s_0_pdf_pos = lig.v(0, W_POS), s_0_pdf_nrm = lig.v(0, W_NS);
+		lig.f(0, W_PFWD) = sampled.pdf_fwd, lig.sv(0, W_POS, sampled.pos), lig.sv(0, W_NS, sampled.n_s);
+		s_0_changed = true;
+	}
+	if (t == 1) {
+		s_0_pdf = cam.f(0, W_PFWD), s_0_pdf_pos = cam.v(0, W_POS), s_0_pdf_nrm = cam.v(0, W_NS);
+		cam.f(0, W_PFWD) = sampled.pdf_fwd, cam.sv(0, W_POS, sampled.pos), cam.sv(0, W_NS, sampled.n_s);
+		t_0_changed = true;
+	}
+	if (t > 0) {
+		delta_t_old = cam.u(t - 1, W_DELTA);
+		cam.su(t - 1, W_DELTA, 0);
+	}
+	if (s > 0) {
+		delta_s_old = lig.u(s - 1, W_DELTA);
+		lig.su(s - 1, W_DELTA, 0);
+	}
+	if (t > 0) {
+		idx_1_val = cam.f(t - 1, W_PREV);
+		idx_1 = (uint32_t)t;
+		if (s > 0) {
+			V3 dir = cam.v(t - 1, W_POS) - lig.v(s - 1, W_POS);
+			const float dir_len = length(dir);
+			dir /= dir_len;
+			float pdf_rev = 0;
+			if (s >= 2) {
+				const lmb_material mat = load_material(k.sc, lig.u(s - 1, W_MAT), lig.uv(s - 1));
+				const V3 wo = normalize(lig.v(s - 2, W_POS) - lig.v(s - 1, W_POS));
+				pdf_rev = bsdf_pdf(mat, lig.v(s - 1, W_NS), wo, dir, lig.u(s - 1, W_SIDE) == 1);
+				pdf_rev *= fabsf(dot(dir, cam.v(t - 1, W_NS))) / (dir_len * dir_len);
+			} else {
+				if (!is_light_finite(lig.u(0, W_LFLAGS))) {
+					pdf_rev = k.light_pdf_pos;
+					pdf_rev *= fabsf(dot(dir, cam.v(t - 1, W_NS)));
+				} else {
+					pdf_rev = light_pdf(lig.u(0, W_LFLAGS), lig.v(0, W_NS), dir);
+					pdf_rev *= fabsf(dot(dir, cam.v(t - 1, W_NS))) / (dir_len * dir_len);
+				}
+			}
+			cam.f(t - 1, W_PREV) = pdf_rev;
+		} else {
+			cam.f(t - 1, W_PREV) = 1.0f / ((float)k.P.light_triangle_count * cam.f(t - 1, W_AREA));
+		}
+	}
+	if (t > 1) {
+		idx_2_val = cam.f(t - 2, W_PREV);
+		idx_2 = (uint32_t)t;
+		V3 dir = cam.v(t - 2, W_POS) - cam.v(t - 1, W_POS);
+		const float dir_len = length(dir);
+		dir /= dir_len;
+		if (s > 0) {
+			const lmb_material mat = load_material(k.sc, cam.u(t - 1, W_MAT), cam.uv(t - 1));
+			const V3 wo = normalize(lig.v(s - 1, W_POS) - cam.v(t - 1, W_POS));
+			float pr = bsdf_pdf(mat, cam.v(t - 1, W_NS), wo, dir, cam.u(t - 1, W_SIDE) == 1);
+			if (pr != 0) pr *= fabsf(dot(dir, cam.v(t - 2, W_NS))) / (dir_len * dir_len);
+			cam.f(t - 2, W_PREV) = pr;
+		} else {
+			const float cos_x = dot(cam.v(t - 1, W_NS), dir);
+			const float cos_y = dot(cam.v(t - 2, W_NS), dir);
+			cam.f(t - 2, W_PREV) = fabsf(cos_x * cos_y) / (LMB_PI * dir_len * dir_len);
+		}
+	}
+	if (s > 0) {
+		idx_3_val = lig.f(s - 1, W_PREV);
+		idx_3 = (uint32_t)s;
+		V3 dir = lig.v(s - 1, W_POS) - cam.v(t - 1, W_POS);
+		const float dir_len = length(dir);
+		dir /= dir_len;
+		if (t == 1) {
+			const float cos_theta = dot(cam.v(0, W_NS), dir);
+			float pdf = 1.0f / (cam.f(0, W_AREA) * k.screen_size * cos_theta * cos_theta * cos_theta);
+			pdf *= fabsf(dot(dir, lig.v(s - 1, W_NS))) / (dir_len * dir_len);
+			lig.f(s - 1, W_PREV) = pdf;
+		} else {
+			const V3 wo = normalize(cam.v(t - 2, W_POS) - cam.v(t - 1, W_POS));
+			const lmb_material mat = load_material(k.sc, cam.u(t - 1, W_MAT), cam.uv(t - 1));
+			float pr = bsdf_pdf(mat, cam.v(t - 1, W_NS), wo, dir, cam.u(t - 1, W_SIDE) == 1);
+			if ((s == 1 && is_light_finite(lig.u(0, W_LFLAGS))) || s > 1) pr *= fabsf(dot(dir, lig.v(s - 1, W_NS))) / (dir_len * dir_len);
+			lig.f(s - 1, W_PREV) = pr;
+		}
+	}
+	if (s > 1) {
+		idx_4_val = lig.f(s - 2, W_PREV);
+		idx_4 = (uint32_t)s;
+		V3 dir = lig.v(s - 2, W_POS) - lig.v(s - 1, W_POS);
+		const V3 wo = normalize(cam.v(t - 1, W_POS) - lig.v(s - 1, W_POS));
+		const float dir_len = length(dir);
+		dir /= dir_len;
+		const lmb_material mat = load_material(k.sc, lig.u(s - 1, W_MAT), lig.uv(s - 1));
+		float pr = bsdf_pdf(mat, lig.v(s - 1, W_NS), wo, dir, lig.u(s - 1, W_SIDE) == 1);
+		if ((s == 2 && is_light_finite(lig.u(0, W_LFLAGS))) || s > 2) pr *= fabsf(dot(dir, lig.v(s - 2, W_NS))) / (dir_len * dir_len);
+		lig.f(s - 2, W_PREV) = pr;
+	}
+	float sum_ri = 0.0f;
+	float weight = 1.0f;
+	for (int i = t - 1; i > 0; i--) {
+		weight *= remap0(cam.f(i, W_PREV)) / remap0(cam.f(i, W_PFWD));
+		if (cam.u(i, W_DELTA) == 0 && cam.u(i - 1, W_DELTA) == 0) sum_ri += weight;
+	}
+	weight = 1.0f;
+	for (int i = s - 1; i >= 0; i--) {
+		weight *= remap0(lig.f(i, W_PREV)) / remap0(lig.f(i, W_PFWD));
+		const bool delta_prev = i > 0 ? lig.u(i - 1, W_DELTA) == 1 : is_light_delta(lig.u(0, W_LFLAGS));
+		if (lig.u(i, W_DELTA) == 0 && !delta_prev) sum_ri += weight;
+	}
+	if (s_0_changed) lig.f(0, W_PFWD) = s_0_pdf, lig.sv(0, W_POS, s_0_pdf_pos), lig.sv(0, W_NS, s_0_pdf_nrm);
+	if (t_0_changed) cam.f(0, W_PFWD) = s_0_pdf, cam.sv(0, W_POS, s_0_pdf_pos), cam.sv(0, W_NS, s_0_pdf_nrm);
+	if (idx_1 != 0xFFFFFFFFu) {
+		cam.f(idx_1 - 1, W_PREV) = idx_1_val;
+		cam.su(idx_1 - 1, W_DELTA, delta_t_old);
+	}
+	if (idx_2 != 0xFFFFFFFFu) cam.f(idx_2 - 2, W_PREV) = idx_2_val;
+	if (idx_3 != 0xFFFFFFFFu) {
+		lig.f(idx_3 - 1, W_PREV) = idx_3_val;
+		lig.su(idx_3 - 1, W_DELTA, delta_s_old);
+	}
+	if (idx_4 != 0xFFFFFFFFu) lig.f(idx_4 - 2, W_PREV) = idx_4_val;
+	return 1 / (1 + sum_ri);
+}
+
+// `ivec2(...)` of a float with no int value is undefined in GLSL: the splat is dropped (oracle/bdpt.h B5)
+LMB_D bool splat_coord(float v, int& out) {
+	if (!(fabsf(v) < 1e9f)) return false;
+	out = (int)v;
+	return true;
+}
+
+// bdpt_commons.glsl:472-530
+LMB_DN V3 connect_cam(Kctx& k, int s, int& cx, int& cy) {
+	const Verts& cam = k.cam;
+	const Verts& lig = k.lig;
+	Sampled sampled{v3(0.0f), v3(0.0f), 0.0f};
+	V3 L = v3(0.0f);
+	cx = cy = -1;
+	const V3 cam_pos = cam.v(0, W_POS), cam_n = cam.v(0, W_NS);
+	const V3 lpos = lig.v(s - 1, W_POS), ln = lig.v(s - 1, W_NS);
+	V3 dir = cam_pos - lpos;
+	const float len = length(dir);
+	dir /= len;
+	const float cos_y = dot(dir, ln);
+	const float cos_theta = dot(cam_n, -dir);
+	if (cos_theta <= 0.0f) return v3(0.0f);
+	const float cos_3_theta = cos_theta * cos_theta * cos_theta;
+	const float cam_pdf_ratio = fabsf(cos_y) / (cam.f(0, W_AREA) * cos_3_theta * len * len);
+	const V3 ray_origin = offset_ray2(lpos, ln);
+	const lmb_material mat = load_material(k.sc, lig.u(s - 1, W_MAT), lig.uv(s - 1));
+	const V3 wo = normalize(lig.v(s - 2, W_POS) - lpos);
+	float unused_pdf;
+	const V3 f = eval_bsdf(ln, wo, mat, lig.u(s - 1, W_SIDE) == 1, dir, unused_pdf);
+	if (is_zero(f)) return L;
+	if (cam_pdf_ratio > 0.0f) {
+		if (!occluded(k, ray_origin, dir, len - LMB_EPS)) {
+			sampled.pos = cam_pos;
+			sampled.n_s = cam_n;
+			L = lig.v(s - 1, W_THR) * cam_pdf_ratio * f / k.screen_size;
+		}
+	}
+	dir = -dir;
+	V4 target = mul(k.P.view, v4(dir.x, dir.y, dir.z, 0));
+	target = v4(target.x / target.z, target.y / target.z, target.z / target.z, target.w / target.z);
+	target = mul(k.P.neg_proj, target);
+	const V2 cf = 0.5f * (v2(target.x, target.y) + 1.0f) * v2((float)k.P.width, (float)k.P.height) - 0.5f;
+	if (!splat_coord(cf.x, cx) || !splat_coord(cf.y, cy)) {
+		cx = cy = -1;
+		return v3(0.0f);
+	}
+	if (cx < 0 || (uint32_t)cx >= k.P.width || cy < 0 || (uint32_t)cy >= k.P.height || dot(dir, cam_n) < 0) return v3(0.0f);
+	float mis_weight = 1.0f;
+	if (luminance(L) != 0.0f) mis_weight = calc_mis_weight(k, s, 1, sampled);
+	return mis_weight * L;
+}
+
+// bdpt_commons.glsl:532-641
+LMB_DN V3 connect(Kctx& k, int s, int t) {
+	const Verts& cam = k.cam;
+	const Verts& lig = k.lig;
+	V3 L = v3(0.0f);
+	Sampled sampled{v3(0.0f), v3(0.0f), 0.0f};
+	if (s == 0) {
+		const lmb_material& mat = k.sc.materials[cam.u(t - 1, W_MAT)];  // `materials.m[mat_idx]`: un-textured, and material 0 for an escaped vertex (B3)
+		L = v3(mat.emissive_factor) * cam.v(t - 1, W_THR);
+	} else if (s == 1) {
+		const V4 r4 = rand4(k.seed);
+		const V3 cpos = cam.v(t - 1, W_POS), cn = cam.v(t - 1, W_NS);
+		const LightSample ls = sample_light_Li(k.sc, r4, cpos, k.P.num_lights);
+		const float cos_x = fabsf(dot(ls.wi, cn));
+		const V3 ray_origin = offset_ray2(cpos, cn);
+		const V3 wo = normalize(cam.v(t - 2, W_POS) - cpos);
+		const lmb_material mat = load_material(k.sc, cam.u(t - 1, W_MAT), cam.uv(t - 1));
+		float unused_pdf;
+		const V3 f = eval_bsdf(cn, wo, mat, cam.u(t - 1, W_SIDE) == 1, ls.wi, unused_pdf);
+		if (!is_zero(f)) {
+			if (!occluded(k, ray_origin, ls.wi, ls.wi_len - LMB_EPS)) {
+				const float pdf_light_w = light_pdf_a_to_w(ls.flags, ls.pdf_a, ls.wi_len * ls.wi_len, ls.cos_from_light) / (float)k.P.light_triangle_count;
+				sampled.pdf_fwd = ls.pdf_a / (float)k.P.light_triangle_count;
+				light_sample_n_pos(k.sc, r4, cpos, k.P.num_lights, ls, sampled.n_s, sampled.pos);
+				L = cam.v(t - 1, W_THR) * f * fabsf(cos_x) * ls.Le / pdf_light_w;
+			}
+		}
+	} else {
+		const V3 n_s = lig.v(s - 1, W_NS);
+		const V3 n_t = cam.v(t - 1, W_NS);
+		const V3 cpos = cam.v(t - 1, W_POS), lpos = lig.v(s - 1, W_POS);
+		V3 d = lpos - cpos;
+		const float len = length(d);
+		d /= len;
+		const float G = dot(n_s, -d) * dot(n_t, d) / (len * len);
+		if (G > 0) {
+			const lmb_material mat_1 = load_material(k.sc, cam.u(t - 1, W_MAT), cam.uv(t - 1));
+			const lmb_material mat_2 = load_material(k.sc, lig.u(s - 1, W_MAT), lig.uv(s - 1));
+			const V3 wo_1 = normalize(cam.v(t - 2, W_POS) - cpos);
+			const V3 wo_2 = normalize(lig.v(s - 2, W_POS) - lpos);
+			float unused_pdf;
+			const V3 brdf1 = eval_bsdf(n_t, wo_1, mat_1, cam.u(t - 1, W_SIDE) == 1, d, unused_pdf);
+			const V3 brdf2 = eval_bsdf(n_s, wo_2, mat_2, lig.u(s - 1, W_SIDE) == 1, -d, unused_pdf);
+			if (!is_zero(brdf1) && !is_zero(brdf2)) {
+				const V3 ray_origin = offset_ray2(cpos, n_t);
+				if (!occluded(k, ray_origin, d, len - LMB_EPS)) L = lig.v(s - 1, W_THR) * G * brdf1 * brdf2 * cam.v(t - 1, W_THR);
+			}
+		}
+	}
+	if (luminance(L) != 0.0f) {
+		const float mis_weight = calc_mis_weight(k, s, t, sampled);
+		L *= mis_weight;
+	}
+	return L;
+}
+
+// bdpt.rgen:39-75 for one pixel of one frame
+__global__ void __launch_bounds__(128) k_bdpt(BdptParams P, DeviceScene sc, BvhView bvh) {
+	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t n_closest = 0, n_shadow = 0, n_nodes = 0, n_tris = 0;
+	if (pix < P.n_pix) {
+		const uint32_t px = pix % P.width, py = pix / P.width;
+		Kctx k{P, sc, bvh, Rng{px, py, P.seed_z, 0u}, Verts{P.light_verts + pix, P.n_pix}, Verts{P.camera_verts + pix, P.n_pix}, 0.0f,
+			   (float)(P.width * P.height), 0u, 0u, 0u, 0u};
+		const V2 size = v2((float)P.width, (float)P.height);
+		const V2 pixel = v2((float)px, (float)py) + 0.5f;
+		const V2 in_uv = pixel / size;
+		const V2 d = in_uv * 2.0f - 1.0f;
+		const V4 origin = mul(P.inv_view, v4(0, 0, 0, 1));
+		V3 col = v3(0.0f);
+		V4 area_int = mul(P.inv_proj, v4(2.0f / (float)P.width, 2.0f / (float)P.height, 0, 1));
+		area_int = v4(area_int.x / area_int.w, area_int.y / area_int.w, area_int.z / area_int.w, area_int.w / area_int.w);
+		const float cam_area = fabsf(area_int.x * area_int.y);
+		const int num_light_paths = generate_light_subpath(k, P.max_depth + 1);
+		const int num_cam_paths = generate_camera_subpath(k, d, xyz(origin), P.max_depth + 1, cam_area);
+		for (int t = 1; t <= num_cam_paths; t++) {
+			for (int s = 0; s <= num_light_paths; s++) {
+				const int depth = s + t - 2;
+				if (depth > (P.max_depth - 1) || depth < 0 || (s == 1 && t == 1)) continue;
+				if (t == 1) {
+					int cx, cy;
+					const V3 splat_col = connect_cam(k, s, cx, cy);
+					if (luminance(splat_col) > 0) {
+						float* o = P.splat + 3 * ((size_t)cy * P.width + cx);
+						atomicAdd(o + 0, splat_col.x), atomicAdd(o + 1, splat_col.y), atomicAdd(o + 2, splat_col.z);
+					}
+				} else {
+					col += connect(k, s, t);
+				}
+			}
+		}
+		P.col[pix] = make_float4(col.x, col.y, col.z, 0.0f);
+		n_closest = k.n_closest, n_shadow = k.n_shadow, n_nodes = k.n_nodes, n_tris = k.n_tris;
+	}
+	// ray counters: one atomic per warp and counter
+	for (int o = 16; o > 0; o >>= 1) {
+		n_closest += __shfl_down_sync(0xFFFFFFFFu, n_closest, o);
+		n_shadow += __shfl_down_sync(0xFFFFFFFFu, n_shadow, o);
+		n_nodes += __shfl_down_sync(0xFFFFFFFFu, n_nodes, o);
+		n_tris += __shfl_down_sync(0xFFFFFFFFu, n_tris, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		atomicAdd(&P.stats[ST_CLOSEST], (unsigned long long)n_closest);
+		atomicAdd(&P.stats[ST_SHADOW], (unsigned long long)n_shadow);
+		atomicAdd(&P.stats[ST_NODES], (unsigned long long)n_nodes);
+		atomicAdd(&P.stats[ST_TRIS], (unsigned long long)n_tris);
+	}
+}
+
+// bdpt.rgen:76-89: own strategies + this frame's splats -> running-mean film (NaN samples leave the pixel untouched); clears the
+// splat image for the next frame.
+__global__ void __launch_bounds__(256) k_bdpt_film(uint32_t n_pix, uint32_t frame, const float4* __restrict__ colb, float* __restrict__ splat,
+													float4* __restrict__ film, unsigned long long* stats) {
+	uint32_t nan_count = 0;
+	for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n_pix; pix += gridDim.x * blockDim.x) {
+		V3 col = xyz(V4{colb[pix].x, colb[pix].y, colb[pix].z, 0.0f});
+		col += v3(splat[3 * (size_t)pix + 0], splat[3 * (size_t)pix + 1], splat[3 * (size_t)pix + 2]);
+		splat[3 * (size_t)pix + 0] = 0.0f, splat[3 * (size_t)pix + 1] = 0.0f, splat[3 * (size_t)pix + 2] = 0.0f;
+		const float lum = luminance(col);
+		if (lum != lum) {
+			nan_count++;
+			continue;
+		}
+		if (frame > 0) {
+			const float w = 1.0f / float(frame + 1);
+			const float4 old = film[pix];
+			const V3 m = mix(v3(old.x, old.y, old.z), col, w);
+			film[pix] = make_float4(m.x, m.y, m.z, 1.0f);
+		} else {
+			film[pix] = make_float4(col.x, col.y, col.z, 1.0f);
+		}
+	}
+	if (nan_count) atomicAdd(&stats[ST_NAN], (unsigned long long)nan_count);
+}
+
+}  // namespace
+
+void bdpt_free(lmb_ctx* ctx) {
+	BdptState& b = ctx->bdpt;
+	cudaFree(b.light_verts), cudaFree(b.camera_verts), cudaFree(b.col), cudaFree(b.splat);
+	b = BdptState{};
+}
+
+int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, uint32_t first_frame, uint32_t n_frames, float* raw_col, float* raw_splat) {
+	if (ctx->row_stride != 1) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: pixel shards are not supported (light-tracer splats cross rows)");
+	if (pc.max_depth < 1 || pc.max_depth > 63) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: max_depth must be in [1, 63]");
+	if (!ctx->wf.stats) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: call lmb_init first");
+	BdptState& b = ctx->bdpt;
+	cudaStream_t st = ctx->stream;
+	const uint32_t n_pix = ctx->width * ctx->height;
+	const uint32_t n_verts = (uint32_t)pc.max_depth + 1;
+	const size_t vert_bytes = (size_t)n_pix * n_verts * W_COUNT * 4;
+	if (b.n_pix != n_pix || b.n_verts < n_verts) {
+		bdpt_free(ctx);
+		LMB_CUDA(ctx, cudaMalloc((void**)&b.light_verts, vert_bytes));
+		LMB_CUDA(ctx, cudaMalloc((void**)&b.camera_verts, vert_bytes));
+		LMB_CUDA(ctx, cudaMalloc((void**)&b.col, (size_t)n_pix * 16));
+		LMB_CUDA(ctx, cudaMalloc((void**)&b.splat, (size_t)n_pix * 12));
+		b.n_pix = n_pix, b.n_verts = n_verts;
+	}
+	LMB_CUDA(ctx, cudaMemsetAsync(b.splat, 0, (size_t)n_pix * 12, st));
+	auto load = [](const float* p) {
+		M4 m;
+		for (int c = 0; c < 4; c++) m.c[c] = V4{p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]};
+		return m;
+	};
+	BdptParams P;
+	P.inv_view = load(ubo.inv_view), P.inv_proj = load(ubo.inv_projection), P.view = load(ubo.view);
+	P.neg_proj = load(ubo.projection);
+	for (int c = 0; c < 4; c++) P.neg_proj.c[c] = V4{-P.neg_proj.c[c].x, -P.neg_proj.c[c].y, -P.neg_proj.c[c].z, -P.neg_proj.c[c].w};
+	P.width = ctx->width, P.height = ctx->height, P.n_pix = n_pix;
+	P.num_lights = pc.num_lights, P.max_depth = pc.max_depth, P.light_triangle_count = pc.light_triangle_count;
+	P.light_verts = b.light_verts, P.camera_verts = b.camera_verts, P.col = b.col, P.splat = b.splat, P.stats = ctx->wf.stats;
+	const BvhView bvh{ctx->bvh.nodes, ctx->bvh.tris, ctx->bvh.n};
+	cudaEventRecord(ctx->ev[0], st);
+	for (uint32_t i = 0; i < n_frames; i++) {
+		const uint32_t frame = first_frame + i;
+		P.frame = frame, P.seed_z = frame ^ pc.time;
+		// BDPT.cpp:79-80: both vertex buffers are zeroed before every frame
+		LMB_CUDA(ctx, cudaMemsetAsync(b.light_verts, 0, vert_bytes, st));
+		LMB_CUDA(ctx, cudaMemsetAsync(b.camera_verts, 0, vert_bytes, st));
+		k_bdpt<<<(n_pix + 127) / 128, 128, 0, st>>>(P, ctx->scene, bvh);
+		if (raw_col) {  // test hook: the two images before the film update
+			LMB_CUDA(ctx, cudaMemcpyAsync(raw_col, b.col, (size_t)n_pix * 16, cudaMemcpyDeviceToHost, st));
+			LMB_CUDA(ctx, cudaMemcpyAsync(raw_splat, b.splat, (size_t)n_pix * 12, cudaMemcpyDeviceToHost, st));
+		}
+		k_bdpt_film<<<ctx->sm_count * 8, 256, 0, st>>>(n_pix, frame, b.col, b.splat, ctx->film, ctx->wf.stats);
+		ctx->stats.kernel_launches += 2;
+	}
+	cudaEventRecord(ctx->ev[5], st);
+	LMB_CUDA(ctx, cudaStreamSynchronize(st));
+	LMB_CUDA(ctx, cudaGetLastError());
+	float ms = 0;
+	cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[5]);
+	ctx->stats.ms_render += ms;
+	ctx->stats.frames += n_frames;
+	return 0;
+}
+
+}  // namespace lmb

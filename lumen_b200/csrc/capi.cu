@@ -8,6 +8,7 @@
 #include <algorithm>
 
 #include "context.h"
+#include "lumen_b200_testhooks.h"
 
 static thread_local std::string g_create_error;
 
@@ -268,6 +269,30 @@ int lmb_render(lmb_ctx* ctx, const lmb_pc_path* pc, const lmb_scene_ubo* ubo, ui
 	cudaSetDevice(ctx->device);
 	if (n_frames == 0) return LMB_OK;
 	return wavefront_render(ctx, *pc, *ubo, first_frame, n_frames, frame_stride, film_mode);
+}
+
+static int check_bdpt_args(lmb_ctx* ctx, const lmb_pc_bdpt* pc) {
+	if (!ctx->bvh.built) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: call lmb_build_accel first");
+	if (!ctx->film) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: call lmb_init first");
+	if (pc->size_x != ctx->width || pc->size_y != ctx->height) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: PCBDPT size != lmb_init size");
+	return LMB_OK;
+}
+
+int lmb_render_bdpt(lmb_ctx* ctx, const lmb_pc_bdpt* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames) {
+	if (!ctx || !pc || !ubo) return LMB_ERR_INVALID;
+	const int rc = check_bdpt_args(ctx, pc);
+	if (rc) return rc;
+	cudaSetDevice(ctx->device);
+	if (n_frames == 0) return LMB_OK;
+	return bdpt_render(ctx, *pc, *ubo, first_frame, n_frames, nullptr, nullptr);
+}
+
+int lmb_kat_bdpt_frame_raw(lmb_ctx* ctx, const lmb_pc_bdpt* pc, const lmb_scene_ubo* ubo, uint32_t frame, float* col_rgba, float* splat_rgb) {
+	if (!ctx || !pc || !ubo || !col_rgba || !splat_rgb) return LMB_ERR_INVALID;
+	const int rc = check_bdpt_args(ctx, pc);
+	if (rc) return rc;
+	cudaSetDevice(ctx->device);
+	return bdpt_render(ctx, *pc, *ubo, frame, 1, col_rgba, splat_rgb);
 }
 
 int lmb_clear_film(lmb_ctx* ctx) {

@@ -94,6 +94,16 @@ struct Wavefront {
 	uint32_t frames_in_flight = 0;
 };
 
+// BDPT state (bdpt.cu): the two sub-paths of every pixel (struct of arrays over pixels, 23 words per vertex), the radiance of the
+// pixel's own strategies and the light-tracer splat image of the frame in flight. Allocated by the first lmb_render_bdpt.
+struct BdptState {
+	float* light_verts = nullptr;
+	float* camera_verts = nullptr;
+	float4* col = nullptr;
+	float* splat = nullptr;
+	uint32_t n_pix = 0, n_verts = 0;
+};
+
 enum StatSlot {
 	ST_CLOSEST = 0, ST_SHADOW, ST_PROBE, ST_NODES, ST_TRIS, ST_NAN,
 	// k_trace scheduling counters, filled only by a -DLMB_TRACE_PROFILE build (tools/gpu_variants.sh): warp trips of the inner
@@ -127,6 +137,7 @@ struct lmb_ctx {
 	uint32_t row_first = 0, row_stride = 1;  // pixel shard: this context renders image rows row_first + k * row_stride
 	float4* film = nullptr;
 	lmb::Wavefront wf;
+	lmb::BdptState bdpt;
 	// post steps (post.cu)
 	float4* film_snapshot = nullptr;  // lmb_download_async: copy of the film the copy stream sends home while rendering goes on
 	cudaStream_t copy_stream = nullptr;
@@ -157,6 +168,8 @@ uint32_t shard_rows(const lmb_ctx* ctx);
 void wavefront_free(lmb_ctx* ctx);
 int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& ubo, uint32_t first_frame, uint32_t n_frames, uint32_t stride,
 					 int film_mode);
+int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, uint32_t first_frame, uint32_t n_frames, float* raw_col, float* raw_splat);
+void bdpt_free(lmb_ctx* ctx);
 int launch_trace_closest(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits);
 int launch_trace_any(lmb_ctx* ctx, const float4* d_rays, uint32_t n, uint8_t* d_occ);
 int launch_resolve(lmb_ctx* ctx);

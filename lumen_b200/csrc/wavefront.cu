@@ -630,6 +630,7 @@ int wavefront_alloc(lmb_ctx* ctx, uint32_t frames_in_flight) {
 }
 
 void wavefront_free(lmb_ctx* ctx) {
+	bdpt_free(ctx);  // sized by the same image
 	Wavefront& wf = ctx->wf;
 	for (int p = 0; p < 2; p++) cudaFree(wf.ray_o[p]), cudaFree(wf.ray_d[p]), cudaFree(wf.thr[p]), cudaFree(wf.col[p]), cudaFree(wf.pix[p]);
 	cudaFree(wf.hit), cudaFree(wf.acc), cudaFree(wf.nee), cudaFree(wf.nee_path);

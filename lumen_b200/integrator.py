@@ -50,6 +50,7 @@ def lib():
         L.lmb_build_accel.argtypes = [vp]
         L.lmb_init.argtypes = [vp, u32, u32, u32]
         L.lmb_render.argtypes = [vp, vp, vp, u32, u32, u32, i32]
+        L.lmb_render_bdpt.argtypes = [vp, vp, vp, u32, u32]
         L.lmb_clear_film.argtypes = [vp]
         L.lmb_set_pixel_shard.argtypes = [vp, C.c_uint32, C.c_uint32]
         L.lmb_resolve.argtypes = [vp]
@@ -81,16 +82,17 @@ def lib():
         L.lmb_kat_sample_light.argtypes = [vp, i32, vp, vp, u32, vp]
         L.lmb_kat_texture.argtypes = [vp, u32, vp, u32, vp]
         L.lmb_kat_wide_bvh_check.argtypes = [vp, vp]
+        L.lmb_kat_bdpt_frame_raw.argtypes = [vp, vp, vp, u32, vp, vp]
         _LIB = L
     return _LIB
 
 
-EXPORTS = ["lmb_create", "lmb_destroy", "lmb_last_error", "lmb_upload_scene", "lmb_build_accel", "lmb_init", "lmb_render", "lmb_set_pixel_shard", "lmb_clear_film",
+EXPORTS = ["lmb_create", "lmb_destroy", "lmb_last_error", "lmb_upload_scene", "lmb_build_accel", "lmb_init", "lmb_render", "lmb_render_bdpt", "lmb_set_pixel_shard", "lmb_clear_film",
            "lmb_resolve", "lmb_download", "lmb_upload_film", "lmb_film_add_from", "lmb_film_device_ptr", "lmb_stream", "lmb_set_profile_stages", "lmb_get_stats",
            "lmb_reset_stats", "lmb_trace_closest", "lmb_trace_any", "lmb_trace_closest_device", "lmb_accel_num_tris", "lmb_accel_download",
            "lmb_download_async", "lmb_sync", "lmb_download_half_bgr", "lmb_set_reference_image", "lmb_rmse"]
 TESTHOOK_EXPORTS = ["lmb_kat_pcg4d", "lmb_kat_rand", "lmb_kat_detmath", "lmb_kat_offset_ray", "lmb_kat_sample_bsdf", "lmb_kat_eval_bsdf",
-                    "lmb_kat_atmosphere", "lmb_kat_sample_light", "lmb_kat_texture", "lmb_kat_wide_bvh_check"]
+                    "lmb_kat_atmosphere", "lmb_kat_sample_light", "lmb_kat_texture", "lmb_kat_wide_bvh_check", "lmb_kat_bdpt_frame_raw"]
 
 
 def _f32(a):
@@ -152,6 +154,18 @@ class Device:
     def render(self, pc, ubo, first_frame, n_frames, frame_stride=1, film_mode=FILM_RUNNING_MEAN):
         self._ck(lib().lmb_render(self._h, C.addressof(pc), C.addressof(ubo), int(first_frame), int(n_frames), int(frame_stride), int(film_mode)),
                  "lmb_render")
+
+    def render_bdpt(self, pc, ubo, first_frame, n_frames):
+        """BDPT::render for frames [first_frame, first_frame + n_frames); pc is a PCBdpt."""
+        self._ck(lib().lmb_render_bdpt(self._h, C.addressof(pc), C.addressof(ubo), int(first_frame), int(n_frames)), "lmb_render_bdpt")
+
+    def kat_bdpt_frame_raw(self, pc, ubo, frame):
+        """One BDPT frame (film updated) + the two images it is made of: (col (H, W, 3), splat (H, W, 3))."""
+        col = np.zeros((pc.size_y, pc.size_x, 4), dtype=np.float32)
+        splat = np.zeros((pc.size_y, pc.size_x, 3), dtype=np.float32)
+        self._ck(lib().lmb_kat_bdpt_frame_raw(self._h, C.addressof(pc), C.addressof(ubo), int(frame), col.ctypes.data, splat.ctypes.data),
+                 "lmb_kat_bdpt_frame_raw")
+        return col[..., :3].copy(), splat
 
     def clear_film(self):
         self._ck(lib().lmb_clear_film(self._h), "lmb_clear_film")
@@ -306,6 +320,50 @@ class Device:
         self._ck(lib().lmb_kat_wide_bvh_check(self._h, out.ctypes.data), "lmb_kat_wide_bvh_check")
         keys = ("nodes", "reachable", "depth", "errors", "dup_or_missing", "internal_children", "leaf_children", "leaf_tris")
         return dict(zip(keys, (int(v) for v in out)))
+
+
+class BDPTB200:
+    """Drop-in for Lumen's `BDPT` integrator behind the same lifecycle (BDPT.cpp:4-108).
+
+    init()    -> Integrator::init + BDPT::init + create_accel (the vertex buffers of BDPT.cpp:7-24 are allocated by the first render)
+    render(n) -> BDPT::render for frames [frame_num, frame_num + n): PCBDPT filled as BDPT.cpp:56-64; `time` is this object's
+                 (BDPT.cpp:57 draws rand() % UINT_MAX: set .time before render() to do the same; the default 0 keeps renders reproducible)
+    update()  -> BDPT::update: advances frame_num
+    destroy() -> BDPT::destroy
+    """
+
+    def __init__(self, scene, device=0):
+        self.scene = scene
+        self.dev = Device(device)
+        self.frame_num = 0
+        self.path_length = scene.info.path_length
+        self.time = 0
+        self._pending = 0
+
+    def init(self):
+        self.dev.upload_scene(self.scene.desc)
+        self.dev.build_accel()
+        self.dev.init(self.scene.width, self.scene.height, 1)
+        self.ubo = self.scene.make_ubo()
+        self.frame_num = 0
+
+    def render(self, n_frames=1):
+        from ._ctypes_types import PCBdpt
+        pc = PCBdpt.from_path_pc(self.scene.make_pc(self.path_length, True), self.time)
+        pc.frame_num = self.frame_num
+        self.dev.render_bdpt(pc, self.ubo, self.frame_num, n_frames)
+        self._pending = n_frames
+
+    def update(self):
+        self.frame_num += self._pending
+        self._pending = 0
+        return False
+
+    def output(self):
+        return self.dev.download()
+
+    def destroy(self):
+        self.dev.close()
 
 
 class PathB200:

@@ -10,6 +10,7 @@
 
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -144,6 +145,7 @@ struct LightSample {
 	float wi_len = 0, pdf_w = 0, pdf_a = 0, cos_from_light = 0;
 	uint light_idx = 0, flags = 0, triangle_idx = 0, instance_idx = 0;
 	vec2 bary{0};
+	vec3 n{0}, pos{0};  // `out vec3 n, out vec3 pos` of commons.glsl:224-226 (read by bdpt_commons.glsl only)
 };
 
 // commons.glsl:224-300
@@ -174,6 +176,8 @@ inline LightSample sample_light_Li(const orc_scene& s, const vec4& rands, const 
 			o.pdf_a = rec.triangle_pdf;
 			o.pdf_w = o.pdf_a * wi_len_sqr / o.cos_from_light;
 			o.instance_idx = light.prim_mesh_idx;
+			o.n = rec.n_s;
+			o.pos = rec.pos;
 		} break;
 		case LMB_LIGHT_SPOT: {
 			o.wi = v3(light.pos) - p;
@@ -196,6 +200,8 @@ inline LightSample sample_light_Li(const orc_scene& s, const vec4& rands, const 
 			o.pdf_a = 1;
 			o.pdf_w = wi_len_sqr;
 			o.Le = v3(light.L) * faloff;
+			o.n = -o.wi;
+			o.pos = v3(light.pos);
 		} break;
 		case LMB_LIGHT_DIRECTIONAL: {
 			const vec3 dir = glm::normalize(v3(light.pos) - v3(light.to));
@@ -207,6 +213,8 @@ inline LightSample sample_light_Li(const orc_scene& s, const vec4& rands, const 
 			o.pdf_w = 1;
 			o.Le = v3(light.L);
 			o.cos_from_light = 1.0f;
+			o.n = -o.wi;
+			o.pos = light_p;
 		} break;
 		default:
 			break;
@@ -339,6 +347,8 @@ inline vec3 trace_pixel(const orc_scene& s, const lmb_pc_path& pc, const lmb_sce
 	return col;
 }
 
+#include "bdpt.h"
+
 void add_counters(orc_stats* st, const Counters& c) {
 	if (!st) return;
 	st->rays_closest += c.closest;
@@ -456,6 +466,80 @@ int orc_render(const orc_scene* s, const lmb_pc_path* pc, const lmb_scene_ubo* u
 	return 0;
 }
 
+// bdpt.rgen:39-89 for one frame, split in the two passes of quirk B2 (oracle/bdpt.h): col_rgb = the pixel's own strategies,
+// splat_rgb = the light-tracer image of the same frame (splats applied in source-pixel order, rows then columns).
+int orc_render_bdpt_frame_raw(const orc_scene* s, const lmb_pc_bdpt* pc, const lmb_scene_ubo* ubo, uint32_t frame, float* col_rgb,
+							  float* splat_rgb, orc_stats* stats, int n_threads) {
+	if (!s || !pc || !ubo || !col_rgb || !splat_rgb) return -1;
+	if (pc->max_depth < 1 || pc->max_depth + 1 > BDPT_MAX_VERTS) return -2;
+	const uint W = pc->size_x, H = pc->size_y;
+	const int nt = pick_threads(n_threads);
+	const auto t0 = std::chrono::steady_clock::now();
+	struct SplatRec {
+		uint x, y;
+		vec3 c;
+	};
+	std::vector<std::vector<SplatRec>> rows(H);
+	Counters total;
+#pragma omp parallel num_threads(nt)
+	{
+		Counters c;
+#pragma omp for schedule(dynamic, 1)
+		for (int y = 0; y < (int)H; y++) {
+			for (uint x = 0; x < W; x++) {
+				const vec3 col = bdpt_pixel(*s, *pc, *ubo, x, (uint)y, frame, c, [&](uint cx, uint cy, const vec3& v) { rows[y].push_back({cx, cy, v}); });
+				float* o = col_rgb + 3 * ((size_t)y * W + x);
+				o[0] = col.x, o[1] = col.y, o[2] = col.z;
+			}
+		}
+#pragma omp critical
+		{
+			total.closest += c.closest, total.shadow += c.shadow;
+			total.ts.nodes += c.ts.nodes, total.ts.tris += c.ts.tris;
+		}
+	}
+	std::memset(splat_rgb, 0, (size_t)W * H * 3 * sizeof(float));
+	for (uint y = 0; y < H; y++)
+		for (const SplatRec& r : rows[y]) {
+			float* o = splat_rgb + 3 * ((size_t)r.y * W + r.x);
+			o[0] += r.c.x, o[1] += r.c.y, o[2] += r.c.z;
+		}
+	if (stats) {
+		add_counters(stats, total);
+		stats->seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		stats->threads = nt;
+	}
+	return 0;
+}
+
+int orc_render_bdpt(const orc_scene* s, const lmb_pc_bdpt* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames, float* rgba,
+					orc_stats* stats, int n_threads) {
+	if (!s || !pc || !ubo || !rgba) return -1;
+	const uint W = pc->size_x, H = pc->size_y;
+	std::vector<float> col((size_t)W * H * 3), splat((size_t)W * H * 3);
+	for (uint32_t frame = first_frame; frame < first_frame + n_frames; frame++) {
+		const int rc = orc_render_bdpt_frame_raw(s, pc, ubo, frame, col.data(), splat.data(), stats, n_threads);
+		if (rc) return rc;
+		for (size_t i = 0; i < (size_t)W * H; i++) {  // bdpt.rgen:76-89
+			vec3 c(col[3 * i], col[3 * i + 1], col[3 * i + 2]);
+			c += vec3(splat[3 * i], splat[3 * i + 1], splat[3 * i + 2]);
+			if (g_isnan(luminance(c))) {
+				if (stats) stats->nan_pixels++;
+				continue;
+			}
+			float* o = rgba + 4 * i;
+			if (frame > 0) {
+				const float w = 1.0f / float(frame + 1);
+				const vec3 m = glm::mix(vec3(o[0], o[1], o[2]), c, w);
+				o[0] = m.x, o[1] = m.y, o[2] = m.z, o[3] = 1.0f;
+			} else {
+				o[0] = c.x, o[1] = c.y, o[2] = c.z, o[3] = 1.0f;
+			}
+		}
+	}
+	return 0;
+}
+
 int orc_trace_closest(const orc_scene* s, const float* rays, uint32_t n, orc_hit* hits, orc_stats* stats, int n_threads) {
 	const int nt = pick_threads(n_threads);
 	uint64_t nodes = 0, tris = 0;
@@ -540,6 +624,9 @@ void orc_kat_eval_bsdf(const lmb_material* mat, const float* n_s3, const float* 
 		float* o = out4 + 4 * (size_t)i;
 		o[0] = f.x, o[1] = f.y, o[2] = f.z, o[3] = pdf;
 	}
+}
+void orc_kat_bsdf_pdf(const lmb_material* mat, const float* n_s3, const float* wo3, const float* wi3, const uint8_t* side, uint32_t n, float* out) {
+	for (uint32_t i = 0; i < n; i++) out[i] = bsdf_pdf(*mat, v3(n_s3 + 3 * i), v3(wo3 + 3 * i), v3(wi3 + 3 * i), side[i] != 0);
 }
 void orc_kat_atmosphere(const float* origin3, const float* dir3, const float* light_dir3, const float* light_L3, uint32_t n, float* out3) {
 #pragma omp parallel for schedule(dynamic, 16)

@@ -58,6 +58,14 @@ int orc_render(const orc_scene* s, const lmb_pc_path* pc, const lmb_scene_ubo* u
 int orc_render_frame_raw(const orc_scene* s, const lmb_pc_path* pc, const lmb_scene_ubo* ubo, uint32_t frame, float* rgb,
 						 orc_stats* stats, int n_threads);
 
+/* BDPT (bdpt.rgen + bdpt_commons.glsl, quirks B1-B6 in oracle/bdpt.h). Film update as orc_render.
+ * RNG seed of a sample is (x, y, frame ^ pc->time, 0); pc->frame_num is ignored. */
+int orc_render_bdpt(const orc_scene* s, const lmb_pc_bdpt* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames,
+					float* rgba, orc_stats* stats, int n_threads);
+/* One frame without the film: col_rgb[W*H*3] = the pixel's own (s, t >= 2) strategies, splat_rgb[W*H*3] = light-tracer image. */
+int orc_render_bdpt_frame_raw(const orc_scene* s, const lmb_pc_bdpt* pc, const lmb_scene_ubo* ubo, uint32_t frame, float* col_rgb,
+							  float* splat_rgb, orc_stats* stats, int n_threads);
+
 /* Ray queries: rays = n x 8 floats (ox, oy, oz, tmin, dx, dy, dz, tmax). */
 int orc_trace_closest(const orc_scene* s, const float* rays, uint32_t n, orc_hit* hits, orc_stats* stats, int n_threads);
 /* the hit definition evaluated over ALL triangles, no tree: what orc_trace_closest must equal bit for bit */
@@ -72,6 +80,8 @@ void orc_kat_offset_ray(const float* p3, const float* n3, uint32_t n, float* out
 /* sample: out 8 floats per item = f.xyz, wi.xyz, pdf, cos_theta.  eval: out 4 floats = f.xyz, pdf. */
 void orc_kat_sample_bsdf(const lmb_material* mat, const float* n_s3, const float* wo3, const float* rands3, const uint8_t* side,
 						 uint32_t n, float* out8);
+/* bsdf_pdf of bsdf_commons.glsl:26-66 (the stand-alone pdf functions BDPT uses): out[n] */
+void orc_kat_bsdf_pdf(const lmb_material* mat, const float* n_s3, const float* wo3, const float* wi3, const uint8_t* side, uint32_t n, float* out);
 void orc_kat_eval_bsdf(const lmb_material* mat, const float* n_s3, const float* wo3, const float* wi3, const uint8_t* side,
 					   uint32_t n, float* out4);
 /* sky: out 3 floats per item */

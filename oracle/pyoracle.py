@@ -43,6 +43,8 @@ def lib():
         L.orc_lbvh_num_tris.restype = u32
         L.orc_render.argtypes = [vp, vp, vp, u32, u32, vp, vp, i32]
         L.orc_render_frame_raw.argtypes = [vp, vp, vp, u32, vp, vp, i32]
+        L.orc_render_bdpt.argtypes = [vp, vp, vp, u32, u32, vp, vp, i32]
+        L.orc_render_bdpt_frame_raw.argtypes = [vp, vp, vp, u32, vp, vp, vp, i32]
         L.orc_trace_closest.argtypes = [vp, vp, u32, vp, vp, i32]
         L.orc_trace_any.argtypes = [vp, vp, u32, vp, vp, i32]
         L.orc_trace_closest_brute.argtypes = [vp, vp, u32, vp, i32]
@@ -52,6 +54,7 @@ def lib():
         L.orc_kat_offset_ray.argtypes = [vp, vp, u32, vp, vp]
         L.orc_kat_sample_bsdf.argtypes = [vp, vp, vp, vp, vp, u32, vp]
         L.orc_kat_eval_bsdf.argtypes = [vp, vp, vp, vp, vp, u32, vp]
+        L.orc_kat_bsdf_pdf.argtypes = [vp, vp, vp, vp, vp, u32, vp]
         L.orc_kat_atmosphere.argtypes = [vp, vp, vp, vp, u32, vp]
         L.orc_kat_sample_light.argtypes = [vp, i32, vp, vp, u32, vp]
         L.orc_kat_texture.argtypes = [vp, u32, vp, u32, vp]
@@ -109,6 +112,30 @@ class OracleScene:
         st = Stats()
         lib().orc_render_frame_raw(self._h, C.addressof(pc), C.addressof(ubo), frame, rgb.ctypes.data, C.addressof(st), threads)
         return rgb, st
+
+    def render_bdpt(self, pc, ubo, first_frame, n_frames, rgba=None, threads=0):
+        """bdpt.rgen restated (oracle/bdpt.h); pc is a PCBdpt."""
+        W, H = pc.size_x, pc.size_y
+        if rgba is None:
+            rgba = np.zeros((H, W, 4), dtype=np.float32)
+        assert rgba.dtype == np.float32 and rgba.flags.c_contiguous
+        st = Stats()
+        rc = lib().orc_render_bdpt(self._h, C.addressof(pc), C.addressof(ubo), first_frame, n_frames, rgba.ctypes.data, C.addressof(st), threads)
+        if rc != 0:
+            raise RuntimeError(f"orc_render_bdpt failed ({rc})")
+        return rgba, st
+
+    def render_bdpt_frame_raw(self, pc, ubo, frame, threads=0):
+        """(col, splat, stats) of one frame: the pixel's own strategies and the light-tracer image, before the film."""
+        W, H = pc.size_x, pc.size_y
+        col = np.zeros((H, W, 3), dtype=np.float32)
+        splat = np.zeros((H, W, 3), dtype=np.float32)
+        st = Stats()
+        rc = lib().orc_render_bdpt_frame_raw(self._h, C.addressof(pc), C.addressof(ubo), frame, col.ctypes.data, splat.ctypes.data,
+                                             C.addressof(st), threads)
+        if rc != 0:
+            raise RuntimeError(f"orc_render_bdpt_frame_raw failed ({rc})")
+        return col, splat, st
 
     def trace_closest(self, rays, threads=0):
         rays = _f32(rays).reshape(-1, 8)
@@ -196,6 +223,15 @@ def eval_bsdf(mat, n_s, wo, wi, side):
     side = np.ascontiguousarray(side, dtype=np.uint8)
     out = np.zeros((n_s.shape[0], 4), dtype=np.float32)
     lib().orc_kat_eval_bsdf(C.addressof(mat), n_s.ctypes.data, wo.ctypes.data, wi.ctypes.data, side.ctypes.data, n_s.shape[0], out.ctypes.data)
+    return out
+
+
+def bsdf_pdf(mat, n_s, wo, wi, side):
+    """bsdf_pdf of bsdf_commons.glsl:26-66 (the stand-alone pdf functions): (n,) float32."""
+    n_s, wo, wi = _f32(n_s).reshape(-1, 3), _f32(wo).reshape(-1, 3), _f32(wi).reshape(-1, 3)
+    side = np.ascontiguousarray(side, dtype=np.uint8)
+    out = np.zeros(n_s.shape[0], dtype=np.float32)
+    lib().orc_kat_bsdf_pdf(C.addressof(mat), n_s.ctypes.data, wo.ctypes.data, wi.ctypes.data, side.ctypes.data, n_s.shape[0], out.ctypes.data)
     return out
 
 

@@ -760,6 +760,114 @@ inline vec3 eval_bsdf(const vec3& n_s, const vec3& wo_world, const lmb_material&
 	return vec3(0);
 }
 
+// ------------------------------------------------------------------------------------------------ bsdf_pdf (BDPT side of the BSDFs)
+// The stand-alone pdf functions of the reference (used by bdpt_commons.glsl, not by the Path integrator). Restated here as an
+// INDEPENDENT check of the sampling code above: where the GLSL means sample_*'s pdf, eval_*'s pdf_w and *_pdf to be the same
+// density, tests/test_oracle.py compares the three (SURVEY.md 8f-3 groundwork).
+// diffuse.glsl:85-90
+inline float lambertian_diffuse_pdf(const vec3& wo, const vec3& wi) {
+	if (glm::min(wi.z, wo.z) <= 0.0f) return 0.0f;
+	return wi.z * INV_PI;
+}
+// dielectric.glsl:191-240
+inline float dielectric_pdf(const lmb_material& mat, const vec3& wo, const vec3& wi, bool forward_facing) {
+	const float roughness = mat.thin == 1 ? modify_thin_roughness(mat.ior, mat.roughness) : mat.roughness;
+	const float alpha = roughness * roughness;
+	if (alpha == 0 || mat.ior == 1) return 0.0f;
+	const bool has_reflection = has_prop(mat.bsdf_props, LMB_FLAG_REFLECTION);
+	const bool has_transmission = has_prop(mat.bsdf_props, LMB_FLAG_TRANSMISSION);
+	if (!has_reflection && !has_transmission) return 0.0f;
+	const bool is_reflection = wi.z * wo.z > 0;
+	float eta = 1.0f;
+	if (!is_reflection) eta = forward_facing ? mat.ior : 1.0f / mat.ior;
+	vec3 h = glm::normalize(wo + wi * eta);
+	h *= float(glm::sign(h.z));
+	if (wi.z == 0 || wo.z == 0 || glm::dot(h, h) == 0) return 0.0f;
+	if (glm::dot(wi, h) * wi.z < 0 || glm::dot(wo, h) * wo.z < 0) return 0.0f;
+	const float F = fresnel_dielectric(glm::dot(wo, h), mat.ior, forward_facing);
+	const float pr = has_reflection ? F : 0.0f;
+	const float pt = has_transmission ? (1.0f - F) : 0.0f;
+	float D;
+	float pdf_w = vndf_pdf_iso(alpha, wo, h, D);
+	if (is_reflection) {
+		const float jacobian = 1.0f / (4.0f * std::fabs(glm::dot(wo, h)));
+		const float prob_reflection = pr / (pr + pt);
+		pdf_w = pdf_w * jacobian * prob_reflection;
+	} else {
+		float jacobian_denom = glm::dot(wi, h) + glm::dot(wo, h) / eta;
+		jacobian_denom = jacobian_denom * jacobian_denom;
+		const float jacobian = std::fabs(glm::dot(wi, h)) / jacobian_denom;
+		const float prob_refraction = pt / (pr + pt);
+		pdf_w = pdf_w * jacobian * prob_refraction;
+	}
+	return pdf_w;
+}
+// conductor.glsl:74-90
+inline float conductor_pdf(const lmb_material& mat, const vec3& wo, const vec3& wi) {
+	const float alpha = mat.roughness * mat.roughness;
+	if (effectively_delta(alpha)) return 0.0f;
+	if (wo.z * wi.z < 0) return 0.0f;
+	if (wo.z == 0 || wi.z == 0) return 0.0f;
+	vec3 h = glm::normalize(wo + wi);
+	h *= float(glm::sign(h.z));
+	float D;
+	return vndf_pdf_iso(alpha, wo, h, D) / (4.0f * glm::dot(wo, h));
+}
+// principled.glsl:177-181
+inline float clearcoat_pdf(const lmb_material& mat, const vec3& wo, const vec3& wi) {
+	const vec3 h = glm::normalize(wo + wi);
+	const float D = d_ggx_iso(glm::mix(0.1f, 0.001f, mat.clearcoat_gloss), h.z);
+	return D / (4.0f * glm::dot(wo, h));
+}
+// principled.glsl:226-251 (ANISOTROPIC == 1)
+inline float principled_brdf_pdf(const lmb_material& mat, const vec3& wo, const vec3& wi) {
+	const vec2 alpha = calc_anisotropy(mat.roughness, mat.anisotropy);
+	if (effectively_delta(alpha)) return 0.0f;
+	if (wo.z * wi.z < 0) return 0.0f;
+	if (wo.z == 0 || wi.z == 0) return 0.0f;
+	vec3 h = glm::normalize(wo + wi);
+	h *= float(glm::sign(h.z));
+	float D;
+	return vndf_pdf_aniso(alpha, wo, h, D) / (4.0f * glm::dot(wo, h));
+}
+// principled.glsl:338-360
+inline float principled_pdf(const lmb_material& mat, const vec3& wo, const vec3& wi, bool forward_facing) {
+	float pdf = 0.0f;
+	const float F = fresnel_dielectric(wo.z, mat.ior, forward_facing);
+	const LobeProbs p = sampling_probs(mat, F, forward_facing);
+	if (p.spec > 0) pdf += p.spec * principled_brdf_pdf(mat, wo, wi);
+	const bool upper = glm::min(wi.z, wo.z) > 0;
+	if (upper) {
+		if (p.diff > 0) pdf += p.diff * lambertian_diffuse_pdf(wo, wi);
+		if (p.clearcoat > 0) pdf += p.clearcoat * clearcoat_pdf(mat, wo, wi);
+	}
+	if (p.spec_trans > 0) pdf += p.spec_trans * dielectric_pdf(mat, wo, wi, forward_facing);
+	return pdf;
+}
+// bsdf_commons.glsl:26-66
+inline float bsdf_pdf(const lmb_material& mat, const vec3& n_s, const vec3& wo_world, const vec3& wi_world, bool forward_facing) {
+	vec3 T, B;
+	branchless_onb(n_s, T, B);
+	const vec3 wo = to_local(wo_world, T, B, n_s);
+	const vec3 wi = to_local(wi_world, T, B, n_s);
+	switch (mat.bsdf_type) {
+		case LMB_BSDF_DIFFUSE:
+			return lambertian_diffuse_pdf(wo, wi);
+		case LMB_BSDF_MIRROR:
+		case LMB_BSDF_GLASS:
+			return 0.0f;
+		case LMB_BSDF_DIELECTRIC:
+			return dielectric_pdf(mat, wo, wi, forward_facing);
+		case LMB_BSDF_CONDUCTOR:
+			return conductor_pdf(mat, wo, wi);
+		case LMB_BSDF_PRINCIPLED:
+			return principled_pdf(mat, wo, wi, forward_facing);
+		default:
+			break;
+	}
+	return 0.0f;
+}
+
 // ------------------------------------------------------------------------------------------------ atmosphere.glsl
 namespace atmo {
 constexpr float PLANET_RADIUS = 6371000.0f;
