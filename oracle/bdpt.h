@@ -303,16 +303,11 @@ inline int bdpt_generate_camera_subpath(Bdpt& k, const vec2& d, const vec3& orig
 
 inline float remap0(float v) { return v != 0.0f ? v : 1.0f; }
 
-// Diagnostics of the restatement itself (tests/test_oracle.py): ORC_BDPT_ONLY_S=<s> keeps only the strategies with that many
-// light vertices and gives them weight 1 (s = 0: emission found by the camera walk; s = 1: next-event estimation; their sum
-// with t >= 2 is a plain path tracer, which must converge to the Path integrator's image). Unset: the reference's weights.
-inline int bdpt_only_s() {
-	static const int v = [] {
-		const char* e = std::getenv("ORC_BDPT_ONLY_S");
-		return e ? std::atoi(e) : -1;
-	}();
-	return v;
-}
+// Diagnostics of the restatement itself (tests/test_oracle_bdpt.py): orc_bdpt_set_only_s(s) keeps only the strategies with that
+// many light vertices and gives them weight 1 (s = 0: emission found by the camera walk; s = 1: next-event estimation -- each an
+// unbiased estimator on its own, so their images must converge to each other where both apply). -1 (default): the reference's weights.
+static int g_bdpt_only_s = -1;
+inline int bdpt_only_s() { return g_bdpt_only_s; }
 
 // bdpt_commons.glsl:288-470
 inline float calc_mis_weight(Bdpt& k, int s, int t, const PathVertex& sampled) {

@@ -10,7 +10,6 @@
 
 #include <chrono>
 #include <cmath>
-#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -511,6 +510,8 @@ int orc_render_bdpt_frame_raw(const orc_scene* s, const lmb_pc_bdpt* pc, const l
 	}
 	return 0;
 }
+
+void orc_bdpt_set_only_s(int s) { g_bdpt_only_s = s; }
 
 int orc_render_bdpt(const orc_scene* s, const lmb_pc_bdpt* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames, float* rgba,
 					orc_stats* stats, int n_threads) {

@@ -66,6 +66,9 @@ int orc_render_bdpt(const orc_scene* s, const lmb_pc_bdpt* pc, const lmb_scene_u
 int orc_render_bdpt_frame_raw(const orc_scene* s, const lmb_pc_bdpt* pc, const lmb_scene_ubo* ubo, uint32_t frame, float* col_rgb,
 							  float* splat_rgb, orc_stats* stats, int n_threads);
 
+/* Diagnostic: keep only the BDPT strategies with `s` light vertices, weight 1 (-1 = all strategies, the reference's MIS weights). */
+void orc_bdpt_set_only_s(int s);
+
 /* Ray queries: rays = n x 8 floats (ox, oy, oz, tmin, dx, dy, dz, tmax). */
 int orc_trace_closest(const orc_scene* s, const float* rays, uint32_t n, orc_hit* hits, orc_stats* stats, int n_threads);
 /* the hit definition evaluated over ALL triangles, no tree: what orc_trace_closest must equal bit for bit */

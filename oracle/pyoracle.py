@@ -45,6 +45,7 @@ def lib():
         L.orc_render_frame_raw.argtypes = [vp, vp, vp, u32, vp, vp, i32]
         L.orc_render_bdpt.argtypes = [vp, vp, vp, u32, u32, vp, vp, i32]
         L.orc_render_bdpt_frame_raw.argtypes = [vp, vp, vp, u32, vp, vp, vp, i32]
+        L.orc_bdpt_set_only_s.argtypes = [i32]
         L.orc_trace_closest.argtypes = [vp, vp, u32, vp, vp, i32]
         L.orc_trace_any.argtypes = [vp, vp, u32, vp, vp, i32]
         L.orc_trace_closest_brute.argtypes = [vp, vp, u32, vp, i32]
@@ -66,6 +67,11 @@ def lib():
         L.orc_max_threads.restype = i32
         _LIB = L
     return _LIB
+
+
+def bdpt_set_only_s(s):
+    """Diagnostic switch of oracle/bdpt.h: only the strategies with s light vertices, weight 1 (-1 restores the MIS weights)."""
+    lib().orc_bdpt_set_only_s(int(s))
 
 
 def _f32(a):
