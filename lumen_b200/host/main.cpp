@@ -5,6 +5,7 @@
 //
 //   lumen_headless scene.(json|xml) [--width W] [--height H] [--spp N] [--depth D] [--out out.exr] [--device i] [--batch F]
 //                  [--ref gt.exr [--target-rmse X]] [--checkpoint file [--checkpoint-every N] [--resume]]
+//                  [--integrator path|bdpt|scene] [--time T]   BDPT (BDPTB200); --time fixes PCBDPT.time
 //                  [--devices 0,1,...]   several GPUs of one box: sample-index sharding, sum films reduced device to device
 //                                        (PathB200Multi; a device may be listed twice; not combined with --ref / --checkpoint)
 // Progressive service: with --ref the RMSE against the ground-truth image is computed on the device
@@ -19,6 +20,7 @@
 #include <vector>
 #include <stdexcept>
 
+#include "bdpt_b200.h"
 #include "path_b200.h"
 
 int main(int argc, char** argv) {
@@ -29,6 +31,8 @@ int main(int argc, char** argv) {
 	double target_rmse = -1.0;
 	uint32_t ckpt_every = 0;
 	bool resume = false;
+	std::string integrator_name = "path";
+	long bdpt_time = -1;  // --time: fixed PCBDPT.time (default: rand() per frame as BDPT.cpp:57)
 	std::vector<int> devices;
 	const std::regex fn("(.*).(.json|.xml)");  // RayTracer::parse_args, RayTracer.cpp:468-476
 	for (int i = 1; i < argc; i++) {
@@ -46,6 +50,8 @@ int main(int argc, char** argv) {
 		else if (a == "--checkpoint") ckpt_path = next();
 		else if (a == "--checkpoint-every") ckpt_every = (uint32_t)atoi(next());
 		else if (a == "--resume") resume = true;
+		else if (a == "--integrator") integrator_name = next();
+		else if (a == "--time") bdpt_time = atol(next());
 		else if (a == "--devices") {
 			const std::string list = next();
 			for (size_t b = 0; b < list.size();) {
@@ -60,9 +66,35 @@ int main(int argc, char** argv) {
 	try {
 		lmh::Scene scene;
 		scene.load(scene_name, width, height);
-		if (scene.config.integrator_name != "path")
-			fprintf(stderr, "note: scene asks for integrator '%s'; this build provides the Path integrator and uses it\n", scene.config.integrator_name.c_str());
+		// create_integrator (RayTracer.cpp:244-282) picks by scene.config; here --integrator path | bdpt | scene (default path)
+		if (integrator_name == "scene") integrator_name = scene.config.integrator_name;
+		if (integrator_name != "path" && integrator_name != "bdpt") {
+			fprintf(stderr, "note: integrator '%s' is not provided (path, bdpt); using path\n", integrator_name.c_str());
+			integrator_name = "path";
+		} else if (scene.config.integrator_name != integrator_name) {
+			fprintf(stderr, "note: scene asks for integrator '%s'; rendering with '%s'\n", scene.config.integrator_name.c_str(), integrator_name.c_str());
+		}
 		batch = std::max(1u, std::min(batch, spp));
+		if (integrator_name == "bdpt") {
+			if (devices.size() > 1 || !ref_path.empty() || !ckpt_path.empty()) throw std::runtime_error("--integrator bdpt cannot be combined with --devices / --ref / --checkpoint");
+			BDPTB200 bdpt(&scene, device, batch);
+			if (depth > 0) bdpt.path_length = (uint32_t)depth;
+			if (bdpt_time >= 0) bdpt.set_time((uint32_t)bdpt_time);
+			bdpt.init();
+			bdpt.create_accel();
+			while (bdpt.frame_num + batch <= spp) {
+				bdpt.render();
+				bdpt.update();
+			}
+			const lmb_stats st = bdpt.stats();
+			const double rays = (double)(st.rays_closest + st.rays_shadow);
+			printf("%u x %u, %llu frames, BDPT depth %u: %.1f ms on device, %.1f Mrays/s, %.2f spp/s\n", width, height, (unsigned long long)st.frames,
+				   bdpt.path_length, st.ms_render, rays / st.ms_render / 1e3, st.frames / (st.ms_render * 1e-3));
+			bdpt.save_exr(out.c_str());
+			printf("wrote %s\n", out.c_str());
+			bdpt.destroy();
+			return 0;
+		}
 		if (devices.size() > 1) {
 			if (!ref_path.empty() || !ckpt_path.empty()) throw std::runtime_error("--devices cannot be combined with --ref / --checkpoint");
 			const uint32_t n = (uint32_t)devices.size();

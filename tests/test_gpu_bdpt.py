@@ -108,3 +108,24 @@ def test_bdpt_rejects_pixel_shards():
         dev.render_bdpt(pc, sc.make_ubo(), 0, 1)  # the context stays usable
     finally:
         dev.close()
+
+
+def test_cli_bdpt_equals_oracle_at_half_precision(tmp_path):
+    """lumen_headless --integrator bdpt: BDPTB200 (lumen_b200/host/bdpt_b200.h) through init / create_accel / render / update /
+    save_exr, with --time fixed so that the render is reproducible; the EXR equals the oracle's film at half precision."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "lumen_b200", "host", "lumen_headless")
+    out = tmp_path / "bdpt.exr"
+    r = subprocess.run([exe, scene_path("cornell"), "--integrator", "bdpt", "--time", "9", "--width", "80", "--height", "64", "--spp", "4", "--depth", "5",
+                        "--batch", "2", "--out", str(out)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "BDPT depth 5" in r.stdout and "wrote" in r.stdout
+    sc = host.Scene(scene_path("cornell"), 80, 64)
+    pc = PCBdpt.from_path_pc(sc.make_pc(5, True), 9)
+    cpu, _ = po.OracleScene(sc).render_bdpt(pc, sc.make_ubo(), 0, 4)
+    want = cpu[..., :3].astype(np.float16).astype(np.float32)
+    got = host.load_exr(str(out))[..., :3]
+    close = np.abs(got - want) <= 2.0 ** -9 * np.maximum(np.abs(want), 1e-4)
+    assert close.mean() > 0.999
