@@ -18,6 +18,8 @@
 // per-thread walker of trace.cuh (hits do not depend on the tree: DESIGN.md section 2). This is the first correct state of the
 // BDPT row -- a megakernel, divergent by construction; the wavefront split the Path integrator has is the next step.
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "context.h"
 #include "scene_device.cuh"
@@ -370,6 +372,23 @@ struct BdptParams {
 	float4* col;    // per pixel: radiance of the pixel's own strategies (t >= 2)
 	float* splat;   // 3 floats per pixel: light-tracer image of this frame
 	unsigned long long* stats;
+	// staged pipeline only
+	float* walk;      // WalkWord struct of arrays: the random walk in flight
+	uint32_t* misc;   // MiscWord struct of arrays
+	float4* rays;     // ray slots, 2 float4 each: n_pix for a walk step, n_conn_slots * n_pix for the connections
+	float4* hits;     // closest hit of each pixel's walk ray
+	uint8_t* occ;     // any-hit result of each connection slot
+	uint32_t n_conn_slots;
+};
+
+enum WalkWord { WW_POS = 0, WW_WI = 3, WW_THR = 6, WW_PDF = 9, WW_B = 10, WW_ALIVE = 11, WW_COUNT = 12 };
+enum MiscWord { MW_RNG = 0, MW_LPDFPOS = 1, MW_NLIGHT = 2, MW_COUNT = 3 };
+
+struct WalkSt {  // the loop-carried variables of bdpt_random_walk_*
+	V3 ray_pos, wi, thr;
+	float pdf_fwd;
+	int b;
+	bool alive;
 };
 
 struct Kctx {  // per-thread state of one pixel
@@ -380,6 +399,7 @@ struct Kctx {  // per-thread state of one pixel
 	Verts lig, cam;
 	float light_pdf_pos;
 	float screen_size;
+	uint32_t pix, slot;  // staged: this pixel and the connection slot of the (t, s) pair being evaluated
 	uint32_t n_closest, n_shadow, n_nodes, n_tris;
 };
 
@@ -395,78 +415,99 @@ LMB_DN bool occluded(Kctx& k, const V3& o, const V3& d, float tmax) {
 	return trace_ray<true>(k.bvh, o, d, 0.0f, tmax, k.n_nodes, k.n_tris).prim != 0xFFFFFFFFu;
 }
 
-// bdpt_commons.glsl:13-111 (EYE = false), :113-216 (EYE = true). V.x(i + 1, ..) is the GLSL's vtx(i, ..).
-template <bool EYE>
-LMB_DN int random_walk(Kctx& k, const Verts& V, int max_depth, V3 throughput, float pdf) {
-	if (max_depth == 0) return 0;
-	int b = 0;
-	int prev = 0;
-	V3 ray_pos = V.v(0, W_POS);
-	float pdf_fwd = pdf;
-	float pdf_rev = 0.0f;
-	V3 wi = V.v(0, W_DIR);
-	const bool finite_light = is_light_finite(V.u(0, W_LFLAGS));
-	while (true) {
-		prev = b - 1;
-		const Hit h = trace_closest(k, ray_pos, wi, BDPT_T_MIN, BDPT_T_MAX);
-		if (h.prim == 0xFFFFFFFFu) {
-			if (EYE) {
-				V.sv(b + 1, W_THR, throughput);
-				V.f(b + 1, W_PFWD) = pdf_fwd;
-				b++;
-			}
-			break;
-		}
-		const HitPayload payload = build_hit(k.sc, h.prim, h.b1, h.b2);
-		V3 wo = V.v(prev + 1, W_POS) - payload.pos;
-		const float wo_len = length(wo);
-		wo /= wo_len;
-		V3 n_s = payload.n_s;
-		bool side = true;
-		V3 n_g = payload.n_g;
-		if (dot(payload.n_g, wo) < 0.0f) n_g = -n_g;
-		if (dot(n_g, n_s) < 0) {
-			n_s *= -1.0f;
-			side = false;
-		}
-		V.f(b + 1, W_PFWD) = pdf_fwd * fabsf(dot(wo, n_s)) / (wo_len * wo_len);
-		V.sv(b + 1, W_NS, n_s);
-		V.f(b + 1, W_AREA) = hit_area(k.sc, h.prim);
-		V.sv(b + 1, W_POS, payload.pos);
-		V.f(b + 1, W_UV) = payload.uv.x, V.f(b + 1, W_UV + 1) = payload.uv.y;
-		V.su(b + 1, W_MAT, payload.material_idx);
-		V.sv(b + 1, W_THR, throughput);
-		V.su(b + 1, W_SIDE, side ? 1u : 0u);
-		V.su(b + 1, W_MODE, EYE ? 1u : 0u);
-		const lmb_material mat = load_material(k.sc, payload.material_idx, payload.uv);
-		const bool mat_specular = (mat.bsdf_props & LMB_FLAG_SPECULAR) == LMB_FLAG_SPECULAR;
-		const bool mat_transmissive = (mat.bsdf_props & LMB_FLAG_TRANSMISSION) == LMB_FLAG_TRANSMISSION;
-		V.su(b + 1, W_DELTA, mat_specular ? 1u : 0u);
-		if (++b >= max_depth) break;
-		const V3 r3 = rand3(k.seed);
-		const BsdfSample bs = sample_bsdf(n_s, wo, mat, EYE ? 1u : 0u, side, r3);
-		wi = bs.wi;
-		pdf_fwd = bs.pdf;
-		const bool same_hem = same_hemisphere(wi, wo, n_s);
-		if (is_zero(bs.f) || pdf_fwd == 0 || (!same_hem && !mat_transmissive)) break;
-		throughput *= bs.f * fabsf(bs.cos_theta) / pdf_fwd;
-		pdf_rev = pdf_fwd;
-		if (!mat_specular) pdf_rev = bsdf_pdf(mat, n_s, wi, wo, side);
-		const bool g_term = EYE ? true : (prev > -1 || finite_light);
-		if (g_term) pdf_rev *= fabsf(dot(V.v(prev + 1, W_NS), wo)) / (wo_len * wo_len);
-		V.f(prev + 1, W_PREV) = pdf_rev;
-		ray_pos = offset_ray(payload.pos, n_g);
+// Visibility test of a connection. MODE 0 (megakernel): trace here. MODE 1 (staged, emit pass): write the ray into this pair's slot
+// and report "not visible", so nothing downstream is evaluated yet. MODE 2 (staged, resolve pass): read the traced result.
+template <int MODE>
+LMB_D bool shadow_visible(Kctx& k, const V3& o, const V3& d, float tmax) {
+	if (MODE == 0) return !occluded(k, o, d, tmax);
+	const size_t i = (size_t)k.slot * k.P.n_pix + k.pix;
+	if (MODE == 1) {
+		k.P.rays[2 * i] = make_float4(o.x, o.y, o.z, 0.0f);
+		k.P.rays[2 * i + 1] = make_float4(d.x, d.y, d.z, tmax);
+		k.n_shadow++;
+		return false;
 	}
-	return b;
+	return k.P.occ[i] == 0;
 }
 
-// bdpt_commons.glsl:218-260
-LMB_DN int generate_light_subpath(Kctx& k, int max_depth) {
+// One trip of the `while (true)` of bdpt_random_walk_light (bdpt_commons.glsl:13-111, EYE = false) / _eye (:113-216, EYE = true),
+// given the closest hit `h` of the ray in `st`. st.alive = false where the GLSL breaks. V.x(i + 1, ..) is the GLSL's vtx(i, ..).
+template <bool EYE>
+LMB_DN void walk_step(Kctx& k, const Verts& V, int max_depth, WalkSt& st, const Hit& h) {
+	int b = st.b;
+	const int prev = b - 1;
+	st.alive = false;
+	if (h.prim == 0xFFFFFFFFu) {
+		if (EYE) {
+			V.sv(b + 1, W_THR, st.thr);
+			V.f(b + 1, W_PFWD) = st.pdf_fwd;
+			st.b = b + 1;
+		}
+		return;
+	}
+	const bool finite_light = is_light_finite(V.u(0, W_LFLAGS));
+	const HitPayload payload = build_hit(k.sc, h.prim, h.b1, h.b2);
+	V3 wo = V.v(prev + 1, W_POS) - payload.pos;
+	const float wo_len = length(wo);
+	wo /= wo_len;
+	V3 n_s = payload.n_s;
+	bool side = true;
+	V3 n_g = payload.n_g;
+	if (dot(payload.n_g, wo) < 0.0f) n_g = -n_g;
+	if (dot(n_g, n_s) < 0) {
+		n_s *= -1.0f;
+		side = false;
+	}
+	V.f(b + 1, W_PFWD) = st.pdf_fwd * fabsf(dot(wo, n_s)) / (wo_len * wo_len);
+	V.sv(b + 1, W_NS, n_s);
+	V.f(b + 1, W_AREA) = hit_area(k.sc, h.prim);
+	V.sv(b + 1, W_POS, payload.pos);
+	V.f(b + 1, W_UV) = payload.uv.x, V.f(b + 1, W_UV + 1) = payload.uv.y;
+	V.su(b + 1, W_MAT, payload.material_idx);
+	V.sv(b + 1, W_THR, st.thr);
+	V.su(b + 1, W_SIDE, side ? 1u : 0u);
+	V.su(b + 1, W_MODE, EYE ? 1u : 0u);
+	const lmb_material mat = load_material(k.sc, payload.material_idx, payload.uv);
+	const bool mat_specular = (mat.bsdf_props & LMB_FLAG_SPECULAR) == LMB_FLAG_SPECULAR;
+	const bool mat_transmissive = (mat.bsdf_props & LMB_FLAG_TRANSMISSION) == LMB_FLAG_TRANSMISSION;
+	V.su(b + 1, W_DELTA, mat_specular ? 1u : 0u);
+	st.b = ++b;
+	if (b >= max_depth) return;
+	const V3 r3 = rand3(k.seed);
+	const BsdfSample bs = sample_bsdf(n_s, wo, mat, EYE ? 1u : 0u, side, r3);
+	st.wi = bs.wi;
+	st.pdf_fwd = bs.pdf;
+	const bool same_hem = same_hemisphere(bs.wi, wo, n_s);
+	if (is_zero(bs.f) || bs.pdf == 0 || (!same_hem && !mat_transmissive)) return;
+	st.thr *= bs.f * fabsf(bs.cos_theta) / bs.pdf;
+	float pdf_rev = bs.pdf;
+	if (!mat_specular) pdf_rev = bsdf_pdf(mat, n_s, bs.wi, wo, side);
+	const bool g_term = EYE ? true : (prev > -1 || finite_light);
+	if (g_term) pdf_rev *= fabsf(dot(V.v(prev + 1, W_NS), wo)) / (wo_len * wo_len);
+	V.f(prev + 1, W_PREV) = pdf_rev;
+	st.ray_pos = offset_ray(payload.pos, n_g);
+	st.alive = true;
+}
+
+// megakernel: the whole walk in this thread
+template <bool EYE>
+LMB_DN int random_walk(Kctx& k, const Verts& V, int max_depth, const V3& throughput, float pdf) {
+	if (max_depth == 0) return 0;
+	WalkSt st{V.v(0, W_POS), V.v(0, W_DIR), throughput, pdf, 0, true};
+	while (st.alive) {
+		const Hit h = trace_closest(k, st.ray_pos, st.wi, BDPT_T_MIN, BDPT_T_MAX);
+		walk_step<EYE>(k, V, max_depth, st, h);
+	}
+	return st.b;
+}
+
+// bdpt_generate_light_subpath, bdpt_commons.glsl:218-249: emission sample and vertex 0. false = no light sub-path (pdf_dir <= 0)
+LMB_DN bool light_begin(Kctx& k, V3& throughput, float& pdf_dir) {
 	const V4 rands_pos = rand4(k.seed);
 	const float d0 = rand1(k.seed);
 	const float d1 = rand1(k.seed);
 	const LightEmission le = sample_light_Le(k.sc, rands_pos, v2(d0, d1), k.P.num_lights, k.P.light_triangle_count);
-	if (le.pdf_dir_w <= 0) return 0;
+	if (le.pdf_dir_w <= 0) return false;
 	k.light_pdf_pos = le.pdf_pos_a;
 	const Verts& L = k.lig;
 	L.sv(0, W_POS, le.pos);
@@ -477,12 +518,17 @@ LMB_DN int generate_light_subpath(Kctx& k, int max_depth) {
 	L.sv(0, W_NS, le.n);
 	L.su(0, W_SIDE, 1);
 	L.su(0, W_MODE, 0);
-	const V3 throughput = le.L * le.cos_from_light / (le.pdf_dir_w * le.pdf_pos_a);
+	throughput = le.L * le.cos_from_light / (le.pdf_dir_w * le.pdf_pos_a);
 	L.sv(0, W_THR, le.L);
-	const int num_light_verts = random_walk<false>(k, L, max_depth - 1, throughput, le.pdf_dir_w) + 1;
-	if (!is_light_finite(le.flags)) L.f(1, W_PFWD) = le.pdf_pos_a * fabsf(dot(le.wi, L.v(1, W_NS)));
-	if (is_light_delta(le.flags)) L.f(0, W_PFWD) = 0.0f;
-	return num_light_verts;
+	pdf_dir = le.pdf_dir_w;
+	return true;
+}
+// ... :252-259, after the walk. pdf_pos and wi are read back from where light_begin stored them.
+LMB_D void light_end(Kctx& k) {
+	const Verts& L = k.lig;
+	const uint32_t flags = L.u(0, W_LFLAGS);
+	if (!is_light_finite(flags)) L.f(1, W_PFWD) = k.light_pdf_pos * fabsf(dot(L.v(0, W_DIR), L.v(1, W_NS)));
+	if (is_light_delta(flags)) L.f(0, W_PFWD) = 0.0f;
 }
 
 LMB_D M4 neg_m4(const M4& m) {
@@ -492,23 +538,31 @@ LMB_D M4 neg_m4(const M4& m) {
 	return r;
 }
 
-// bdpt_commons.glsl:262-286
-LMB_DN int generate_camera_subpath(Kctx& k, const V2& d, const V3& origin, int max_depth, float cam_area) {
+// bdpt.rgen:40-53 + bdpt_generate_camera_subpath, bdpt_commons.glsl:262-284: camera vertex 0; returns the pdf the eye walk starts with
+LMB_DN float camera_begin(Kctx& k, uint32_t px, uint32_t py) {
+	const BdptParams& P = k.P;
+	const V2 size = v2((float)P.width, (float)P.height);
+	const V2 pixel = v2((float)px, (float)py) + 0.5f;
+	const V2 in_uv = pixel / size;
+	const V2 d = in_uv * 2.0f - 1.0f;
+	const V4 origin = mul(P.inv_view, v4(0, 0, 0, 1));
+	V4 area_int = mul(P.inv_proj, v4(2.0f / (float)P.width, 2.0f / (float)P.height, 0, 1));
+	area_int = v4(area_int.x / area_int.w, area_int.y / area_int.w, area_int.z / area_int.w, area_int.w / area_int.w);
+	const float cam_area = fabsf(area_int.x * area_int.y);
 	const Verts& C = k.cam;
-	C.sv(0, W_POS, origin);
-	const V4 target = mul(k.P.inv_proj, v4(d.x, d.y, 1, 1));
-	const V3 dir = xyz(mul(k.P.inv_view, v4(normalize(xyz(target)), 0)));  // sample_camera, commons.glsl:30-33
+	C.sv(0, W_POS, xyz(origin));
+	const V4 target = mul(P.inv_proj, v4(d.x, d.y, 1, 1));
+	const V3 dir = xyz(mul(P.inv_view, v4(normalize(xyz(target)), 0)));  // sample_camera, commons.glsl:30-33
 	C.sv(0, W_DIR, dir);
 	C.f(0, W_AREA) = cam_area;
 	C.sv(0, W_THR, v3(1.0f));
 	C.su(0, W_DELTA, 0);
-	const V3 n_s = xyz(mul(neg_m4(k.P.inv_view), v4(0, 0, 1, 0)));
+	const V3 n_s = xyz(mul(neg_m4(P.inv_view), v4(0, 0, 1, 0)));
 	C.sv(0, W_NS, n_s);
 	C.su(0, W_SIDE, 1);
 	k.lig.su(0, W_MODE, 1);  // sic, :272
 	const float cos_theta = dot(dir, n_s);
-	const float pdf = 1 / (cam_area * k.screen_size * cos_theta * cos_theta * cos_theta);
-	return random_walk<true>(k, C, max_depth - 1, v3(1.0f), pdf) + 1;
+	return 1 / (cam_area * k.screen_size * cos_theta * cos_theta * cos_theta);
 }
 
 LMB_D float remap0(float v) { return v != 0.0f ? v : 1.0f; }
@@ -653,6 +707,7 @@ LMB_D bool splat_coord(float v, int& out) {
 }
 
 // bdpt_commons.glsl:472-530
+template <int MODE>
 LMB_DN V3 connect_cam(Kctx& k, int s, int& cx, int& cy) {
 	const Verts& cam = k.cam;
 	const Verts& lig = k.lig;
@@ -676,7 +731,7 @@ LMB_DN V3 connect_cam(Kctx& k, int s, int& cx, int& cy) {
 	const V3 f = eval_bsdf(ln, wo, mat, lig.u(s - 1, W_SIDE) == 1, dir, unused_pdf);
 	if (is_zero(f)) return L;
 	if (cam_pdf_ratio > 0.0f) {
-		if (!occluded(k, ray_origin, dir, len - LMB_EPS)) {
+		if (shadow_visible<MODE>(k, ray_origin, dir, len - LMB_EPS)) {
 			sampled.pos = cam_pos;
 			sampled.n_s = cam_n;
 			L = lig.v(s - 1, W_THR) * cam_pdf_ratio * f / k.screen_size;
@@ -698,6 +753,7 @@ LMB_DN V3 connect_cam(Kctx& k, int s, int& cx, int& cy) {
 }
 
 // bdpt_commons.glsl:532-641
+template <int MODE>
 LMB_DN V3 connect(Kctx& k, int s, int t) {
 	const Verts& cam = k.cam;
 	const Verts& lig = k.lig;
@@ -717,7 +773,7 @@ LMB_DN V3 connect(Kctx& k, int s, int t) {
 		float unused_pdf;
 		const V3 f = eval_bsdf(cn, wo, mat, cam.u(t - 1, W_SIDE) == 1, ls.wi, unused_pdf);
 		if (!is_zero(f)) {
-			if (!occluded(k, ray_origin, ls.wi, ls.wi_len - LMB_EPS)) {
+			if (shadow_visible<MODE>(k, ray_origin, ls.wi, ls.wi_len - LMB_EPS)) {
 				const float pdf_light_w = light_pdf_a_to_w(ls.flags, ls.pdf_a, ls.wi_len * ls.wi_len, ls.cos_from_light) / (float)k.P.light_triangle_count;
 				sampled.pdf_fwd = ls.pdf_a / (float)k.P.light_triangle_count;
 				light_sample_n_pos(k.sc, r4, cpos, k.P.num_lights, ls, sampled.n_s, sampled.pos);
@@ -742,7 +798,7 @@ LMB_DN V3 connect(Kctx& k, int s, int t) {
 			const V3 brdf2 = eval_bsdf(n_s, wo_2, mat_2, lig.u(s - 1, W_SIDE) == 1, -d, unused_pdf);
 			if (!is_zero(brdf1) && !is_zero(brdf2)) {
 				const V3 ray_origin = offset_ray2(cpos, n_t);
-				if (!occluded(k, ray_origin, d, len - LMB_EPS)) L = lig.v(s - 1, W_THR) * G * brdf1 * brdf2 * cam.v(t - 1, W_THR);
+				if (shadow_visible<MODE>(k, ray_origin, d, len - LMB_EPS)) L = lig.v(s - 1, W_THR) * G * brdf1 * brdf2 * cam.v(t - 1, W_THR);
 			}
 		}
 	}
@@ -753,57 +809,187 @@ LMB_DN V3 connect(Kctx& k, int s, int t) {
 	return L;
 }
 
-// bdpt.rgen:39-75 for one pixel of one frame
-__global__ void __launch_bounds__(128) k_bdpt(BdptParams P, DeviceScene sc, BvhView bvh) {
-	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
-	uint32_t n_closest = 0, n_shadow = 0, n_nodes = 0, n_tris = 0;
-	if (pix < P.n_pix) {
-		const uint32_t px = pix % P.width, py = pix / P.width;
-		Kctx k{P, sc, bvh, Rng{px, py, P.seed_z, 0u}, Verts{P.light_verts + pix, P.n_pix}, Verts{P.camera_verts + pix, P.n_pix}, 0.0f,
-			   (float)(P.width * P.height), 0u, 0u, 0u, 0u};
-		const V2 size = v2((float)P.width, (float)P.height);
-		const V2 pixel = v2((float)px, (float)py) + 0.5f;
-		const V2 in_uv = pixel / size;
-		const V2 d = in_uv * 2.0f - 1.0f;
-		const V4 origin = mul(P.inv_view, v4(0, 0, 0, 1));
-		V3 col = v3(0.0f);
-		V4 area_int = mul(P.inv_proj, v4(2.0f / (float)P.width, 2.0f / (float)P.height, 0, 1));
-		area_int = v4(area_int.x / area_int.w, area_int.y / area_int.w, area_int.z / area_int.w, area_int.w / area_int.w);
-		const float cam_area = fabsf(area_int.x * area_int.y);
-		const int num_light_paths = generate_light_subpath(k, P.max_depth + 1);
-		const int num_cam_paths = generate_camera_subpath(k, d, xyz(origin), P.max_depth + 1, cam_area);
-		for (int t = 1; t <= num_cam_paths; t++) {
-			for (int s = 0; s <= num_light_paths; s++) {
-				const int depth = s + t - 2;
-				if (depth > (P.max_depth - 1) || depth < 0 || (s == 1 && t == 1)) continue;
-				if (t == 1) {
-					int cx, cy;
-					const V3 splat_col = connect_cam(k, s, cx, cy);
-					if (luminance(splat_col) > 0) {
-						float* o = P.splat + 3 * ((size_t)cy * P.width + cx);
-						atomicAdd(o + 0, splat_col.x), atomicAdd(o + 1, splat_col.y), atomicAdd(o + 2, splat_col.z);
-					}
-				} else {
-					col += connect(k, s, t);
+// bdpt.rgen:55-75: the (s, t) loop. Every pair the loop body reaches owns one connection slot (staged pipeline).
+template <int MODE>
+LMB_D V3 connect_all(Kctx& k, int num_light_paths, int num_cam_paths) {
+	const BdptParams& P = k.P;
+	V3 col = v3(0.0f);
+	k.slot = 0;
+	const float4 dead = make_float4(__int_as_float(0x7FC00000), 0.0f, 0.0f, 0.0f);  // NaN origin: the ray hits nothing (ray_finite)
+	for (int t = 1; t <= num_cam_paths; t++) {
+		for (int s = 0; s <= num_light_paths; s++) {
+			const int depth = s + t - 2;
+			if (depth > (P.max_depth - 1) || depth < 0 || (s == 1 && t == 1)) continue;
+			if (MODE == 1) P.rays[2 * ((size_t)k.slot * P.n_pix + k.pix)] = dead;
+			if (t == 1) {
+				int cx, cy;
+				const V3 splat_col = connect_cam<MODE>(k, s, cx, cy);
+				if (MODE != 1 && luminance(splat_col) > 0) {
+					float* o = P.splat + 3 * ((size_t)cy * P.width + cx);
+					atomicAdd(o + 0, splat_col.x), atomicAdd(o + 1, splat_col.y), atomicAdd(o + 2, splat_col.z);
 				}
+			} else {
+				col += connect<MODE>(k, s, t);
 			}
+			k.slot++;
 		}
-		P.col[pix] = make_float4(col.x, col.y, col.z, 0.0f);
-		n_closest = k.n_closest, n_shadow = k.n_shadow, n_nodes = k.n_nodes, n_tris = k.n_tris;
 	}
-	// ray counters: one atomic per warp and counter
-	for (int o = 16; o > 0; o >>= 1) {
+	if (MODE == 1)
+		for (uint32_t c = k.slot; c < P.n_conn_slots; c++) P.rays[2 * ((size_t)c * P.n_pix + k.pix)] = dead;
+	return col;
+}
+
+LMB_D void flush_counts(unsigned long long* stats, uint32_t n_closest, uint32_t n_shadow, uint32_t n_nodes, uint32_t n_tris) {
+	for (int o = 16; o > 0; o >>= 1) {  // one atomic per warp and counter
 		n_closest += __shfl_down_sync(0xFFFFFFFFu, n_closest, o);
 		n_shadow += __shfl_down_sync(0xFFFFFFFFu, n_shadow, o);
 		n_nodes += __shfl_down_sync(0xFFFFFFFFu, n_nodes, o);
 		n_tris += __shfl_down_sync(0xFFFFFFFFu, n_tris, o);
 	}
 	if ((threadIdx.x & 31) == 0) {
-		atomicAdd(&P.stats[ST_CLOSEST], (unsigned long long)n_closest);
-		atomicAdd(&P.stats[ST_SHADOW], (unsigned long long)n_shadow);
-		atomicAdd(&P.stats[ST_NODES], (unsigned long long)n_nodes);
-		atomicAdd(&P.stats[ST_TRIS], (unsigned long long)n_tris);
+		if (n_closest) atomicAdd(&stats[ST_CLOSEST], (unsigned long long)n_closest);
+		if (n_shadow) atomicAdd(&stats[ST_SHADOW], (unsigned long long)n_shadow);
+		if (n_nodes) atomicAdd(&stats[ST_NODES], (unsigned long long)n_nodes);
+		if (n_tris) atomicAdd(&stats[ST_TRIS], (unsigned long long)n_tris);
 	}
+}
+
+LMB_D Kctx make_kctx(const BdptParams& P, const DeviceScene& sc, const BvhView& bvh, uint32_t pix, uint32_t rng_w) {
+	return Kctx{P, sc, bvh, Rng{pix % P.width, pix / P.width, P.seed_z, rng_w}, Verts{P.light_verts + pix, P.n_pix}, Verts{P.camera_verts + pix, P.n_pix}, 0.0f,
+				(float)(P.width * P.height), pix, 0u, 0u, 0u, 0u, 0u};
+}
+
+// ---------------------------------------------------------------------------------------------- megakernel (LMB_BDPT=mega)
+// bdpt.rgen:39-75 for one pixel of one frame, rays traced in the thread
+__global__ void __launch_bounds__(128) k_bdpt(BdptParams P, DeviceScene sc, BvhView bvh) {
+	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t n_closest = 0, n_shadow = 0, n_nodes = 0, n_tris = 0;
+	if (pix < P.n_pix) {
+		Kctx k = make_kctx(P, sc, bvh, pix, 0u);
+		int num_light_paths = 0;
+		V3 thr;
+		float pdf_dir;
+		if (light_begin(k, thr, pdf_dir)) {
+			num_light_paths = random_walk<false>(k, k.lig, P.max_depth, thr, pdf_dir) + 1;
+			light_end(k);
+		}
+		const float pdf = camera_begin(k, pix % P.width, pix / P.width);
+		const int num_cam_paths = random_walk<true>(k, k.cam, P.max_depth, v3(1.0f), pdf) + 1;
+		const V3 col = connect_all<0>(k, num_light_paths, num_cam_paths);
+		P.col[pix] = make_float4(col.x, col.y, col.z, 0.0f);
+		n_closest = k.n_closest, n_shadow = k.n_shadow, n_nodes = k.n_nodes, n_tris = k.n_tris;
+	}
+	flush_counts(P.stats, n_closest, n_shadow, n_nodes, n_tris);
+}
+
+// ---------------------------------------------------------------------------------------------- staged pipeline (default)
+// The same per-pixel code cut at every ray: k_bdpt_begin -> [trace, k_bdpt_walk<light>] x max_depth -> k_bdpt_mid ->
+// [trace, k_bdpt_walk<eye>] x max_depth -> k_bdpt_connect<emit> -> trace (any-hit) -> k_bdpt_connect<resolve>. Rays go through the
+// Path integrator's persistent 8-wide walker (k_trace_array) as per-pixel slots; a slot without a ray holds a NaN origin.
+LMB_D void store_walk(const BdptParams& P, uint32_t pix, const WalkSt& st, uint32_t& n_closest) {
+	float* w = P.walk + pix;
+	const size_t n = P.n_pix;
+	w[(WW_POS + 0) * n] = st.ray_pos.x, w[(WW_POS + 1) * n] = st.ray_pos.y, w[(WW_POS + 2) * n] = st.ray_pos.z;
+	w[(WW_WI + 0) * n] = st.wi.x, w[(WW_WI + 1) * n] = st.wi.y, w[(WW_WI + 2) * n] = st.wi.z;
+	w[(WW_THR + 0) * n] = st.thr.x, w[(WW_THR + 1) * n] = st.thr.y, w[(WW_THR + 2) * n] = st.thr.z;
+	w[WW_PDF * n] = st.pdf_fwd;
+	w[WW_B * n] = __int_as_float(st.b);
+	w[WW_ALIVE * n] = __int_as_float(st.alive ? 1 : 0);
+	if (st.alive) {
+		P.rays[2 * (size_t)pix] = make_float4(st.ray_pos.x, st.ray_pos.y, st.ray_pos.z, BDPT_T_MIN);
+		P.rays[2 * (size_t)pix + 1] = make_float4(st.wi.x, st.wi.y, st.wi.z, BDPT_T_MAX);
+		n_closest++;
+	} else {
+		P.rays[2 * (size_t)pix] = make_float4(__int_as_float(0x7FC00000), 0.0f, 0.0f, 0.0f);
+	}
+}
+LMB_D WalkSt load_walk(const BdptParams& P, uint32_t pix) {
+	const float* w = P.walk + pix;
+	const size_t n = P.n_pix;
+	WalkSt st;
+	st.ray_pos = v3(w[(WW_POS + 0) * n], w[(WW_POS + 1) * n], w[(WW_POS + 2) * n]);
+	st.wi = v3(w[(WW_WI + 0) * n], w[(WW_WI + 1) * n], w[(WW_WI + 2) * n]);
+	st.thr = v3(w[(WW_THR + 0) * n], w[(WW_THR + 1) * n], w[(WW_THR + 2) * n]);
+	st.pdf_fwd = w[WW_PDF * n];
+	st.b = __float_as_int(w[WW_B * n]);
+	st.alive = __float_as_int(w[WW_ALIVE * n]) != 0;
+	return st;
+}
+
+__global__ void __launch_bounds__(128) k_bdpt_begin(BdptParams P, DeviceScene sc) {
+	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t n_closest = 0;
+	if (pix < P.n_pix) {
+		const BvhView none{nullptr, nullptr, 0};
+		Kctx k = make_kctx(P, sc, none, pix, 0u);
+		WalkSt st{v3(0.0f), v3(0.0f), v3(0.0f), 0.0f, 0, false};
+		float pdf_dir;
+		const bool ok = light_begin(k, st.thr, pdf_dir);
+		if (ok) st.ray_pos = k.lig.v(0, W_POS), st.wi = k.lig.v(0, W_DIR), st.pdf_fwd = pdf_dir, st.alive = true;  // walk max_depth = pc.max_depth >= 1
+		store_walk(P, pix, st, n_closest);
+		P.misc[MW_RNG * (size_t)P.n_pix + pix] = k.seed.w;
+		P.misc[MW_LPDFPOS * (size_t)P.n_pix + pix] = __float_as_uint(k.light_pdf_pos);
+		P.misc[MW_NLIGHT * (size_t)P.n_pix + pix] = ok ? 1u : 0u;
+	}
+	flush_counts(P.stats, n_closest, 0, 0, 0);
+}
+
+template <bool EYE>
+__global__ void __launch_bounds__(128) k_bdpt_walk(BdptParams P, DeviceScene sc) {
+	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t n_closest = 0;
+	if (pix < P.n_pix) {
+		WalkSt st = load_walk(P, pix);
+		if (st.alive) {
+			const BvhView none{nullptr, nullptr, 0};
+			Kctx k = make_kctx(P, sc, none, pix, P.misc[MW_RNG * (size_t)P.n_pix + pix]);
+			const float4 h4 = P.hits[pix];
+			const Hit h{h4.x, h4.y, h4.z, __float_as_uint(h4.w)};
+			walk_step<EYE>(k, EYE ? k.cam : k.lig, P.max_depth, st, h);
+			store_walk(P, pix, st, n_closest);
+			P.misc[MW_RNG * (size_t)P.n_pix + pix] = k.seed.w;
+		}
+	}
+	flush_counts(P.stats, n_closest, 0, 0, 0);
+}
+
+// end of the light sub-path, camera vertex 0, first ray of the eye walk
+__global__ void __launch_bounds__(128) k_bdpt_mid(BdptParams P, DeviceScene sc) {
+	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t n_closest = 0;
+	if (pix < P.n_pix) {
+		const BvhView none{nullptr, nullptr, 0};
+		Kctx k = make_kctx(P, sc, none, pix, 0u);
+		k.light_pdf_pos = __uint_as_float(P.misc[MW_LPDFPOS * (size_t)P.n_pix + pix]);
+		const WalkSt lst = load_walk(P, pix);
+		uint32_t num_light_paths = 0;
+		if (P.misc[MW_NLIGHT * (size_t)P.n_pix + pix]) {
+			num_light_paths = (uint32_t)lst.b + 1;
+			light_end(k);
+		}
+		P.misc[MW_NLIGHT * (size_t)P.n_pix + pix] = num_light_paths;
+		const float pdf = camera_begin(k, pix % P.width, pix / P.width);
+		const WalkSt st{k.cam.v(0, W_POS), k.cam.v(0, W_DIR), v3(1.0f), pdf, 0, true};
+		store_walk(P, pix, st, n_closest);
+	}
+	flush_counts(P.stats, n_closest, 0, 0, 0);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_bdpt_connect(BdptParams P, DeviceScene sc) {
+	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t n_shadow = 0;
+	if (pix < P.n_pix) {
+		const BvhView none{nullptr, nullptr, 0};
+		Kctx k = make_kctx(P, sc, none, pix, P.misc[MW_RNG * (size_t)P.n_pix + pix]);
+		k.light_pdf_pos = __uint_as_float(P.misc[MW_LPDFPOS * (size_t)P.n_pix + pix]);
+		const int num_light_paths = (int)P.misc[MW_NLIGHT * (size_t)P.n_pix + pix];
+		const int num_cam_paths = __float_as_int(P.walk[WW_B * (size_t)P.n_pix + pix]) + 1;
+		const V3 col = connect_all<MODE>(k, num_light_paths, num_cam_paths);
+		if (MODE == 2) P.col[pix] = make_float4(col.x, col.y, col.z, 0.0f);
+		n_shadow = k.n_shadow;
+	}
+	flush_counts(P.stats, 0, n_shadow, 0, 0);
 }
 
 // bdpt.rgen:76-89: own strategies + this frame's splats -> running-mean film (NaN samples leave the pixel untouched); clears the
@@ -837,25 +1023,51 @@ __global__ void __launch_bounds__(256) k_bdpt_film(uint32_t n_pix, uint32_t fram
 void bdpt_free(lmb_ctx* ctx) {
 	BdptState& b = ctx->bdpt;
 	cudaFree(b.light_verts), cudaFree(b.camera_verts), cudaFree(b.col), cudaFree(b.splat);
+	cudaFree(b.walk), cudaFree(b.misc), cudaFree(b.rays), cudaFree(b.hits), cudaFree(b.occ);
 	b = BdptState{};
+}
+
+// connection slots a pixel can use: the pairs bdpt.rgen:57-62 lets through when both sub-paths have their full length
+static uint32_t count_conn_slots(int max_depth) {
+	uint32_t n = 0;
+	for (int t = 1; t <= max_depth + 1; t++)
+		for (int s = 0; s <= max_depth + 1; s++) {
+			const int depth = s + t - 2;
+			if (depth > (max_depth - 1) || depth < 0 || (s == 1 && t == 1)) continue;
+			n++;
+		}
+	return n;
 }
 
 int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, uint32_t first_frame, uint32_t n_frames, float* raw_col, float* raw_splat) {
 	if (ctx->row_stride != 1) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: pixel shards are not supported (light-tracer splats cross rows)");
 	if (pc.max_depth < 1 || pc.max_depth > 63) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: max_depth must be in [1, 63]");
 	if (!ctx->wf.stats) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: call lmb_init first");
+	// LMB_BDPT=mega: the one-kernel version (rays traced in the thread over the binary LBVH); default: the staged pipeline
+	const char* mode_env = getenv("LMB_BDPT");
+	const bool mega = mode_env && strcmp(mode_env, "mega") == 0;
 	BdptState& b = ctx->bdpt;
 	cudaStream_t st = ctx->stream;
 	const uint32_t n_pix = ctx->width * ctx->height;
 	const uint32_t n_verts = (uint32_t)pc.max_depth + 1;
+	const uint32_t n_conn_slots = count_conn_slots(pc.max_depth);
+	if ((uint64_t)n_pix * n_conn_slots > 0x7FFFFFFFull) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: width * height * connection slots out of range");
 	const size_t vert_bytes = (size_t)n_pix * n_verts * W_COUNT * 4;
-	if (b.n_pix != n_pix || b.n_verts < n_verts) {
+	if (b.n_pix != n_pix || b.n_verts != n_verts) {
 		bdpt_free(ctx);
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.light_verts, vert_bytes));
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.camera_verts, vert_bytes));
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.col, (size_t)n_pix * 16));
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.splat, (size_t)n_pix * 12));
 		b.n_pix = n_pix, b.n_verts = n_verts;
+	}
+	if (!mega && !b.rays) {
+		LMB_CUDA(ctx, cudaMalloc((void**)&b.walk, (size_t)n_pix * WW_COUNT * 4));
+		LMB_CUDA(ctx, cudaMalloc((void**)&b.misc, (size_t)n_pix * MW_COUNT * 4));
+		LMB_CUDA(ctx, cudaMalloc((void**)&b.rays, (size_t)n_pix * n_conn_slots * 32));
+		LMB_CUDA(ctx, cudaMalloc((void**)&b.hits, (size_t)n_pix * 16));
+		LMB_CUDA(ctx, cudaMalloc((void**)&b.occ, (size_t)n_pix * n_conn_slots));
+		b.n_conn_slots = n_conn_slots;
 	}
 	LMB_CUDA(ctx, cudaMemsetAsync(b.splat, 0, (size_t)n_pix * 12, st));
 	auto load = [](const float* p) {
@@ -870,7 +1082,10 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 	P.width = ctx->width, P.height = ctx->height, P.n_pix = n_pix;
 	P.num_lights = pc.num_lights, P.max_depth = pc.max_depth, P.light_triangle_count = pc.light_triangle_count;
 	P.light_verts = b.light_verts, P.camera_verts = b.camera_verts, P.col = b.col, P.splat = b.splat, P.stats = ctx->wf.stats;
+	P.walk = b.walk, P.misc = b.misc, P.rays = b.rays, P.hits = b.hits, P.occ = b.occ, P.n_conn_slots = n_conn_slots;
 	const BvhView bvh{ctx->bvh.nodes, ctx->bvh.tris, ctx->bvh.n};
+	const uint32_t grid = (n_pix + 127) / 128;
+	int rc;
 	cudaEventRecord(ctx->ev[0], st);
 	for (uint32_t i = 0; i < n_frames; i++) {
 		const uint32_t frame = first_frame + i;
@@ -878,13 +1093,31 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 		// BDPT.cpp:79-80: both vertex buffers are zeroed before every frame
 		LMB_CUDA(ctx, cudaMemsetAsync(b.light_verts, 0, vert_bytes, st));
 		LMB_CUDA(ctx, cudaMemsetAsync(b.camera_verts, 0, vert_bytes, st));
-		k_bdpt<<<(n_pix + 127) / 128, 128, 0, st>>>(P, ctx->scene, bvh);
+		if (mega) {
+			k_bdpt<<<grid, 128, 0, st>>>(P, ctx->scene, bvh);
+			ctx->stats.kernel_launches += 1;
+		} else {
+			k_bdpt_begin<<<grid, 128, 0, st>>>(P, ctx->scene);
+			for (int d = 0; d < pc.max_depth; d++) {
+				if ((rc = launch_trace_slots(ctx, b.rays, n_pix, b.hits, nullptr, false))) return rc;
+				k_bdpt_walk<false><<<grid, 128, 0, st>>>(P, ctx->scene);
+			}
+			k_bdpt_mid<<<grid, 128, 0, st>>>(P, ctx->scene);
+			for (int d = 0; d < pc.max_depth; d++) {
+				if ((rc = launch_trace_slots(ctx, b.rays, n_pix, b.hits, nullptr, false))) return rc;
+				k_bdpt_walk<true><<<grid, 128, 0, st>>>(P, ctx->scene);
+			}
+			k_bdpt_connect<1><<<grid, 128, 0, st>>>(P, ctx->scene);
+			if ((rc = launch_trace_slots(ctx, b.rays, n_pix * n_conn_slots, nullptr, b.occ, true))) return rc;
+			k_bdpt_connect<2><<<grid, 128, 0, st>>>(P, ctx->scene);
+			ctx->stats.kernel_launches += 5 + 4 * (uint64_t)pc.max_depth;
+		}
 		if (raw_col) {  // test hook: the two images before the film update
 			LMB_CUDA(ctx, cudaMemcpyAsync(raw_col, b.col, (size_t)n_pix * 16, cudaMemcpyDeviceToHost, st));
 			LMB_CUDA(ctx, cudaMemcpyAsync(raw_splat, b.splat, (size_t)n_pix * 12, cudaMemcpyDeviceToHost, st));
 		}
 		k_bdpt_film<<<ctx->sm_count * 8, 256, 0, st>>>(n_pix, frame, b.col, b.splat, ctx->film, ctx->wf.stats);
-		ctx->stats.kernel_launches += 2;
+		ctx->stats.kernel_launches += 1;
 	}
 	cudaEventRecord(ctx->ev[5], st);
 	LMB_CUDA(ctx, cudaStreamSynchronize(st));

@@ -101,7 +101,13 @@ struct BdptState {
 	float* camera_verts = nullptr;
 	float4* col = nullptr;
 	float* splat = nullptr;
-	uint32_t n_pix = 0, n_verts = 0;
+	// staged pipeline: walk state and per-pixel scalars (struct of arrays over pixels), ray slots and their results
+	float* walk = nullptr;
+	uint32_t* misc = nullptr;
+	float4* rays = nullptr;   // 2 float4 per slot: walk rays use n_pix slots, connection rays n_conn_slots * n_pix
+	float4* hits = nullptr;   // n_pix
+	uint8_t* occ = nullptr;   // n_conn_slots * n_pix
+	uint32_t n_pix = 0, n_verts = 0, n_conn_slots = 0;
 };
 
 enum StatSlot {
@@ -172,6 +178,8 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 void bdpt_free(lmb_ctx* ctx);
 int launch_trace_closest(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits);
 int launch_trace_any(lmb_ctx* ctx, const float4* d_rays, uint32_t n, uint8_t* d_occ);
+// ray slots with dead entries (NaN origin = hits nothing): closest hits into d_hits or occlusion bytes into d_occ; rays are NOT counted
+int launch_trace_slots(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits, uint8_t* d_occ, bool any);
 int launch_resolve(lmb_ctx* ctx);
 int ingest_triangles(lmb_ctx* ctx, const uint32_t* d_tri_first, const uint8_t* d_mat_q, uint32_t n_meshes, uint32_t n_materials, uint32_t n_tris,
 					 uint32_t* tri_mesh, uint32_t* tri_local, uint4* tri_rec, uint8_t* tri_matq);

@@ -557,11 +557,12 @@ struct ArraySource {
 };
 
 template <bool PIN>
-__global__ void __launch_bounds__(LMB_TRACE_THREADS, LMB_WIDE_BLOCKS_PER_SM) k_trace_array(WideBvhView bvh, ArraySource src, uint32_t n, uint32_t* cursor, unsigned long long* stats) {
-	trace_wide_persistent<PIN>(bvh, src, n, cursor, stats, ST_CLOSEST, ST_SHADOW);
+__global__ void __launch_bounds__(LMB_TRACE_THREADS, LMB_WIDE_BLOCKS_PER_SM) k_trace_array(WideBvhView bvh, ArraySource src, uint32_t n, uint32_t* cursor, unsigned long long* stats,
+																							 int count_rays) {
+	trace_wide_persistent<PIN>(bvh, src, n, cursor, stats, count_rays ? ST_CLOSEST : -1, count_rays ? ST_SHADOW : -1);
 }
-__global__ void __launch_bounds__(LMB_TRACE_THREADS) k_trace_array_bvh2(BvhView bvh, ArraySource src, uint32_t n, uint32_t* cursor, unsigned long long* stats) {
-	trace_persistent(bvh, src, n, cursor, stats, ST_CLOSEST, ST_SHADOW);
+__global__ void __launch_bounds__(LMB_TRACE_THREADS) k_trace_array_bvh2(BvhView bvh, ArraySource src, uint32_t n, uint32_t* cursor, unsigned long long* stats, int count_rays) {
+	trace_persistent(bvh, src, n, cursor, stats, count_rays ? ST_CLOSEST : -1, count_rays ? ST_SHADOW : -1);
 }
 
 BvhView view_of(const lmb_ctx* ctx) { return BvhView{ctx->bvh.nodes, ctx->bvh.tris, ctx->bvh.n}; }
@@ -759,7 +760,8 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 	return 0;
 }
 
-static int launch_trace_array(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits, uint8_t* d_occ, bool any) {
+// count_rays = 0: the caller counts its own rays (BDPT's ray slots hold dead entries, which must not be counted)
+static int launch_trace_array(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits, uint8_t* d_occ, bool any, int count_rays = 1) {
 	uint32_t* cursor = ctx->wf.trace_cursor;
 	if (!cursor) {
 		LMB_CUDA(ctx, cudaMalloc((void**)&ctx->wf.trace_cursor, 4));
@@ -768,11 +770,11 @@ static int launch_trace_array(lmb_ctx* ctx, const float4* d_rays, uint32_t n, fl
 	LMB_CUDA(ctx, cudaMemsetAsync(cursor, 0, 4, ctx->stream));
 	const ArraySource src{d_rays, d_hits, d_occ, any};
 	if (ctx->use_bvh2)
-		k_trace_array_bvh2<<<ctx->sm_count * 7, LMB_TRACE_THREADS, 0, ctx->stream>>>(view_of(ctx), src, n, cursor, ctx->wf.stats);
+		k_trace_array_bvh2<<<ctx->sm_count * 7, LMB_TRACE_THREADS, 0, ctx->stream>>>(view_of(ctx), src, n, cursor, ctx->wf.stats, count_rays);
 	else if (trace_pinned(ctx))
-		k_trace_array<true><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n, cursor, ctx->wf.stats);
+		k_trace_array<true><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n, cursor, ctx->wf.stats, count_rays);
 	else
-		k_trace_array<false><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n, cursor, ctx->wf.stats);
+		k_trace_array<false><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n, cursor, ctx->wf.stats, count_rays);
 	return check_cuda(ctx, cudaGetLastError(), "k_trace_array");
 }
 // Probe rays for the choice of the traversal tree (lbvh.cu): they leave a random point of a random triangle in a uniformly random
@@ -811,9 +813,9 @@ int probe_wide_tree(lmb_ctx* ctx, uint32_t n_rays, double* steps_per_ray) {
 	k_probe_rays<<<(n_rays + 255) / 256, 256, 0, ctx->stream>>>(ctx->bvh.n, ctx->bvh.tris, n_rays, rays);
 	const ArraySource src{rays, hits, nullptr, false};
 	if (trace_pinned(ctx))
-		k_trace_array<true><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n_rays, cursor, st);
+		k_trace_array<true><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n_rays, cursor, st, 1);
 	else
-		k_trace_array<false><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n_rays, cursor, st);
+		k_trace_array<false><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n_rays, cursor, st, 1);
 	unsigned long long h[ST_COUNT];
 	LMB_CUDA(ctx, cudaMemcpyAsync(h, st, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
 	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -825,6 +827,7 @@ int probe_wide_tree(lmb_ctx* ctx, uint32_t n_rays, double* steps_per_ray) {
 
 int launch_trace_closest(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits) { return launch_trace_array(ctx, d_rays, n, d_hits, nullptr, false); }
 int launch_trace_any(lmb_ctx* ctx, const float4* d_rays, uint32_t n, uint8_t* d_occ) { return launch_trace_array(ctx, d_rays, n, nullptr, d_occ, true); }
+int launch_trace_slots(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits, uint8_t* d_occ, bool any) { return launch_trace_array(ctx, d_rays, n, d_hits, d_occ, any, 0); }
 int launch_resolve(lmb_ctx* ctx) {
 	k_resolve<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->width * ctx->height, ctx->film);
 	return check_cuda(ctx, cudaGetLastError(), "k_resolve");

@@ -36,18 +36,21 @@ for name, depth in [("cornell", 6), ("caustics", 8), ("materials", 7), ("cornell
             print("   mismatch at", x, y, col[y, x], ocol[y, x], "rel", np.nanmax(rel[y, x]))
     osc.close()
 # throughput at a larger size (device time, rays from the device counters)
-for name, depth, big in [("cornell", 6, 512)]:
-    sc = host.Scene(scene_path(name), big, big)
-    dev.upload_scene(sc.desc)
-    dev.build_accel()
-    dev.init(big, big, 1)
-    pc = PCBdpt.from_path_pc(sc.make_pc(depth, True))
-    ubo = sc.make_ubo()
-    dev.render_bdpt(pc, ubo, 0, 2)
-    dev.reset_stats()
-    t0 = time.time()
-    dev.render_bdpt(pc, ubo, 2, 8)
-    st = dev.stats()
-    rays = st.rays_closest + st.rays_shadow
-    print(f"{name} {big}x{big} depth {depth}: {st.ms_render / 8:.2f} ms/frame, {rays / st.ms_render / 1e3:.1f} Mrays/s ({rays / 8 / big / big:.2f} rays/pixel), wall {time.time() - t0:.2f}s")
+import os
+for mode in ("staged", "mega"):
+  os.environ["LMB_BDPT"] = mode
+  for name, depth, big in [("cornell", 6, 512)]:
+      sc = host.Scene(scene_path(name), big, big)
+      dev.upload_scene(sc.desc)
+      dev.build_accel()
+      dev.init(big, big, 1)
+      pc = PCBdpt.from_path_pc(sc.make_pc(depth, True))
+      ubo = sc.make_ubo()
+      dev.render_bdpt(pc, ubo, 0, 2)
+      dev.reset_stats()
+      t0 = time.time()
+      dev.render_bdpt(pc, ubo, 2, 8)
+      st = dev.stats()
+      rays = st.rays_closest + st.rays_shadow
+      print(f"{mode} {name} {big}x{big} depth {depth}: {st.ms_render / 8:.2f} ms/frame, {rays / st.ms_render / 1e3:.1f} Mrays/s ({rays / 8 / big / big:.2f} rays/pixel), wall {time.time() - t0:.2f}s")
 dev.close()
