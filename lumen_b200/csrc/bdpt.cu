@@ -378,6 +378,7 @@ struct BdptParams {
 	float4* rays;     // ray slots, 2 float4 each: n_pix for a walk step, n_conn_slots * n_pix for the connections
 	float4* hits;     // closest hit of each pixel's walk ray
 	uint8_t* occ;     // any-hit result of each connection slot
+	float4* contrib;  // pair-parallel resolve: weighted radiance of each (slot, pixel), .w = splat target pixel (bits) or ~0
 	uint32_t n_conn_slots;
 };
 
@@ -699,6 +700,107 @@ LMB_DN float calc_mis_weight(Kctx& k, int s, int t, const Sampled& sampled) {
 	return 1 / (1 + sum_ri);
 }
 
+// calc_mis_weight without the in-place patches: the values the GLSL writes into the vertices (and restores) live in registers and
+// are substituted where the GLSL reads them back, so threads working on different (s, t) pairs of one pixel can run side by side
+// (k_bdpt_pair). Same arithmetic, same order. t == 1 patches cam[0].pos / n_s with copies of themselves (connect_cam), and
+// cam[0].pdf_fwd is not read by the camera sum (i > 0), so only the s == 1 patch of light vertex 0 needs substituting.
+LMB_DN float calc_mis_weight_ro(Kctx& k, int s, int t, const Sampled& sampled) {
+	const Verts& cam = k.cam;
+	const Verts& lig = k.lig;
+	if (s + t == 2) return 1.0f;
+	const bool s1 = s == 1;
+	auto lpos = [&](int i) { return (s1 && i == 0) ? sampled.pos : lig.v(i, W_POS); };
+	auto lns = [&](int i) { return (s1 && i == 0) ? sampled.n_s : lig.v(i, W_NS); };
+	float new1 = 0, new2 = 0, new3 = 0, new4 = 0;  // cam[t-1].pdf_rev, cam[t-2].pdf_rev, lig[s-1].pdf_rev, lig[s-2].pdf_rev
+	const uint32_t lflags = lig.u(0, W_LFLAGS);
+	{
+		if (s > 0) {
+			V3 dir = cam.v(t - 1, W_POS) - lpos(s - 1);
+			const float dir_len = length(dir);
+			dir /= dir_len;
+			float pdf_rev = 0;
+			if (s >= 2) {
+				const lmb_material mat = load_material(k.sc, lig.u(s - 1, W_MAT), lig.uv(s - 1));
+				const V3 wo = normalize(lig.v(s - 2, W_POS) - lig.v(s - 1, W_POS));
+				pdf_rev = bsdf_pdf(mat, lig.v(s - 1, W_NS), wo, dir, lig.u(s - 1, W_SIDE) == 1);
+				pdf_rev *= fabsf(dot(dir, cam.v(t - 1, W_NS))) / (dir_len * dir_len);
+			} else {
+				if (!is_light_finite(lflags)) {
+					pdf_rev = k.light_pdf_pos;
+					pdf_rev *= fabsf(dot(dir, cam.v(t - 1, W_NS)));
+				} else {
+					pdf_rev = light_pdf(lflags, lns(0), dir);
+					pdf_rev *= fabsf(dot(dir, cam.v(t - 1, W_NS))) / (dir_len * dir_len);
+				}
+			}
+			new1 = pdf_rev;
+		} else {
+			new1 = 1.0f / ((float)k.P.light_triangle_count * cam.f(t - 1, W_AREA));
+		}
+	}
+	if (t > 1) {
+		V3 dir = cam.v(t - 2, W_POS) - cam.v(t - 1, W_POS);
+		const float dir_len = length(dir);
+		dir /= dir_len;
+		if (s > 0) {
+			const lmb_material mat = load_material(k.sc, cam.u(t - 1, W_MAT), cam.uv(t - 1));
+			const V3 wo = normalize(lpos(s - 1) - cam.v(t - 1, W_POS));
+			float pr = bsdf_pdf(mat, cam.v(t - 1, W_NS), wo, dir, cam.u(t - 1, W_SIDE) == 1);
+			if (pr != 0) pr *= fabsf(dot(dir, cam.v(t - 2, W_NS))) / (dir_len * dir_len);
+			new2 = pr;
+		} else {
+			const float cos_x = dot(cam.v(t - 1, W_NS), dir);
+			const float cos_y = dot(cam.v(t - 2, W_NS), dir);
+			new2 = fabsf(cos_x * cos_y) / (LMB_PI * dir_len * dir_len);
+		}
+	}
+	if (s > 0) {
+		V3 dir = lpos(s - 1) - cam.v(t - 1, W_POS);
+		const float dir_len = length(dir);
+		dir /= dir_len;
+		if (t == 1) {
+			const float cos_theta = dot(cam.v(0, W_NS), dir);
+			float pdf = 1.0f / (cam.f(0, W_AREA) * k.screen_size * cos_theta * cos_theta * cos_theta);
+			pdf *= fabsf(dot(dir, lns(s - 1))) / (dir_len * dir_len);
+			new3 = pdf;
+		} else {
+			const V3 wo = normalize(cam.v(t - 2, W_POS) - cam.v(t - 1, W_POS));
+			const lmb_material mat = load_material(k.sc, cam.u(t - 1, W_MAT), cam.uv(t - 1));
+			float pr = bsdf_pdf(mat, cam.v(t - 1, W_NS), wo, dir, cam.u(t - 1, W_SIDE) == 1);
+			if ((s == 1 && is_light_finite(lflags)) || s > 1) pr *= fabsf(dot(dir, lns(s - 1))) / (dir_len * dir_len);
+			new3 = pr;
+		}
+	}
+	if (s > 1) {
+		V3 dir = lig.v(s - 2, W_POS) - lig.v(s - 1, W_POS);
+		const V3 wo = normalize(cam.v(t - 1, W_POS) - lig.v(s - 1, W_POS));
+		const float dir_len = length(dir);
+		dir /= dir_len;
+		const lmb_material mat = load_material(k.sc, lig.u(s - 1, W_MAT), lig.uv(s - 1));
+		float pr = bsdf_pdf(mat, lig.v(s - 1, W_NS), wo, dir, lig.u(s - 1, W_SIDE) == 1);
+		if ((s == 2 && is_light_finite(lflags)) || s > 2) pr *= fabsf(dot(dir, lig.v(s - 2, W_NS))) / (dir_len * dir_len);
+		new4 = pr;
+	}
+	float sum_ri = 0.0f;
+	float weight = 1.0f;
+	for (int i = t - 1; i > 0; i--) {
+		const float prev_i = i == t - 1 ? new1 : (i == t - 2 ? new2 : cam.f(i, W_PREV));
+		weight *= remap0(prev_i) / remap0(cam.f(i, W_PFWD));
+		const uint32_t delta_i = i == t - 1 ? 0u : cam.u(i, W_DELTA);
+		if (delta_i == 0 && cam.u(i - 1, W_DELTA) == 0) sum_ri += weight;
+	}
+	weight = 1.0f;
+	for (int i = s - 1; i >= 0; i--) {
+		const float prev_i = i == s - 1 ? new3 : (i == s - 2 ? new4 : lig.f(i, W_PREV));
+		const float pfwd_i = (s1 && i == 0) ? sampled.pdf_fwd : lig.f(i, W_PFWD);
+		weight *= remap0(prev_i) / remap0(pfwd_i);
+		const bool delta_prev = i > 0 ? lig.u(i - 1, W_DELTA) == 1 : is_light_delta(lflags);
+		const uint32_t delta_i = i == s - 1 ? 0u : lig.u(i, W_DELTA);
+		if (delta_i == 0 && !delta_prev) sum_ri += weight;
+	}
+	return 1 / (1 + sum_ri);
+}
+
 // `ivec2(...)` of a float with no int value is undefined in GLSL: the splat is dropped (oracle/bdpt.h B5)
 LMB_D bool splat_coord(float v, int& out) {
 	if (!(fabsf(v) < 1e9f)) return false;
@@ -748,7 +850,7 @@ LMB_DN V3 connect_cam(Kctx& k, int s, int& cx, int& cy) {
 	}
 	if (cx < 0 || (uint32_t)cx >= k.P.width || cy < 0 || (uint32_t)cy >= k.P.height || dot(dir, cam_n) < 0) return v3(0.0f);
 	float mis_weight = 1.0f;
-	if (luminance(L) != 0.0f) mis_weight = calc_mis_weight(k, s, 1, sampled);
+	if (luminance(L) != 0.0f) mis_weight = MODE == 3 ? calc_mis_weight_ro(k, s, 1, sampled) : calc_mis_weight(k, s, 1, sampled);
 	return mis_weight * L;
 }
 
@@ -803,7 +905,7 @@ LMB_DN V3 connect(Kctx& k, int s, int t) {
 		}
 	}
 	if (luminance(L) != 0.0f) {
-		const float mis_weight = calc_mis_weight(k, s, t, sampled);
+		const float mis_weight = MODE == 3 ? calc_mis_weight_ro(k, s, t, sampled) : calc_mis_weight(k, s, t, sampled);
 		L *= mis_weight;
 	}
 	return L;
@@ -992,6 +1094,67 @@ __global__ void __launch_bounds__(128) k_bdpt_connect(BdptParams P, DeviceScene 
 	flush_counts(P.stats, 0, n_shadow, 0, 0);
 }
 
+// Pair-parallel connections (default): one thread per (connection slot, pixel), slot-major, so a warp works on ONE (s, t) strategy
+// for 32 neighbouring pixels -- the per-pixel loop of k_bdpt_connect runs ~30 pairs in sequence with every lane in another branch
+// (profiles/r01j: 57 % of the frame). Slots are numbered over the pairs bdpt.rgen:57-62 admits for full-length sub-paths (pair_ts),
+// a pixel whose sub-paths are shorter leaves the rest dead. The rand4 of the s == 1 strategy of camera vertex t is the (t - 2)-th
+// draw after the walks: every earlier t has that strategy too. MODE 1 emits the shadow rays, MODE 3 weights what was visible;
+// k_bdpt_gather adds a pixel's pairs in slot order = the order of the GLSL loop, so the float sum is the same.
+template <int MODE>
+__global__ void __launch_bounds__(128) k_bdpt_pair(BdptParams P, DeviceScene sc, const uint8_t* __restrict__ pair_ts) {
+	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t c = blockIdx.y;
+	const int t = pair_ts[2 * c], s = pair_ts[2 * c + 1];
+	uint32_t n_shadow = 0;
+	if (pix < P.n_pix) {
+		const size_t i = (size_t)c * P.n_pix + pix;
+		const int num_light_paths = (int)P.misc[MW_NLIGHT * (size_t)P.n_pix + pix];
+		const int num_cam_paths = __float_as_int(P.walk[WW_B * (size_t)P.n_pix + pix]) + 1;
+		if (MODE == 1) P.rays[2 * i] = make_float4(__int_as_float(0x7FC00000), 0.0f, 0.0f, 0.0f);
+		float4 out = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
+		if (t <= num_cam_paths && s <= num_light_paths) {
+			const BvhView none{nullptr, nullptr, 0};
+			Kctx k = make_kctx(P, sc, none, pix, P.misc[MW_RNG * (size_t)P.n_pix + pix] + (s == 1 ? 4u * (uint32_t)(t - 2) : 0u));
+			k.light_pdf_pos = __uint_as_float(P.misc[MW_LPDFPOS * (size_t)P.n_pix + pix]);
+			k.slot = c;
+			if (t == 1) {
+				int cx, cy;
+				const V3 sp = connect_cam<MODE>(k, s, cx, cy);
+				if (MODE == 3 && luminance(sp) > 0) out = make_float4(sp.x, sp.y, sp.z, __uint_as_float((uint32_t)cy * P.width + (uint32_t)cx));
+			} else {
+				const V3 L = connect<MODE>(k, s, t);
+				out = make_float4(L.x, L.y, L.z, __uint_as_float(0xFFFFFFFFu));
+			}
+			n_shadow = k.n_shadow;
+		}
+		if (MODE == 3) P.contrib[i] = out;
+	}
+	flush_counts(P.stats, 0, n_shadow, 0, 0);
+}
+
+__global__ void __launch_bounds__(256) k_bdpt_gather(BdptParams P, const uint8_t* __restrict__ pair_ts) {
+	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pix >= P.n_pix) return;
+	const int num_light_paths = (int)P.misc[MW_NLIGHT * (size_t)P.n_pix + pix];
+	const int num_cam_paths = __float_as_int(P.walk[WW_B * (size_t)P.n_pix + pix]) + 1;
+	V3 col = v3(0.0f);
+	for (uint32_t c = 0; c < P.n_conn_slots; c++) {
+		const int t = pair_ts[2 * c], s = pair_ts[2 * c + 1];
+		if (t > num_cam_paths || s > num_light_paths) continue;
+		const float4 v = P.contrib[(size_t)c * P.n_pix + pix];
+		if (t == 1) {
+			const uint32_t target = __float_as_uint(v.w);
+			if (target != 0xFFFFFFFFu) {
+				float* o = P.splat + 3 * (size_t)target;
+				atomicAdd(o + 0, v.x), atomicAdd(o + 1, v.y), atomicAdd(o + 2, v.z);
+			}
+		} else {
+			col += v3(v.x, v.y, v.z);
+		}
+	}
+	P.col[pix] = make_float4(col.x, col.y, col.z, 0.0f);
+}
+
 // bdpt.rgen:76-89: own strategies + this frame's splats -> running-mean film (NaN samples leave the pixel untouched); clears the
 // splat image for the next frame.
 __global__ void __launch_bounds__(256) k_bdpt_film(uint32_t n_pix, uint32_t frame, const float4* __restrict__ colb, float* __restrict__ splat,
@@ -1023,7 +1186,7 @@ __global__ void __launch_bounds__(256) k_bdpt_film(uint32_t n_pix, uint32_t fram
 void bdpt_free(lmb_ctx* ctx) {
 	BdptState& b = ctx->bdpt;
 	cudaFree(b.light_verts), cudaFree(b.camera_verts), cudaFree(b.col), cudaFree(b.splat);
-	cudaFree(b.walk), cudaFree(b.misc), cudaFree(b.rays), cudaFree(b.hits), cudaFree(b.occ);
+	cudaFree(b.walk), cudaFree(b.misc), cudaFree(b.rays), cudaFree(b.hits), cudaFree(b.occ), cudaFree(b.contrib), cudaFree(b.pair_ts);
 	b = BdptState{};
 }
 
@@ -1046,6 +1209,7 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 	// LMB_BDPT=mega: the one-kernel version (rays traced in the thread over the binary LBVH); default: the staged pipeline
 	const char* mode_env = getenv("LMB_BDPT");
 	const bool mega = mode_env && strcmp(mode_env, "mega") == 0;
+	const bool per_pixel = mode_env && strcmp(mode_env, "pixel") == 0;  // staged, connections looped per pixel (k_bdpt_connect)
 	BdptState& b = ctx->bdpt;
 	cudaStream_t st = ctx->stream;
 	const uint32_t n_pix = ctx->width * ctx->height;
@@ -1069,6 +1233,18 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.occ, (size_t)n_pix * n_conn_slots));
 		b.n_conn_slots = n_conn_slots;
 	}
+	if (!mega && !per_pixel && !b.contrib) {
+		std::vector<uint8_t> ts;
+		for (int t = 1; t <= pc.max_depth + 1; t++)
+			for (int s = 0; s <= pc.max_depth + 1; s++) {
+				const int depth = s + t - 2;
+				if (depth > (pc.max_depth - 1) || depth < 0 || (s == 1 && t == 1)) continue;
+				ts.push_back((uint8_t)t), ts.push_back((uint8_t)s);
+			}
+		LMB_CUDA(ctx, cudaMalloc((void**)&b.contrib, (size_t)n_pix * n_conn_slots * 16));
+		LMB_CUDA(ctx, cudaMalloc((void**)&b.pair_ts, ts.size()));
+		LMB_CUDA(ctx, cudaMemcpy(b.pair_ts, ts.data(), ts.size(), cudaMemcpyHostToDevice));
+	}
 	LMB_CUDA(ctx, cudaMemsetAsync(b.splat, 0, (size_t)n_pix * 12, st));
 	auto load = [](const float* p) {
 		M4 m;
@@ -1082,7 +1258,7 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 	P.width = ctx->width, P.height = ctx->height, P.n_pix = n_pix;
 	P.num_lights = pc.num_lights, P.max_depth = pc.max_depth, P.light_triangle_count = pc.light_triangle_count;
 	P.light_verts = b.light_verts, P.camera_verts = b.camera_verts, P.col = b.col, P.splat = b.splat, P.stats = ctx->wf.stats;
-	P.walk = b.walk, P.misc = b.misc, P.rays = b.rays, P.hits = b.hits, P.occ = b.occ, P.n_conn_slots = n_conn_slots;
+	P.walk = b.walk, P.misc = b.misc, P.rays = b.rays, P.hits = b.hits, P.occ = b.occ, P.contrib = b.contrib, P.n_conn_slots = n_conn_slots;
 	const BvhView bvh{ctx->bvh.nodes, ctx->bvh.tris, ctx->bvh.n};
 	const uint32_t grid = (n_pix + 127) / 128;
 	int rc;
@@ -1107,10 +1283,19 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 				if ((rc = launch_trace_slots(ctx, b.rays, n_pix, b.hits, nullptr, false))) return rc;
 				k_bdpt_walk<true><<<grid, 128, 0, st>>>(P, ctx->scene);
 			}
-			k_bdpt_connect<1><<<grid, 128, 0, st>>>(P, ctx->scene);
-			if ((rc = launch_trace_slots(ctx, b.rays, n_pix * n_conn_slots, nullptr, b.occ, true))) return rc;
-			k_bdpt_connect<2><<<grid, 128, 0, st>>>(P, ctx->scene);
-			ctx->stats.kernel_launches += 5 + 4 * (uint64_t)pc.max_depth;
+			if (per_pixel) {
+				k_bdpt_connect<1><<<grid, 128, 0, st>>>(P, ctx->scene);
+				if ((rc = launch_trace_slots(ctx, b.rays, n_pix * n_conn_slots, nullptr, b.occ, true))) return rc;
+				k_bdpt_connect<2><<<grid, 128, 0, st>>>(P, ctx->scene);
+				ctx->stats.kernel_launches += 5 + 4 * (uint64_t)pc.max_depth;
+			} else {
+				const dim3 pgrid(grid, n_conn_slots);
+				k_bdpt_pair<1><<<pgrid, 128, 0, st>>>(P, ctx->scene, b.pair_ts);
+				if ((rc = launch_trace_slots(ctx, b.rays, n_pix * n_conn_slots, nullptr, b.occ, true))) return rc;
+				k_bdpt_pair<3><<<pgrid, 128, 0, st>>>(P, ctx->scene, b.pair_ts);
+				k_bdpt_gather<<<(n_pix + 255) / 256, 256, 0, st>>>(P, b.pair_ts);
+				ctx->stats.kernel_launches += 6 + 4 * (uint64_t)pc.max_depth;
+			}
 		}
 		if (raw_col) {  // test hook: the two images before the film update
 			LMB_CUDA(ctx, cudaMemcpyAsync(raw_col, b.col, (size_t)n_pix * 16, cudaMemcpyDeviceToHost, st));

@@ -107,6 +107,8 @@ struct BdptState {
 	float4* rays = nullptr;   // 2 float4 per slot: walk rays use n_pix slots, connection rays n_conn_slots * n_pix
 	float4* hits = nullptr;   // n_pix
 	uint8_t* occ = nullptr;   // n_conn_slots * n_pix
+	float4* contrib = nullptr;  // n_conn_slots * n_pix: weighted radiance of each pair (pair-parallel connections)
+	uint8_t* pair_ts = nullptr; // (t, s) of each connection slot
 	uint32_t n_pix = 0, n_verts = 0, n_conn_slots = 0;
 };
 

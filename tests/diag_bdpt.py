@@ -37,7 +37,7 @@ for name, depth in [("cornell", 6), ("caustics", 8), ("materials", 7), ("cornell
     osc.close()
 # throughput at a larger size (device time, rays from the device counters)
 import os
-for mode in ("staged", "mega"):
+for mode in ("pairs", "pixel", "mega"):
   os.environ["LMB_BDPT"] = mode
   for name, depth, big in [("cornell", 6, 512)]:
       sc = host.Scene(scene_path(name), big, big)

@@ -45,21 +45,23 @@ def test_bdpt_frame_matches_oracle(device, name, size, depth):
     osc.close()
 
 
-@pytest.mark.parametrize("name,size,depth", [("materials", 96, 7), ("caustics", 80, 9)])
-def test_bdpt_megakernel_equals_staged_pipeline(device, monkeypatch, name, size, depth):
-    """LMB_BDPT=mega renders with the one-kernel version (rays traced in the thread over the binary LBVH); the default staged
-    pipeline cuts the same per-pixel code at every ray and traces through the 8-wide walker. Same bits, same ray counts."""
+@pytest.mark.parametrize("name,size,depth", [("materials", 96, 7), ("caustics", 80, 9), ("cornell_dir", 64, 5)])
+def test_bdpt_three_pipelines_agree(device, monkeypatch, name, size, depth):
+    """Default: staged pipeline with pair-parallel connections (k_bdpt_pair: one thread per (s, t) pair and pixel, MIS weights
+    without the in-place vertex patches). LMB_BDPT=pixel: staged, connections looped per pixel with the GLSL's patch-and-restore.
+    LMB_BDPT=mega: one kernel, rays traced in the thread over the binary LBVH. Same bits, same ray counts."""
     sc, pc, ubo = _setup(device, name, size, depth)
     device.reset_stats()
     col, splat = device.kat_bdpt_frame_raw(pc, ubo, 1)
     st = device.stats()
-    monkeypatch.setenv("LMB_BDPT", "mega")
-    device.reset_stats()
-    mcol, msplat = device.kat_bdpt_frame_raw(pc, ubo, 1)
-    mst = device.stats()
-    assert bits_equal(col, mcol).all()
-    assert pixel_agreement(splat, msplat, rel=1e-5) >= 0.999
-    assert (st.rays_closest, st.rays_shadow) == (mst.rays_closest, mst.rays_shadow)
+    for mode in ("pixel", "mega"):
+        monkeypatch.setenv("LMB_BDPT", mode)
+        device.reset_stats()
+        mcol, msplat = device.kat_bdpt_frame_raw(pc, ubo, 1)
+        mst = device.stats()
+        assert bits_equal(col, mcol).all(), mode
+        assert pixel_agreement(splat, msplat, rel=1e-5) >= 0.999, mode
+        assert (st.rays_closest, st.rays_shadow) == (mst.rays_closest, mst.rays_shadow), mode
 
 
 def test_bdpt_film_matches_oracle(device):
