@@ -963,7 +963,7 @@ LMB_D Kctx make_kctx(const BdptParams& P, const DeviceScene& sc, const BvhView& 
 
 // ---------------------------------------------------------------------------------------------- megakernel (LMB_BDPT=mega)
 // bdpt.rgen:39-75 for one pixel of one frame, rays traced in the thread
-__global__ void __launch_bounds__(128) k_bdpt(BdptParams P, DeviceScene sc, BvhView bvh) {
+__global__ void __launch_bounds__(128) k_bdpt(const __grid_constant__ BdptParams P, const __grid_constant__ DeviceScene sc, const __grid_constant__ BvhView bvh) {
 	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t n_closest = 0, n_shadow = 0, n_nodes = 0, n_tris = 0;
 	if (pix < P.n_pix) {
@@ -1018,7 +1018,7 @@ LMB_D WalkSt load_walk(const BdptParams& P, uint32_t pix) {
 	return st;
 }
 
-__global__ void __launch_bounds__(128) k_bdpt_begin(BdptParams P, DeviceScene sc) {
+__global__ void __launch_bounds__(128) k_bdpt_begin(const __grid_constant__ BdptParams P, const __grid_constant__ DeviceScene sc) {
 	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t n_closest = 0;
 	if (pix < P.n_pix) {
@@ -1037,7 +1037,7 @@ __global__ void __launch_bounds__(128) k_bdpt_begin(BdptParams P, DeviceScene sc
 }
 
 template <bool EYE>
-__global__ void __launch_bounds__(128) k_bdpt_walk(BdptParams P, DeviceScene sc) {
+__global__ void __launch_bounds__(128) k_bdpt_walk(const __grid_constant__ BdptParams P, const __grid_constant__ DeviceScene sc) {
 	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t n_closest = 0;
 	if (pix < P.n_pix) {
@@ -1056,7 +1056,7 @@ __global__ void __launch_bounds__(128) k_bdpt_walk(BdptParams P, DeviceScene sc)
 }
 
 // end of the light sub-path, camera vertex 0, first ray of the eye walk
-__global__ void __launch_bounds__(128) k_bdpt_mid(BdptParams P, DeviceScene sc) {
+__global__ void __launch_bounds__(128) k_bdpt_mid(const __grid_constant__ BdptParams P, const __grid_constant__ DeviceScene sc) {
 	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t n_closest = 0;
 	if (pix < P.n_pix) {
@@ -1078,7 +1078,7 @@ __global__ void __launch_bounds__(128) k_bdpt_mid(BdptParams P, DeviceScene sc) 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(128) k_bdpt_connect(BdptParams P, DeviceScene sc) {
+__global__ void __launch_bounds__(128) k_bdpt_connect(const __grid_constant__ BdptParams P, const __grid_constant__ DeviceScene sc) {
 	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t n_shadow = 0;
 	if (pix < P.n_pix) {
@@ -1100,8 +1100,11 @@ __global__ void __launch_bounds__(128) k_bdpt_connect(BdptParams P, DeviceScene 
 // a pixel whose sub-paths are shorter leaves the rest dead. The rand4 of the s == 1 strategy of camera vertex t is the (t - 2)-th
 // draw after the walks: every earlier t has that strategy too. MODE 1 emits the shadow rays, MODE 3 weights what was visible;
 // k_bdpt_gather adds a pixel's pairs in slot order = the order of the GLSL loop, so the float sum is the same.
+#ifndef LMB_BDPT_PAIR_BLOCKS
+#define LMB_BDPT_PAIR_BLOCKS 6  // 4 / 6 / 8 blocks per SM: classroom stand-in 52.9 / 48.8 / 47.0 ms, cornell 3.98 / 4.02 / 4.32 ms per frame
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(128) k_bdpt_pair(BdptParams P, DeviceScene sc, const uint8_t* __restrict__ pair_ts) {
+__global__ void __launch_bounds__(128, LMB_BDPT_PAIR_BLOCKS) k_bdpt_pair(const __grid_constant__ BdptParams P, const __grid_constant__ DeviceScene sc, const uint8_t* __restrict__ pair_ts) {
 	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t c = blockIdx.y;
 	const int t = pair_ts[2 * c], s = pair_ts[2 * c + 1];
@@ -1110,9 +1113,16 @@ __global__ void __launch_bounds__(128) k_bdpt_pair(BdptParams P, DeviceScene sc,
 		const size_t i = (size_t)c * P.n_pix + pix;
 		const int num_light_paths = (int)P.misc[MW_NLIGHT * (size_t)P.n_pix + pix];
 		const int num_cam_paths = __float_as_int(P.walk[WW_B * (size_t)P.n_pix + pix]) + 1;
-		if (MODE == 1) P.rays[2 * i] = make_float4(__int_as_float(0x7FC00000), 0.0f, 0.0f, 0.0f);
+		// dead slot: NaN origin (hits nothing) and NaN tmin -- a connection ray always has tmin = 0, so .w tells the two apart exactly
+		if (MODE == 1) P.rays[2 * i] = make_float4(__int_as_float(0x7FC00000), 0.0f, 0.0f, __int_as_float(0x7FC00000));
 		float4 out = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
-		if (t <= num_cam_paths && s <= num_light_paths) {
+		bool work = t <= num_cam_paths && s <= num_light_paths;
+		if (MODE == 3 && work && s > 0) {
+			// every strategy with a light vertex is zero unless its shadow ray was emitted and found nothing: skip the re-evaluation
+			const float tmin = P.rays[2 * i].w;
+			work = tmin == tmin && P.occ[i] == 0;
+		}
+		if (work) {
 			const BvhView none{nullptr, nullptr, 0};
 			Kctx k = make_kctx(P, sc, none, pix, P.misc[MW_RNG * (size_t)P.n_pix + pix] + (s == 1 ? 4u * (uint32_t)(t - 2) : 0u));
 			k.light_pdf_pos = __uint_as_float(P.misc[MW_LPDFPOS * (size_t)P.n_pix + pix]);
@@ -1132,7 +1142,7 @@ __global__ void __launch_bounds__(128) k_bdpt_pair(BdptParams P, DeviceScene sc,
 	flush_counts(P.stats, 0, n_shadow, 0, 0);
 }
 
-__global__ void __launch_bounds__(256) k_bdpt_gather(BdptParams P, const uint8_t* __restrict__ pair_ts) {
+__global__ void __launch_bounds__(256) k_bdpt_gather(const __grid_constant__ BdptParams P, const uint8_t* __restrict__ pair_ts) {
 	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
 	if (pix >= P.n_pix) return;
 	const int num_light_paths = (int)P.misc[MW_NLIGHT * (size_t)P.n_pix + pix];

@@ -1,5 +1,5 @@
 """BDPT throughput on the product path (no oracle): device time per frame, Mrays/s and spp/s per scene. Run on a GPU box:
-    python tools/bdpt_table.py [--json gpurun_out/bdpt_table.json] [--quick]
+    python tools/bdpt_table.py [--json gpurun_out/bdpt_table.json] [--quick] [--scene NAME]
 --quick renders one scene at 512 x 512 for ncu (tools: ncu -k regex:k_bdpt ... python tools/bdpt_table.py --quick)."""
 import json
 import os
@@ -18,6 +18,9 @@ if not quick:
     cases += [("caustics", os.path.join(ROOT, "scenes/caustics.json"), 1280, 720, 12, 8),
               ("materials", os.path.join(ROOT, "scenes/material_test/materials.json"), 1024, 1024, 10, 8),
               ("classroom_standin", None, bench.WIDTH, bench.HEIGHT, bench.MAX_DEPTH, 4)]
+if "--scene" in sys.argv:  # one scene only (ncu launch lists)
+    want = sys.argv[sys.argv.index("--scene") + 1]
+    cases = [c for c in cases if c[0] == want]
 dev = integrator.Device(0)
 rows = []
 for name, path, w, h, depth, frames in cases:
