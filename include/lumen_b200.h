@@ -109,8 +109,11 @@ int lmb_render(lmb_ctx* ctx, const lmb_pc_path* pc, const lmb_scene_ubo* ubo, ui
  * first_frame .. first_frame + n_frames - 1 into the running-mean film (bdpt.rgen:79-89). pc->frame_num is ignored; the RNG
  * seed of a sample is (x, y, frame ^ pc->time, 0) as bdpt.rgen:36-37 -- `time` is the caller's (BDPT.cpp:57 draws rand() per
  * frame; pass a fresh value per call to do the same). Light-tracer splats of a frame land in that frame. Vertex storage
- * (2 x (max_depth + 1) x 92 B per pixel) is allocated on first use. Not available with pixel shards. Synchronous. */
-int lmb_render_bdpt(lmb_ctx* ctx, const lmb_pc_bdpt* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames);
+ * (2 x (max_depth + 1) x 92 B per pixel) is allocated on first use. frame_stride / film_mode as lmb_render: LMB_FILM_SUM with
+ * frames first_frame + k * frame_stride is the sample-index shard of one GPU; the caller adds the films and calls
+ * lmb_resolve. Not available with pixel shards (splats cross rows). Synchronous. */
+int lmb_render_bdpt(lmb_ctx* ctx, const lmb_pc_bdpt* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames,
+					uint32_t frame_stride, int film_mode);
 /* Zeroes the film (Path::update resets frame_num to 0 on camera change; sum mode needs an explicit clear). */
 int lmb_clear_film(lmb_ctx* ctx);
 /* LMB_FILM_SUM epilogue: rgb /= alpha (pixels with alpha 0 stay 0), alpha = 1. */

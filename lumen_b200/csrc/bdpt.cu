@@ -1165,9 +1165,9 @@ __global__ void __launch_bounds__(256) k_bdpt_gather(const __grid_constant__ Bdp
 	P.col[pix] = make_float4(col.x, col.y, col.z, 0.0f);
 }
 
-// bdpt.rgen:76-89: own strategies + this frame's splats -> running-mean film (NaN samples leave the pixel untouched); clears the
-// splat image for the next frame.
-__global__ void __launch_bounds__(256) k_bdpt_film(uint32_t n_pix, uint32_t frame, const float4* __restrict__ colb, float* __restrict__ splat,
+// bdpt.rgen:76-89: own strategies + this frame's splats -> running-mean film (NaN samples leave the pixel untouched) or sum film;
+// clears the splat image for the next frame.
+__global__ void __launch_bounds__(256) k_bdpt_film(uint32_t n_pix, uint32_t frame, int film_mode, const float4* __restrict__ colb, float* __restrict__ splat,
 													float4* __restrict__ film, unsigned long long* stats) {
 	uint32_t nan_count = 0;
 	for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n_pix; pix += gridDim.x * blockDim.x) {
@@ -1179,7 +1179,10 @@ __global__ void __launch_bounds__(256) k_bdpt_film(uint32_t n_pix, uint32_t fram
 			nan_count++;
 			continue;
 		}
-		if (frame > 0) {
+		if (film_mode == LMB_FILM_SUM) {  // un-normalised sum, valid-sample count in alpha (multi-GPU sample-index shards; lmb_resolve divides)
+			const float4 old = film[pix];
+			film[pix] = make_float4(old.x + col.x, old.y + col.y, old.z + col.z, old.w + 1.0f);
+		} else if (frame > 0) {
 			const float w = 1.0f / float(frame + 1);
 			const float4 old = film[pix];
 			const V3 m = mix(v3(old.x, old.y, old.z), col, w);
@@ -1212,7 +1215,8 @@ static uint32_t count_conn_slots(int max_depth) {
 	return n;
 }
 
-int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, uint32_t first_frame, uint32_t n_frames, float* raw_col, float* raw_splat) {
+int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, uint32_t first_frame, uint32_t n_frames, uint32_t frame_stride, int film_mode,
+				float* raw_col, float* raw_splat) {
 	if (ctx->row_stride != 1) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: pixel shards are not supported (light-tracer splats cross rows)");
 	if (pc.max_depth < 1 || pc.max_depth > 63) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: max_depth must be in [1, 63]");
 	if (!ctx->wf.stats) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: call lmb_init first");
@@ -1274,7 +1278,7 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 	int rc;
 	cudaEventRecord(ctx->ev[0], st);
 	for (uint32_t i = 0; i < n_frames; i++) {
-		const uint32_t frame = first_frame + i;
+		const uint32_t frame = first_frame + i * frame_stride;
 		P.frame = frame, P.seed_z = frame ^ pc.time;
 		// BDPT.cpp:79-80: both vertex buffers are zeroed before every frame
 		LMB_CUDA(ctx, cudaMemsetAsync(b.light_verts, 0, vert_bytes, st));
@@ -1311,7 +1315,7 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 			LMB_CUDA(ctx, cudaMemcpyAsync(raw_col, b.col, (size_t)n_pix * 16, cudaMemcpyDeviceToHost, st));
 			LMB_CUDA(ctx, cudaMemcpyAsync(raw_splat, b.splat, (size_t)n_pix * 12, cudaMemcpyDeviceToHost, st));
 		}
-		k_bdpt_film<<<ctx->sm_count * 8, 256, 0, st>>>(n_pix, frame, b.col, b.splat, ctx->film, ctx->wf.stats);
+		k_bdpt_film<<<ctx->sm_count * 8, 256, 0, st>>>(n_pix, frame, film_mode, b.col, b.splat, ctx->film, ctx->wf.stats);
 		ctx->stats.kernel_launches += 1;
 	}
 	cudaEventRecord(ctx->ev[5], st);

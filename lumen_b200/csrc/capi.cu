@@ -278,13 +278,18 @@ static int check_bdpt_args(lmb_ctx* ctx, const lmb_pc_bdpt* pc) {
 	return LMB_OK;
 }
 
-int lmb_render_bdpt(lmb_ctx* ctx, const lmb_pc_bdpt* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames) {
+int lmb_render_bdpt(lmb_ctx* ctx, const lmb_pc_bdpt* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames, uint32_t frame_stride,
+					int film_mode) {
 	if (!ctx || !pc || !ubo) return LMB_ERR_INVALID;
 	const int rc = check_bdpt_args(ctx, pc);
 	if (rc) return rc;
+	if (frame_stride == 0) frame_stride = 1;
+	if (film_mode == LMB_FILM_RUNNING_MEAN && frame_stride != 1)
+		return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: running-mean film needs frame_stride 1");
+	if (film_mode != LMB_FILM_RUNNING_MEAN && film_mode != LMB_FILM_SUM) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: bad film_mode");
 	cudaSetDevice(ctx->device);
 	if (n_frames == 0) return LMB_OK;
-	return bdpt_render(ctx, *pc, *ubo, first_frame, n_frames, nullptr, nullptr);
+	return bdpt_render(ctx, *pc, *ubo, first_frame, n_frames, frame_stride, film_mode, nullptr, nullptr);
 }
 
 int lmb_kat_bdpt_frame_raw(lmb_ctx* ctx, const lmb_pc_bdpt* pc, const lmb_scene_ubo* ubo, uint32_t frame, float* col_rgba, float* splat_rgb) {
@@ -292,7 +297,7 @@ int lmb_kat_bdpt_frame_raw(lmb_ctx* ctx, const lmb_pc_bdpt* pc, const lmb_scene_
 	const int rc = check_bdpt_args(ctx, pc);
 	if (rc) return rc;
 	cudaSetDevice(ctx->device);
-	return bdpt_render(ctx, *pc, *ubo, frame, 1, col_rgba, splat_rgb);
+	return bdpt_render(ctx, *pc, *ubo, frame, 1, 1, LMB_FILM_RUNNING_MEAN, col_rgba, splat_rgb);
 }
 
 int lmb_clear_film(lmb_ctx* ctx) {

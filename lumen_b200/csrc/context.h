@@ -176,7 +176,8 @@ uint32_t shard_rows(const lmb_ctx* ctx);
 void wavefront_free(lmb_ctx* ctx);
 int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& ubo, uint32_t first_frame, uint32_t n_frames, uint32_t stride,
 					 int film_mode);
-int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, uint32_t first_frame, uint32_t n_frames, float* raw_col, float* raw_splat);
+int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, uint32_t first_frame, uint32_t n_frames, uint32_t frame_stride, int film_mode,
+				float* raw_col, float* raw_splat);
 void bdpt_free(lmb_ctx* ctx);
 int launch_trace_closest(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits);
 int launch_trace_any(lmb_ctx* ctx, const float4* d_rays, uint32_t n, uint8_t* d_occ);

@@ -38,7 +38,7 @@ class BDPTB200 final : public Integrator {
 		std::memcpy(&pc_ray, &p, sizeof(pc_ray));
 		pc_ray.frame_num = frame_num;
 		pc_ray.time = has_fixed_time ? fixed_time : (uint32_t)(rand() % UINT_MAX);
-		check(lmb_render_bdpt(ctx, &pc_ray, &scene_ubo, frame_num, frames_per_call), "lmb_render_bdpt");
+		check(lmb_render_bdpt(ctx, &pc_ray, &scene_ubo, frame_num, frames_per_call, 1, LMB_FILM_RUNNING_MEAN), "lmb_render_bdpt");
 	}
 	bool update() override {
 		frame_num += frames_per_call;

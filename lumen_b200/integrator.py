@@ -50,7 +50,7 @@ def lib():
         L.lmb_build_accel.argtypes = [vp]
         L.lmb_init.argtypes = [vp, u32, u32, u32]
         L.lmb_render.argtypes = [vp, vp, vp, u32, u32, u32, i32]
-        L.lmb_render_bdpt.argtypes = [vp, vp, vp, u32, u32]
+        L.lmb_render_bdpt.argtypes = [vp, vp, vp, u32, u32, u32, i32]
         L.lmb_clear_film.argtypes = [vp]
         L.lmb_set_pixel_shard.argtypes = [vp, C.c_uint32, C.c_uint32]
         L.lmb_resolve.argtypes = [vp]
@@ -155,9 +155,10 @@ class Device:
         self._ck(lib().lmb_render(self._h, C.addressof(pc), C.addressof(ubo), int(first_frame), int(n_frames), int(frame_stride), int(film_mode)),
                  "lmb_render")
 
-    def render_bdpt(self, pc, ubo, first_frame, n_frames):
-        """BDPT::render for frames [first_frame, first_frame + n_frames); pc is a PCBdpt."""
-        self._ck(lib().lmb_render_bdpt(self._h, C.addressof(pc), C.addressof(ubo), int(first_frame), int(n_frames)), "lmb_render_bdpt")
+    def render_bdpt(self, pc, ubo, first_frame, n_frames, frame_stride=1, film_mode=FILM_RUNNING_MEAN):
+        """BDPT::render for frames first_frame + k * frame_stride, k < n_frames; pc is a PCBdpt."""
+        self._ck(lib().lmb_render_bdpt(self._h, C.addressof(pc), C.addressof(ubo), int(first_frame), int(n_frames), int(frame_stride), int(film_mode)),
+                 "lmb_render_bdpt")
 
     def kat_bdpt_frame_raw(self, pc, ubo, frame):
         """One BDPT frame (film updated) + the two images it is made of: (col (H, W, 3), splat (H, W, 3))."""

@@ -148,3 +148,29 @@ def test_cli_bdpt_equals_oracle_at_half_precision(tmp_path):
     got = host.load_exr(str(out))[..., :3]
     close = np.abs(got - want) <= 2.0 ** -9 * np.maximum(np.abs(want), 1e-4)
     assert close.mean() > 0.999
+
+
+def test_bdpt_sample_index_shards_sum_to_the_running_mean(device):
+    """SURVEY.md 8e for the BDPT row: two contexts render the even / odd frames into LMB_FILM_SUM films (valid-sample count in
+    alpha), lmb_film_add_from adds them, lmb_resolve divides -- the same image as one context's running mean, up to fp32 summation
+    order (and the light tracer's float atomics)."""
+    sc, pc, ubo = _setup(device, "cornell", 80, 5)
+    device.clear_film()
+    device.render_bdpt(pc, ubo, 0, 8)
+    whole = device.download()
+    other = integrator.Device(0)
+    try:
+        other.upload_scene(sc.desc)
+        other.build_accel()
+        other.init(80, 80, 1)
+        device.clear_film()
+        device.render_bdpt(pc, ubo, 0, 4, 2, integrator.FILM_SUM)
+        other.render_bdpt(pc, ubo, 1, 4, 2, integrator.FILM_SUM)
+        device.film_add_from(other)
+        device.resolve()
+        sharded = device.download()
+    finally:
+        other.close()
+    assert pixel_agreement(sharded, whole, rel=1e-4) >= 0.999
+    with pytest.raises(RuntimeError, match="frame_stride 1"):
+        device.render_bdpt(pc, ubo, 0, 2, 2, integrator.FILM_RUNNING_MEAN)

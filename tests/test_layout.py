@@ -16,6 +16,9 @@ def test_struct_sizes_match_reference_layouts():
     assert T.Material.bsdf_type.offset == 28 and T.Material.texture_id.offset == 48 and T.Material.thin.offset == 100
     assert T.Light.pos.offset == 64 and T.Light.light_flags.offset == 108 and T.Light.world_radius.offset == 124
     assert T.PCPath.frame_num.offset == 12 and T.PCPath.max_depth.offset == 32 and T.PCPath.direct_lighting.offset == 48
+    # PCBDPT (bdpt_commons.h:5-16) = PCPath without its last field
+    assert C.sizeof(T.PCBdpt) == 48 and [f[0] for f in T.PCBdpt._fields_] == [f[0] for f in T.PCPath._fields_][:-1]
+    assert T.PCBdpt.time.offset == T.PCPath.time.offset == 28 and T.PCBdpt.dir_light_idx.offset == 44
     assert T.SceneUBO.inv_view.offset == 192 and T.SceneUBO.inv_projection.offset == 256
 
 
