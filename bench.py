@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=16, help="frames (samples per pixel) one step renders in one wavefront batch per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bdpt", action="store_true", help="skip the BDPT leg (4 frames of lmb_render_bdpt on the same workload, N = 1 only)")
     ap.add_argument("--pixel-shards", type=int, default=1, help="P: ranks form a P x (N/P) grid of interleaved-row pixel shards x sample shards (config 4)")
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
@@ -307,6 +308,23 @@ def main():
                 n += 1
             cpu_baseline = {"value": cst.rays / cst.seconds / 1e6, "unit": "Mrays/s", "cores": cst.threads, "kind": "port",
                             "sample": f"{n} frames at {pcs.size_x}x{pcs.size_y} (full view, half resolution), depth {MAX_DEPTH}, {cst.seconds:.1f} s"}
+        # ---- the sibling integrator of SURVEY.md 8f rank 3 on the same workload (reported beside the headline, never part of it)
+        bdpt = None
+        if world == 1 and not args.no_bdpt:
+            try:
+                from lumen_b200._ctypes_types import PCBdpt
+                pcb = PCBdpt.from_path_pc(pc)
+                dev.clear_film()
+                dev.render_bdpt(pcb, ubo, 0, 2)  # warm-up: allocates the vertex / slot buffers
+                dev.reset_stats()
+                dev.render_bdpt(pcb, ubo, 2, 4)
+                bs = dev.stats()
+                brays = bs.rays_closest + bs.rays_shadow
+                bdpt = {"value": brays / bs.ms_render / 1e3, "unit": "Mrays/s", "spp_per_s": 4 / (bs.ms_render * 1e-3), "ms_per_frame": bs.ms_render / 4,
+                        "rays_per_pixel": brays / 4 / (WIDTH * HEIGHT), "frames": 4, "gpu_launches": int(bs.kernel_launches),
+                        "note": "lmb_render_bdpt (bdpt.rgen + bdpt_commons.glsl restated, DESIGN.md section 8), same scene / size / max_depth, device time (CUDA events)"}
+            except Exception as e:  # the headline line must not depend on this leg
+                bdpt = {"error": str(e)}
         total_frames = args.steps * fps * n_sshards  # whole-image frames: a pixel shard renders 1/P of each
         line = {
             "metric": "Mrays/s", "value": rays / dt / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -324,6 +342,7 @@ def main():
             "clocks": clk,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "bdpt": bdpt,
             "lbvh_build_ms": {"total": build.ms_build_accel, "morton": build.ms_build_morton, "sort": build.ms_build_sort, "tree": build.ms_build_tree,
                               "refit_pack": build.ms_build_refit},
         }

@@ -46,6 +46,31 @@ def test_full_resolution_parity(device, label, path_fn, w, h, depth, frames):
     assert bits_equal(gpu, cpu).mean() >= 0.9999
 
 
+@pytest.mark.parametrize("label,path_fn,w,h,depth,frames", [CASES[0][:5] + (2,), CASES[1][:5] + (1,), CASES[2][:5] + (1,)], ids=["config 1", "config 2", "config 3"])
+def test_full_resolution_parity_bdpt(device, label, path_fn, w, h, depth, frames):
+    """The same three configurations through lmb_render_bdpt against the oracle's BDPT: the pixels' own
+    strategies bit-equal, the light-tracer image and the film within 1e-4 on >= 99.9 % of pixels, equal ray counts."""
+    from lumen_b200._ctypes_types import PCBdpt
+    sc = host.Scene(path_fn(), w, h)
+    orc = po.OracleScene(sc)
+    pc, ubo = PCBdpt.from_path_pc(sc.make_pc(depth, True)), sc.make_ubo()
+    device.set_pixel_shard(0, 1)
+    device.upload_scene(sc.desc)
+    device.build_accel()
+    device.init(w, h, 1)
+    for frame in range(frames):
+        device.reset_stats()
+        col, splat = device.kat_bdpt_frame_raw(pc, ubo, frame)
+        gs = device.stats()
+        ocol, osplat, cs = orc.render_bdpt_frame_raw(pc, ubo, frame)
+        assert (gs.rays_closest, gs.rays_shadow) == (cs.rays_closest, cs.rays_shadow), label
+        assert bits_equal(col, ocol).all(axis=-1).mean() >= 0.9999, label
+        assert pixel_agreement(splat, osplat) >= 0.999, label
+    gpu = device.download()
+    cpu, _ = orc.render_bdpt(pc, ubo, 0, frames)
+    assert pixel_agreement(gpu, cpu) >= 0.999
+
+
 def test_config5_full_size_lbvh_and_hits(device):
     """Config 5 at its full size (10 x 10 x 10 tori, 10 M triangles): the canonical LBVH of the GPU build is memcmp-equal to the
     CPU build (acceptance criterion 1), the 8-wide tree holds every triangle once, and 2^18 incoherent closest / any-hit rays
