@@ -1243,6 +1243,8 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.walk, (size_t)n_pix * WW_COUNT * 4));
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.misc, (size_t)n_pix * MW_COUNT * 4));
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.rays, (size_t)n_pix * n_conn_slots * 32));
+		// a dead slot is marked in its first float4 only; the walker loads both halves of every slot, so the second must be defined
+		LMB_CUDA(ctx, cudaMemsetAsync(b.rays, 0, (size_t)n_pix * n_conn_slots * 32, st));
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.hits, (size_t)n_pix * 16));
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.occ, (size_t)n_pix * n_conn_slots));
 		b.n_conn_slots = n_conn_slots;
