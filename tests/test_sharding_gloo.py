@@ -118,3 +118,37 @@ def test_pixel_x_sample_grid_partition():
         assert False
     except ValueError:
         pass
+
+
+def _bdpt_worker(rank, world, port, tmpdir):
+    """The BDPT row shards the same way: a frame's sample is col + splat of that frame (quirk B2 makes the
+    light-tracer image a function of the frame alone), so sample-index shards add up exactly like the Path integrator's."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lumen_b200 import host
+    from lumen_b200._ctypes_types import PCBdpt
+    from oracle import pyoracle as po
+    sc = host.Scene(scene_path("cornell"), 32, 32)
+    orc = po.OracleScene(sc)
+    pc, ubo = PCBdpt.from_path_pc(sc.make_pc(5, True)), sc.make_ubo()
+    film = np.zeros((32, 32, 4), dtype=np.float32)
+    for f in sharding.shard_frame_list(0, 3, rank, world):
+        col, splat, _ = orc.render_bdpt_frame_raw(pc, ubo, f, threads=1)
+        sharding.accumulate_sum(film, col + splat)
+    t = torch.from_numpy(film)
+    sharding.all_reduce_film(t, dist)
+    np.save(os.path.join(tmpdir, f"bdpt{rank}.npy"), sharding.resolve(t.numpy()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_bdpt_equals_single(tmp_path):
+    world, port = 2, 33500 + os.getpid() % 2000
+    mp.spawn(_bdpt_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "bdpt0.npy"), np.load(tmp_path / "bdpt1.npy")
+    assert r0.tobytes() == r1.tobytes()
+    from lumen_b200 import host
+    from lumen_b200._ctypes_types import PCBdpt
+    from oracle import pyoracle as po
+    sc = host.Scene(scene_path("cornell"), 32, 32)
+    single, _ = po.OracleScene(sc).render_bdpt(PCBdpt.from_path_pc(sc.make_pc(5, True)), sc.make_ubo(), 0, 6)
+    assert np.allclose(r0[..., :3], single[..., :3], rtol=3e-6, atol=1e-7)
