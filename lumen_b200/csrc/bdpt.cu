@@ -342,6 +342,18 @@ LMB_DN float hit_area(const DeviceScene& sc, uint32_t prim_global) {
 	return 0.5f * length(cross(e0t, e1t));
 }
 
+// load_material (bsdf_commons.glsl:16-22) without the 104-byte copy when there is no texture to fold into the albedo: the callee reads
+// the scene's own record (the BSDF functions take the material by reference). Same values either way; the copies of the connection
+// kernels were most of their local-memory traffic (profiles/r01j_summary.md).
+LMB_D const lmb_material& material_at(const DeviceScene& sc, uint32_t material_idx, const V2& uv, lmb_material& scratch) {
+	const lmb_material& m = sc.materials[material_idx];
+	if (m.texture_id > -1) {
+		scratch = load_material(sc, material_idx, uv);
+		return scratch;
+	}
+	return m;
+}
+
 // ------------------------------------------------------------------------------------------------ vertex storage
 // PathVertex (bdpt_commons.h:18-33), 23 words, struct of arrays over pixels.
 enum VertexWord { W_DIR = 0, W_NS = 3, W_POS = 6, W_UV = 9, W_THR = 11, W_LFLAGS = 14, W_LIDX = 15, W_MAT = 16, W_DELTA = 17, W_SIDE = 18, W_MODE = 19,
@@ -468,7 +480,8 @@ LMB_DN void walk_step(Kctx& k, const Verts& V, int max_depth, WalkSt& st, const 
 	V.sv(b + 1, W_THR, st.thr);
 	V.su(b + 1, W_SIDE, side ? 1u : 0u);
 	V.su(b + 1, W_MODE, EYE ? 1u : 0u);
-	const lmb_material mat = load_material(k.sc, payload.material_idx, payload.uv);
+	lmb_material mat_tex;
+	const lmb_material& mat = material_at(k.sc, payload.material_idx, payload.uv, mat_tex);
 	const bool mat_specular = (mat.bsdf_props & LMB_FLAG_SPECULAR) == LMB_FLAG_SPECULAR;
 	const bool mat_transmissive = (mat.bsdf_props & LMB_FLAG_TRANSMISSION) == LMB_FLAG_TRANSMISSION;
 	V.su(b + 1, W_DELTA, mat_specular ? 1u : 0u);
@@ -606,7 +619,8 @@ LMB_DN float calc_mis_weight(Kctx& k, int s, int t, const Sampled& sampled) {
 			dir /= dir_len;
 			float pdf_rev = 0;
 			if (s >= 2) {
-				const lmb_material mat = load_material(k.sc, lig.u(s - 1, W_MAT), lig.uv(s - 1));
+				lmb_material mat_tex;
+				const lmb_material& mat = material_at(k.sc, lig.u(s - 1, W_MAT), lig.uv(s - 1), mat_tex);
 				const V3 wo = normalize(lig.v(s - 2, W_POS) - lig.v(s - 1, W_POS));
 				pdf_rev = bsdf_pdf(mat, lig.v(s - 1, W_NS), wo, dir, lig.u(s - 1, W_SIDE) == 1);
 				pdf_rev *= fabsf(dot(dir, cam.v(t - 1, W_NS))) / (dir_len * dir_len);
@@ -631,7 +645,8 @@ LMB_DN float calc_mis_weight(Kctx& k, int s, int t, const Sampled& sampled) {
 		const float dir_len = length(dir);
 		dir /= dir_len;
 		if (s > 0) {
-			const lmb_material mat = load_material(k.sc, cam.u(t - 1, W_MAT), cam.uv(t - 1));
+			lmb_material mat_tex;
+			const lmb_material& mat = material_at(k.sc, cam.u(t - 1, W_MAT), cam.uv(t - 1), mat_tex);
 			const V3 wo = normalize(lig.v(s - 1, W_POS) - cam.v(t - 1, W_POS));
 			float pr = bsdf_pdf(mat, cam.v(t - 1, W_NS), wo, dir, cam.u(t - 1, W_SIDE) == 1);
 			if (pr != 0) pr *= fabsf(dot(dir, cam.v(t - 2, W_NS))) / (dir_len * dir_len);
@@ -655,7 +670,8 @@ LMB_DN float calc_mis_weight(Kctx& k, int s, int t, const Sampled& sampled) {
 			lig.f(s - 1, W_PREV) = pdf;
 		} else {
 			const V3 wo = normalize(cam.v(t - 2, W_POS) - cam.v(t - 1, W_POS));
-			const lmb_material mat = load_material(k.sc, cam.u(t - 1, W_MAT), cam.uv(t - 1));
+			lmb_material mat_tex;
+			const lmb_material& mat = material_at(k.sc, cam.u(t - 1, W_MAT), cam.uv(t - 1), mat_tex);
 			float pr = bsdf_pdf(mat, cam.v(t - 1, W_NS), wo, dir, cam.u(t - 1, W_SIDE) == 1);
 			if ((s == 1 && is_light_finite(lig.u(0, W_LFLAGS))) || s > 1) pr *= fabsf(dot(dir, lig.v(s - 1, W_NS))) / (dir_len * dir_len);
 			lig.f(s - 1, W_PREV) = pr;
@@ -668,7 +684,8 @@ LMB_DN float calc_mis_weight(Kctx& k, int s, int t, const Sampled& sampled) {
 		const V3 wo = normalize(cam.v(t - 1, W_POS) - lig.v(s - 1, W_POS));
 		const float dir_len = length(dir);
 		dir /= dir_len;
-		const lmb_material mat = load_material(k.sc, lig.u(s - 1, W_MAT), lig.uv(s - 1));
+		lmb_material mat_tex;
+		const lmb_material& mat = material_at(k.sc, lig.u(s - 1, W_MAT), lig.uv(s - 1), mat_tex);
 		float pr = bsdf_pdf(mat, lig.v(s - 1, W_NS), wo, dir, lig.u(s - 1, W_SIDE) == 1);
 		if ((s == 2 && is_light_finite(lig.u(0, W_LFLAGS))) || s > 2) pr *= fabsf(dot(dir, lig.v(s - 2, W_NS))) / (dir_len * dir_len);
 		lig.f(s - 2, W_PREV) = pr;
@@ -720,7 +737,8 @@ LMB_DN float calc_mis_weight_ro(Kctx& k, int s, int t, const Sampled& sampled) {
 			dir /= dir_len;
 			float pdf_rev = 0;
 			if (s >= 2) {
-				const lmb_material mat = load_material(k.sc, lig.u(s - 1, W_MAT), lig.uv(s - 1));
+				lmb_material mat_tex;
+				const lmb_material& mat = material_at(k.sc, lig.u(s - 1, W_MAT), lig.uv(s - 1), mat_tex);
 				const V3 wo = normalize(lig.v(s - 2, W_POS) - lig.v(s - 1, W_POS));
 				pdf_rev = bsdf_pdf(mat, lig.v(s - 1, W_NS), wo, dir, lig.u(s - 1, W_SIDE) == 1);
 				pdf_rev *= fabsf(dot(dir, cam.v(t - 1, W_NS))) / (dir_len * dir_len);
@@ -743,7 +761,8 @@ LMB_DN float calc_mis_weight_ro(Kctx& k, int s, int t, const Sampled& sampled) {
 		const float dir_len = length(dir);
 		dir /= dir_len;
 		if (s > 0) {
-			const lmb_material mat = load_material(k.sc, cam.u(t - 1, W_MAT), cam.uv(t - 1));
+			lmb_material mat_tex;
+			const lmb_material& mat = material_at(k.sc, cam.u(t - 1, W_MAT), cam.uv(t - 1), mat_tex);
 			const V3 wo = normalize(lpos(s - 1) - cam.v(t - 1, W_POS));
 			float pr = bsdf_pdf(mat, cam.v(t - 1, W_NS), wo, dir, cam.u(t - 1, W_SIDE) == 1);
 			if (pr != 0) pr *= fabsf(dot(dir, cam.v(t - 2, W_NS))) / (dir_len * dir_len);
@@ -765,7 +784,8 @@ LMB_DN float calc_mis_weight_ro(Kctx& k, int s, int t, const Sampled& sampled) {
 			new3 = pdf;
 		} else {
 			const V3 wo = normalize(cam.v(t - 2, W_POS) - cam.v(t - 1, W_POS));
-			const lmb_material mat = load_material(k.sc, cam.u(t - 1, W_MAT), cam.uv(t - 1));
+			lmb_material mat_tex;
+			const lmb_material& mat = material_at(k.sc, cam.u(t - 1, W_MAT), cam.uv(t - 1), mat_tex);
 			float pr = bsdf_pdf(mat, cam.v(t - 1, W_NS), wo, dir, cam.u(t - 1, W_SIDE) == 1);
 			if ((s == 1 && is_light_finite(lflags)) || s > 1) pr *= fabsf(dot(dir, lns(s - 1))) / (dir_len * dir_len);
 			new3 = pr;
@@ -776,7 +796,8 @@ LMB_DN float calc_mis_weight_ro(Kctx& k, int s, int t, const Sampled& sampled) {
 		const V3 wo = normalize(cam.v(t - 1, W_POS) - lig.v(s - 1, W_POS));
 		const float dir_len = length(dir);
 		dir /= dir_len;
-		const lmb_material mat = load_material(k.sc, lig.u(s - 1, W_MAT), lig.uv(s - 1));
+		lmb_material mat_tex;
+		const lmb_material& mat = material_at(k.sc, lig.u(s - 1, W_MAT), lig.uv(s - 1), mat_tex);
 		float pr = bsdf_pdf(mat, lig.v(s - 1, W_NS), wo, dir, lig.u(s - 1, W_SIDE) == 1);
 		if ((s == 2 && is_light_finite(lflags)) || s > 2) pr *= fabsf(dot(dir, lig.v(s - 2, W_NS))) / (dir_len * dir_len);
 		new4 = pr;
@@ -827,7 +848,8 @@ LMB_DN V3 connect_cam(Kctx& k, int s, int& cx, int& cy) {
 	const float cos_3_theta = cos_theta * cos_theta * cos_theta;
 	const float cam_pdf_ratio = fabsf(cos_y) / (cam.f(0, W_AREA) * cos_3_theta * len * len);
 	const V3 ray_origin = offset_ray2(lpos, ln);
-	const lmb_material mat = load_material(k.sc, lig.u(s - 1, W_MAT), lig.uv(s - 1));
+	lmb_material mat_tex;
+	const lmb_material& mat = material_at(k.sc, lig.u(s - 1, W_MAT), lig.uv(s - 1), mat_tex);
 	const V3 wo = normalize(lig.v(s - 2, W_POS) - lpos);
 	float unused_pdf;
 	const V3 f = eval_bsdf(ln, wo, mat, lig.u(s - 1, W_SIDE) == 1, dir, unused_pdf);
@@ -871,7 +893,8 @@ LMB_DN V3 connect(Kctx& k, int s, int t) {
 		const float cos_x = fabsf(dot(ls.wi, cn));
 		const V3 ray_origin = offset_ray2(cpos, cn);
 		const V3 wo = normalize(cam.v(t - 2, W_POS) - cpos);
-		const lmb_material mat = load_material(k.sc, cam.u(t - 1, W_MAT), cam.uv(t - 1));
+		lmb_material mat_tex;
+		const lmb_material& mat = material_at(k.sc, cam.u(t - 1, W_MAT), cam.uv(t - 1), mat_tex);
 		float unused_pdf;
 		const V3 f = eval_bsdf(cn, wo, mat, cam.u(t - 1, W_SIDE) == 1, ls.wi, unused_pdf);
 		if (!is_zero(f)) {
@@ -891,8 +914,10 @@ LMB_DN V3 connect(Kctx& k, int s, int t) {
 		d /= len;
 		const float G = dot(n_s, -d) * dot(n_t, d) / (len * len);
 		if (G > 0) {
-			const lmb_material mat_1 = load_material(k.sc, cam.u(t - 1, W_MAT), cam.uv(t - 1));
-			const lmb_material mat_2 = load_material(k.sc, lig.u(s - 1, W_MAT), lig.uv(s - 1));
+			lmb_material mat_1_tex;
+			const lmb_material& mat_1 = material_at(k.sc, cam.u(t - 1, W_MAT), cam.uv(t - 1), mat_1_tex);
+			lmb_material mat_2_tex;
+			const lmb_material& mat_2 = material_at(k.sc, lig.u(s - 1, W_MAT), lig.uv(s - 1), mat_2_tex);
 			const V3 wo_1 = normalize(cam.v(t - 2, W_POS) - cpos);
 			const V3 wo_2 = normalize(lig.v(s - 2, W_POS) - lpos);
 			float unused_pdf;
