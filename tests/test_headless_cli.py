@@ -28,6 +28,8 @@ def test_cli_is_built_and_fails_loudly_without_a_device(tmp_path):
     out = tmp_path / "x.exr"
     r = _run([scene_path("cornell"), "--width", "16", "--height", "16", "--spp", "1", "--out", str(out)])
     assert r.returncode != 0 and "no CPU fallback" in r.stderr and not out.exists()
+    r = _run([scene_path("cornell"), "--integrator", "bdpt", "--width", "16", "--height", "16", "--spp", "1", "--out", str(out)])  # BDPTB200, same rule
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr and not out.exists()
 
 
 @pytest.mark.gpu
