@@ -174,3 +174,33 @@ def test_bdpt_sample_index_shards_sum_to_the_running_mean(device):
     assert pixel_agreement(sharded, whole, rel=1e-4) >= 0.999
     with pytest.raises(RuntimeError, match="frame_stride 1"):
         device.render_bdpt(pc, ubo, 0, 2, 2, integrator.FILM_RUNNING_MEAN)
+
+
+def test_bdpt_scene_without_lights_matches_oracle(device):
+    """No light buffer (num_lights = 0, light_triangle_count = 0): no light sub-path, no connection ray; material 0 made emissive
+    after the scene was built, so that the s = 0 strategies (and the escaped-vertex rule, oracle/bdpt.h B3) return something."""
+    import ctypes as C
+    from helpers import MATERIALS, make_material
+    from lumen_b200._ctypes_types import Material
+    rng = np.random.default_rng(7)
+    n_tri = 64
+    v = np.zeros((n_tri * 3, 8), dtype=np.float32)
+    v[:, :3] = rng.uniform(-1, 1, (n_tri * 3, 3))
+    v[:, 3:6] = (0, 1, 0)
+    sc = host.Scene.from_arrays(v, [n_tri], [0], [make_material(**MATERIALS["diffuse"])], width=48, height=48)
+    assert sc.info.n_lights == 0
+    mat0 = C.cast(sc.desc.materials, C.POINTER(Material))[0]  # both sides borrow / copy the scene's arrays after this patch
+    mat0.emissive_factor[0], mat0.emissive_factor[1], mat0.emissive_factor[2] = 0.5, 0.25, 0.125
+    device.upload_scene(sc.desc)
+    device.build_accel()
+    device.init(48, 48, 1)
+    pc, ubo = PCBdpt.from_path_pc(sc.make_pc(4, True)), sc.make_ubo()
+    osc = po.OracleScene(sc)
+    device.reset_stats()
+    col, splat = device.kat_bdpt_frame_raw(pc, ubo, 0)
+    st = device.stats()
+    ocol, osplat, ost = osc.render_bdpt_frame_raw(pc, ubo, 0)
+    assert (st.rays_closest, st.rays_shadow) == (ost.rays_closest, ost.rays_shadow) and st.rays_shadow == 0
+    assert bits_equal(col, ocol).all() and (splat == 0).all() and (osplat == 0).all()
+    assert (ocol > 0).any()
+    osc.close()

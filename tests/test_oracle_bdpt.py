@@ -152,3 +152,24 @@ def test_bdpt_golden_vectors():
         assert bits_equal(splat, g[f"{name}_splat"]).all(), name
         assert (st.rays_closest, st.rays_shadow) == tuple(int(v) for v in g[f"{name}_rays"])
         orc.close()
+
+
+def test_bdpt_on_a_scene_without_lights():
+    """num_lights = 0, light_triangle_count = 0 (LumenScene.cpp:134 creates no light buffer): sample_light_Le reads the all-zero
+    Light, pdf_dir = 0, so there is no light sub-path and no connection ray; only the s = 0 strategies run. Must not crash, must
+    be deterministic, and traces exactly the camera walk."""
+    rng = np.random.default_rng(7)
+    n_tri = 64
+    v = np.zeros((n_tri * 3, 8), dtype=np.float32)
+    v[:, :3] = rng.uniform(-1, 1, (n_tri * 3, 3))
+    v[:, 3:6] = (0, 1, 0)
+    mats = [make_material(**MATERIALS["diffuse"])]  # not emissive: an emissive material would make the mesh an area light (LumenScene.cpp:83-95)
+    sc = host.Scene.from_arrays(v, [n_tri], [0], mats, width=32, height=32)
+    assert sc.info.n_lights == 0
+    orc = po.OracleScene(sc)
+    pc, ubo = PCBdpt.from_path_pc(sc.make_pc(4, True)), sc.make_ubo()
+    a, sa, st = orc.render_bdpt_frame_raw(pc, ubo, 0)
+    b, sb, _ = orc.render_bdpt_frame_raw(pc, ubo, 0, threads=1)
+    assert bits_equal(a, b).all() and bits_equal(sa, sb).all()
+    assert st.rays_shadow == 0 and st.rays_closest >= 32 * 32
+    assert (sa == 0).all() and (a == 0).all()  # nothing emits: every s = 0 strategy multiplies a zero emissive_factor
