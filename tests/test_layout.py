@@ -55,6 +55,12 @@ def test_no_cpu_fallback_without_device():
         pytest.skip("a CUDA device is present")
     with pytest.raises(RuntimeError, match="no CUDA device|no CPU fallback"):
         integrator.Device(0)
+    from conftest import scene_path
+    from lumen_b200 import host
+    sc = host.Scene(scene_path("cornell"), 16, 16)
+    for cls in (integrator.PathB200, integrator.BDPTB200):  # both integrator mirrors own a Device: same rule
+        with pytest.raises(RuntimeError, match="no CUDA device|no CPU fallback"):
+            cls(sc)
 
 
 def test_product_never_imports_oracle():
