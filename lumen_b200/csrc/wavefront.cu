@@ -288,7 +288,15 @@ __global__ void __launch_bounds__(128, LAST ? 8 : LMB_SHADE_MIN_BLOCKS) k_shade(
 		V3 col = v3(0.0f), throughput = v3(0.0f), origin = v3(0.0f), wo = v3(0.0f), n_s = v3(0.0f), pos = v3(0.0f), payload_n_s = v3(0.0f);
 		bool side = true, want_nee = false;
 		uint32_t payload_instance = 0;
+#ifdef LMB_SHADE_MATERIAL_REF
+		// A/B variant (tools/build_variant.sh matref -DLMB_SHADE_MATERIAL_REF=1): an untextured material is read through
+		// a pointer to the scene's record instead of a 104-byte local copy. Off by default: not measured yet, same values either way.
+		lmb_material hit_mat_tex;
+		const lmb_material* hit_mat_p = &hit_mat_tex;
+#define hit_mat (*hit_mat_p)
+#else
 		lmb_material hit_mat;
+#endif
 		if (active) {
 			const uint32_t at = LAST ? i : queue[i];
 			const float4 c4 = pl.col[at];
@@ -304,7 +312,19 @@ __global__ void __launch_bounds__(128, LAST ? 8 : LMB_SHADE_MIN_BLOCKS) k_shade(
 				col = xyz(c4);
 				const bool last_specular_in = (__float_as_uint(c4.w) & COL_LAST_SPECULAR) != 0;
 				const HitPayload payload = build_hit(sc, prim, h4.y, h4.z);
+#ifdef LMB_SHADE_MATERIAL_REF
+				{
+					const lmb_material& m0 = sc.materials[payload.material_idx];
+					if (m0.texture_id > -1) {
+						hit_mat_tex = load_material(sc, payload.material_idx, payload.uv);
+						hit_mat_p = &hit_mat_tex;
+					} else {
+						hit_mat_p = &m0;
+					}
+				}
+#else
 				hit_mat = load_material(sc, payload.material_idx, payload.uv);
+#endif
 				if ((depth == 0 && rp.direct_lighting == 1) || last_specular_in) col += throughput * v3(hit_mat.emissive_factor);
 				if (LAST || depth >= rp.max_depth - 1) {
 					acc[slot] = f4(col, 0.0f);
@@ -436,6 +456,9 @@ __global__ void __launch_bounds__(128, LAST ? 8 : LMB_SHADE_MIN_BLOCKS) k_shade(
 	flush_stats(stats, ST_PROBE, n_probe);
 	flush_stats(stats, ST_CLOSEST, n_cont);
 }
+#ifdef LMB_SHADE_MATERIAL_REF
+#undef hit_mat
+#endif
 
 // pt_commons.glsl:23-27, 33-39 and the accumulation of path.rgen:78, once both rays of the light sample are traced: the
 // result goes to the radiance of the path at its position in the current list (before this bounce adds emission)
