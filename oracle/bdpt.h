@@ -308,9 +308,27 @@ inline float remap0(float v) { return v != 0.0f ? v : 1.0f; }
 // unbiased estimator on its own, so their images must converge to each other where both apply). -1 (default): the reference's weights.
 static int g_bdpt_only_s = -1;
 inline int bdpt_only_s() { return g_bdpt_only_s; }
+// orc_bdpt_set_check_restore(1): after every calc_mis_weight both sub-paths are compared byte for byte with their state before the
+// call. The GLSL patches vertices in place and restores them (bdpt_commons.glsl:311-340, 441-466); the CUDA path's pair-parallel
+// kernels evaluate the pairs of a pixel side by side and therefore RELY on that restore being complete. Violations are counted.
+static int g_bdpt_check_restore = 0;
+static long long g_bdpt_restore_violations = 0;
 
 // bdpt_commons.glsl:288-470
+inline float calc_mis_weight_impl(Bdpt& k, int s, int t, const PathVertex& sampled);
 inline float calc_mis_weight(Bdpt& k, int s, int t, const PathVertex& sampled) {
+	if (!g_bdpt_check_restore) return calc_mis_weight_impl(k, s, t, sampled);
+	PathVertex before_l[BDPT_MAX_VERTS], before_c[BDPT_MAX_VERTS];
+	std::memcpy(before_l, k.light_verts, sizeof(before_l));
+	std::memcpy(before_c, k.camera_verts, sizeof(before_c));
+	const float w = calc_mis_weight_impl(k, s, t, sampled);
+	if (std::memcmp(before_l, k.light_verts, sizeof(before_l)) != 0 || std::memcmp(before_c, k.camera_verts, sizeof(before_c)) != 0) {
+#pragma omp atomic
+		g_bdpt_restore_violations++;
+	}
+	return w;
+}
+inline float calc_mis_weight_impl(Bdpt& k, int s, int t, const PathVertex& sampled) {
 	if (bdpt_only_s() >= 0) return s == bdpt_only_s() ? 1.0f : 0.0f;
 	PathVertex* cam = k.camera_verts;
 	PathVertex* lig = k.light_verts;

@@ -512,6 +512,8 @@ int orc_render_bdpt_frame_raw(const orc_scene* s, const lmb_pc_bdpt* pc, const l
 }
 
 void orc_bdpt_set_only_s(int s) { g_bdpt_only_s = s; }
+void orc_bdpt_set_check_restore(int on) { g_bdpt_check_restore = on; }
+long long orc_bdpt_restore_violations(void) { return g_bdpt_restore_violations; }
 
 int orc_render_bdpt(const orc_scene* s, const lmb_pc_bdpt* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames, float* rgba,
 					orc_stats* stats, int n_threads) {

@@ -68,6 +68,10 @@ int orc_render_bdpt_frame_raw(const orc_scene* s, const lmb_pc_bdpt* pc, const l
 
 /* Diagnostic: keep only the BDPT strategies with `s` light vertices, weight 1 (-1 = all strategies, the reference's MIS weights). */
 void orc_bdpt_set_only_s(int s);
+/* Diagnostic: check after every calc_mis_weight that its in-place vertex patches were restored completely (the pair-parallel CUDA
+ * kernels rely on it); orc_bdpt_restore_violations() = calls so far that left a vertex changed. */
+void orc_bdpt_set_check_restore(int on);
+long long orc_bdpt_restore_violations(void);
 
 /* Ray queries: rays = n x 8 floats (ox, oy, oz, tmin, dx, dy, dz, tmax). */
 int orc_trace_closest(const orc_scene* s, const float* rays, uint32_t n, orc_hit* hits, orc_stats* stats, int n_threads);

@@ -46,6 +46,8 @@ def lib():
         L.orc_render_bdpt.argtypes = [vp, vp, vp, u32, u32, vp, vp, i32]
         L.orc_render_bdpt_frame_raw.argtypes = [vp, vp, vp, u32, vp, vp, vp, i32]
         L.orc_bdpt_set_only_s.argtypes = [i32]
+        L.orc_bdpt_set_check_restore.argtypes = [i32]
+        L.orc_bdpt_restore_violations.restype = C.c_longlong
         L.orc_trace_closest.argtypes = [vp, vp, u32, vp, vp, i32]
         L.orc_trace_any.argtypes = [vp, vp, u32, vp, vp, i32]
         L.orc_trace_closest_brute.argtypes = [vp, vp, u32, vp, i32]
@@ -72,6 +74,15 @@ def lib():
 def bdpt_set_only_s(s):
     """Diagnostic switch of oracle/bdpt.h: only the strategies with s light vertices, weight 1 (-1 restores the MIS weights)."""
     lib().orc_bdpt_set_only_s(int(s))
+
+
+def bdpt_check_restore(on):
+    """Diagnostic switch of oracle/bdpt.h: verify that calc_mis_weight restores every vertex it patches."""
+    lib().orc_bdpt_set_check_restore(1 if on else 0)
+
+
+def bdpt_restore_violations():
+    return int(lib().orc_bdpt_restore_violations())
 
 
 def _f32(a):

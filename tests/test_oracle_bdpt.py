@@ -173,3 +173,19 @@ def test_bdpt_on_a_scene_without_lights():
     assert bits_equal(a, b).all() and bits_equal(sa, sb).all()
     assert st.rays_shadow == 0 and st.rays_closest >= 32 * 32
     assert (sa == 0).all() and (a == 0).all()  # nothing emits: every s = 0 strategy multiplies a zero emissive_factor
+
+
+def test_calc_mis_weight_restores_every_vertex_it_patches():
+    """bdpt_commons.glsl:311-340 patches up to eight vertex fields in place and :441-466 puts them back. The CUDA path evaluates
+    the (s, t) pairs of a pixel in parallel (k_bdpt_pair) and substitutes the patched values in registers, which is only the
+    same computation if the GLSL's restore is complete -- checked here byte for byte after every call, on all four scenes."""
+    po.bdpt_check_restore(True)
+    try:
+        before = po.bdpt_restore_violations()
+        for name, depth in (("cornell", 6), ("caustics", 8), ("materials", 7), ("cornell_dir", 5)):
+            sc, orc, pc, ubo = _bdpt(name, 40, depth)
+            orc.render_bdpt_frame_raw(pc, ubo, 0)
+            orc.close()
+        assert po.bdpt_restore_violations() == before
+    finally:
+        po.bdpt_check_restore(False)
