@@ -43,6 +43,7 @@ struct Bdpt {
 	uvec4 seed;
 	uint screen_size;
 	float light_pdf_pos = 0;
+	uint rng_after_walks = 0;  // seed.w when the connection loop starts (diagnostic: orc_bdpt_set_check_restore)
 	PathVertex light_verts[BDPT_MAX_VERTS];
 	PathVertex camera_verts[BDPT_MAX_VERTS];
 };
@@ -524,6 +525,11 @@ inline vec3 bdpt_connect(Bdpt& k, int s, int t) {
 		const lmb_material& mat = k.s.sd.materials[mat_idx];  // un-textured read (`materials.m[mat_idx]`), quirk B3
 		L = v3(mat.emissive_factor) * cam[t - 1].throughput;
 	} else if (s == 1) {
+		// second assumption of the pair-parallel kernels: this is the (t - 2)-th rand4 after the walks
+		if (g_bdpt_check_restore && k.seed.w != k.rng_after_walks + 4u * (uint)(t - 2)) {
+#pragma omp atomic
+			g_bdpt_restore_violations++;
+		}
 		const vec4 r4 = rand4(k.seed);
 		const LightSample ls = sample_light_Li(k.s, r4, cam[t - 1].pos, k.pc.num_lights);
 		const float cos_x = std::fabs(glm::dot(ls.wi, cam[t - 1].n_s));
@@ -592,6 +598,7 @@ inline vec3 bdpt_pixel(const orc_scene& s, const lmb_pc_bdpt& pc, const lmb_scen
 	const float cam_area = std::fabs(area_int.x * area_int.y);
 	const int num_light_paths = bdpt_generate_light_subpath(k, pc.max_depth + 1);
 	const int num_cam_paths = bdpt_generate_camera_subpath(k, d, vec3(origin), pc.max_depth + 1, cam_area);
+	k.rng_after_walks = k.seed.w;
 	for (int t = 1; t <= num_cam_paths; t++) {
 		for (int sl = 0; sl <= num_light_paths; sl++) {
 			const int depth = sl + t - 2;

@@ -178,7 +178,9 @@ def test_bdpt_on_a_scene_without_lights():
 def test_calc_mis_weight_restores_every_vertex_it_patches():
     """bdpt_commons.glsl:311-340 patches up to eight vertex fields in place and :441-466 puts them back. The CUDA path evaluates
     the (s, t) pairs of a pixel in parallel (k_bdpt_pair) and substitutes the patched values in registers, which is only the
-    same computation if the GLSL's restore is complete -- checked here byte for byte after every call, on all four scenes."""
+    same computation if the GLSL's restore is complete -- checked here byte for byte after every call, on all four scenes. The
+    same switch checks the kernels' second assumption: the rand4 of the s = 1 strategy of camera vertex t is the (t - 2)-th
+    draw after the walks."""
     po.bdpt_check_restore(True)
     try:
         before = po.bdpt_restore_violations()
