@@ -8,15 +8,21 @@
 //
 // Frozen where the reference is undefined (the same definitions as the CPU oracle, oracle/bdpt.h B1-B6): the RNG seed is
 // (x, y, frame ^ pc.time, 0) with `time` an input; vertex storage is zeroed before every frame exactly as BDPT.cpp:79-80 does;
-// the light tracer's splats (t == 1) of frame f all land in frame f: k_bdpt adds them to a splat image with float atomics and
-// k_bdpt_film, a second launch, adds that image to the pixel's own strategies before the film update (the reference reads and
+// the light tracer's splats (t == 1) of frame f all land in frame f: they are added to a splat image with float atomics and
+// k_bdpt_film, a later launch, adds that image to the pixel's own strategies before the film update (the reference reads and
 // clears the splat buffer inside the same dispatch that is still writing it).
 //
-// Layout: one thread per pixel per frame. The two sub-paths of a pixel live in HBM as a struct of arrays over pixels -- word w
-// of vertex i of pixel p at verts[((i * 23 + w) * n_pix) + p] -- so every vertex field access of a warp is one coalesced
-// 128-byte transaction; 2 x (max_depth + 1) x 92 B per pixel (2.7 GB at 1080p, depth 6). Rays walk the binary LBVH with the
-// per-thread walker of trace.cuh (hits do not depend on the tree: DESIGN.md section 2). This is the first correct state of the
-// BDPT row -- a megakernel, divergent by construction; the wavefront split the Path integrator has is the next step.
+// Layout: the two sub-paths of a pixel live in HBM as a struct of arrays over pixels -- word w of vertex i of pixel p at
+// verts[((i * 23 + w) * n_pix) + p] -- so every vertex field access of a warp is one coalesced 128-byte transaction;
+// 2 x (max_depth + 1) x 92 B per pixel (2.7 GB at 1080p, depth 6).
+//
+// Three pipelines over the same device functions, bit-equal to each other (tests/test_gpu_bdpt.py) -- DESIGN.md section 8:
+//   default      staged: the per-pixel GLSL is cut at every ray (k_bdpt_begin, k_bdpt_walk, k_bdpt_mid), rays go through the Path
+//                integrator's persistent 8-wide walker as slots (NaN origin = no ray), connections run one thread per
+//                ((s, t) pair, pixel) with register substitutes for calc_mis_weight's in-place patches (k_bdpt_pair, k_bdpt_gather)
+//   LMB_BDPT=pixel   staged walks, connections looped per pixel with the GLSL's patch-and-restore (k_bdpt_connect)
+//   LMB_BDPT=mega    one kernel per frame, rays walked in the thread over the binary LBVH (k_bdpt): the first correct state of
+//                    this row, kept as the plainest statement of the algorithm (3.3-6 x slower: profiles/r01j_summary.md)
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
