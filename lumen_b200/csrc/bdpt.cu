@@ -36,13 +36,20 @@ namespace lmb {
 namespace {
 
 // ------------------------------------------------------------------------------------------------ bsdf_pdf
+// A/B variant (off): -DLMB_BDPT_V3_BYVAL=1 hands the direction vectors of the noinline pdf functions over by value, so that the
+// callers need not park them in local memory to take their address.
+#ifdef LMB_BDPT_V3_BYVAL
+typedef V3 V3arg;
+#else
+typedef const V3& V3arg;
+#endif
 // diffuse.glsl:85-90
 LMB_D float lambertian_diffuse_pdf(const V3& wo, const V3& wi) {
 	if (gmin(wi.z, wo.z) <= 0.0f) return 0.0f;
 	return wi.z * LMB_INV_PI;
 }
 // dielectric.glsl:191-240
-LMB_DN float dielectric_pdf(const lmb_material& mat, const V3& wo, const V3& wi, bool forward_facing) {
+LMB_DN float dielectric_pdf(const lmb_material& mat, V3arg wo, V3arg wi, bool forward_facing) {
 	const float roughness = mat.thin == 1 ? modify_thin_roughness(mat.ior, mat.roughness) : mat.roughness;
 	const float alpha = roughness * roughness;
 	if (alpha == 0 || mat.ior == 1) return 0.0f;
@@ -75,7 +82,7 @@ LMB_DN float dielectric_pdf(const lmb_material& mat, const V3& wo, const V3& wi,
 	return pdf_w;
 }
 // conductor.glsl:74-90
-LMB_DN float conductor_pdf(const lmb_material& mat, const V3& wo, const V3& wi) {
+LMB_DN float conductor_pdf(const lmb_material& mat, V3arg wo, V3arg wi) {
 	const float alpha = mat.roughness * mat.roughness;
 	if (effectively_delta(alpha)) return 0.0f;
 	if (wo.z * wi.z < 0) return 0.0f;
@@ -92,7 +99,7 @@ LMB_D float clearcoat_pdf(const lmb_material& mat, const V3& wo, const V3& wi) {
 	return D / (4.0f * dot(wo, h));
 }
 // principled.glsl:226-251
-LMB_DN float principled_brdf_pdf(const lmb_material& mat, const V3& wo, const V3& wi) {
+LMB_DN float principled_brdf_pdf(const lmb_material& mat, V3arg wo, V3arg wi) {
 	const V2 alpha = calc_anisotropy(mat.roughness, mat.anisotropy);
 	if (effectively_delta(alpha)) return 0.0f;
 	if (wo.z * wi.z < 0) return 0.0f;
@@ -103,7 +110,7 @@ LMB_DN float principled_brdf_pdf(const lmb_material& mat, const V3& wo, const V3
 	return vndf_pdf_aniso(alpha, wo, h, D) / (4.0f * dot(wo, h));
 }
 // principled.glsl:338-360
-LMB_DN float principled_pdf(const lmb_material& mat, const V3& wo, const V3& wi, bool forward_facing) {
+LMB_DN float principled_pdf(const lmb_material& mat, V3arg wo, V3arg wi, bool forward_facing) {
 	float pdf = 0.0f;
 	const float F = fresnel_dielectric(wo.z, mat.ior, forward_facing);
 	const LobeProbs p = sampling_probs(mat, F, forward_facing);
@@ -117,7 +124,7 @@ LMB_DN float principled_pdf(const lmb_material& mat, const V3& wo, const V3& wi,
 	return pdf;
 }
 // bsdf_commons.glsl:26-66
-LMB_DN float bsdf_pdf(const lmb_material& mat, const V3& n_s, const V3& wo_world, const V3& wi_world, bool forward_facing) {
+LMB_DN float bsdf_pdf(const lmb_material& mat, V3arg n_s, V3arg wo_world, V3arg wi_world, bool forward_facing) {
 	V3 T, B;
 	branchless_onb(n_s, T, B);
 	const V3 wo = to_local(wo_world, T, B, n_s);
