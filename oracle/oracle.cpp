@@ -653,6 +653,15 @@ void orc_kat_sample_light(const orc_scene* s, int32_t num_lights, const float* r
 		o[14] = l.bary.x, o[15] = l.bary.y;
 	}
 }
+void orc_kat_light_Le(const orc_scene* s, int32_t num_lights, int32_t total_light, const float* rands6, uint32_t n, float* out16) {
+	for (uint32_t i = 0; i < n; i++) {
+		const float* r = rands6 + 6 * i;
+		const LightEmission l = sample_light_Le(*s, vec4(r[0], r[1], r[2], r[3]), vec2(r[4], r[5]), num_lights, total_light);
+		float* o = out16 + 16 * (size_t)i;
+		o[0] = l.L.x, o[1] = l.L.y, o[2] = l.L.z, o[3] = l.pos.x, o[4] = l.pos.y, o[5] = l.pos.z, o[6] = l.wi.x, o[7] = l.wi.y, o[8] = l.wi.z;
+		o[9] = l.n.x, o[10] = l.n.y, o[11] = l.n.z, o[12] = l.cos_from_light, o[13] = l.pdf_pos_a, o[14] = l.pdf_dir_w, o[15] = (float)l.flags;
+	}
+}
 void orc_kat_texture(const orc_scene* s, uint32_t tex, const float* uv2, uint32_t n, float* out3) {
 	for (uint32_t i = 0; i < n; i++) {
 		const vec3 c = sample_texture(*s, tex, vec2(uv2[2 * i], uv2[2 * i + 1]));

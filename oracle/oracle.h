@@ -97,6 +97,9 @@ void orc_kat_atmosphere(const float* origin3, const float* dir3, const float* li
 /* light sampling at shading points p: out 16 floats = Le.xyz, wi.xyz, wi_len, pdf_w, pdf_a, cos_from_light,
  * light_idx, flags, triangle_idx, instance_idx, bary.xy */
 void orc_kat_sample_light(const orc_scene* s, int32_t num_lights, const float* rands4, const float* p3, uint32_t n, float* out16);
+/* light EMISSION sampling of the BDPT light walk (sample_light_Le, commons.glsl:335-406): rands6 = rands_pos.xyzw, rands_dir.xy;
+ * out 16 floats = L.xyz, pos.xyz, wi.xyz, n.xyz, cos_from_light, pdf_pos_a (already / total_light), pdf_dir_w, flags */
+void orc_kat_light_Le(const orc_scene* s, int32_t num_lights, int32_t total_light, const float* rands6, uint32_t n, float* out16);
 /* texture fetch: out 3 floats */
 void orc_kat_texture(const orc_scene* s, uint32_t tex, const float* uv2, uint32_t n, float* out3);
 

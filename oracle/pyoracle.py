@@ -60,6 +60,7 @@ def lib():
         L.orc_kat_bsdf_pdf.argtypes = [vp, vp, vp, vp, vp, u32, vp]
         L.orc_kat_atmosphere.argtypes = [vp, vp, vp, vp, u32, vp]
         L.orc_kat_sample_light.argtypes = [vp, i32, vp, vp, u32, vp]
+        L.orc_kat_light_Le.argtypes = [vp, i32, i32, vp, u32, vp]
         L.orc_kat_texture.argtypes = [vp, u32, vp, u32, vp]
         L.orc_rmse_literal.argtypes = [vp, vp, u32]
         L.orc_rmse_literal.restype = C.c_float
@@ -179,6 +180,13 @@ class OracleScene:
         r, p = _f32(rands4).reshape(-1, 4), _f32(p3).reshape(-1, 3)
         out = np.zeros((r.shape[0], 16), dtype=np.float32)
         lib().orc_kat_sample_light(self._h, num_lights, r.ctypes.data, p.ctypes.data, r.shape[0], out.ctypes.data)
+        return out
+
+    def light_Le(self, num_lights, total_light, rands6):
+        """sample_light_Le (commons.glsl:335-406): (n, 16) = L, pos, wi, n, cos_from_light, pdf_pos_a, pdf_dir_w, flags."""
+        r = _f32(rands6).reshape(-1, 6)
+        out = np.zeros((r.shape[0], 16), dtype=np.float32)
+        lib().orc_kat_light_Le(self._h, num_lights, total_light, r.ctypes.data, r.shape[0], out.ctypes.data)
         return out
 
     def texture(self, tex, uv):

@@ -191,3 +191,68 @@ def test_calc_mis_weight_restores_every_vertex_it_patches():
         assert po.bdpt_restore_violations() == before
     finally:
         po.bdpt_check_restore(False)
+
+
+def _lights(sc):
+    import ctypes as C
+    from lumen_b200._ctypes_types import Light
+    return C.cast(sc.desc.lights, C.POINTER(Light))
+
+
+def test_light_emission_sampling_spot_against_numpy():
+    """sample_light_Le, LIGHT_SPOT (commons.glsl:362-385): uniform cone of 30 degrees around the light's axis, rotated out of the
+    local frame by the inverse of to_local_quat (utils.glsl:157-173). Independent fp64 restatement."""
+    sc, orc, pc, ubo = _bdpt("caustics", 16, 4)
+    L = _lights(sc)[0]
+    assert L.light_flags & 7 == 1
+    rng = np.random.default_rng(21)
+    r = rng.uniform(0, 1, (4000, 6)).astype(np.float32)
+    out = orc.light_Le(pc.num_lights, pc.light_triangle_count, r)
+    pos, to = np.array(list(L.pos), np.float64), np.array(list(L.to), np.float64)
+    axis = (to - pos) / np.linalg.norm(to - pos)
+    cw = np.cos(np.float32(30 * np.float32(3.14159265359) / 180), dtype=np.float64)
+    u, v = r[:, 4].astype(np.float64), r[:, 5].astype(np.float64)
+    ct = (1 - u) + u * cw
+    st = np.sqrt(1 - ct * ct)
+    phi = v * 6.28318530718
+    local = np.stack([np.cos(phi) * st, np.sin(phi) * st, ct], axis=1)
+    q = np.array([axis[1], -axis[0], 0.0, 1.0 + axis[2]])
+    q /= np.linalg.norm(q)
+    qi = np.array([-q[0], -q[1], -q[2], q[3]])  # invert_quat
+    qa = qi[:3]
+    want = 2 * (local @ qa)[:, None] * qa + (qi[3] ** 2 - qa @ qa) * local + 2 * qi[3] * np.cross(qa, local)
+    assert np.abs(out[:, 6:9] - want).max() < 5e-6  # fp32 detmath sin / cos against fp64
+    assert np.abs(out[:, 12] - ct).max() < 5e-6  # cos_from_light = the sampled cos(theta): the rotation maps z onto the axis
+    assert (out[:, 3:6] == np.array(list(L.pos), np.float32)).all()
+    assert np.allclose(out[:, 14], 1 / (6.28318530718 * (1 - cw)), rtol=1e-6) and (out[:, 13] == 1.0 / pc.light_triangle_count).all()
+    assert bits_equal(out[:, 9:12], out[:, 6:9]).all()  # n = wi
+
+
+def test_light_emission_sampling_directional_and_area_properties():
+    """LIGHT_DIRECTIONAL (commons.glsl:386-400): a point of the disk of radius world_radius that faces the scene, direction -dir,
+    pdf_pos = 1 / (pi r^2) / total. LIGHT_AREA (:347-361): cosine-weighted direction about the sampled normal, pdf_dir = cos / pi,
+    pdf_pos = 1 / (triangle area) / total."""
+    sc, orc, pc, ubo = _bdpt("cornell_dir", 16, 4)
+    L = _lights(sc)[0]
+    assert L.light_flags & 7 == 3
+    rng = np.random.default_rng(22)
+    out = orc.light_Le(pc.num_lights, pc.light_triangle_count, rng.uniform(0, 1, (4000, 6)).astype(np.float32))
+    d = np.array(list(L.pos), np.float64) - np.array(list(L.to), np.float64)
+    d /= np.linalg.norm(d)  # -normalize(to - pos)
+    assert np.abs(out[:, 6:9] + d).max() < 1e-6  # wi = -dir
+    rel = out[:, 3:6].astype(np.float64) - (np.array(list(L.world_center), np.float64) + d * L.world_radius)
+    assert np.abs(rel @ d).max() < 1e-4 * L.world_radius and np.linalg.norm(rel, axis=1).max() <= L.world_radius * (1 + 1e-5)
+    assert np.allclose(out[:, 13], 1 / (np.pi * L.world_radius ** 2) / pc.light_triangle_count, rtol=1e-5)
+    assert (out[:, 14] == 1).all() and (out[:, 12] == 1).all()
+
+    sc, orc, pc, ubo = _bdpt("cornell", 16, 4)
+    assert _lights(sc)[0].light_flags & 7 == 2
+    out = orc.light_Le(pc.num_lights, pc.light_triangle_count, rng.uniform(0, 1, (4000, 6)).astype(np.float32))
+    wi, n = out[:, 6:9].astype(np.float64), out[:, 9:12].astype(np.float64)
+    cos = np.sum(wi * n, axis=1)
+    assert (cos >= -1e-6).all() and np.abs(np.linalg.norm(wi, axis=1) - 1).max() < 1e-5
+    assert np.allclose(out[:, 14], cos / np.pi, atol=1e-6) and np.allclose(out[:, 12], np.maximum(cos, 0), atol=1e-6)
+    areas = 1 / (out[:, 13].astype(np.float64) * pc.light_triangle_count)
+    assert (areas > 0).all() and areas.max() <= pc.total_light_area and len(np.unique(np.round(areas, 4))) <= _lights(sc)[0].num_triangles
+    # a cosine-weighted hemisphere has E[cos] = 2/3
+    assert abs(cos.mean() - 2 / 3) < 0.02
