@@ -12,4 +12,8 @@ python bench.py --impl reference --steps 3 --warmup 1 | tee gpurun_out/bench_ref
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/ncu_target.py 16 2 | tail -2
 timeout 900 ncu --set full --clock-control none -k regex:"^k_trace$" -s 0 -c 8 -f -o gpurun_out/prof_trace python tools/ncu_target.py 16 1 | tail -2
 timeout 900 ncu --set full --clock-control none -k regex:"k_shade|k_classify|k_connect|k_miss" -s 0 -c 10 -f -o gpurun_out/prof_shade python tools/ncu_target.py 16 1 | tail -2
+# BDPT row: per-scene table, launch list and one full capture of the pair kernels
+python tools/bdpt_table.py --json gpurun_out/bdpt_table.json | cut -c1-160
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/bdpt_launches.csv python tools/bdpt_table.py --quick | tail -1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_bdpt_pair -s 2 -c 2 -f -o gpurun_out/prof_bdpt_pair python tools/bdpt_table.py --quick | tail -1
 ls -la gpurun_out
