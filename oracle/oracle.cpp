@@ -558,6 +558,16 @@ int orc_trace_closest(const orc_scene* s, const float* rays, uint32_t n, orc_hit
 	return 0;
 }
 
+// One ray, no OpenMP: the intersection callback of the mechanically translated reference shaders (oracle/glslref), whose
+// traceRayEXT is outside the shader source. mesh / local = gl_InstanceCustomIndexEXT / gl_PrimitiveID of the hit.
+int orc_trace1(const orc_scene* s, const float* r, int any_hit, orc_hit* hit, uint32_t* mesh, uint32_t* local) {
+	const vec3 o(r[0], r[1], r[2]), d(r[4], r[5], r[6]);
+	const Hit h = any_hit ? trace<true>(s->bvh, o, d, r[3], r[7], nullptr) : trace<false>(s->bvh, o, d, r[3], r[7], nullptr);
+	*hit = {h.t, h.b1, h.b2, h.prim};
+	if (h.prim != 0xFFFFFFFFu) *mesh = s->bvh.tri_mesh[h.prim], *local = s->bvh.tri_local[h.prim];
+	return h.prim != 0xFFFFFFFFu;
+}
+
 int orc_trace_closest_brute(const orc_scene* s, const float* rays, uint32_t n, orc_hit* hits, int n_threads) {
 	const int nt = pick_threads(n_threads);
 #pragma omp parallel for num_threads(nt) schedule(dynamic, 64)

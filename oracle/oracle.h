@@ -75,6 +75,9 @@ long long orc_bdpt_restore_violations(void);
 
 /* Ray queries: rays = n x 8 floats (ox, oy, oz, tmin, dx, dy, dz, tmax). */
 int orc_trace_closest(const orc_scene* s, const float* rays, uint32_t n, orc_hit* hits, orc_stats* stats, int n_threads);
+/* one ray without OpenMP (callback of oracle/glslref's traceRayEXT); returns 1 on a hit and fills mesh / local with
+ * gl_InstanceCustomIndexEXT / gl_PrimitiveID */
+int orc_trace1(const orc_scene* s, const float* ray8, int any_hit, orc_hit* hit, uint32_t* mesh, uint32_t* local);
 /* the hit definition evaluated over ALL triangles, no tree: what orc_trace_closest must equal bit for bit */
 int orc_trace_closest_brute(const orc_scene* s, const float* rays, uint32_t n, orc_hit* hits, int n_threads);
 int orc_trace_any(const orc_scene* s, const float* rays, uint32_t n, uint8_t* occluded, orc_stats* stats, int n_threads);
