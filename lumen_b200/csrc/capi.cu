@@ -138,6 +138,11 @@ static int validate_scene(lmb_ctx* ctx, const lmb_scene_desc* sd) {
 		if ((l.light_flags & 0x7u) != LMB_LIGHT_AREA) continue;
 		if (l.prim_mesh_idx >= sd->n_prim_meshes) return bad("area light " + std::to_string(i) + ": prim_mesh_idx out of range");
 		if (l.num_triangles == 0 || l.num_triangles > sd->prim_idx_counts[l.prim_mesh_idx] / 3) return bad("area light " + std::to_string(i) + ": num_triangles does not fit its mesh");
+		// sample_triangle (commons.glsl:130) takes transpose(inverse(light.world_matrix)); the kernels read the host-inverted MESH
+		// matrix instead (inv_world_matrices[prim_mesh_idx]), which is the same thing only while the two matrices are equal -- as
+		// LumenScene.cpp:86-93 builds them
+		if (memcmp(l.world_matrix, sd->world_matrices + 16 * (size_t)l.prim_mesh_idx, 64) != 0)
+			return bad("area light " + std::to_string(i) + ": world_matrix differs from the world matrix of its mesh");
 	}
 	return 0;
 }
@@ -213,6 +218,8 @@ int lmb_upload_scene(lmb_ctx* ctx, const lmb_scene_desc* sd) {
 	sc.n_prim_meshes = sd->n_prim_meshes;
 	sc.n_lights = sd->n_lights;
 	sc.n_textures = sd->n_textures;
+	ctx->h_light_flags.resize(sd->n_lights);
+	for (uint32_t i = 0; i < sd->n_lights; i++) ctx->h_light_flags[i] = sd->lights[i].light_flags;
 	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host staging vectors go out of scope
 	ctx->scene_loaded = true;
 	return LMB_OK;
@@ -236,7 +243,12 @@ int lmb_init(lmb_ctx* ctx, uint32_t width, uint32_t height, uint32_t frames_in_f
 	LMB_CUDA(ctx, cudaMalloc((void**)&ctx->film, (size_t)width * height * 16));
 	LMB_CUDA(ctx, cudaMemsetAsync(ctx->film, 0, (size_t)width * height * 16, ctx->stream));
 	const int rc = wavefront_alloc(ctx, frames_in_flight);
-	if (rc) return rc;
+	if (rc) {  // leave no half-initialised context behind: lmb_render's guard is ctx->film
+		wavefront_free(ctx);
+		cudaFree(ctx->film);
+		ctx->film = nullptr;
+		return rc;
+	}
 	return lmb_reset_stats(ctx);
 }
 
@@ -256,12 +268,34 @@ int lmb_set_pixel_shard(lmb_ctx* ctx, uint32_t row_first, uint32_t row_stride) {
 	return LMB_OK;
 }
 
+// The push-constant fields the kernels use as indices or divisors, against the uploaded scene: sample_light_Li reads
+// lights[uint(rand * num_lights)], shade_atmosphere / k_miss read lights[dir_light_idx] (commons.glsl:227,160). The reference
+// fills them from its own scene (Path.cpp:27-37); a C ABI has to check.
+static int check_light_args(lmb_ctx* ctx, const char* who, int32_t num_lights, uint32_t dir_light_idx, int32_t light_triangle_count, int32_t max_depth,
+							int32_t max_depth_limit) {
+	const std::string w(who);
+	const uint32_t n_lights = ctx->scene.n_lights;
+	if (num_lights < 0 || (uint32_t)num_lights > n_lights)
+		return set_error(ctx, LMB_ERR_INVALID, w + ": num_lights " + std::to_string(num_lights) + " is outside [0, " + std::to_string(n_lights) + "] (uploaded lights)");
+	if (dir_light_idx != 0xFFFFFFFFu) {
+		if (dir_light_idx >= n_lights) return set_error(ctx, LMB_ERR_INVALID, w + ": dir_light_idx is neither 0xFFFFFFFF nor an uploaded light");
+		if ((ctx->h_light_flags[dir_light_idx] & 0x7u) != LMB_LIGHT_DIRECTIONAL)
+			return set_error(ctx, LMB_ERR_INVALID, w + ": dir_light_idx does not name a directional light");
+	}
+	if (light_triangle_count < 0 || (light_triangle_count == 0 && num_lights > 0))
+		return set_error(ctx, LMB_ERR_INVALID, w + ": light_triangle_count must be positive when there are lights (1 / light_triangle_count is the light pick pdf, path.rgen:76)");
+	if (max_depth < 0 || max_depth > max_depth_limit)
+		return set_error(ctx, LMB_ERR_INVALID, w + ": max_depth " + std::to_string(max_depth) + " is outside [0, " + std::to_string(max_depth_limit) + "]");
+	return LMB_OK;
+}
+
 int lmb_render(lmb_ctx* ctx, const lmb_pc_path* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames, uint32_t frame_stride,
 			   int film_mode) {
 	if (!ctx || !pc || !ubo) return LMB_ERR_INVALID;
 	if (!ctx->bvh.built) return set_error(ctx, LMB_ERR_INVALID, "lmb_render: call lmb_build_accel first");
 	if (!ctx->film) return set_error(ctx, LMB_ERR_INVALID, "lmb_render: call lmb_init first");
 	if (pc->size_x != ctx->width || pc->size_y != ctx->height) return set_error(ctx, LMB_ERR_INVALID, "lmb_render: PCPath size != lmb_init size");
+	if (const int bad = check_light_args(ctx, "lmb_render", pc->num_lights, pc->dir_light_idx, pc->light_triangle_count, pc->max_depth, 4096)) return bad;
 	if (frame_stride == 0) frame_stride = 1;
 	if (film_mode == LMB_FILM_RUNNING_MEAN && frame_stride != 1)
 		return set_error(ctx, LMB_ERR_INVALID, "lmb_render: running-mean film needs frame_stride 1");
@@ -275,7 +309,8 @@ static int check_bdpt_args(lmb_ctx* ctx, const lmb_pc_bdpt* pc) {
 	if (!ctx->bvh.built) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: call lmb_build_accel first");
 	if (!ctx->film) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: call lmb_init first");
 	if (pc->size_x != ctx->width || pc->size_y != ctx->height) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: PCBDPT size != lmb_init size");
-	return LMB_OK;
+	// two sub-paths of max_depth + 1 vertices (92 B each) are kept per pixel: the depth bounds the allocation
+	return check_light_args(ctx, "lmb_render_bdpt", pc->num_lights, pc->dir_light_idx, pc->light_triangle_count, pc->max_depth, 64);
 }
 
 int lmb_render_bdpt(lmb_ctx* ctx, const lmb_pc_bdpt* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames, uint32_t frame_stride,
@@ -487,10 +522,10 @@ int lmb_trace_closest(lmb_ctx* ctx, const float* rays, uint32_t n, lmb_hit* hits
 	int rc = ensure_stats(ctx);
 	if (rc) return rc;
 	float4 *d_rays = nullptr, *d_hits = nullptr;
-	LMB_CUDA(ctx, cudaMalloc((void**)&d_rays, (size_t)n * 32));
-	LMB_CUDA(ctx, cudaMalloc((void**)&d_hits, (size_t)n * 16));
-	LMB_CUDA(ctx, cudaMemcpyAsync(d_rays, rays, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream));
-	rc = launch_trace_closest(ctx, d_rays, n, d_hits);
+	rc = check_cuda(ctx, cudaMalloc((void**)&d_rays, (size_t)n * 32), "lmb_trace_closest: rays");
+	if (!rc) rc = check_cuda(ctx, cudaMalloc((void**)&d_hits, (size_t)n * 16), "lmb_trace_closest: hits");
+	if (!rc) rc = check_cuda(ctx, cudaMemcpyAsync(d_rays, rays, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream), "lmb_trace_closest: copy rays");
+	if (!rc) rc = launch_trace_closest(ctx, d_rays, n, d_hits);
 	if (!rc) rc = check_cuda(ctx, cudaMemcpyAsync(hits, d_hits, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream), "copy hits");
 	if (!rc) rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "lmb_trace_closest");
 	cudaFree(d_rays), cudaFree(d_hits);
@@ -506,10 +541,10 @@ int lmb_trace_any(lmb_ctx* ctx, const float* rays, uint32_t n, uint8_t* occluded
 	if (rc) return rc;
 	float4* d_rays = nullptr;
 	uint8_t* d_occ = nullptr;
-	LMB_CUDA(ctx, cudaMalloc((void**)&d_rays, (size_t)n * 32));
-	LMB_CUDA(ctx, cudaMalloc((void**)&d_occ, n));
-	LMB_CUDA(ctx, cudaMemcpyAsync(d_rays, rays, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream));
-	rc = launch_trace_any(ctx, d_rays, n, d_occ);
+	rc = check_cuda(ctx, cudaMalloc((void**)&d_rays, (size_t)n * 32), "lmb_trace_any: rays");
+	if (!rc) rc = check_cuda(ctx, cudaMalloc((void**)&d_occ, n), "lmb_trace_any: occlusion bytes");
+	if (!rc) rc = check_cuda(ctx, cudaMemcpyAsync(d_rays, rays, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream), "lmb_trace_any: copy rays");
+	if (!rc) rc = launch_trace_any(ctx, d_rays, n, d_occ);
 	if (!rc) rc = check_cuda(ctx, cudaMemcpyAsync(occluded, d_occ, n, cudaMemcpyDeviceToHost, ctx->stream), "copy occ");
 	if (!rc) rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "lmb_trace_any");
 	cudaFree(d_rays), cudaFree(d_occ);

@@ -134,6 +134,7 @@ struct lmb_ctx {
 	std::vector<void*> scene_allocs;
 	std::vector<lmb_prim_mesh_info> h_prim_infos;
 	std::vector<uint32_t> h_idx_counts;
+	std::vector<uint32_t> h_light_flags;  // host copy of Light.light_flags: lmb_render checks PCPath's light indices against it
 	lmb::DeviceBvh bvh;
 	lmb::DeviceWideBvh wide;
 	bool use_ploc = true;   // LMB_TREE=lbvh: collapse the canonical Karras tree instead of the PLOC tree

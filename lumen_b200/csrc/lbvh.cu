@@ -367,7 +367,11 @@ int build_lbvh(lmb_ctx* ctx) {
 		// neither the surface-area cost of the binary trees (0.90) nor that of the wide trees (0.95) sees that: both favour clustering
 		// there, because they price rays that never stop, while a closest-hit ray ends at the first surface.
 		double cost_ploc = 0.0, cost_karras = 0.0;
-		if ((rc = build_wide_bvh(ctx)) || (rc = probe_wide_tree(ctx, 1u << 16, &cost_ploc))) return rc;
+		if ((rc = build_wide_bvh(ctx))) return rc;
+		// the traversal stack holds one entry per level (11 shared + 53 local = 64): a clustering deeper than 56 levels is not walked
+		// at all, not even by the probe (it loses below and the canonical tree, whose depth the 62 key bits bound, is taken)
+		const bool ploc_walkable = ctx->wide.levels <= 56;
+		if (ploc_walkable && (rc = probe_wide_tree(ctx, 1u << 16, &cost_ploc))) return rc;
 		const DeviceWideBvh wide_ploc = ctx->wide;
 		const float ms_ploc_wide = ctx->stats.ms_build_wide;
 		ctx->wide = DeviceWideBvh{};
@@ -381,7 +385,7 @@ int build_lbvh(lmb_ctx* ctx) {
 		if (getenv("LMB_VERBOSE")) fprintf(stderr, "lumen_b200: probe steps per ray: karras %.3f clustered %.3f ratio %.4f\n", cost_karras, cost_ploc, ctx->stats.tree_cost_ratio);
 		// the probe is a stand-in for the real ray distribution, where clustering tends to do better than on the probe (classroom stand-in:
 		// probe 0.99, path tracing 0.875): the Karras tree has to win by 3 % to be taken
-		const bool keep_ploc = !rc && cost_ploc < 1.03 * cost_karras && wide_ploc.levels <= 56;
+		const bool keep_ploc = !rc && ploc_walkable && cost_ploc < 1.03 * cost_karras;
 		if (keep_ploc) {
 			free_wide_bvh(ctx);
 			ctx->wide = wide_ploc;

@@ -287,6 +287,60 @@ def test_upload_rejects_out_of_range_indices(device):
         dev2.close()
 
 
+def test_render_rejects_push_constants_that_do_not_fit_the_scene(device, loaded):
+    """lmb_render / lmb_render_bdpt check the PCPath fields the kernels index or divide by (num_lights, dir_light_idx,
+    light_triangle_count, max_depth) against the uploaded scene and report instead of reading lights[] out of bounds; an area light
+    whose world_matrix is not its mesh's is refused at upload. The context stays usable."""
+    import ctypes as C
+    from lumen_b200._ctypes_types import Light, PCBdpt, SceneDesc
+    sc, orc = loaded("cornell_dir", 48, 32)
+    device.init(48, 32, 1)
+    ubo = sc.make_ubo()
+
+    def broken(**kw):
+        pc = sc.make_pc(6, True)
+        for k, v in kw.items():
+            setattr(pc, k, v)
+        return pc
+
+    n = sc.info.n_lights
+    for kw, msg in ((dict(num_lights=n + 1), "num_lights"), (dict(num_lights=-1), "num_lights"), (dict(dir_light_idx=n), "dir_light_idx"),
+                    (dict(light_triangle_count=0), "light_triangle_count"), (dict(light_triangle_count=-3), "light_triangle_count"),
+                    (dict(max_depth=-1), "max_depth"), (dict(max_depth=100000), "max_depth")):
+        with pytest.raises(RuntimeError, match=msg):
+            device.render(broken(**kw), ubo, 0, 1)
+    bp = PCBdpt.from_path_pc(sc.make_pc(6, True))
+    bp.num_lights = n + 7
+    with pytest.raises(RuntimeError, match="num_lights"):
+        device.render_bdpt(bp, ubo, 0, 1)
+    bp = PCBdpt.from_path_pc(sc.make_pc(6, True))
+    bp.max_depth = 65
+    with pytest.raises(RuntimeError, match="max_depth"):
+        device.render_bdpt(bp, ubo, 0, 1)
+    device.render(sc.make_pc(6, True), ubo, 0, 1)  # still good
+    got = device.download()
+    want, _ = orc.render(sc.make_pc(6, True), ubo, 0, 1)
+    assert bits_equal(got, want).all()
+    # dir_light_idx naming a light that is not directional
+    sc2, _ = loaded("cornell", 48, 32)
+    pc = sc2.make_pc(6, True)
+    pc.dir_light_idx = 0
+    with pytest.raises(RuntimeError, match="directional"):
+        device.render(pc, sc2.make_ubo(), 0, 1)
+    # area light with a world matrix of its own
+    dev2 = integrator.Device(0)
+    try:
+        bad = SceneDesc.from_buffer_copy(sc2.desc)
+        lights = (Light * sc2.desc.n_lights).from_address(sc2.desc.lights)
+        copy = (Light * sc2.desc.n_lights)(*lights)
+        copy[0].world_matrix[12] += 1.0
+        bad.lights = C.addressof(copy)
+        with pytest.raises(RuntimeError, match="world_matrix differs"):
+            dev2.upload_scene(bad)
+    finally:
+        dev2.close()
+
+
 def test_film_add_from_reduces_sum_films(device, loaded):
     """lmb_film_add_from: dst.film += src.film, device to device -- the multi-GPU reduce of the C++ host (PathB200Multi). Two contexts
     render the even and the odd frames in sum mode; added and resolved they give the mean of all frames."""
