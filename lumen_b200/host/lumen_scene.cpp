@@ -289,6 +289,7 @@ struct MBsdf {
 struct MMesh {
 	std::string file, shape_type;
 	int bsdf_idx = -1;
+	int inline_bsdf = -1;  // index into the loader's list of id-less <bsdf> children (opt-in emitters only)
 	glm::mat4 transform{1};
 	bool has_emitter = false;  // nested <emitter type="area">
 	glm::vec3 radiance{0};
@@ -314,6 +315,29 @@ void Scene::load_mitsuba_scene(const std::string& path) {
 	glm::vec3 sky(0.0f);
 	float cam_fov = 45.0f;
 	glm::mat4 cam_matrix(0.0f);
+	// MitsubaParser.cpp:40-73
+	auto parse_bsdf = [](Object* obj) {
+		MBsdf b;
+		b.name = obj->id();
+		while ((obj->pluginType() == "twosided" || obj->pluginType() == "mask") && obj->anonymousChildren().size())
+			obj = obj->anonymousChildren()[0].get();
+		b.type = obj->pluginType();
+		for (const auto& prop : obj->properties()) {
+			if (prop.second.type() == PT_COLOR) {
+				if (prop.first.find("reflectance") == std::string::npos && prop.first.find("specularReflectance") == std::string::npos)
+					continue;
+				b.albedo = glm::vec3((float)prop.second.getColor().r, (float)prop.second.getColor().g, (float)prop.second.getColor().b);
+			}
+			if (prop.first == "alpha") b.roughness = std::sqrt((float)prop.second.getNumber());
+			if (prop.first == "int_ior") b.ior = (float)prop.second.getNumber();
+		}
+		for (const auto& nc : obj->namedChildren())
+			if (nc.second->type() == OT_TEXTURE)
+				for (const auto& tp : nc.second->properties())
+					if (tp.first == "filename") b.texture = tp.second.getString();
+		return b;
+	};
+	std::vector<MBsdf> inline_bsdfs;  // <bsdf> nested in a shape without an id (bedroom's lamp rectangles); only the opt-in emitters use them
 	for (const auto& child : scene.anonymousChildren()) {
 		Object* obj = child.get();
 		switch (obj->type()) {
@@ -335,25 +359,7 @@ void Scene::load_mitsuba_scene(const std::string& path) {
 				}
 			} break;
 			case OT_BSDF: {
-				MBsdf b;
-				b.name = obj->id();
-				while ((obj->pluginType() == "twosided" || obj->pluginType() == "mask") && obj->anonymousChildren().size())
-					obj = obj->anonymousChildren()[0].get();
-				b.type = obj->pluginType();
-				for (const auto& prop : obj->properties()) {
-					if (prop.second.type() == PT_COLOR) {
-						if (prop.first.find("reflectance") == std::string::npos && prop.first.find("specularReflectance") == std::string::npos)
-							continue;
-						b.albedo = glm::vec3((float)prop.second.getColor().r, (float)prop.second.getColor().g, (float)prop.second.getColor().b);
-					}
-					if (prop.first == "alpha") b.roughness = std::sqrt((float)prop.second.getNumber());
-					if (prop.first == "int_ior") b.ior = (float)prop.second.getNumber();
-				}
-				for (const auto& nc : obj->namedChildren())
-					if (nc.second->type() == OT_TEXTURE)
-						for (const auto& tp : nc.second->properties())
-							if (tp.first == "filename") b.texture = tp.second.getString();
-				bsdfs.push_back(b);
+				bsdfs.push_back(parse_bsdf(obj));
 			} break;
 			case OT_SHAPE: {
 				MMesh m;
@@ -383,6 +389,10 @@ void Scene::load_mitsuba_scene(const std::string& path) {
 					const auto ref = mc->id();
 					for (size_t i = 0; i < bsdfs.size(); i++)
 						if (bsdfs[i].name == ref) m.bsdf_idx = (int)i;
+					if (mc->type() == OT_BSDF && ref.empty()) {
+						inline_bsdfs.push_back(parse_bsdf(mc.get()));
+						m.inline_bsdf = (int)inline_bsdfs.size() - 1;
+					}
 				}
 				meshes.push_back(m);
 			} break;
@@ -444,8 +454,8 @@ void Scene::load_mitsuba_scene(const std::string& path) {
 		pm.world_matrix = glm::mat4(1.0f);
 	};
 	auto emitter_material = [&](const MMesh& mesh) -> uint32_t {
-		MBsdf b = mesh.bsdf_idx >= 0 ? bsdfs[(size_t)mesh.bsdf_idx] : MBsdf{};
-		if (mesh.bsdf_idx < 0) b.type = "diffuse", b.albedo = glm::vec3(0.5f);  // Mitsuba's default bsdf
+		MBsdf b = mesh.bsdf_idx >= 0 ? bsdfs[(size_t)mesh.bsdf_idx] : (mesh.inline_bsdf >= 0 ? inline_bsdfs[(size_t)mesh.inline_bsdf] : MBsdf{});
+		if (mesh.bsdf_idx < 0 && mesh.inline_bsdf < 0) b.type = "diffuse", b.albedo = glm::vec3(0.5f);  // Mitsuba's default bsdf
 		b.name += "#emitter" + std::to_string(emissive.size());
 		bsdfs.push_back(b);
 		emissive.emplace_back(bsdfs.size() - 1, mesh.radiance);
