@@ -143,6 +143,26 @@ int lmb_upload_film(lmb_ctx* ctx, const float* rgba);
  * contexts may sit on different devices -- the copy goes device to device, over NVLink where the peers are connected).
  * Synchronous on return. No reference equivalent (Lumen drives one GPU). */
 int lmb_film_add_from(lmb_ctx* dst, lmb_ctx* src);
+/* ---- the exchange step of a multi-GPU render (SURVEY.md 8e / 2.3 "Collectives": no reference equivalent, Lumen drives one GPU).
+ * One rank = one context = one GPU. The only message is the fp32 sum of the LMB_FILM_SUM films (RGB sums + valid-sample count in
+ * alpha), reduced by ncclAllReduce over NVLink / NVSwitch with the "/ count" epilogue of lmb_resolve queued behind it on the same
+ * stream. NCCL is bound at run time (libnccl.so.2); without it these calls fail with a message and everything else works. */
+#define LMB_COMM_ID_BYTES 128
+/* rank 0 makes the id (ncclGetUniqueId) and hands the 128 bytes to the other ranks by whatever means the host has (MPI, a file,
+ * torch.distributed ...); every rank then calls lmb_comm_init -- collectively, it returns once all n_ranks have joined. */
+int lmb_comm_get_unique_id(uint8_t* id128);
+int lmb_comm_init(lmb_ctx* ctx, const uint8_t* id128, int rank, int n_ranks);
+/* the same for n contexts of ONE process (one per device): rank i = ctxs[i] */
+int lmb_comm_init_all(lmb_ctx** ctxs, int n);
+int lmb_comm_destroy(lmb_ctx* ctx);
+int lmb_comm_info(lmb_ctx* ctx, int* rank, int* n_ranks, int* nccl_version); /* n_ranks = 0: no communicator */
+/* film -> sum over the ranks -> rgb / alpha, alpha = 1 (every rank gets the whole image). Collective; nothing waits on the host
+ * (lmb_sync does). out_rgba == NULL: in place on the render stream, the film IS the resolved image afterwards. out_rgba != NULL
+ * (host, pinned for a truly asynchronous copy, or device; width*height*4 floats): the film is snapshotted in stream order and, with
+ * clear_film != 0, zeroed for the next batch; reduce, resolve and the copy to out_rgba run on the context's own high-priority
+ * stream while lmb_render goes on with the next frames. */
+int lmb_film_allreduce(lmb_ctx* ctx, float* out_rgba, int clear_film);
+
 /* Device pointer of the film and the CUDA stream (cudaStream_t) the context works on, for zero-copy consumers
  * (e.g. an NCCL all-reduce issued by the caller). */
 int lmb_film_device_ptr(lmb_ctx* ctx, void** dptr, uint64_t* n_floats);

@@ -98,6 +98,7 @@ void lmb_destroy(lmb_ctx* ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
+	comm_free(ctx);
 	wavefront_free(ctx);
 	cudaFree(ctx->film);
 	free_post(ctx);
@@ -238,6 +239,9 @@ int lmb_init(lmb_ctx* ctx, uint32_t width, uint32_t height, uint32_t frames_in_f
 	cudaFree(ctx->film);
 	ctx->film = nullptr;
 	free_post(ctx);
+	if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
+	cudaFree(ctx->reduce_buf);  // sized by the film
+	ctx->reduce_buf = nullptr, ctx->reduce_pending = false;
 	ctx->width = width, ctx->height = height;
 	if (shard_rows(ctx) == 0) return set_error(ctx, LMB_ERR_INVALID, "lmb_init: the pixel shard owns no row of this image");
 	LMB_CUDA(ctx, cudaMalloc((void**)&ctx->film, (size_t)width * height * 16));
@@ -387,7 +391,8 @@ int lmb_sync(lmb_ctx* ctx) {
 	cudaSetDevice(ctx->device);
 	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	if (ctx->copy_stream) LMB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
-	ctx->copy_pending = false;
+	if (ctx->comm_stream) LMB_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
+	ctx->copy_pending = false, ctx->reduce_pending = false;
 	return LMB_OK;
 }
 

@@ -156,6 +156,14 @@ struct lmb_ctx {
 	float4* gt_img = nullptr;         // ground-truth image of the RMSE routine ("gt_img_addr")
 	void* rmse_scratch = nullptr;
 	bool has_gt = false;
+	// multi-GPU exchange (comm.cu): NCCL communicator (ncclComm_t) of this rank, its own high-priority stream, the film snapshot the
+	// overlapped reduce works on
+	void* comm = nullptr;
+	int comm_rank = 0, comm_size = 1;
+	cudaStream_t comm_stream = nullptr;
+	cudaEvent_t ev_comm_ready = nullptr, ev_comm_done = nullptr;
+	float4* reduce_buf = nullptr;
+	bool reduce_pending = false;
 	// stats
 	lmb_stats stats{};
 	bool profile_stages = false;
@@ -185,6 +193,8 @@ int launch_trace_any(lmb_ctx* ctx, const float4* d_rays, uint32_t n, uint8_t* d_
 // ray slots with dead entries (NaN origin = hits nothing): closest hits into d_hits or occlusion bytes into d_occ; rays are NOT counted
 int launch_trace_slots(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits, uint8_t* d_occ, bool any);
 int launch_resolve(lmb_ctx* ctx);
+int launch_resolve_on(lmb_ctx* ctx, float4* film, cudaStream_t stream);  // k_resolve on any RGBA32F sum image of the film's size
+void comm_free(lmb_ctx* ctx);
 int ingest_triangles(lmb_ctx* ctx, const uint32_t* d_tri_first, const uint8_t* d_mat_q, uint32_t n_meshes, uint32_t n_materials, uint32_t n_tris,
 					 uint32_t* tri_mesh, uint32_t* tri_local, uint4* tri_rec, uint8_t* tri_matq);
 int launch_film_to_half(lmb_ctx* ctx, uint16_t* d_planes);

@@ -851,9 +851,10 @@ int probe_wide_tree(lmb_ctx* ctx, uint32_t n_rays, double* steps_per_ray) {
 int launch_trace_closest(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits) { return launch_trace_array(ctx, d_rays, n, d_hits, nullptr, false); }
 int launch_trace_any(lmb_ctx* ctx, const float4* d_rays, uint32_t n, uint8_t* d_occ) { return launch_trace_array(ctx, d_rays, n, nullptr, d_occ, true); }
 int launch_trace_slots(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits, uint8_t* d_occ, bool any) { return launch_trace_array(ctx, d_rays, n, d_hits, d_occ, any, 0); }
-int launch_resolve(lmb_ctx* ctx) {
-	k_resolve<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->width * ctx->height, ctx->film);
+int launch_resolve_on(lmb_ctx* ctx, float4* film, cudaStream_t stream) {
+	k_resolve<<<ctx->sm_count * 8, 256, 0, stream>>>(ctx->width * ctx->height, film);
 	return check_cuda(ctx, cudaGetLastError(), "k_resolve");
 }
+int launch_resolve(lmb_ctx* ctx) { return launch_resolve_on(ctx, ctx->film, ctx->stream); }
 
 }  // namespace lmb

@@ -6,7 +6,7 @@
 //   lumen_headless scene.(json|xml) [--width W] [--height H] [--spp N] [--depth D] [--out out.exr] [--device i] [--batch F]
 //                  [--ref gt.exr [--target-rmse X]] [--checkpoint file [--checkpoint-every N] [--resume]]
 //                  [--integrator path|bdpt|scene] [--time T]   BDPT (BDPTB200); --time fixes PCBDPT.time
-//                  [--devices 0,1,...]   several GPUs of one box: sample-index sharding, sum films reduced device to device
+//                  [--devices 0,1,...]   several GPUs of one box: sample-index sharding, sum films reduced by one NCCL all-reduce
 //                                        (PathB200Multi; a device may be listed twice; not combined with --ref / --checkpoint)
 // Progressive service: with --ref the RMSE against the ground-truth image is computed on the device
 // after every batch (Lumen does it every 5 s, RayTracer.cpp:453-461, and prints rmse * 1e6) and rendering stops early once
@@ -111,7 +111,7 @@ int main(int argc, char** argv) {
 			printf("%u x %u, %llu frames on %u devices, depth %u: %.1f ms on the slowest device, %.1f Mrays/s, %.2f spp/s\n", width, height,
 				   (unsigned long long)st.frames, n, multi.path_length, st.ms_render, rays / st.ms_render / 1e3, st.frames / (st.ms_render * 1e-3));
 			multi.save_exr(out.c_str());
-			printf("wrote %s\n", out.c_str());
+			printf("wrote %s (films reduced by %s)\n", out.c_str(), multi.reduces_with_nccl() ? "one NCCL all-reduce" : "device-to-device adds on device 0");
 			multi.destroy();
 			return 0;
 		}

@@ -101,8 +101,10 @@ class PathB200 final : public Integrator {
 
 // PathB200Multi: the same integrator over several GPUs of one box. Every device holds a full scene + BVH replica
 // and renders the frames f with f mod N == its rank over the whole image (sample-index sharding: perfect balance, no seams)
-// into an un-normalised sum film with the per-pixel valid-sample count in alpha (LMB_FILM_SUM); read_output() adds the films
-// on device 0 (lmb_film_add_from: device-to-device copies, NVLink where the peers are connected) in rank order and resolves.
+// into an un-normalised sum film with the per-pixel valid-sample count in alpha (LMB_FILM_SUM); read_output() reduces the films
+// with ONE NCCL all-reduce over NVLink / NVSwitch followed by the "/ count" epilogue on every device (lmb_comm_init_all +
+// lmb_film_allreduce; the contexts must sit on distinct GPUs). Where the same GPU is listed twice (one-GPU test boxes) NCCL cannot
+// be used (one rank per device) and the films are added on device 0 by device-to-device copies instead (lmb_film_add_from).
 // One host thread per device, because lmb_render is synchronous on return. render() advances frame_num by N * frames_per_call.
 #include <thread>
 
@@ -125,7 +127,16 @@ class PathB200Multi final : public Integrator {
 		scene_ubo = lumen_scene->make_ubo();
 		frame_num = 0;
 		reduced = false;
+		bool distinct = ctx.size() > 1;
+		for (size_t a = 0; a < devices.size(); a++)
+			for (size_t b = 0; b < a; b++) distinct = distinct && devices[a] != devices[b];
+		use_nccl = false;
+		if (distinct) {
+			check(0, lmb_comm_init_all(ctx.data(), (int)ctx.size()), "lmb_comm_init_all");
+			use_nccl = true;
+		}
 	}
+	bool reduces_with_nccl() const { return use_nccl; }
 	void create_accel() override {
 		each([&](size_t r) { check(r, lmb_build_accel(ctx[r]), "lmb_build_accel"); });
 	}
@@ -182,8 +193,16 @@ class PathB200Multi final : public Integrator {
 	// sum films -> device 0, in rank order, then rgb /= valid-sample count
 	void reduce() {
 		if (reduced) return;
-		for (size_t r = 1; r < ctx.size(); r++) check(0, lmb_film_add_from(ctx[0], ctx[r]), "lmb_film_add_from");
-		check(0, lmb_resolve(ctx[0]), "lmb_resolve");
+		if (use_nccl) {
+			// collective: every rank enqueues its all-reduce + resolve, then waits for its own stream
+			each([&](size_t r) {
+				check(r, lmb_film_allreduce(ctx[r], nullptr, 0), "lmb_film_allreduce");
+				check(r, lmb_sync(ctx[r]), "lmb_sync");
+			});
+		} else {
+			for (size_t r = 1; r < ctx.size(); r++) check(0, lmb_film_add_from(ctx[0], ctx[r]), "lmb_film_add_from");
+			check(0, lmb_resolve(ctx[0]), "lmb_resolve");
+		}
 		reduced = true;
 	}
 	template <typename F>
@@ -209,6 +228,7 @@ class PathB200Multi final : public Integrator {
 	uint32_t frames_per_call;
 	std::vector<lmb_ctx*> ctx;
 	bool reduced = false;
+	bool use_nccl = false;
 	lmb_pc_path pc_ray{};
 	lmb_scene_ubo scene_ubo{};
 	std::vector<float> film;

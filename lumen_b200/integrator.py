@@ -57,6 +57,12 @@ def lib():
         L.lmb_download.argtypes = [vp, vp]
         L.lmb_upload_film.argtypes = [vp, vp]
         L.lmb_film_add_from.argtypes = [vp, vp]
+        L.lmb_comm_get_unique_id.argtypes = [vp]
+        L.lmb_comm_init.argtypes = [vp, vp, i32, i32]
+        L.lmb_comm_init_all.argtypes = [vp, i32]
+        L.lmb_comm_destroy.argtypes = [vp]
+        L.lmb_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+        L.lmb_film_allreduce.argtypes = [vp, vp, i32]
         L.lmb_download_async.argtypes = [vp, vp]
         L.lmb_sync.argtypes = [vp]
         L.lmb_download_half_bgr.argtypes = [vp, vp]
@@ -90,9 +96,30 @@ def lib():
 EXPORTS = ["lmb_create", "lmb_destroy", "lmb_last_error", "lmb_upload_scene", "lmb_build_accel", "lmb_init", "lmb_render", "lmb_render_bdpt", "lmb_set_pixel_shard", "lmb_clear_film",
            "lmb_resolve", "lmb_download", "lmb_upload_film", "lmb_film_add_from", "lmb_film_device_ptr", "lmb_stream", "lmb_set_profile_stages", "lmb_get_stats",
            "lmb_reset_stats", "lmb_trace_closest", "lmb_trace_any", "lmb_trace_closest_device", "lmb_accel_num_tris", "lmb_accel_download",
-           "lmb_download_async", "lmb_sync", "lmb_download_half_bgr", "lmb_set_reference_image", "lmb_rmse"]
+           "lmb_download_async", "lmb_sync", "lmb_download_half_bgr", "lmb_set_reference_image", "lmb_rmse",
+           "lmb_comm_get_unique_id", "lmb_comm_init", "lmb_comm_init_all", "lmb_comm_destroy", "lmb_comm_info", "lmb_film_allreduce"]
 TESTHOOK_EXPORTS = ["lmb_kat_pcg4d", "lmb_kat_rand", "lmb_kat_detmath", "lmb_kat_offset_ray", "lmb_kat_sample_bsdf", "lmb_kat_eval_bsdf",
                     "lmb_kat_atmosphere", "lmb_kat_sample_light", "lmb_kat_texture", "lmb_kat_wide_bvh_check", "lmb_kat_bdpt_frame_raw"]
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the C ABI: rank 0 calls it and hands the bytes to the other ranks."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    rc = lib().lmb_comm_get_unique_id(C.addressof(buf))
+    if rc != 0:
+        raise RuntimeError(f"lmb_comm_get_unique_id failed ({rc}): " + lib().lmb_last_error(None).decode())
+    return bytes(buf)
+
+
+def comm_init_all(devices):
+    """One communicator over the Devices of THIS process (one per GPU): rank i = devices[i]."""
+    arr = (C.c_void_p * len(devices))(*[d._h for d in devices])
+    rc = lib().lmb_comm_init_all(C.addressof(arr), len(devices))
+    if rc != 0:
+        raise RuntimeError(f"lmb_comm_init_all failed ({rc}): " + lib().lmb_last_error(devices[0]._h).decode())
 
 
 def _f32(a):
@@ -214,6 +241,26 @@ class Device:
     def film_add_from(self, other):
         """self.film += other.film (sum films of a multi-GPU render; device-to-device copy)."""
         self._ck(lib().lmb_film_add_from(self._h, other._h), "lmb_film_add_from")
+
+    # ---- the exchange step of a multi-GPU render (include/lumen_b200.h lmb_comm_*): NCCL sum of the LMB_FILM_SUM films + resolve
+    def comm_init(self, unique_id, rank, n_ranks):
+        """Collective: every rank passes the 128 bytes rank 0 got from comm_unique_id()."""
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        self._ck(lib().lmb_comm_init(self._h, C.addressof(buf), int(rank), int(n_ranks)), "lmb_comm_init")
+
+    def comm_destroy(self):
+        self._ck(lib().lmb_comm_destroy(self._h), "lmb_comm_destroy")
+
+    def comm_info(self):
+        """(rank, n_ranks, nccl_version); n_ranks = 0 without a communicator."""
+        r, n, v = C.c_int32(), C.c_int32(), C.c_int32()
+        self._ck(lib().lmb_comm_info(self._h, C.byref(r), C.byref(n), C.byref(v)), "lmb_comm_info")
+        return r.value, n.value, v.value
+
+    def film_allreduce(self, out_ptr=None, clear_film=False):
+        """film -> NCCL sum over the ranks -> rgb / alpha. out_ptr None: in place on the render stream; else the snapshot is reduced
+        on the comm stream and copied to out_ptr (host or device address) while rendering goes on; sync() waits."""
+        self._ck(lib().lmb_film_allreduce(self._h, out_ptr, 1 if clear_film else 0), "lmb_film_allreduce")
 
     def film_device_ptr(self):
         p, n = C.c_void_p(), C.c_uint64()

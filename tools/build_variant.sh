@@ -9,10 +9,10 @@ mkdir -p "$out"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -prec-div=true -prec-sqrt=true -ftz=false -Xcompiler -fPIC -I$src/../../include --expt-relaxed-constexpr"
 pids=()
-for f in capi lbvh ploc wide_bvh wavefront bdpt post testhooks; do
+for f in capi lbvh ploc wide_bvh wavefront bdpt post testhooks comm; do
 	$NVCC $FLAGS "$@" -c "$src/$f.cu" -o "$out/$f.o" & pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$out/liblumen_b200.so" "$out"/*.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$out/liblumen_b200.so" "$out"/*.o -lcudart -ldl
 rm -f "$out"/*.o
 echo "built $out/liblumen_b200.so ($*)"
