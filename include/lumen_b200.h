@@ -71,6 +71,10 @@ typedef struct lmb_stats {
 	uint32_t ploc_iterations; /* clustering iterations of the traversal tree (0: the Karras tree is walked) */
 	float ms_build_ploc;   /* PLOC clustering over the sorted leaves (included in ms_build_accel) */
 	float tree_cost_ratio; /* probe-ray traversal steps of the clustered 8-wide tree / of the Karras one (the cheaper is walked; 0: not compared) */
+	/* k_trace's own scheduling counters (warp level, always on): trips of the traversal loop, trips in which some lane stepped a node,
+	 * warp-cooperative triangle rounds, 32-ray refills. With the per-section instruction counts of the committed ncu capture
+	 * (profiles/ktrace_calibration.json) they give the warp instructions the kernel issued -- the issue roofline of bench.py. */
+	uint64_t trace_warp_iters, trace_node_trips, trace_tri_rounds, trace_refills;
 } lmb_stats;
 
 typedef struct lmb_hit {

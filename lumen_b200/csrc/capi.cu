@@ -88,6 +88,8 @@ int lmb_create(lmb_ctx** out, int device_id) {
 	const char* tree = getenv("LMB_TREE");
 	ctx->use_ploc = !(tree && strcmp(tree, "lbvh") == 0);
 	ctx->tree_auto = !(tree && (strcmp(tree, "lbvh") == 0 || strcmp(tree, "ploc") == 0));
+	const char* spl = getenv("LMB_STATS_PER_LAUNCH");
+	ctx->stats_per_launch = spl && *spl && strcmp(spl, "0") != 0;
 	const char* pin = getenv("LMB_TRACE_PIN");
 	ctx->trace_pin = (pin && *pin) ? (atoi(pin) != 0) : -1;
 	*out = ctx;
@@ -486,6 +488,8 @@ int lmb_get_stats(lmb_ctx* ctx, lmb_stats* out) {
 		LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 		ctx->stats.rays_closest = h[ST_CLOSEST], ctx->stats.rays_shadow = h[ST_SHADOW], ctx->stats.rays_probe = h[ST_PROBE];
 		ctx->stats.nodes_visited = h[ST_NODES], ctx->stats.tris_tested = h[ST_TRIS], ctx->stats.nan_samples = h[ST_NAN];
+		ctx->stats.trace_warp_iters = h[ST_W_ITERS], ctx->stats.trace_node_trips = h[ST_W_NODE_TRIPS];
+		ctx->stats.trace_tri_rounds = h[ST_W_ROUNDS], ctx->stats.trace_refills = h[ST_W_REFILLS];
 #ifdef LMB_TRACE_PROFILE
 		fprintf(stderr, "k_trace profile: iters %llu node_trips %llu node_lanes %llu has_lanes %llu parked_lanes %llu rounds %llu pairs %llu refills %llu\n",
 				h[ST_P_ITERS], h[ST_P_NODE_TRIPS], h[ST_P_NODE_LANES], h[ST_P_HAS_LANES], h[ST_P_PARKED_LANES], h[ST_P_ROUNDS], h[ST_P_PAIRS], h[ST_P_REFILLS]);

@@ -114,6 +114,8 @@ struct BdptState {
 
 enum StatSlot {
 	ST_CLOSEST = 0, ST_SHADOW, ST_PROBE, ST_NODES, ST_TRIS, ST_NAN,
+	// warp-level scheduling counters of the wide walker, always on (lmb_stats.trace_*)
+	ST_W_ITERS, ST_W_NODE_TRIPS, ST_W_ROUNDS, ST_W_REFILLS,
 	// k_trace scheduling counters, filled only by a -DLMB_TRACE_PROFILE build (tools/gpu_variants.sh): warp trips of the inner
 	// loop, trips with a node step, lanes stepping, lanes owning a ray, lanes parked on triangles, rounds, pairs, refills
 	ST_P_ITERS, ST_P_NODE_TRIPS, ST_P_NODE_LANES, ST_P_HAS_LANES, ST_P_PARKED_LANES, ST_P_ROUNDS, ST_P_PAIRS, ST_P_REFILLS,
@@ -167,6 +169,7 @@ struct lmb_ctx {
 	// stats
 	lmb_stats stats{};
 	bool profile_stages = false;
+	bool stats_per_launch = false;  // LMB_STATS_PER_LAUNCH=1: print k_trace's counters after every launch (calibration runs only)
 	cudaEvent_t ev[8]{};
 };
 

@@ -142,6 +142,7 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 	uint32_t oct_inv4 = 0;
 	int sp = 0;
 	uint32_t n_nodes = 0, n_tris = 0, n_closest = 0, n_any = 0;
+	uint32_t w_iters = 0, w_node_trips = 0, w_rounds = 0, w_refills = 0;  // warp-uniform scheduling counters (lmb_stats.trace_*)
 #ifdef LMB_TRACE_PROFILE
 	uint32_t p_iters = 0, p_node_trips = 0, p_node_lanes = 0, p_has = 0, p_parked = 0, p_rounds = 0, p_pairs = 0, p_refills = 0;  // lane 0 only
 #endif
@@ -160,6 +161,7 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 #ifdef LMB_TRACE_PROFILE
 				p_refills++;
 #endif
+				w_refills++;
 				if (lane == 0) base = atomicAdd(cursor, 32u);
 				base = __shfl_sync(0xFFFFFFFFu, base, 0);
 				rq_head = 0, rq_count = base < count ? min(32u, count - base) : 0u;
@@ -211,7 +213,9 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 			}
 #endif
 			// ---- one node step
-			if (has && tg.y == 0u && ng.y > 0x00FFFFFFu) {
+			const bool stepping = has && tg.y == 0u && ng.y > 0x00FFFFFFu;
+			w_iters++, w_node_trips += __any_sync(0xFFFFFFFFu, stepping) ? 1u : 0u;
+			if (stepping) {
 				const uint32_t hits = ng.y;
 				const int bit = 31 - __clz(hits);
 				ng.y = hits & ~(1u << bit);
@@ -296,6 +300,7 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 				tri_lanes = 0u;
 			}
 			while (tri_lanes) {
+				w_rounds++;
 				const uint32_t cnt = (uint32_t)__popc(tg.y);
 				uint32_t incl = cnt;
 #pragma unroll
@@ -377,6 +382,8 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 	}
 #endif
 	if (lane == 0 && stats) {
+		atomicAdd(&stats[ST_W_ITERS], (unsigned long long)w_iters), atomicAdd(&stats[ST_W_NODE_TRIPS], (unsigned long long)w_node_trips);
+		atomicAdd(&stats[ST_W_ROUNDS], (unsigned long long)w_rounds), atomicAdd(&stats[ST_W_REFILLS], (unsigned long long)w_refills);
 		if (n_nodes) atomicAdd(&stats[ST_NODES], (unsigned long long)n_nodes);
 		if (n_tris) atomicAdd(&stats[ST_TRIS], (unsigned long long)n_tris);
 		if (n_closest && stat_closest >= 0) atomicAdd(&stats[stat_closest], (unsigned long long)n_closest);

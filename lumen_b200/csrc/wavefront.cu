@@ -719,6 +719,19 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 				k_trace<false><<<grid_trace_wide, LMB_TRACE_THREADS, 0, st>>>(wide, src, wf.counters, par, wf.stats);
 			ctx->stats.kernel_launches += 1;
 			if (prof) cudaEventRecord(ctx->ev[2], st);
+			if (ctx->stats_per_launch) {
+				// calibration aid (LMB_STATS_PER_LAUNCH=1, tools/calibrate_ktrace.py): the counters of THIS k_trace launch, in launch order,
+				// to be joined with ncu's per-launch smsp__inst_executed.sum
+				unsigned long long h[ST_COUNT];
+				cudaMemcpyAsync(h, wf.stats, sizeof(h), cudaMemcpyDeviceToHost, st);
+				cudaStreamSynchronize(st);
+				static thread_local unsigned long long prev[ST_COUNT] = {};
+				fprintf(stderr, "k_trace_launch {\"rays\": %llu, \"nodes\": %llu, \"tris\": %llu, \"iters\": %llu, \"node_trips\": %llu, \"rounds\": %llu, \"refills\": %llu}\n",
+						(h[ST_CLOSEST] + h[ST_SHADOW] + h[ST_PROBE]) - (prev[ST_CLOSEST] + prev[ST_SHADOW] + prev[ST_PROBE]), h[ST_NODES] - prev[ST_NODES],
+						h[ST_TRIS] - prev[ST_TRIS], h[ST_W_ITERS] - prev[ST_W_ITERS], h[ST_W_NODE_TRIPS] - prev[ST_W_NODE_TRIPS], h[ST_W_ROUNDS] - prev[ST_W_ROUNDS],
+						h[ST_W_REFILLS] - prev[ST_W_REFILLS]);
+				memcpy(prev, h, sizeof(h));
+			}
 			if (depth > 0) {
 				k_connect<<<grid_wide, 128, 0, st>>>(rp, ctx->scene, wf.counters, par, wf.nee_path, wf.nee, wf.probe_hit, wf.shadow_occ, wf.col[par], wf.n_slots);
 				ctx->stats.kernel_launches += 1;

@@ -25,7 +25,8 @@ class Stats(C.Structure):
                 ("ms_render", C.c_float), ("ms_extend", C.c_float), ("ms_shade", C.c_float), ("ms_connect", C.c_float), ("ms_film", C.c_float),
                 ("ms_build_accel", C.c_float), ("ms_build_morton", C.c_float), ("ms_build_sort", C.c_float), ("ms_build_tree", C.c_float),
                 ("ms_build_refit", C.c_float), ("ms_build_wide", C.c_float), ("wide_nodes", C.c_uint32), ("wide_levels", C.c_uint32),
-                ("ploc_iterations", C.c_uint32), ("ms_build_ploc", C.c_float), ("tree_cost_ratio", C.c_float)]
+                ("ploc_iterations", C.c_uint32), ("ms_build_ploc", C.c_float), ("tree_cost_ratio", C.c_float),
+                ("trace_warp_iters", C.c_uint64), ("trace_node_trips", C.c_uint64), ("trace_tri_rounds", C.c_uint64), ("trace_refills", C.c_uint64)]
 
     @property
     def rays(self):
