@@ -412,8 +412,7 @@ def main():
         sm_mhz = (clk or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
         issue_peak = n_sms * 4 * sm_mhz * 1e6 / 1e9  # G warp-instructions / s: 4 schedulers per SM, one warp instruction per cycle each
         w = cal.get("warp_inst_per", {})
-        warp_inst = (ps.trace_warp_iters * w.get("iters", 0.0) + ps.trace_node_trips * w.get("node_trips", 0.0) + ps.trace_tri_rounds * w.get("rounds", 0.0)
-                     + ps.trace_refills * w.get("refills", 0.0)) if w else None
+        warp_inst = (ps.trace_warp_iters * w.get("iters", 0.0) + ps.rays * w.get("rays", 0.0)) if w else None
         issue_achieved = warp_inst / (trav_ms * 1e-3) / 1e9 if (warp_inst and trav_ms > 0) else None
         mem_achieved = trav_bytes / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else 0.0
         roofline = {
@@ -421,8 +420,7 @@ def main():
             "achieved": issue_achieved, "peak": issue_peak, "unit": "Gwarp-inst/s", "frac": (issue_achieved / issue_peak) if issue_achieved else None,
             "peak_source": f"{n_sms} SMs x 4 schedulers x {sm_mhz:.0f} MHz (SM clock sampled by nvidia-smi during the timed region of this run)",
             "warp_inst_per_ray": (warp_inst / max(ps.rays, 1)) if warp_inst else None,
-            "counters": {"loop_trips": int(ps.trace_warp_iters), "node_trips": int(ps.trace_node_trips), "triangle_rounds": int(ps.trace_tri_rounds),
-                         "refills": int(ps.trace_refills), "rays": int(ps.rays)},
+            "counters": {"loop_trips": int(ps.trace_warp_iters), "rays": int(ps.rays)},
             "calibration": {"warp_inst_per": w, "max_rel_residual": cal.get("max_rel_residual"), "source": "profiles/ktrace_calibration.json (ncu smsp__inst_executed.sum per launch fitted on the kernel's counters)",
                             "stale": cal.get("stale", True)},
             "avg_launch_ms": trav_ms / n_trav_launches,
@@ -433,7 +431,7 @@ def main():
                             "nodes_per_ray": ps.nodes_visited / max(ps.rays, 1), "tris_per_ray": ps.tris_tested / max(ps.rays, 1)},
             "ncu": {k: traffic.get(k) for k in ("issue_active_pct", "alu_pipe_pct", "fma_pipe_pct", "active_lanes_per_instruction", "source")},
             "stage_ms": {"trace": ps.ms_extend, "shade": ps.ms_shade, "connect": ps.ms_connect, "raygen_sky_film": ps.ms_film, "total": ps.ms_render},
-            "note": "issue bound: warp instructions = the kernel's own trip / node-step / round / refill counters of THIS run x the per-counter instruction costs fitted on the committed ncu launch list; "
+            "note": "issue bound: warp instructions = the kernel's own loop-trip counter and ray count of THIS run x the per-trip / per-ray instruction costs fitted on the committed ncu launch list; "
                     "algorithmic bytes = wide nodes visited*80 + triangles tested*48 + rays*48 (DESIGN.md), served by L1/L2 here (traffic = ncu dram bytes per launch)",
         }
         roofline5 = None

@@ -71,9 +71,10 @@ typedef struct lmb_stats {
 	uint32_t ploc_iterations; /* clustering iterations of the traversal tree (0: the Karras tree is walked) */
 	float ms_build_ploc;   /* PLOC clustering over the sorted leaves (included in ms_build_accel) */
 	float tree_cost_ratio; /* probe-ray traversal steps of the clustered 8-wide tree / of the Karras one (the cheaper is walked; 0: not compared) */
-	/* k_trace's own scheduling counters (warp level, always on): trips of the traversal loop, trips in which some lane stepped a node,
-	 * warp-cooperative triangle rounds, 32-ray refills. With the per-section instruction counts of the committed ncu capture
-	 * (profiles/ktrace_calibration.json) they give the warp instructions the kernel issued -- the issue roofline of bench.py. */
+	/* k_trace's own scheduling counters (warp level, always on, one integer add each): trips of the traversal loop (every trip steps a
+	 * node in some lane: measured), warp-cooperative triangle rounds, 32-ray refills. With the per-counter instruction costs fitted on
+	 * the committed ncu launch list (profiles/ktrace_calibration.json) they give the warp instructions the kernel issued -- the
+	 * numerator of bench.py's issue roofline. trace_node_trips is kept for layout stability and equals trace_warp_iters. */
 	uint64_t trace_warp_iters, trace_node_trips, trace_tri_rounds, trace_refills;
 } lmb_stats;
 
@@ -182,6 +183,10 @@ int lmb_trace_closest(lmb_ctx* ctx, const float* rays, uint32_t n, lmb_hit* hits
 int lmb_trace_any(lmb_ctx* ctx, const float* rays, uint32_t n, uint8_t* occluded);
 /* Same on DEVICE pointers, timed with CUDA events (ms_out may be NULL); `repeat` launches back to back. */
 int lmb_trace_closest_device(lmb_ctx* ctx, const void* d_rays, uint32_t n, void* d_hits, uint32_t repeat, float* ms_out);
+/* ... with sort_rays != 0 every launch first orders the rays by (origin cell, direction octant) -- 18-bit keys, a counting sort on the
+ * device, timed with the launch -- so that the persistent walker's 32-ray fetches are coherent; hits land at the rays' own indices and
+ * do not depend on the order. Pays when the BVH does not fit the L2 (BASELINE config 5). */
+int lmb_trace_closest_device_ex(lmb_ctx* ctx, const void* d_rays, uint32_t n, void* d_hits, uint32_t repeat, int sort_rays, float* ms_out);
 
 /* LBVH read-back for the bit-exact topology check. n = triangle count.
  * left/right: n-1, parent: 2n-1, leaf_prim / morton: n, keys: n (uint64), aabb: 6*(2n-1). NULL pointers are skipped. */

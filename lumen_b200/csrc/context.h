@@ -23,6 +23,7 @@ struct DeviceScene {
 	const uint32_t* tri_mesh;   // global triangle id -> prim mesh index
 	const uint32_t* tri_local;  // global triangle id -> mesh-local triangle number
 	const uint4* tri_rec;       // global triangle id -> (vertex index of corner 0, 1, 2, prim mesh index)
+	const float4* tri_shade;    // global triangle id -> 8 float4 (one 128-byte line): corner positions / normals / uvs, mesh, material (build_hit)
 	const uint8_t* tri_matq;    // global triangle id -> shade queue of its material's BSDF type (0..5 = log2(bsdf_type), 6 = unknown)
 	const uint8_t* const* tex_data;  // per texture: RGBA8 texels
 	const uint2* tex_dims;
@@ -158,6 +159,9 @@ struct lmb_ctx {
 	float4* gt_img = nullptr;         // ground-truth image of the RMSE routine ("gt_img_addr")
 	void* rmse_scratch = nullptr;
 	bool has_gt = false;
+	// ray ordering scratch of the array queries (lbvh.cu sort_rays)
+	uint32_t *ray_keys = nullptr, *ray_order = nullptr, *ray_hist = nullptr;
+	uint32_t ray_sort_cap = 0;
 	// multi-GPU exchange (comm.cu): NCCL communicator (ncclComm_t) of this rank, its own high-priority stream, the film snapshot the
 	// overlapped reduce works on
 	void* comm = nullptr;
@@ -191,7 +195,8 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, uint32_t first_frame, uint32_t n_frames, uint32_t frame_stride, int film_mode,
 				float* raw_col, float* raw_splat);
 void bdpt_free(lmb_ctx* ctx);
-int launch_trace_closest(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits);
+int launch_trace_closest(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits, const uint32_t* order = nullptr);
+int sort_rays(lmb_ctx* ctx, const float4* d_rays, uint32_t n, const uint32_t** order_out);
 int launch_trace_any(lmb_ctx* ctx, const float4* d_rays, uint32_t n, uint8_t* d_occ);
 // ray slots with dead entries (NaN origin = hits nothing): closest hits into d_hits or occlusion bytes into d_occ; rays are NOT counted
 int launch_trace_slots(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits, uint8_t* d_occ, bool any);
@@ -199,7 +204,7 @@ int launch_resolve(lmb_ctx* ctx);
 int launch_resolve_on(lmb_ctx* ctx, float4* film, cudaStream_t stream);  // k_resolve on any RGBA32F sum image of the film's size
 void comm_free(lmb_ctx* ctx);
 int ingest_triangles(lmb_ctx* ctx, const uint32_t* d_tri_first, const uint8_t* d_mat_q, uint32_t n_meshes, uint32_t n_materials, uint32_t n_tris,
-					 uint32_t* tri_mesh, uint32_t* tri_local, uint4* tri_rec, uint8_t* tri_matq);
+					 uint32_t* tri_mesh, uint32_t* tri_local, uint4* tri_rec, uint8_t* tri_matq, float4* tri_shade);
 int launch_film_to_half(lmb_ctx* ctx, uint16_t* d_planes);
 int launch_film_add(lmb_ctx* ctx, const float4* d_other);
 size_t rmse_scratch_bytes(uint32_t n_pix);

@@ -191,6 +191,36 @@ __global__ void __launch_bounds__(RADIX_THREADS) k_radix_scatter(const uint64_t*
 	}
 }
 
+// ---- ray ordering for array queries (lmb_trace_closest_device_ex, sort_rays): key = 15-bit Morton code of the origin's cell in the
+// scene box (5 bits per axis, outside origins clamp) followed by the direction octant (3 bits). A counting sort over the 2^18 bins
+// (histogram by global atomics, one scan, scatter by atomics on the bin cursors: three light kernels, ~0.1 ms per million rays; an
+// LSD radix sort of the same keys cost three times that and ate the gain). Rays that start in the same region and head the same
+// way become neighbours in the persistent walker's 32-ray fetches: their node and triangle fetches hit the same L1 / L2 lines.
+// The order inside a bin is whatever the atomics give; hits land at the rays' own indices and do not depend on it.
+constexpr uint32_t RAY_BINS = 1u << 18;
+__global__ void __launch_bounds__(256) k_ray_keys(const float4* __restrict__ rays, uint32_t n, const uint32_t* __restrict__ bounds_enc, uint32_t* __restrict__ keys,
+												   uint32_t* __restrict__ hist) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float4 o = rays[2 * (size_t)i], d = rays[2 * (size_t)i + 1];
+	const V3 lo = v3(dec_float(bounds_enc[0]), dec_float(bounds_enc[1]), dec_float(bounds_enc[2]));
+	const V3 hi = v3(dec_float(bounds_enc[3]), dec_float(bounds_enc[4]), dec_float(bounds_enc[5]));
+	auto cell = [](float v, float a, float b) {
+		const float t = (v - a) / fmaxf(b - a, 1e-30f) * 32.0f;
+		return (uint32_t)fminf(fmaxf(t, 0.0f), 31.0f);  // NaN -> 0
+	};
+	const uint32_t om = (expand_bits10(cell(o.x, lo.x, hi.x)) << 2) | (expand_bits10(cell(o.y, lo.y, hi.y)) << 1) | expand_bits10(cell(o.z, lo.z, hi.z));
+	const uint32_t oct = (d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u);
+	const uint32_t key = ((om & 0x7FFFu) << 3) | oct;
+	keys[i] = key;
+	atomicAdd(&hist[key], 1u);
+}
+__global__ void __launch_bounds__(256) k_ray_scatter(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	order[atomicAdd(&cursor[keys[i]], 1u)] = i;
+}
+
 // ---- Karras 2012 ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, uint64_t ki, int j) {
 	if (j < 0 || j >= n) return -1;
@@ -297,6 +327,26 @@ void free_bvh(lmb_ctx* ctx) {
 	b = DeviceBvh{};
 	free_wide_bvh(ctx);
 	free_ploc(ctx);
+}
+
+// Order of `n` rays (device array of 2 float4 each) for the array walker: (*order_out)[i] = index of the i-th ray to trace. Scratch is
+// kept in the context and grows on demand.
+int sort_rays(lmb_ctx* ctx, const float4* d_rays, uint32_t n, const uint32_t** order_out) {
+	if (!ctx->bvh.bounds_enc) return set_error(ctx, LMB_ERR_INVALID, "sort_rays: no accel built");
+	cudaStream_t st = ctx->stream;
+	if (ctx->ray_sort_cap < n) {
+		cudaFree(ctx->ray_keys), cudaFree(ctx->ray_order), cudaFree(ctx->ray_hist);
+		ctx->ray_keys = ctx->ray_order = ctx->ray_hist = nullptr, ctx->ray_sort_cap = 0;
+		int rc;
+		if ((rc = dmalloc(ctx, &ctx->ray_keys, n)) || (rc = dmalloc(ctx, &ctx->ray_order, n)) || (rc = dmalloc(ctx, &ctx->ray_hist, RAY_BINS))) return rc;
+		ctx->ray_sort_cap = n;
+	}
+	cudaMemsetAsync(ctx->ray_hist, 0, RAY_BINS * sizeof(uint32_t), st);
+	k_ray_keys<<<(n + 255) / 256, 256, 0, st>>>(d_rays, n, ctx->bvh.bounds_enc, ctx->ray_keys, ctx->ray_hist);
+	k_scan_exclusive<<<1, 1024, 0, st>>>(ctx->ray_hist, RAY_BINS);
+	k_ray_scatter<<<(n + 255) / 256, 256, 0, st>>>(ctx->ray_keys, n, ctx->ray_hist, ctx->ray_order);
+	*order_out = ctx->ray_order;
+	return check_cuda(ctx, cudaGetLastError(), "sort_rays");
 }
 
 int build_lbvh(lmb_ctx* ctx) {

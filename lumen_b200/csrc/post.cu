@@ -18,7 +18,8 @@ namespace {
 __global__ void __launch_bounds__(256) k_ingest_triangles(const lmb_prim_mesh_info* __restrict__ prim_infos, const uint32_t* __restrict__ indices,
 															 const uint32_t* __restrict__ tri_first, const uint8_t* __restrict__ mat_q, uint32_t n_meshes,
 															 uint32_t n_materials, uint32_t n_tris, uint32_t* __restrict__ tri_mesh, uint32_t* __restrict__ tri_local,
-															 uint4* __restrict__ tri_rec, uint8_t* __restrict__ tri_matq) {
+															 uint4* __restrict__ tri_rec, uint8_t* __restrict__ tri_matq, const lmb_vertex* __restrict__ vertices,
+															 float4* __restrict__ tri_shade) {
 	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tris; t += gridDim.x * blockDim.x) {
 		uint32_t lo = 0, hi = n_meshes;  // last m with tri_first[m] <= t
 		while (hi - lo > 1) {
@@ -33,6 +34,17 @@ __global__ void __launch_bounds__(256) k_ingest_triangles(const lmb_prim_mesh_in
 		tri_local[t] = local;
 		tri_rec[t] = make_uint4(ix[0] + pi.vertex_offset, ix[1] + pi.vertex_offset, ix[2] + pi.vertex_offset, m);
 		tri_matq[t] = pi.material_index < n_materials ? mat_q[pi.material_index] : (uint8_t)6;
+		// the shading record of build_hit (scene_device.cuh): positions, normals, uvs of the three corners, mesh, material
+		const lmb_vertex a = vertices[ix[0] + pi.vertex_offset], b = vertices[ix[1] + pi.vertex_offset], c = vertices[ix[2] + pi.vertex_offset];
+		float4* r = tri_shade + 8 * (size_t)t;
+		r[0] = make_float4(a.pos[0], a.pos[1], a.pos[2], a.uv0[0]);
+		r[1] = make_float4(b.pos[0], b.pos[1], b.pos[2], a.uv0[1]);
+		r[2] = make_float4(c.pos[0], c.pos[1], c.pos[2], b.uv0[0]);
+		r[3] = make_float4(a.normal[0], a.normal[1], a.normal[2], b.uv0[1]);
+		r[4] = make_float4(b.normal[0], b.normal[1], b.normal[2], c.uv0[0]);
+		r[5] = make_float4(c.normal[0], c.normal[1], c.normal[2], c.uv0[1]);
+		r[6] = make_float4(__uint_as_float(m), __uint_as_float(pi.material_index), 0.0f, 0.0f);
+		r[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 	}
 }
 
@@ -146,11 +158,11 @@ __global__ void k_rmse_output(const float* residual, const double* sq_sum, uint3
 }  // namespace
 
 int ingest_triangles(lmb_ctx* ctx, const uint32_t* d_tri_first, const uint8_t* d_mat_q, uint32_t n_meshes, uint32_t n_materials, uint32_t n_tris,
-					 uint32_t* tri_mesh, uint32_t* tri_local, uint4* tri_rec, uint8_t* tri_matq) {
+					 uint32_t* tri_mesh, uint32_t* tri_local, uint4* tri_rec, uint8_t* tri_matq, float4* tri_shade) {
 	if (n_tris == 0) return 0;
 	const int grid = std::min<uint32_t>((n_tris + 255) / 256, (uint32_t)ctx->sm_count * 8);
 	k_ingest_triangles<<<grid, 256, 0, ctx->stream>>>(ctx->scene.prim_infos, ctx->scene.indices, d_tri_first, d_mat_q, n_meshes, n_materials, n_tris, tri_mesh,
-														 tri_local, tri_rec, tri_matq);
+														 tri_local, tri_rec, tri_matq, ctx->scene.vertices, tri_shade);
 	return check_cuda(ctx, cudaGetLastError(), "k_ingest_triangles");
 }
 

@@ -55,8 +55,27 @@ LMB_D V3 vtx_nrm(const lmb_vertex& v) { return v3(v.normal[0], v.normal[1], v.no
 // `tri_rec[prim]` = (absolute vertex index of each corner, prim mesh index): the PrimMeshInfo -> index buffer -> vertex chain
 // of ray.rchit:27-33 resolved once at upload, so the hit record costs one dependent fetch before the vertices instead of three.
 // payload.triangle_idx (gl_PrimitiveID) is only compared by the area-light MIS probe: callers read sc.tri_local[prim] there.
+//
+// LMB_HIT_PACKED (default): `tri_shade[prim]` holds everything ray.rchit reads for one triangle -- the three corners' positions,
+// normals and uvs, the mesh and its material index -- as ONE 128-byte-aligned record (7 x float4 used), gathered once at upload
+// (post.cu k_ingest_triangles). The hit record then costs a single dependent 128-byte line instead of tri_rec (16 B) followed by three
+// 32-byte vertex fetches at scattered addresses and the PrimMeshInfo: one level less in k_shade's dependent gather chain, which is
+// what that kernel waits on (profiles/r01i: 24 % occupancy, long-scoreboard stalls 4-6 warps per issue). Same values, same
+// arithmetic, same results.
+#ifndef LMB_HIT_PACKED
+#define LMB_HIT_PACKED 1
+#endif
 LMB_DN HitPayload build_hit(const DeviceScene& sc, uint32_t prim_global, float b1, float b2) {
 	HitPayload p;
+#if LMB_HIT_PACKED
+	const float4* __restrict__ r = sc.tri_shade + 8 * (size_t)prim_global;
+	const float4 r0 = __ldg(r + 0), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3), r4 = __ldg(r + 4), r5 = __ldg(r + 5), r6 = __ldg(r + 6);
+	const uint32_t mesh = __float_as_uint(r6.x);
+	const V3 q0 = v3(r0.x, r0.y, r0.z), q1 = v3(r1.x, r1.y, r1.z), q2 = v3(r2.x, r2.y, r2.z);
+	const V3 n0 = v3(r3.x, r3.y, r3.z), n1 = v3(r4.x, r4.y, r4.z), n2 = v3(r5.x, r5.y, r5.z);
+	const V2 t0 = v2(r0.w, r1.w), t1 = v2(r2.w, r3.w), t2 = v2(r4.w, r5.w);
+	p.material_idx = __float_as_uint(r6.y);
+#else
 	const uint4 rec = __ldg(&sc.tri_rec[prim_global]);
 	const uint32_t mesh = rec.w;
 	const lmb_vertex a0 = sc.vertices[rec.x];
@@ -64,6 +83,9 @@ LMB_DN HitPayload build_hit(const DeviceScene& sc, uint32_t prim_global, float b
 	const lmb_vertex a2 = sc.vertices[rec.z];
 	const V3 q0 = vtx_pos(a0), q1 = vtx_pos(a1), q2 = vtx_pos(a2);
 	const V3 n0 = vtx_nrm(a0), n1 = vtx_nrm(a1), n2 = vtx_nrm(a2);
+	const V2 t0 = v2(a0.uv0[0], a0.uv0[1]), t1 = v2(a1.uv0[0], a1.uv0[1]), t2 = v2(a2.uv0[0], a2.uv0[1]);
+	p.material_idx = sc.prim_infos[mesh].material_index;
+#endif
 	const V3 bary = v3(1.0f - b1 - b2, b1, b2);
 	const M4 o2w = load_m4(sc.world_matrices + 16 * mesh);
 	const M4 w2o = load_m4(sc.inv_world_matrices + 16 * mesh);
@@ -71,11 +93,10 @@ LMB_DN HitPayload build_hit(const DeviceScene& sc, uint32_t prim_global, float b
 	p.pos = xyz(mul(o2w, v4(pos, 1.0f)));
 	const V3 nrm = normalize(n0 * bary.x + n1 * bary.y + n2 * bary.z);
 	p.n_s = normalize(mul_row(nrm, w2o));
-	p.uv = v2(a0.uv0[0], a0.uv0[1]) * bary.x + v2(a1.uv0[0], a1.uv0[1]) * bary.y + v2(a2.uv0[0], a2.uv0[1]) * bary.z;
+	p.uv = t0 * bary.x + t1 * bary.y + t2 * bary.z;
 	const V3 e0 = q2 - q0;
 	const V3 e1 = q1 - q0;
 	p.n_g = normalize(mul_row(cross(e0, e1), w2o));
-	p.material_idx = sc.prim_infos[mesh].material_index;
 	p.triangle_idx = 0xFFFFFFFFu;
 	p.instance_idx = mesh;
 	return p;

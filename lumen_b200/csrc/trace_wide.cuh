@@ -45,6 +45,12 @@ struct WideBvhView {
 #ifndef LMB_TRI_ROUND_LANES
 #define LMB_TRI_ROUND_LANES 8
 #endif
+#ifndef LMB_TRACE_WCOUNT
+#define LMB_TRACE_WCOUNT 1  // warp-level scheduling counters kept by the walker: 0 none, 1 loop trips, 3 + triangle rounds and refills
+#endif
+#ifndef LMB_PREFETCH
+#define LMB_PREFETCH 0  // 1: leaf triangles, 2: + entered children, of the unpinned (BVH beyond the L2) instantiation
+#endif
 
 // Ray constants of the triangle test as one lane publishes them for the whole warp (see the triangle phase below).
 struct TriRay {
@@ -142,7 +148,7 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 	uint32_t oct_inv4 = 0;
 	int sp = 0;
 	uint32_t n_nodes = 0, n_tris = 0, n_closest = 0, n_any = 0;
-	uint32_t w_iters = 0, w_node_trips = 0, w_rounds = 0, w_refills = 0;  // warp-uniform scheduling counters (lmb_stats.trace_*)
+	uint32_t w_iters = 0, w_rounds = 0, w_refills = 0;  // warp-uniform scheduling counters (lmb_stats.trace_*): one IADD each
 #ifdef LMB_TRACE_PROFILE
 	uint32_t p_iters = 0, p_node_trips = 0, p_node_lanes = 0, p_has = 0, p_parked = 0, p_rounds = 0, p_pairs = 0, p_refills = 0;  // lane 0 only
 #endif
@@ -161,7 +167,9 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 #ifdef LMB_TRACE_PROFILE
 				p_refills++;
 #endif
+#if LMB_TRACE_WCOUNT > 1
 				w_refills++;
+#endif
 				if (lane == 0) base = atomicAdd(cursor, 32u);
 				base = __shfl_sync(0xFFFFFFFFu, base, 0);
 				rq_head = 0, rq_count = base < count ? min(32u, count - base) : 0u;
@@ -213,9 +221,10 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 			}
 #endif
 			// ---- one node step
-			const bool stepping = has && tg.y == 0u && ng.y > 0x00FFFFFFu;
-			w_iters++, w_node_trips += __any_sync(0xFFFFFFFFu, stepping) ? 1u : 0u;
-			if (stepping) {
+#if LMB_TRACE_WCOUNT > 0
+			w_iters++;
+#endif
+			if (has && tg.y == 0u && ng.y > 0x00FFFFFFu) {
 				const uint32_t hits = ng.y;
 				const int bit = 31 - __clz(hits);
 				ng.y = hits & ~(1u << bit);
@@ -285,6 +294,30 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 				tl = mw & 0x00FFFFFFu;
 				ng = make_uint2(__float_as_uint(n1.x), (ih << 24) | imask);
 				tg = make_uint2(__float_as_uint(n1.y), (lh * 7u) & tl);
+#if LMB_PREFETCH
+				if (!PIN) {
+					// The unpinned instantiation runs when nodes + triangles exceed the L2 (wavefront.cu trace_pinned): the walk then waits on
+					// DRAM at every level (10 M-triangle grid: long-scoreboard stalls 6 warps per issue, DRAM 14 % of peak). What this node step
+					// just found out is fetched ahead: the leaf triangles of the coming round (contiguous per node: one or two lines) and the
+					// entered children (the 8 children of a node are contiguous, 80 B each), which otherwise miss one after the other as the
+					// ray comes back to them.
+					if (tg.y) {
+						const char* tp = (const char*)(bvh.tris + 3 * (size_t)tg.x);
+						asm volatile("prefetch.global.L2 [%0];" ::"l"(tp));
+						asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + 128));
+					}
+#if LMB_PREFETCH > 1
+					uint32_t pm = hits8 & imask;
+					while (pm) {
+						const int slot = __ffs((int)pm) - 1;
+						pm &= pm - 1u;
+						const char* cp = (const char*)(bvh.nodes + 5 * (size_t)(ng.x + __popc(imask & ((1u << slot) - 1u))));
+						asm volatile("prefetch.global.L2 [%0];" ::"l"(cp));
+						asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + 79));
+					}
+#endif
+				}
+#endif
 			}
 			// ---- triangle phase, warp-cooperative: the (owner lane, triangle) pairs of all lanes are spread over the 32 lanes,
 			// tested once each (any lane tests for any owner: the owner's ray constants sit in shared memory), and every owner
@@ -300,7 +333,9 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 				tri_lanes = 0u;
 			}
 			while (tri_lanes) {
+#if LMB_TRACE_WCOUNT > 1
 				w_rounds++;
+#endif
 				const uint32_t cnt = (uint32_t)__popc(tg.y);
 				uint32_t incl = cnt;
 #pragma unroll
@@ -382,8 +417,9 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 	}
 #endif
 	if (lane == 0 && stats) {
-		atomicAdd(&stats[ST_W_ITERS], (unsigned long long)w_iters), atomicAdd(&stats[ST_W_NODE_TRIPS], (unsigned long long)w_node_trips);
-		atomicAdd(&stats[ST_W_ROUNDS], (unsigned long long)w_rounds), atomicAdd(&stats[ST_W_REFILLS], (unsigned long long)w_refills);
+		if (w_iters) atomicAdd(&stats[ST_W_ITERS], (unsigned long long)w_iters);
+		if (w_rounds) atomicAdd(&stats[ST_W_ROUNDS], (unsigned long long)w_rounds);
+		if (w_refills) atomicAdd(&stats[ST_W_REFILLS], (unsigned long long)w_refills);
 		if (n_nodes) atomicAdd(&stats[ST_NODES], (unsigned long long)n_nodes);
 		if (n_tris) atomicAdd(&stats[ST_TRIS], (unsigned long long)n_tris);
 		if (n_closest && stat_closest >= 0) atomicAdd(&stats[stat_closest], (unsigned long long)n_closest);

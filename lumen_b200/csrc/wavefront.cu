@@ -566,8 +566,10 @@ struct ArraySource {
 	float4* __restrict__ hits;
 	uint8_t* __restrict__ occ;
 	bool any_hit;
+	const uint32_t* __restrict__ order;  // optional: entry i = index of the i-th ray to trace (sort_rays)
 	__device__ __forceinline__ bool is_any(uint32_t) const { return any_hit; }
 	__device__ __forceinline__ void load(uint32_t i, V3& o, V3& d, float& tmin, float& tmax, uint32_t& tag) const {
+		if (order) i = order[i];
 		const float4 o4 = rays[2 * (size_t)i], d4 = rays[2 * (size_t)i + 1];
 		o = xyz(o4), d = xyz(d4), tmin = o4.w, tmax = d4.w, tag = i;
 	}
@@ -728,7 +730,7 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 				static thread_local unsigned long long prev[ST_COUNT] = {};
 				fprintf(stderr, "k_trace_launch {\"rays\": %llu, \"nodes\": %llu, \"tris\": %llu, \"iters\": %llu, \"node_trips\": %llu, \"rounds\": %llu, \"refills\": %llu}\n",
 						(h[ST_CLOSEST] + h[ST_SHADOW] + h[ST_PROBE]) - (prev[ST_CLOSEST] + prev[ST_SHADOW] + prev[ST_PROBE]), h[ST_NODES] - prev[ST_NODES],
-						h[ST_TRIS] - prev[ST_TRIS], h[ST_W_ITERS] - prev[ST_W_ITERS], h[ST_W_NODE_TRIPS] - prev[ST_W_NODE_TRIPS], h[ST_W_ROUNDS] - prev[ST_W_ROUNDS],
+						h[ST_TRIS] - prev[ST_TRIS], h[ST_W_ITERS] - prev[ST_W_ITERS], h[ST_W_ITERS] - prev[ST_W_ITERS], h[ST_W_ROUNDS] - prev[ST_W_ROUNDS],
 						h[ST_W_REFILLS] - prev[ST_W_REFILLS]);
 				memcpy(prev, h, sizeof(h));
 			}
@@ -797,14 +799,14 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 }
 
 // count_rays = 0: the caller counts its own rays (BDPT's ray slots hold dead entries, which must not be counted)
-static int launch_trace_array(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits, uint8_t* d_occ, bool any, int count_rays = 1) {
+static int launch_trace_array(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits, uint8_t* d_occ, bool any, int count_rays = 1, const uint32_t* order = nullptr) {
 	uint32_t* cursor = ctx->wf.trace_cursor;
 	if (!cursor) {
 		LMB_CUDA(ctx, cudaMalloc((void**)&ctx->wf.trace_cursor, 4));
 		cursor = ctx->wf.trace_cursor;
 	}
 	LMB_CUDA(ctx, cudaMemsetAsync(cursor, 0, 4, ctx->stream));
-	const ArraySource src{d_rays, d_hits, d_occ, any};
+	const ArraySource src{d_rays, d_hits, d_occ, any, order};
 	if (ctx->use_bvh2)
 		k_trace_array_bvh2<<<ctx->sm_count * 7, LMB_TRACE_THREADS, 0, ctx->stream>>>(view_of(ctx), src, n, cursor, ctx->wf.stats, count_rays);
 	else if (trace_pinned(ctx))
@@ -861,7 +863,9 @@ int probe_wide_tree(lmb_ctx* ctx, uint32_t n_rays, double* steps_per_ray) {
 	return rc;
 }
 
-int launch_trace_closest(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits) { return launch_trace_array(ctx, d_rays, n, d_hits, nullptr, false); }
+int launch_trace_closest(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits, const uint32_t* order) {
+	return launch_trace_array(ctx, d_rays, n, d_hits, nullptr, false, 1, order);
+}
 int launch_trace_any(lmb_ctx* ctx, const float4* d_rays, uint32_t n, uint8_t* d_occ) { return launch_trace_array(ctx, d_rays, n, nullptr, d_occ, true); }
 int launch_trace_slots(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits, uint8_t* d_occ, bool any) { return launch_trace_array(ctx, d_rays, n, d_hits, d_occ, any, 0); }
 int launch_resolve_on(lmb_ctx* ctx, float4* film, cudaStream_t stream) {

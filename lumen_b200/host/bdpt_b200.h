@@ -16,6 +16,7 @@
 
 #include "integrator.h"
 #include "lumen_b200.h"
+#include "path_b200.h"  // ShardedMulti
 
 class BDPTB200 final : public Integrator {
   public:
@@ -87,4 +88,31 @@ class BDPTB200 final : public Integrator {
 	lmb_scene_ubo scene_ubo{};
 	std::vector<float> film;
 	std::vector<uint16_t> half_planes;
+};
+
+// BDPTB200Multi: BDPT over several GPUs of one box (SURVEY.md 8e on the 8f-3 row; the reference's BDPT drives one GPU,
+// src/RayTracer/BDPT.cpp:55-95). Same sharding and the same reduce as PathB200Multi: device r renders the frames f with f mod N == r
+// through lmb_render_bdpt into its LMB_FILM_SUM film (col + the frame's own light-tracer splats), one NCCL all-reduce + resolve.
+// pc.time is one value per render() round, the same on every device (bdpt.rgen:36-37 seeds with frame ^ time).
+class BDPTB200Multi final : public ShardedMulti {
+  public:
+	using ShardedMulti::ShardedMulti;
+	void set_time(uint32_t t) { has_fixed_time = true, fixed_time = t; }
+
+  protected:
+	void prepare_frame() override {
+		const lmb_pc_path p = lumen_scene->make_pc((int)path_length, true);
+		std::memcpy(&pc_ray, &p, sizeof(pc_ray));
+		pc_ray.frame_num = frame_num;
+		pc_ray.time = has_fixed_time ? fixed_time : (uint32_t)(rand() % UINT_MAX);
+	}
+	int render_shard(lmb_ctx* c, uint32_t first_frame, uint32_t n_frames, uint32_t frame_stride) override {
+		return lmb_render_bdpt(c, &pc_ray, &scene_ubo, first_frame, n_frames, frame_stride, LMB_FILM_SUM);
+	}
+	const char* what() const override { return "lmb_render_bdpt"; }
+
+  private:
+	bool has_fixed_time = false;
+	uint32_t fixed_time = 0;
+	lmb_pc_bdpt pc_ray{};
 };

@@ -75,8 +75,29 @@ int main(int argc, char** argv) {
 			fprintf(stderr, "note: scene asks for integrator '%s'; rendering with '%s'\n", scene.config.integrator_name.c_str(), integrator_name.c_str());
 		}
 		batch = std::max(1u, std::min(batch, spp));
+		if (integrator_name == "bdpt" && devices.size() > 1) {
+			if (!ref_path.empty() || !ckpt_path.empty()) throw std::runtime_error("--devices cannot be combined with --ref / --checkpoint");
+			const uint32_t n = (uint32_t)devices.size();
+			BDPTB200Multi multi(&scene, devices, batch);
+			if (depth > 0) multi.path_length = (uint32_t)depth;
+			if (bdpt_time >= 0) multi.set_time((uint32_t)bdpt_time);
+			multi.init();
+			multi.create_accel();
+			while (multi.frame_num + batch * n <= spp) {
+				multi.render();
+				multi.update();
+			}
+			const lmb_stats st = multi.stats();
+			const double rays = (double)(st.rays_closest + st.rays_shadow);
+			printf("%u x %u, %llu frames on %u devices, BDPT depth %u: %.1f ms on the slowest device, %.1f Mrays/s, %.2f spp/s\n", width, height,
+				   (unsigned long long)st.frames, n, multi.path_length, st.ms_render, rays / st.ms_render / 1e3, st.frames / (st.ms_render * 1e-3));
+			multi.save_exr(out.c_str());
+			printf("wrote %s (films reduced by %s)\n", out.c_str(), multi.reduces_with_nccl() ? "one NCCL all-reduce" : "device-to-device adds on device 0");
+			multi.destroy();
+			return 0;
+		}
 		if (integrator_name == "bdpt") {
-			if (devices.size() > 1 || !ref_path.empty() || !ckpt_path.empty()) throw std::runtime_error("--integrator bdpt cannot be combined with --devices / --ref / --checkpoint");
+			if (!ref_path.empty() || !ckpt_path.empty()) throw std::runtime_error("--integrator bdpt cannot be combined with --ref / --checkpoint");
 			BDPTB200 bdpt(&scene, device, batch);
 			if (depth > 0) bdpt.path_length = (uint32_t)depth;
 			if (bdpt_time >= 0) bdpt.set_time((uint32_t)bdpt_time);

@@ -108,13 +108,14 @@ class PathB200 final : public Integrator {
 // One host thread per device, because lmb_render is synchronous on return. render() advances frame_num by N * frames_per_call.
 #include <thread>
 
-class PathB200Multi final : public Integrator {
+// ShardedMulti holds everything but the render call; PathB200Multi and BDPTB200Multi (bdpt_b200.h) supply it.
+class ShardedMulti : public Integrator {
   public:
-	PathB200Multi(lmh::Scene* scene, std::vector<int> devices, uint32_t frames_per_call = 1)
-		: Integrator(scene), devices(std::move(devices)), frames_per_call(frames_per_call), path_length((uint32_t)scene->config.path_length) {
-		if (this->devices.empty()) throw std::runtime_error("PathB200Multi: no device");
+	ShardedMulti(lmh::Scene* scene, std::vector<int> devices, uint32_t frames_per_call = 1)
+		: Integrator(scene), path_length((uint32_t)scene->config.path_length), devices(std::move(devices)), frames_per_call(frames_per_call) {
+		if (this->devices.empty()) throw std::runtime_error("ShardedMulti: no device");
 	}
-	~PathB200Multi() override { destroy(); }
+	~ShardedMulti() override { destroy(); }
 
 	void init() override {
 		ctx.assign(devices.size(), nullptr);
@@ -141,11 +142,10 @@ class PathB200Multi final : public Integrator {
 		each([&](size_t r) { check(r, lmb_build_accel(ctx[r]), "lmb_build_accel"); });
 	}
 	void render() override {
-		if (reduced) throw std::runtime_error("PathB200Multi: render() after read_output() needs init() (device 0 holds the reduced film)");
-		pc_ray = lumen_scene->make_pc((int)path_length, direct_lighting);
-		pc_ray.frame_num = frame_num;
+		if (reduced) throw std::runtime_error("ShardedMulti: render() after read_output() needs init() (the films hold the reduced image)");
+		prepare_frame();
 		const uint32_t n = (uint32_t)ctx.size();
-		each([&](size_t r) { check(r, lmb_render(ctx[r], &pc_ray, &scene_ubo, frame_num + (uint32_t)r, frames_per_call, n, LMB_FILM_SUM), "lmb_render"); });
+		each([&](size_t r) { check(r, render_shard(ctx[r], frame_num + (uint32_t)r, frames_per_call, n), what()); });
 	}
 	bool update() override {
 		frame_num += frames_per_call * (uint32_t)ctx.size();
@@ -189,6 +189,12 @@ class PathB200Multi final : public Integrator {
 	uint32_t path_length;
 	bool direct_lighting = true;
 
+  protected:
+	virtual void prepare_frame() = 0;  // push constants of this round
+	virtual int render_shard(lmb_ctx* c, uint32_t first_frame, uint32_t n_frames, uint32_t frame_stride) = 0;  // into the LMB_FILM_SUM film
+	virtual const char* what() const = 0;
+	lmb_scene_ubo scene_ubo{};
+
   private:
 	// sum films -> device 0, in rank order, then rgb /= valid-sample count
 	void reduce() {
@@ -229,8 +235,24 @@ class PathB200Multi final : public Integrator {
 	std::vector<lmb_ctx*> ctx;
 	bool reduced = false;
 	bool use_nccl = false;
-	lmb_pc_path pc_ray{};
-	lmb_scene_ubo scene_ubo{};
 	std::vector<float> film;
 	std::vector<uint16_t> half_planes;
+};
+
+class PathB200Multi final : public ShardedMulti {
+  public:
+	using ShardedMulti::ShardedMulti;
+
+  protected:
+	void prepare_frame() override {
+		pc_ray = lumen_scene->make_pc((int)path_length, direct_lighting);
+		pc_ray.frame_num = frame_num;
+	}
+	int render_shard(lmb_ctx* c, uint32_t first_frame, uint32_t n_frames, uint32_t frame_stride) override {
+		return lmb_render(c, &pc_ray, &scene_ubo, first_frame, n_frames, frame_stride, LMB_FILM_SUM);
+	}
+	const char* what() const override { return "lmb_render"; }
+
+  private:
+	lmb_pc_path pc_ray{};
 };

@@ -77,6 +77,7 @@ def lib():
         L.lmb_trace_closest.argtypes = [vp, vp, u32, vp]
         L.lmb_trace_any.argtypes = [vp, vp, u32, vp]
         L.lmb_trace_closest_device.argtypes = [vp, vp, u32, vp, u32, C.POINTER(C.c_float)]
+        L.lmb_trace_closest_device_ex.argtypes = [vp, vp, u32, vp, u32, i32, C.POINTER(C.c_float)]
         L.lmb_accel_num_tris.argtypes = [vp, C.POINTER(u32)]
         L.lmb_accel_download.argtypes = [vp] * 8
         L.lmb_kat_pcg4d.argtypes = [vp, vp, u32, vp]
@@ -98,7 +99,7 @@ EXPORTS = ["lmb_create", "lmb_destroy", "lmb_last_error", "lmb_upload_scene", "l
            "lmb_resolve", "lmb_download", "lmb_upload_film", "lmb_film_add_from", "lmb_film_device_ptr", "lmb_stream", "lmb_set_profile_stages", "lmb_get_stats",
            "lmb_reset_stats", "lmb_trace_closest", "lmb_trace_any", "lmb_trace_closest_device", "lmb_accel_num_tris", "lmb_accel_download",
            "lmb_download_async", "lmb_sync", "lmb_download_half_bgr", "lmb_set_reference_image", "lmb_rmse",
-           "lmb_comm_get_unique_id", "lmb_comm_init", "lmb_comm_init_all", "lmb_comm_destroy", "lmb_comm_info", "lmb_film_allreduce"]
+           "lmb_trace_closest_device_ex", "lmb_comm_get_unique_id", "lmb_comm_init", "lmb_comm_init_all", "lmb_comm_destroy", "lmb_comm_info", "lmb_film_allreduce"]
 TESTHOOK_EXPORTS = ["lmb_kat_pcg4d", "lmb_kat_rand", "lmb_kat_detmath", "lmb_kat_offset_ray", "lmb_kat_sample_bsdf", "lmb_kat_eval_bsdf",
                     "lmb_kat_atmosphere", "lmb_kat_sample_light", "lmb_kat_texture", "lmb_kat_wide_bvh_check", "lmb_kat_bdpt_frame_raw"]
 
@@ -297,9 +298,11 @@ class Device:
         self._ck(lib().lmb_trace_any(self._h, rays.ctypes.data, rays.shape[0], occ.ctypes.data), "lmb_trace_any")
         return occ
 
-    def trace_closest_device(self, d_rays_ptr, n, d_hits_ptr, repeat=1):
+    def trace_closest_device(self, d_rays_ptr, n, d_hits_ptr, repeat=1, sort_rays=False):
+        """ms of `repeat` launches over device arrays; sort_rays: order the rays by (origin cell, direction bin) inside every launch"""
         ms = C.c_float()
-        self._ck(lib().lmb_trace_closest_device(self._h, d_rays_ptr, int(n), d_hits_ptr, int(repeat), C.byref(ms)), "lmb_trace_closest_device")
+        self._ck(lib().lmb_trace_closest_device_ex(self._h, d_rays_ptr, int(n), d_hits_ptr, int(repeat), 1 if sort_rays else 0, C.byref(ms)),
+                 "lmb_trace_closest_device_ex")
         return ms.value
 
     # ---- known-answer probes (include/lumen_b200_testhooks.h)

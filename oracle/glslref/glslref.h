@@ -32,6 +32,13 @@ void ref_scene_destroy(ref_scene* s);
 int ref_render_path(ref_scene* s, const lmb_pc_path* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames, float* rgba,
 					uint64_t* rays3, int n_threads);
 
+/* One dispatch of bdpt.rgen (src/RayTracer/BDPT.cpp:55-95) for frame `frame`, seed (x, y, frame ^ pc->time, 0). Every invocation
+ * runs on a private, zeroed colour storage (the GLSL's non-atomic cross-pixel `tmp_col.d[idx] += splat` makes the reference's own
+ * result depend on scheduling): image_rgba[W*H*4] = what main() stores = the pixel's own (s, t >= 2) strategies + the splats it
+ * sends to itself; splat_rgb[W*H*3] = the splats it sends to other pixels, summed per target pixel. rays3 as ref_render_path. */
+int ref_render_bdpt_frame(ref_scene* s, const lmb_pc_bdpt* pc, const lmb_scene_ubo* ubo, uint32_t frame, float* image_rgba, float* splat_rgb,
+						  uint64_t* rays3, int n_threads);
+
 /* Function probes with the signatures of oracle.h's orc_kat_* (the scene handle provides the bindings the stage needs
  * to exist; BSDF / RNG / sky probes do not read it). */
 void ref_kat_pcg4d(ref_scene* s, const uint32_t* in4, uint32_t n, uint32_t* out4);

@@ -2,9 +2,7 @@
 // bsdf/*.glsl, atmosphere/atmosphere.glsl, integrators/pt_commons.glsl), translated by glsl2cpp.py; plus the emulation of
 // what Path::render sets up around it (descriptor bindings, push constants, the shader binding table) and the probes.
 #include <omp.h>
-#include <vector>
-#include "glslref.h"
-#include "stage_common.h"
+#include "harness.h"
 
 namespace glslref {
 struct PathRgen : Stage {
@@ -15,20 +13,10 @@ struct PathRgen : Stage {
 
 using namespace glslref;
 
-struct ref_scene {
-	lmb_scene_desc sd;
-	const void* user;
-	ref_trace1_fn trace1;
-	ref_texture_fn texture;
-	::SceneDesc scene_desc;  // commons.h:237-312; Path.cpp:6-11 fills four addresses
-	::SceneUBO ubo;
-	::PCPath pc;
-	std::vector<sampler2D> samplers;
-	Env env;
-};
-
-namespace {
+namespace glslref {
 thread_local uint64_t t_rays[3];
+}
+namespace {
 
 void cb_intersect(const Env* env, const float* ray8, int first, Intersection* out) {
 	const ref_scene* S = (const ref_scene*)env->user;

@@ -420,6 +420,10 @@ int orc_render_frame_raw(const orc_scene* s, const lmb_pc_path* pc, const lmb_sc
 	return 0;
 }
 
+// Row subset of orc_render / orc_render_frame_raw (the pixel shards of lmb_set_pixel_shard): rows row_first, row_first + stride, ...
+static uint32_t g_row_first = 0, g_row_stride = 1;
+void orc_set_row_shard(uint32_t row_first, uint32_t row_stride) { g_row_first = row_first, g_row_stride = row_stride ? row_stride : 1; }
+
 int orc_render(const orc_scene* s, const lmb_pc_path* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames, float* rgba,
 			   orc_stats* stats, int n_threads) {
 	const uint W = pc->size_x, H = pc->size_y;
@@ -432,6 +436,7 @@ int orc_render(const orc_scene* s, const lmb_pc_path* pc, const lmb_scene_ubo* u
 		for (uint32_t frame = first_frame; frame < first_frame + n_frames; frame++) {
 #pragma omp for schedule(dynamic, 1)
 			for (int y = 0; y < (int)H; y++) {
+				if ((uint32_t)y % g_row_stride != g_row_first) continue;
 				for (uint x = 0; x < W; x++) {
 					const vec3 col = trace_pixel(*s, *pc, *ubo, x, (uint)y, frame, c);
 					// path.rgen:102-112

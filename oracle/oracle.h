@@ -54,6 +54,9 @@ const float* orc_lbvh_aabb(const orc_scene* s);
  * film update (path.rgen:102-112). `rgba` is read when first_frame > 0. pc->frame_num is ignored (set per frame). */
 int orc_render(const orc_scene* s, const lmb_pc_path* pc, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames,
 			   float* rgba, orc_stats* stats, int n_threads);
+/* Restricts orc_render to the image rows row_first, row_first + row_stride, ... (the pixel shard of lmb_set_pixel_shard; other rows of
+ * `rgba` are left untouched). Process-wide; (0, 1) = every row. */
+void orc_set_row_shard(uint32_t row_first, uint32_t row_stride);
 /* Per-sample radiance of one frame without the film update: out[W*H*3], NaN samples are kept as NaN. */
 int orc_render_frame_raw(const orc_scene* s, const lmb_pc_path* pc, const lmb_scene_ubo* ubo, uint32_t frame, float* rgb,
 						 orc_stats* stats, int n_threads);

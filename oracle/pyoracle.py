@@ -42,6 +42,7 @@ def lib():
         L.orc_lbvh_num_tris.argtypes = [vp]
         L.orc_lbvh_num_tris.restype = u32
         L.orc_render.argtypes = [vp, vp, vp, u32, u32, vp, vp, i32]
+        L.orc_set_row_shard.argtypes = [u32, u32]
         L.orc_render_frame_raw.argtypes = [vp, vp, vp, u32, vp, vp, i32]
         L.orc_render_bdpt.argtypes = [vp, vp, vp, u32, u32, vp, vp, i32]
         L.orc_render_bdpt_frame_raw.argtypes = [vp, vp, vp, u32, vp, vp, vp, i32]
@@ -70,6 +71,11 @@ def lib():
         L.orc_max_threads.restype = i32
         _LIB = L
     return _LIB
+
+
+def set_row_shard(row_first, row_stride):
+    """OracleScene.render then covers only the image rows row_first, row_first + row_stride, ... ((0, 1) = every row)."""
+    lib().orc_set_row_shard(int(row_first), int(row_stride))
 
 
 def bdpt_set_only_s(s):

@@ -178,14 +178,14 @@ def test_converged_rmse_within_sampling_noise(device):
     """BASELINE.json condition 3: the RMSE of the GPU's converged image against the oracle's converged image (independent
     frames) is the oracle's own seed-to-seed noise -- with Lumen's literal RMSE routine (rmse/*.comp, quirks included) and
     with a true RMSE."""
-    w = h = 96
-    n = 48
+    w = h = 256
+    n = 512  # 512 spp at 256 x 256: the image is converged to ~1 % (noise falls as 1 / sqrt(n)); ~30 s of oracle time on the box
     sc = host.Scene(scene_path("cornell"), w, h)
     orc = po.OracleScene(sc)
     device.upload_scene(sc.desc)
     device.build_accel()
     pc, ubo = sc.make_pc(6, True), sc.make_ubo()
-    device.init(w, h, 8)
+    device.init(w, h, 64)
     device.render(pc, ubo, 0, n)
     gpu_a = device.download()
     cpu_a, _ = orc.render(pc, ubo, 0, n)

@@ -39,7 +39,7 @@ def test_offset_ray(device):
 
 @pytest.mark.parametrize("name", sorted(MATERIALS))
 def test_bsdf_sample_and_eval(device, name):
-    rng = np.random.default_rng(abs(hash(name)) % 2**31)
+    rng = np.random.default_rng(1000 + sorted(MATERIALS).index(name))  # fixed per material: a failure reproduces
     m = make_material(**MATERIALS[name])
     n = 60000
     ns, wo, wi = unit_vectors(rng, n), unit_vectors(rng, n), unit_vectors(rng, n)

@@ -90,3 +90,21 @@ def test_cli_multi_device_render_equals_single(tmp_path, devices):
     assert close.mean() > 0.999
     r = _run(base + ["--devices", devices, "--checkpoint", str(tmp_path / "c.bin")])
     assert r.returncode != 0 and "cannot be combined" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices", ["0,0", "0,1"])
+def test_cli_multi_device_bdpt_equals_single(tmp_path, devices):
+    """--integrator bdpt --devices: BDPTB200Multi (the multi-GPU host of the BDPT row, same sharding and reduce as PathB200Multi). With a
+    fixed --time the sharded render is the single-device one up to the order of fp32 adds (light-tracer splats are float atomics)."""
+    if devices == "0,1" and _n_gpus() < 2:
+        pytest.skip("needs two GPUs")
+    one, two = tmp_path / "one.exr", tmp_path / "two.exr"
+    base = [scene_path("cornell"), "--integrator", "bdpt", "--time", "7", "--width", "64", "--height", "48", "--depth", "5", "--spp", "8", "--batch", "2"]
+    assert _run(base + ["--out", str(one)]).returncode == 0
+    r = _run(base + ["--out", str(two), "--devices", devices])
+    assert r.returncode == 0, r.stderr
+    assert "8 frames on 2 devices, BDPT" in r.stdout and ("NCCL" in r.stdout) == (devices == "0,1")
+    a, b = host.load_exr(str(one))[..., :3], host.load_exr(str(two))[..., :3]
+    close = np.abs(a - b) <= 2.0 ** -8 * np.maximum(np.abs(a), 1e-3)
+    assert close.mean() > 0.995

@@ -5,10 +5,12 @@
         --csv --log-file gpurun_out/ktrace_inst.csv python tools/ncu_target.py 16 1 2> gpurun_out/ktrace_counters.log
     python tools/calibrate_ktrace.py gpurun_out/ktrace_inst.csv gpurun_out/ktrace_counters.log [more pairs ...]
 
-ncu gives smsp__inst_executed.sum for every k_trace launch; the library prints the launch's own counters (traversal-loop trips,
-trips with a node step, triangle rounds, refills: lmb_stats.trace_*). A non-negative least-squares fit over the launches gives the
-warp instructions per trip / node step / round / refill; bench.py multiplies the live counters of its run by them to get the
-instructions issued -- the numerator of the issue roofline. Writes profiles/ktrace_calibration.json stamped with the source hash.
+ncu gives smsp__inst_executed.sum for every k_trace launch; the library prints the launch's own counters (traversal-loop trips of all
+warps: lmb_stats.trace_warp_iters, and the rays traced). A non-negative least-squares fit over the launches gives the warp
+instructions per loop trip (node step + its share of triangle rounds, pops and stores) and per ray (fetch, preparation, refill);
+bench.py multiplies the live counters of its run by them to get the instructions issued -- the numerator of the issue roofline.
+(Triangle rounds and refills were counted too at first: across launches they are collinear with trips and rays, their coefficients
+are not identifiable, and the two extra integer adds per trip cost 0.9 ms of a 60 ms trace stage -- dropped.) Writes profiles/ktrace_calibration.json stamped with the source hash.
 """
 import csv
 import json
@@ -45,7 +47,7 @@ def counters(path):
 
 def main():
     pairs = list(zip(sys.argv[1::2], sys.argv[2::2]))
-    A, y, names = [], [], ("iters", "node_trips", "rounds", "refills")
+    A, y, names = [], [], ("iters", "rays")
     for inst_csv, log in pairs:
         n, c = ncu_inst(inst_csv), counters(log)
         if len(n) != len(c):

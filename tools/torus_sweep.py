@@ -50,15 +50,15 @@ def main():
            "wide_levels": int(st.wide_levels), "wide_check": chk, "sweeps": []}
     print(json.dumps({k: res[k] for k in ("triangles", "lbvh_build_ms", "wide_nodes", "wide_levels", "wide_check")}), flush=True)
 
-    def run(kind, rays_np):
+    def run(kind, rays_np, sort_rays=False):
         n = rays_np.shape[0]
         d_rays = torch.from_numpy(rays_np).cuda()
         d_hits = torch.empty((n, 4), dtype=torch.float32, device="cuda")
         torch.cuda.synchronize()
-        dev.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr(), 1)  # warm-up
+        dev.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr(), 1, sort_rays)  # warm-up
         dev.reset_stats()
         reps = 5 if n <= (1 << 24) else 3
-        ms = dev.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr(), reps)
+        ms = dev.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr(), reps, sort_rays)
         s = dev.stats()
         hit_frac = float((d_hits[:, 3].view(torch.int32) != -1).float().mean().item())
         traced = s.rays_closest
@@ -90,6 +90,9 @@ def main():
         r = run("incoherent", rays)
         if lg == 20:
             keep = (rays, r[1].cpu().numpy().copy())
+        rs = run("incoherent, rays sorted by (origin cell, direction bin) inside the timed launch", rays, sort_rays=True)
+        if not torch.equal(r[1].view(torch.int32), rs[1].view(torch.int32)):
+            raise SystemExit("torus_sweep: sorted launch returned different hits")
     # wide walk == binary walk at full size (2^20 incoherent rays)
     os.environ["LMB_TRAVERSAL"] = "bvh2"
     dev2 = integrator.Device(0)
