@@ -17,7 +17,8 @@ statement and control-flow construct of the shader is emitted token for token:
   * `vecN(a(), b())` whose arguments contain more than one call of a function with side effects (the RNG) ->
                             evaluated into temporaries LEFT TO RIGHT (GLSL's order; C++ leaves it unspecified)
   * `layout(...)` interface declarations -> members bound through the stage environment (glslref::Stage::env):
-        buffer_reference blocks  -> pointer wrapper structs constructible from a 64-bit address
+        buffer_reference blocks  -> wrapper structs constructible from a 64-bit address (glslref::BufArray: element count from the
+                                    harness's registry, out-of-range elements read as zero instead of faulting)
         uniform / buffer blocks  -> references to the memory bound at (set, binding)
         push_constant block      -> reference to the bound push-constant bytes
         image2D / sampler2D[] / accelerationStructureEXT -> handles of the environment
@@ -378,8 +379,8 @@ def pass_layout(toks, payload_locs):
                 m = re.match(r"^(.*?)\s+(\w+)\s*(\[\s*\])?$", members[0], re.S)
                 ty, name = m.group(1), m.group(2)
                 const = "const " if "readonly" in head else ""
-                text = (f"struct {block_name} {{ {const}{ty}* {name}; {block_name}() : {name}(nullptr) {{}} "
-                        f"{block_name}(uint64_t glsl_addr) : {name}(reinterpret_cast<{const}{ty}*>(glsl_addr)) {{}} }};")
+                text = (f"struct {block_name} {{ glslref::BufArray<{const}{ty}> {name}; {block_name}() {{}} "
+                        f"{block_name}(uint64_t glsl_addr) : {name}(glsl_addr) {{}} }};")
             elif "push_constant" in la:
                 if tail:
                     raise SyntaxError("named push_constant instances are not handled")

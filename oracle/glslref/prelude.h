@@ -86,6 +86,56 @@ GLSLREF_MIXED_OPS(vec4)
 #undef GLSLREF_MIXED_OPS
 // GLSL's vector == / != give one bool (glm's too); ivec2 == ivec2 is used by the (disabled) logging macros only.
 
+// ------------------------------------------------------------------------------------------------ buffer references
+// `layout(buffer_reference) buffer B { T d[]; }` is a raw 64-bit address on the GPU: indexing past the allocation is undefined there
+// and, in practice, reads whatever is mapped. The reference does it on purpose-free dead paths (bdpt_commons.glsl:332 forms
+// light_vtx(s - 2) with s = 1: `bdpt_path_idx + s - 2` in uint arithmetic, element 0xFFFFFFFF for the first pixel; the value is never
+// used). On the CPU such a read must not fault: the harness registers every buffer it binds, a BufArray resolves its element count
+// once per invocation, and an out-of-range element is a zeroed dummy (reads give 0, writes are dropped).
+struct BufferRegistry {
+	struct Range {
+		uintptr_t base;
+		size_t bytes;
+	};
+	static constexpr int MAX = 64;
+	Range ranges[MAX];
+	int count = 0;
+	static BufferRegistry& get() {
+		static BufferRegistry r;
+		return r;
+	}
+	void add(const void* p, size_t bytes) {  // not thread-safe: called while no stage runs
+		for (int i = 0; i < count; i++)
+			if (ranges[i].base == (uintptr_t)p) {
+				ranges[i].bytes = bytes;
+				return;
+			}
+		if (count < MAX) ranges[count++] = Range{(uintptr_t)p, bytes};
+	}
+	void remove(const void* p) {
+		for (int i = 0; i < count; i++)
+			if (ranges[i].base == (uintptr_t)p) ranges[i] = ranges[--count];
+	}
+	uint64_t elems_from(uint64_t addr, size_t elem) const {
+		for (int i = 0; i < count; i++)
+			if (addr >= ranges[i].base && addr < ranges[i].base + ranges[i].bytes) return (ranges[i].base + ranges[i].bytes - addr) / elem;
+		return addr ? ~0ull : 0ull;  // unregistered: unchecked; null: empty
+	}
+};
+template <class T>
+struct BufArray {
+	T* p = nullptr;
+	uint64_t n = 0;
+	BufArray() = default;
+	explicit BufArray(uint64_t addr) : p(reinterpret_cast<T*>(addr)), n(BufferRegistry::get().elems_from(addr, sizeof(T))) {}
+	T& operator[](uint64_t i) const {
+		if (i < n) return p[i];
+		static thread_local std::remove_const_t<T> dummy;
+		std::memset((void*)&dummy, 0, sizeof(dummy));
+		return dummy;
+	}
+};
+
 // ------------------------------------------------------------------------------------------------ opaque resources
 struct image2D {
 	float* rgba;  // RGBA32F, row-major

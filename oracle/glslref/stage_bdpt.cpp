@@ -32,11 +32,14 @@ extern "C" int ref_render_bdpt_frame(ref_scene* s, const lmb_pc_bdpt* pc_in, con
 	// (bdpt.rgen:79-89) instead of mixing it into the running mean
 	pc.time = frame ^ pc_in->time;
 	pc.frame_num = 0;
-	// one guard vertex in front: bdpt_connect_cam / calc_mis_weight form light_vtx(s - 2) with s = 1, i.e. the slot before the pixel's
-	// own (a dead read: the value is never used); for pixel 0 that is element -1
-	std::vector<::PathVertex> light(n_vtx + 1), camera(n_vtx + 1);
+	// BDPT.cpp:7-24 + :79-80: both path buffers, zeroed per frame. bdpt_connect_cam / calc_mis_weight form light_vtx(s - 2) with s = 1,
+	// the slot before the pixel's own (a dead read: the value is never used); for the first pixel that is element 0xFFFFFFFF in the
+	// shader's uint arithmetic, which glslref::BufArray answers with zeros instead of a fault (prelude.h)
+	std::vector<::PathVertex> light(n_vtx), camera(n_vtx);
 	std::memset(light.data(), 0, light.size() * sizeof(::PathVertex));
 	std::memset(camera.data(), 0, camera.size() * sizeof(::PathVertex));
+	BufferRegistry::get().add(light.data(), light.size() * sizeof(::PathVertex));
+	BufferRegistry::get().add(camera.data(), camera.size() * sizeof(::PathVertex));
 	const int nt = n_threads > 0 ? n_threads : omp_get_max_threads();
 	std::vector<std::vector<float>> splats((size_t)nt, std::vector<float>(n_pix * 3, 0.0f));
 	uint64_t r0 = 0, r1 = 0, r2 = 0;
@@ -47,8 +50,8 @@ extern "C" int ref_render_bdpt_frame(ref_scene* s, const lmb_pc_bdpt* pc_in, con
 		::SceneDesc desc = s->scene_desc;
 		::SceneUBO ubo_local;
 		std::memcpy(&ubo_local, ubo, sizeof(ubo_local));
-		desc.light_path_addr = (uint64_t)(uintptr_t)(light.data() + 1);
-		desc.camera_path_addr = (uint64_t)(uintptr_t)(camera.data() + 1);
+		desc.light_path_addr = (uint64_t)(uintptr_t)light.data();
+		desc.camera_path_addr = (uint64_t)(uintptr_t)camera.data();
 		desc.color_storage_addr = (uint64_t)(uintptr_t)tmp_col.data();
 		Env env = s->env;
 		env.sets[0][1] = &ubo_local;
@@ -86,6 +89,7 @@ extern "C" int ref_render_bdpt_frame(ref_scene* s, const lmb_pc_bdpt* pc_in, con
 				for (int t = 0; t < nt; t++) sum += splats[(size_t)t][3 * ((size_t)x * H + y) + c];
 				splat_rgb[3 * ((size_t)y * W + x) + c] = sum;
 			}
+	BufferRegistry::get().remove(light.data()), BufferRegistry::get().remove(camera.data());
 	if (rays3) rays3[0] += r0, rays3[1] += r1, rays3[2] += r2;
 	return 0;
 }

@@ -88,6 +88,9 @@ int ref_scene_create(const lmb_scene_desc* sd, const void* user, ref_trace1_fn t
 	s->scene_desc.material_addr = (uint64_t)(uintptr_t)sd->materials;
 	s->scene_desc.prim_info_addr = (uint64_t)(uintptr_t)sd->prim_infos;
 	s->scene_desc.compact_vertices_addr = (uint64_t)(uintptr_t)sd->vertices;
+	BufferRegistry& reg = BufferRegistry::get();
+	reg.add(sd->indices, (size_t)sd->n_indices * 4), reg.add(sd->materials, (size_t)sd->n_materials * sizeof(::Material));
+	reg.add(sd->prim_infos, (size_t)sd->n_prim_meshes * sizeof(::PrimMeshInfo)), reg.add(sd->vertices, (size_t)sd->n_vertices * sizeof(::Vertex));
 	s->samplers.resize(sd->n_textures ? sd->n_textures : 1);
 	for (uint32_t i = 0; i < sd->n_textures; i++) s->samplers[i] = sampler2D{s, i};
 	Env& e = s->env;
@@ -104,7 +107,12 @@ int ref_scene_create(const lmb_scene_desc* sd, const void* user, ref_trace1_fn t
 	*out = s;
 	return 0;
 }
-void ref_scene_destroy(ref_scene* s) { delete s; }
+void ref_scene_destroy(ref_scene* s) {
+	if (!s) return;
+	BufferRegistry& reg = BufferRegistry::get();
+	reg.remove(s->sd.indices), reg.remove(s->sd.materials), reg.remove(s->sd.prim_infos), reg.remove(s->sd.vertices);
+	delete s;
+}
 
 int ref_render_path(ref_scene* s, const lmb_pc_path* pc_in, const lmb_scene_ubo* ubo, uint32_t first_frame, uint32_t n_frames, float* rgba,
 					uint64_t* rays3, int n_threads) {

@@ -31,6 +31,7 @@ def lib():
         L.ref_scene_create.argtypes = [vp, vp, vp, vp, C.POINTER(vp)]
         L.ref_scene_destroy.argtypes = [vp]
         L.ref_render_path.argtypes = [vp, vp, vp, u32, u32, vp, vp, i32]
+        L.ref_render_bdpt_frame.argtypes = [vp, vp, vp, u32, vp, vp, vp, i32]
         L.ref_kat_pcg4d.argtypes = [vp, vp, u32, vp]
         L.ref_kat_rand.argtypes = [vp, vp, u32, u32, vp]
         L.ref_kat_offset_ray.argtypes = [vp, vp, vp, u32, vp, vp]
@@ -70,6 +71,16 @@ class RefScene:
         rays = np.zeros(3, dtype=np.uint64)
         lib().ref_render_path(self._h, C.addressof(pc), C.addressof(ubo), first_frame, n_frames, rgba.ctypes.data, rays.ctypes.data, threads)
         return rgba, rays
+
+    def render_bdpt_frame(self, pc, ubo, frame, threads=0):
+        """One dispatch of bdpt.rgen (pc is a PCBdpt): (image (H, W, 4) = own strategies + self-splats as main() stores them,
+        splat (H, W, 3) = the splats the pixels send to OTHER pixels, [closest, shadow, -] ray counts)."""
+        W, H = pc.size_x, pc.size_y
+        image = np.zeros((H, W, 4), dtype=np.float32)
+        splat = np.zeros((H, W, 3), dtype=np.float32)
+        rays = np.zeros(3, dtype=np.uint64)
+        lib().ref_render_bdpt_frame(self._h, C.addressof(pc), C.addressof(ubo), int(frame), image.ctypes.data, splat.ctypes.data, rays.ctypes.data, threads)
+        return image, splat, rays
 
     def pcg4d(self, v4):
         v = np.ascontiguousarray(v4, dtype=np.uint32).reshape(-1, 4)
