@@ -193,12 +193,16 @@ def config5_roofline(integrator, local_rank, hbm_peak, peak_src):
         rays = torch.from_numpy(gen.random_rays(n, K)).cuda()
         hits = torch.empty((n, 4), dtype=torch.float32, device="cuda")
         torch.cuda.synchronize()
-        sorted_ms = None
-        dev.trace_closest_device(rays.data_ptr(), n, hits.data_ptr(), 1)  # warm-up
-        dev.reset_stats()
         reps = 4
-        ms = dev.trace_closest_device(rays.data_ptr(), n, hits.data_ptr(), reps)
+        dev.trace_closest_device(rays.data_ptr(), n, hits.data_ptr(), 1)  # warm-up
+        ms_unsorted = dev.trace_closest_device(rays.data_ptr(), n, hits.data_ptr(), reps)
+        first = hits.clone()
+        # the product's way through an incoherent batch: order the rays by (origin cell, direction octant) inside the timed launch
+        dev.trace_closest_device(rays.data_ptr(), n, hits.data_ptr(), 1, sort_rays=True)  # warm-up (allocates the sort scratch)
+        dev.reset_stats()
+        ms = dev.trace_closest_device(rays.data_ptr(), n, hits.data_ptr(), reps, sort_rays=True)
         s = dev.stats()
+        same = bool(torch.equal(first.view(torch.int32), hits.view(torch.int32)))
         traced = max(s.rays_closest, 1)
         bytes_per_ray = (s.nodes_visited * NODE_BYTES + s.tris_tested * TRI_BYTES) / traced + RAY_BYTES + HIT_BYTES
         mrays = n * reps / ms / 1e3
@@ -207,7 +211,10 @@ def config5_roofline(integrator, local_rank, hbm_peak, peak_src):
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src, "mrays_per_s": mrays,
                 "avg_launch_ms": ms / reps, "algorithmic_bytes_per_launch": bytes_per_ray * n, "bytes_per_ray": bytes_per_ray,
                 "nodes_per_ray": s.nodes_visited / traced, "tris_per_ray": s.tris_tested / traced, "traffic": profile_file("ktrace_config5_traffic.json").get("dram_bytes_per_launch"),
-                "traffic_stale": profile_file("ktrace_config5_traffic.json").get("stale"), "sorted_ms": sorted_ms,
+                "traffic_stale": profile_file("ktrace_config5_traffic.json").get("stale"),
+                "ray_order": "counting sort by (origin cell, direction octant), 15-bit keys, INSIDE the timed launch (lmb_trace_closest_device_ex sort_rays = 1)",
+                "unsorted": {"mrays_per_s": n * reps / ms_unsorted / 1e3, "avg_launch_ms": ms_unsorted / reps, "frac": bytes_per_ray * (n * reps / ms_unsorted / 1e3) / 1e3 / hbm_peak},
+                "hits_identical_sorted_vs_unsorted": same,
                 "lbvh_build_ms": {"total": b.ms_build_accel, "morton": b.ms_build_morton, "sort": b.ms_build_sort, "tree": b.ms_build_tree,
                                   "refit_pack": b.ms_build_refit, "wide": b.ms_build_wide}}
     finally:

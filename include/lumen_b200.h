@@ -183,7 +183,7 @@ int lmb_trace_closest(lmb_ctx* ctx, const float* rays, uint32_t n, lmb_hit* hits
 int lmb_trace_any(lmb_ctx* ctx, const float* rays, uint32_t n, uint8_t* occluded);
 /* Same on DEVICE pointers, timed with CUDA events (ms_out may be NULL); `repeat` launches back to back. */
 int lmb_trace_closest_device(lmb_ctx* ctx, const void* d_rays, uint32_t n, void* d_hits, uint32_t repeat, float* ms_out);
-/* ... with sort_rays != 0 every launch first orders the rays by (origin cell, direction octant) -- 18-bit keys, a counting sort on the
+/* ... with sort_rays != 0 every launch first orders the rays by (origin cell, direction octant) -- 15-bit keys, a counting sort on the
  * device, timed with the launch -- so that the persistent walker's 32-ray fetches are coherent; hits land at the rays' own indices and
  * do not depend on the order. Pays when the BVH does not fit the L2 (BASELINE config 5). */
 int lmb_trace_closest_device_ex(lmb_ctx* ctx, const void* d_rays, uint32_t n, void* d_hits, uint32_t repeat, int sort_rays, float* ms_out);

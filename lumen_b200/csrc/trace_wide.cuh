@@ -45,6 +45,9 @@ struct WideBvhView {
 #ifndef LMB_TRI_ROUND_LANES
 #define LMB_TRI_ROUND_LANES 8
 #endif
+#ifndef LMB_DEFER_STORE
+#define LMB_DEFER_STORE 1
+#endif
 #ifndef LMB_TRACE_WCOUNT
 #define LMB_TRACE_WCOUNT 1  // warp-level scheduling counters kept by the walker: 0 none, 1 loop trips, 3 + triangle rounds and refills
 #endif
@@ -134,6 +137,7 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 	if (PIN) asm volatile("mov.u32 %0, %1;" : "=r"(stack_base) : "r"((uint32_t)__cvta_generic_to_shared(&sm.stack[0][tid])));
 
 	bool has = false;        // this lane owns a ray that is still being traced
+	bool done = false;       // this lane's ray is finished and waits for its store (LMB_DEFER_STORE)
 	bool exhausted = false;  // warp-uniform: the global queue ran dry
 	uint32_t rq_head = 0, rq_count = 0;  // warp-uniform: the ready queue holds entries [rq_head, rq_count)
 	bool any = false;
@@ -154,6 +158,16 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 #endif
 
 	for (;;) {
+#if LMB_DEFER_STORE
+		// ---- finished rays: the two IEEE divisions of the barycentrics (~40 instructions with their slow path) and the store ran at
+		// 2.3 of 32 lanes in 60 % of the loop trips when every lane finished its ray on its own (profiles/r02a: 7 % of the kernel's warp
+		// instructions); here the lanes that finished since the last refill (>= 32 - refill_lanes of them, or all at the end) do it together
+		if (done) {
+			if (!any && h.prim != 0xFFFFFFFFu) h.b1 = h.b1 / det, h.b2 = h.b2 / det;
+			src.store(item, h);
+			done = false;
+		}
+#endif
 		// ---- refill. Rays come out of the global queue 32 at a time: the whole warp fetches and prepares them (coalesced
 		// loads, ray_prepare at 32 of 32 lanes, one cursor atomic per 32 rays) into the warp's ready queue in shared memory;
 		// lanes that ran dry pop from it for the price of a few shared loads, so a refill is worth doing for a handful of
@@ -392,9 +406,13 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 					else if (PIN) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ng.x), "=r"(ng.y) : "r"(stack_base + (uint32_t)sp * (LMB_TRACE_THREADS * 8u)));
 					else ng = sm.stack[sp][tid];
 				} else {
+#if LMB_DEFER_STORE
+					has = false, done = true;  // barycentrics and the store wait for the refill, where several lanes finish together
+#else
 					if (!any && h.prim != 0xFFFFFFFFu) h.b1 = h.b1 / det, h.b2 = h.b2 / det;
 					src.store(item, h);
 					has = false;
+#endif
 				}
 			}
 			const int busy = __popc(__ballot_sync(0xFFFFFFFFu, has));

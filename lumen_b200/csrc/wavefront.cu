@@ -34,6 +34,9 @@ namespace {
 #ifndef LMB_SHADE_MIN_BLOCKS
 #define LMB_SHADE_MIN_BLOCKS 4
 #endif
+#ifndef LMB_SHADE_MIN_BLOCKS_DIFFUSE
+#define LMB_SHADE_MIN_BLOCKS_DIFFUSE LMB_SHADE_MIN_BLOCKS
+#endif
 constexpr float T_MIN = 0.001f;    // path.rgen:19
 constexpr float T_MAX = 10000.0f;  // path.rgen:20
 
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(256) k_classify(RenderParams rp, DeviceScene s
 // LAST = true is the bounce at depth max_depth - 1, which only collects emission (path.rgen:57-62) for any BSDF type and
 // walks list d directly.
 template <uint32_t TYPE, bool LAST>
-__global__ void __launch_bounds__(128, LAST ? 8 : LMB_SHADE_MIN_BLOCKS) k_shade(RenderParams rp, DeviceScene sc, int depth, uint32_t* __restrict__ counters, int parity, int count_idx,
+__global__ void __launch_bounds__(128, LAST ? 8 : (TYPE == LMB_BSDF_DIFFUSE ? LMB_SHADE_MIN_BLOCKS_DIFFUSE : LMB_SHADE_MIN_BLOCKS)) k_shade(RenderParams rp, DeviceScene sc, int depth, uint32_t* __restrict__ counters, int parity, int count_idx,
 													const uint32_t* __restrict__ queue, PathPlanes pl, PathPlanes nx, const float4* __restrict__ hit,
 													uint32_t* __restrict__ trace_queue, float4* __restrict__ nee, uint32_t* __restrict__ nee_path,
 													float4* __restrict__ acc, uint32_t n_slots, unsigned long long* stats) {

@@ -121,7 +121,8 @@ def comm_init_all(devices):
     arr = (C.c_void_p * len(devices))(*[d._h for d in devices])
     rc = lib().lmb_comm_init_all(C.addressof(arr), len(devices))
     if rc != 0:
-        raise RuntimeError(f"lmb_comm_init_all failed ({rc}): " + lib().lmb_last_error(devices[0]._h).decode())
+        msgs = [lib().lmb_last_error(d._h).decode() for d in devices]  # the message sits in the context that was refused
+        raise RuntimeError(f"lmb_comm_init_all failed ({rc}): " + "; ".join(m for m in msgs if m))
 
 
 def _f32(a):

@@ -4,9 +4,16 @@
  * (src/shaders/integrators/path/path.rgen + includes) over a canonical CPU LBVH. Loaded through ctypes by tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs -- never by lumen_b200/.
  *
- * Parity status: the reference ships no tests, golden images or known-answer vectors for this path
- *  and cannot be built or run here (GLSL + Vulkan RT), so this oracle is pinned to the shader
- * SOURCE only -> "parity unpinned" by reference fixtures. tests/golden/ holds vectors minted from this oracle.
+ * Parity status: PINNED TO THE REFERENCE ITSELF RUN HERE. The reference ships no tests, golden images or known-answer
+ * vectors for this path and its executable needs a Vulkan RT GPU, but its shader SOURCE compiles on the CPU
+ * after a mechanical GLSL -> C++ pass (oracle/glslref/glsl2cpp.py over the unmodified files, built into
+ * oracle/_ref/libglslref.so). tests/test_glslref_pins_oracle.py holds this oracle to that library bit for bit: RNG, ray
+ * offsets, every BSDF's sample / eval / pdf, light sampling, the sky model, load_material, and whole path.rgen and
+ * bdpt.rgen dispatches (films and ray counts) on the reference's scenes. Outside the shader source, hence DEFINED by this
+ * build on both sides: ray/triangle intersection and instance transforms (Vulkan driver), bilinear texture filtering
+ * (hardware), transcendental functions (include/lmb_detmath.h), no FMA contraction, uninitialised variables read as zero.
+ * tests/golden/ additionally freezes vectors minted from this oracle so that it cannot drift unnoticed on a box without
+ * the reference checkout.
  */
 #ifndef ORACLE_H
 #define ORACLE_H

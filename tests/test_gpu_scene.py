@@ -370,3 +370,27 @@ def test_film_add_from_reduces_sum_films(device, loaded):
     finally:
         a.close()
         b.close()
+
+
+def test_sorted_ray_batches_return_the_same_hits(device, loaded):
+    """lmb_trace_closest_device_ex(sort_rays = 1): the batch is ordered by (origin cell, direction octant) on the device before it is
+    walked (config 5's incoherent rays). Hits land at the rays' own indices and are those of the unsorted launch and of the oracle,
+    bit for bit -- including rays outside the scene box, non-finite rays and a count that is not a multiple of 32."""
+    import torch
+    sc, orc = loaded("materials", 64, 64)
+    rng = np.random.default_rng(77)
+    lo, hi = np.float32([-6, -1, -6]), np.float32([6, 6, 6])
+    rays = random_rays(rng, lo, hi, 200_003)
+    rays[:50, :3] *= 40.0                    # far outside the box: clamped cells
+    rays[50:60, 0] = np.nan                  # hit nothing by definition
+    rays[60:70, 4] = np.inf
+    d_rays = torch.from_numpy(rays).cuda()
+    a = torch.empty((rays.shape[0], 4), dtype=torch.float32, device="cuda")
+    b = torch.full((rays.shape[0], 4), -7.0, dtype=torch.float32, device="cuda")
+    device.trace_closest_device(d_rays.data_ptr(), rays.shape[0], a.data_ptr(), 1)
+    device.trace_closest_device(d_rays.data_ptr(), rays.shape[0], b.data_ptr(), 2, sort_rays=True)
+    assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+    want, _ = orc.trace_closest(rays)
+    got = b.cpu().numpy()
+    assert (got[:, 3].view(np.uint32) == want["prim"]).all() and bits_equal(got[:, 0][want["prim"] != 0xFFFFFFFF], want["t"][want["prim"] != 0xFFFFFFFF]).all()
+    assert (want["prim"][50:70] == 0xFFFFFFFF).all()
