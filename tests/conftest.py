@@ -24,6 +24,15 @@ def scene_path(name):
     return os.path.join(ROOT, SCENES[name])
 
 
+def free_port():
+    """A TCP port the kernel just handed out on 127.0.0.1 (rendezvous of the two-rank gloo tests): a fixed port derived from the
+    pid can collide with a socket another test left in TIME_WAIT."""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 @pytest.fixture(scope="session")
 def root():
     return ROOT

@@ -114,7 +114,15 @@ def test_two_gpus_allreduce_equals_the_single_gpu_film():
         each(devs, lambda r, d: (d.film_allreduce(), d.sync()))
         films = [d.download() for d in devs]
         assert films[0].tobytes() == films[1].tobytes()
-        assert np.allclose(films[0][..., :3], want[..., :3], rtol=3e-6, atol=1e-7) and (films[0][..., 3] == 1).all()
+        assert (films[0][..., 3] == 1).all()
+        # against the same eight samples summed on ONE device the two-rank film differs only in the association of eight positive
+        # fp32 terms (a few ulp); against the reference's running mean (mix() per frame, path.rgen:104-108) by the rounding of eight
+        # lerps -- measured 4e-6 relative on a handful of dark pixels, so that bound is the looser one
+        single.init(128, 96, 4)
+        single.render(pc, ubo, 0, 8, 1, integrator.FILM_SUM)
+        single.resolve()
+        assert np.allclose(films[0][..., :3], single.download()[..., :3], rtol=1e-6, atol=1e-9)
+        assert np.allclose(films[0][..., :3], want[..., :3], rtol=2e-5, atol=1e-7)
         # (b) pixel shards x all frames: every pixel is owned by one rank, so the reduced film is the single-GPU SUM film bit for bit
         single.init(128, 96, 4)
         single.render(pc, ubo, 0, 8, 1, integrator.FILM_SUM)

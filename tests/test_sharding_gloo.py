@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from conftest import scene_path
+from conftest import free_port, scene_path
 from lumen_b200 import sharding
 
 
@@ -33,7 +33,7 @@ def _worker(rank, world, port, tmpdir):
 
 
 def test_two_rank_sharded_render_equals_single(tmp_path):
-    world, port = 2, 29500 + os.getpid() % 2000
+    world, port = 2, free_port()
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     r0, r1 = np.load(tmp_path / "rank0.npy"), np.load(tmp_path / "rank1.npy")
     assert r0.tobytes() == r1.tobytes()  # all-reduce leaves the same film on every rank
@@ -89,7 +89,7 @@ def _tile_worker(rank, world, port, tmpdir):
 
 
 def test_two_rank_pixel_sharded_render_equals_single(tmp_path):
-    world, port = 2, 31500 + os.getpid() % 2000
+    world, port = 2, free_port()
     mp.spawn(_tile_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     r0, r1 = np.load(tmp_path / "tile0.npy"), np.load(tmp_path / "tile1.npy")
     assert r0.tobytes() == r1.tobytes()
@@ -142,7 +142,7 @@ def _bdpt_worker(rank, world, port, tmpdir):
 
 
 def test_two_rank_sharded_bdpt_equals_single(tmp_path):
-    world, port = 2, 33500 + os.getpid() % 2000
+    world, port = 2, free_port()
     mp.spawn(_bdpt_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     r0, r1 = np.load(tmp_path / "bdpt0.npy"), np.load(tmp_path / "bdpt1.npy")
     assert r0.tobytes() == r1.tobytes()
