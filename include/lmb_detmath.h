@@ -116,6 +116,27 @@ LMB_HD float lmb_expf(float x) {
 	return (p * lmb_pow2i(n1)) * lmb_pow2i(n2);
 }
 
+/* lmb_expf again, bit for bit (tools/check_expf_equiv.c walks all 2^32 inputs), in the form a GPU issues fastest -- the sky march
+ * (atmosphere.glsl:93-144) evaluates ~1500 of these per escaped ray and is bound by instruction issue:
+ *   rintf(t) and (int) are FRND + F2I on the quarter-rate conversion pipe -> s = t + 1.5*2^23 rounds t to the nearest-even integer
+ *   in the FP32 adder (|t| < 2^22), nf = s - 1.5*2^23, and the low bits of s ARE the integer;
+ *   (p * 2^n1) * 2^n2 with n1 + n2 = n is p with n added to its exponent field whenever neither step leaves the normal range
+ *   (-86 < x <= 88: n in [-124, 127], p in [0.70, 1.42]) -> one shift-add on the bit pattern. Outside that window: the form above. */
+LMB_HD float lmb_expf_window(float x) { /* requires -86 < x <= 88 */
+	const float s = x * 1.44269504088896341f + 12582912.0f;
+	const float nf = s - 12582912.0f;
+	float r = fmaf(nf, -0.693359375f, x);
+	r = fmaf(nf, 2.12194440e-4f, r);
+	float p = fmaf(1.9875691500e-4f, r, 1.3981999507e-3f);
+	p = fmaf(p, r, 8.3334519073e-3f);
+	p = fmaf(p, r, 4.1665795894e-2f);
+	p = fmaf(p, r, 1.6666665459e-1f);
+	p = fmaf(p, r, 5.0000001201e-1f);
+	p = fmaf(p * r, r, r) + 1.0f;
+	return lmb_bits2f(lmb_f2bits(p) + (lmb_f2bits(s) << 23)); /* 0x4B400000 << 23 == 0 (mod 2^32): only n is left of s */
+}
+LMB_HD float lmb_expf_fast(float x) { return (x > -86.0f && x <= 88.0f) ? lmb_expf_window(x) : lmb_expf(x); }
+
 /* log2(x) for finite x > 0 (normal or subnormal). */
 LMB_HD float lmb_log2f(float x) {
 	int e = 0;

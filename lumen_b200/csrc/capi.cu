@@ -110,6 +110,9 @@ void lmb_destroy(lmb_ctx* ctx) {
 	if (ctx->ev_snapshot) cudaEventDestroy(ctx->ev_snapshot);
 	if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
 	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+	if (ctx->ev_miss_ready) cudaEventDestroy(ctx->ev_miss_ready);
+	if (ctx->ev_miss_done) cudaEventDestroy(ctx->ev_miss_done);
+	if (ctx->miss_stream) cudaStreamDestroy(ctx->miss_stream);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }

@@ -91,6 +91,7 @@ struct Wavefront {
 	uint32_t* trace_queue = nullptr; // typed ray entries for k_trace: index | type << 30 (up to 3 per path)
 	uint32_t* trace_cursor = nullptr;  // work-fetch cursor of the array ray queries
 	uint32_t* counters = nullptr;  // see enum Counter in wavefront.cu
+	uint32_t* miss_marks = nullptr;  // sky march ranges (k_miss): [0..64] miss-record count after bounce d - 1's k_classify, [65..128] work cursors
 	unsigned long long* stats = nullptr;  // device counters, see StatSlot
 	uint32_t frames_in_flight = 0;
 };
@@ -175,6 +176,9 @@ struct lmb_ctx {
 	bool profile_stages = false;
 	bool stats_per_launch = false;  // LMB_STATS_PER_LAUNCH=1: print k_trace's counters after every launch (calibration runs only)
 	cudaEvent_t ev[8]{};
+	// the sky march of escaped rays runs beside the bounce loop on its own stream (wavefront.cu k_miss)
+	cudaStream_t miss_stream = nullptr;
+	cudaEvent_t ev_miss_ready = nullptr, ev_miss_done = nullptr;
 };
 
 namespace lmb {

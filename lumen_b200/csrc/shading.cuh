@@ -31,6 +31,9 @@ namespace lmb {
 #define LMB_DN static __device__ __noinline__
 LMB_DN float d_powf(float x, float y) { return lmb_powf(x, y); }
 LMB_DN float d_expf(float x) { return lmb_expf(x); }
+// the same function, bit for bit (lmb_detmath.h lmb_expf_fast), inlined: 15 FP32 / integer instructions in the window every exponent
+// of the sky march falls into but the far tail, no call, nothing on the conversion pipe
+LMB_D float d_expf_fast(float x) { return (x > -86.0f && x <= 88.0f) ? lmb_expf_window(x) : d_expf(x); }
 LMB_DN float2 d_sincosf(float x) {
 	float s, c;
 	lmb_sincosf(x, &s, &c);
@@ -773,21 +776,36 @@ LMB_D float height(const V3& p) { return length(planet_center() - p) - LMB_PLANE
 // those take the division instruction. 3 FP instructions instead of the ~9 + FCHK of div.rn; density() runs 9 x 3 of them in
 // each of the 64 march steps of an escaped ray.
 template <typename C>
-LMB_D float div_const(float x, C) {
+LMB_D float div_const(float x, C) {  // requires |x| > 1e-30 (density() tests once for its three divisions)
 	constexpr float c = C::value();
 	constexpr float rc = 1.0f / c;
-	if (!(fabsf(x) > 1e-30f)) return x / c;
 	const float q = x * rc;
 	return fmaf(fmaf(-q, c, x), rc, q);
 }
 struct CRayleighH { static constexpr float value() { return LMB_RAYLEIGH_HEIGHT; } };
 struct CMieH { static constexpr float value() { return LMB_MIE_HEIGHT; } };
 struct COzoneW { static constexpr float value() { return 15000.0f; } };
+// The exponentials go through lmb_expf_window (bit for bit lmb_expf inside its window, lmb_detmath.h) with ONE range test per group:
+// every argument of the march sits in the window (the most negative is -h / 1200 m at the top of the atmosphere, -83.3), so the
+// d_expf calls below are the cold side of a branch that is there for exactness only.
+LMB_D bool exp_in_window(float x) { return fabsf(x) < 86.0f; }
 LMB_D V3 density(float h) {
-	return v3(d_expf(-gmax(0.0f, div_const(h, CRayleighH{}))), d_expf(-gmax(0.0f, div_const(h, CMieH{}))),
-			  gmax(0.0f, 1 - div_const(fabsf(h - 25000.0f), COzoneW{})));
+	const float ho = fabsf(h - 25000.0f);
+	float qr, qm, qo;
+	if (fabsf(h) > 1e-30f && ho > 1e-30f) {  // one guard for the three constant divisions (div_const)
+		qr = div_const(h, CRayleighH{}), qm = div_const(h, CMieH{}), qo = div_const(ho, COzoneW{});
+	} else {
+		qr = h / LMB_RAYLEIGH_HEIGHT, qm = h / LMB_MIE_HEIGHT, qo = ho / 15000.0f;
+	}
+	const float xr = -gmax(0.0f, qr), xm = -gmax(0.0f, qm);
+	const float oz = gmax(0.0f, 1 - qo);
+	if (exp_in_window(xr) && exp_in_window(xm)) return v3(lmb_expf_window(xr), lmb_expf_window(xm), oz);
+	return v3(d_expf(xr), d_expf(xm), oz);
 }
-LMB_D V3 vexp(const V3& a) { return v3(d_expf(a.x), d_expf(a.y), d_expf(a.z)); }
+LMB_D V3 vexp(const V3& a) {
+	if (exp_in_window(a.x) && exp_in_window(a.y) && exp_in_window(a.z)) return v3(lmb_expf_window(a.x), lmb_expf_window(a.y), lmb_expf_window(a.z));
+	return v3(d_expf(a.x), d_expf(a.y), d_expf(a.z));
+}
 LMB_D V3 absorb(const V3& od) { return vexp(-(od.x * c_rayleigh() + od.y * c_mie() * 1.1f + od.z * c_ozone()) * 1.0f); }
 LMB_D V3 optical_depth(const V3& ray_start, const V3& ray_dir) {
 	const V2 isect = atmosphere_intersection(ray_start, ray_dir);

@@ -34,6 +34,9 @@ namespace {
 #ifndef LMB_SHADE_MIN_BLOCKS
 #define LMB_SHADE_MIN_BLOCKS 4
 #endif
+#ifndef LMB_SHADE_PREFETCH
+#define LMB_SHADE_PREFETCH 1
+#endif
 #ifndef LMB_SHADE_MIN_BLOCKS_DIFFUSE
 #define LMB_SHADE_MIN_BLOCKS_DIFFUSE LMB_SHADE_MIN_BLOCKS
 #endif
@@ -283,8 +286,23 @@ __global__ void __launch_bounds__(128, LAST ? 8 : (TYPE == LMB_BSDF_DIFFUSE ? LM
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	uint32_t n_shadow = 0, n_probe = 0, n_cont = 0;
 	const uint32_t stride = gridDim.x * blockDim.x;
+#if LMB_SHADE_PREFETCH
+	// The dependent chain queue -> path state / hit -> 128-byte shading record is where this kernel waits (ncu r02b: a third of its
+	// stall samples sit on those three loads, at 4 warps per scheduler). The NEXT trip's chain is walked ahead in three short hops
+	// spread over the current trip: its queue entry (one register), then its hit's triangle id + L2 prefetches of its state lines,
+	// then an L1 prefetch of its shading record.
+	uint32_t at_ahead = 0xFFFFFFFFu;
+	{
+		const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+		if (!LAST && i0 < count) at_ahead = queue[i0];
+	}
+#endif
 	for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride) {  // warp-uniform trip count
 		const uint32_t i = base + lane;
+#if LMB_SHADE_PREFETCH
+		const uint32_t at_now = at_ahead;
+		at_ahead = (!LAST && i + stride < count) ? queue[i + stride] : 0xFFFFFFFFu;
+#endif
 		// ---- stage 1: hit record, material, emission, depth cut, normal orientation (path.rgen:56-74)
 		bool active = i < count;
 		uint32_t slot = 0, prim = 0xFFFFFFFFu, out_flags = 0, rng_w = 0;
@@ -301,7 +319,11 @@ __global__ void __launch_bounds__(128, LAST ? 8 : (TYPE == LMB_BSDF_DIFFUSE ? LM
 		lmb_material hit_mat;
 #endif
 		if (active) {
+#if LMB_SHADE_PREFETCH
+			const uint32_t at = LAST ? i : at_now;
+#else
 			const uint32_t at = LAST ? i : queue[i];
+#endif
 			const float4 c4 = pl.col[at];
 			const float4 h4 = hit[at];
 			prim = __float_as_uint(h4.w);
@@ -350,6 +372,16 @@ __global__ void __launch_bounds__(128, LAST ? 8 : (TYPE == LMB_BSDF_DIFFUSE ? LM
 			}
 		}
 		if (LAST) continue;
+#if LMB_SHADE_PREFETCH
+		uint32_t prim_ahead = 0xFFFFFFFFu;
+		if (at_ahead != 0xFFFFFFFFu) {
+			prim_ahead = __float_as_uint(hit[at_ahead].w);
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.col + at_ahead));
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.thr + at_ahead));
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.ray_d + at_ahead));
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.pix + at_ahead));
+		}
+#endif
 		const uint32_t fb = slot / rp.n_pix, pix = slot - fb * rp.n_pix;
 		Rng seed{pix % rp.width, rp.row_first + (pix / rp.width) * rp.row_stride, rp.first_frame + fb * rp.frame_stride, rng_w};
 		// ---- stage 2: next-event estimation (path.rgen:75-80, pt_commons.glsl:3-20, 28-30). The NEE record goes straight to
@@ -403,6 +435,9 @@ __global__ void __launch_bounds__(128, LAST ? 8 : (TYPE == LMB_BSDF_DIFFUSE ? LM
 			}
 			nee[NEE_WI * (size_t)n_slots + k] = f4(ls.wi, __uint_as_float(flags));
 		}
+#if LMB_SHADE_PREFETCH
+		if (prim_ahead != 0xFFFFFFFFu) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.tri_shade + 8 * (size_t)prim_ahead));
+#endif
 		// ---- stage 3: continuation sample, throughput, Russian roulette (path.rgen:81-100)
 		bool alive = false;
 		V3 wi_next = v3(0.0f);
@@ -512,15 +547,41 @@ __global__ void __launch_bounds__(128) k_connect(RenderParams rp, DeviceScene sc
 }
 
 // Escaped rays with a sun + sky light: col += throughput * shade_atmosphere(...) (path.rgen:50-53, commons.glsl:156-168).
-// A path misses at most once and nothing is added to its radiance afterwards, so running this after the bounce loop keeps
-// the order of the float additions.
-__global__ void __launch_bounds__(128) k_miss(RenderParams rp, DeviceScene sc, const uint32_t* __restrict__ counters, MissPlanes ms, float4* __restrict__ acc) {
-	const uint32_t count = counters[CNT_MISS];
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-		const float4 c4 = ms.col[i];
-		const V3 sky = shade_atmosphere(sc, rp.dir_light_idx, rp.sky_col, xyz(ms.ray_o[i]), xyz(ms.ray_d[i]), T_MAX);
-		const V3 col = xyz(c4) + xyz(ms.thr[i]) * sky;
-		acc[ms.pix[i]] = f4(col, 0.0f);
+// A path misses at most once and nothing is added to its radiance afterwards, so the march may run any time between the k_classify
+// that found the miss and the film update, and it keeps the order of the float additions.
+// The march (64 x 9 density evaluations, ~1500 exponentials per ray) is pure FP32 issue with no memory traffic -- 13.6 ms of a 100 ms
+// step when it ran after the bounce loop -- while k_trace leaves a quarter of the issue slots idle and k_shade two thirds. So it runs
+// BESIDE the bounce loop: after k_classify(d) a one-thread kernel notes how many miss records exist (marks[d + 1]) and a small
+// persistent grid on a second stream marches records [marks[d], marks[d + 1]) while the render stream goes on with bounce d + 1.
+// Work is handed out 32 records at a time from a cursor per range; when the bounce loop is over the render stream runs the same
+// kernel over ALL ranges with a full grid, so whatever the side grid has not reached is finished at full width, then waits for it.
+constexpr int MISS_RANGES = 64;  // the first 63 bounces have a range of their own; deeper bounces share the last one
+__global__ void k_miss_mark(const uint32_t* __restrict__ counters, uint32_t* __restrict__ marks, int range, bool first) {
+	const uint32_t begin = first ? 0u : marks[range];
+	if (first) marks[range] = 0u;
+	marks[range + 1] = counters[CNT_MISS];
+	marks[MISS_RANGES + 1 + range] = begin;
+}
+__global__ void __launch_bounds__(128, 8) k_miss(RenderParams rp, DeviceScene sc, uint32_t* __restrict__ marks, int range_first, int range_last, MissPlanes ms,
+													 float4* __restrict__ acc) {
+	const int lane = threadIdx.x & 31;
+	for (int range = range_first; range <= range_last; range++) {
+		const uint32_t end = marks[range + 1];
+		uint32_t* cursor = &marks[MISS_RANGES + 1 + range];
+		if (*(volatile uint32_t*)cursor >= end) continue;
+		for (;;) {
+			uint32_t base = 0;
+			if (lane == 0) base = atomicAdd(cursor, 32u);
+			base = __shfl_sync(0xFFFFFFFFu, base, 0);
+			if (base >= end) break;
+			const uint32_t i = base + lane;
+			if (i < end) {
+				const float4 c4 = ms.col[i];
+				const V3 sky = shade_atmosphere(sc, rp.dir_light_idx, rp.sky_col, xyz(ms.ray_o[i]), xyz(ms.ray_d[i]), T_MAX);
+				const V3 col = xyz(c4) + xyz(ms.thr[i]) * sky;
+				acc[ms.pix[i]] = f4(col, 0.0f);
+			}
+		}
 	}
 }
 
@@ -653,6 +714,7 @@ int wavefront_alloc(lmb_ctx* ctx, uint32_t frames_in_flight) {
 	if ((rc = alloc((void**)&wf.probe_hit, n_slots * 16))) return rc;
 	if ((rc = alloc((void**)&wf.shadow_occ, n_slots * 4))) return rc;
 	if ((rc = alloc((void**)&wf.counters, CNT_COUNT * 4))) return rc;
+	if ((rc = alloc((void**)&wf.miss_marks, (2 * MISS_RANGES + 2) * 4))) return rc;
 	if ((rc = alloc((void**)&wf.stats, ST_COUNT * 8))) return rc;
 	LMB_CUDA(ctx, cudaMemsetAsync(wf.stats, 0, ST_COUNT * 8, ctx->stream));
 	return 0;
@@ -664,7 +726,7 @@ void wavefront_free(lmb_ctx* ctx) {
 	for (int p = 0; p < 2; p++) cudaFree(wf.ray_o[p]), cudaFree(wf.ray_d[p]), cudaFree(wf.thr[p]), cudaFree(wf.col[p]), cudaFree(wf.pix[p]);
 	cudaFree(wf.hit), cudaFree(wf.acc), cudaFree(wf.nee), cudaFree(wf.nee_path);
 	cudaFree(wf.miss_ray_o), cudaFree(wf.miss_ray_d), cudaFree(wf.miss_thr), cudaFree(wf.miss_col), cudaFree(wf.miss_pix);
-	cudaFree(wf.mat_queues), cudaFree(wf.trace_queue), cudaFree(wf.probe_hit), cudaFree(wf.shadow_occ), cudaFree(wf.trace_cursor), cudaFree(wf.counters), cudaFree(wf.stats);
+	cudaFree(wf.mat_queues), cudaFree(wf.trace_queue), cudaFree(wf.probe_hit), cudaFree(wf.shadow_occ), cudaFree(wf.trace_cursor), cudaFree(wf.counters), cudaFree(wf.miss_marks), cudaFree(wf.stats);
 	wf = Wavefront{};
 }
 
@@ -697,6 +759,18 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 	const MissPlanes miss{wf.miss_ray_o, wf.miss_ray_d, wf.miss_thr, wf.miss_col, wf.miss_pix};
 	float ms;
 	const bool prof = ctx->profile_stages;  // per-stage timing serialises the bounce loop; off by default
+	// sky march beside the bounce loop (k_miss): LMB_MISS_SIDE_BLOCKS = blocks per SM of the side grid, 0 = march after the loop only
+	static const uint32_t miss_side_blocks_env = env_u32("LMB_MISS_SIDE_BLOCKS", 0);
+	const bool sky_march = pc.dir_light_idx != 0xFFFFFFFFu;
+	const uint32_t miss_side_blocks = (sky_march && !prof) ? miss_side_blocks_env : 0u;
+	bool side_launched = false;
+	if (miss_side_blocks > 0 && !ctx->miss_stream) {
+		int lo = 0, hi = 0;
+		cudaDeviceGetStreamPriorityRange(&lo, &hi);
+		LMB_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->miss_stream, cudaStreamNonBlocking, hi));  // high priority: its few blocks get a seat as soon as one frees
+		LMB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_miss_ready, cudaEventDisableTiming));
+		LMB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_miss_done, cudaEventDisableTiming));
+	}
 	cudaEventRecord(ctx->ev[0], st);
 	for (uint32_t done = 0; done < n_frames;) {
 		const uint32_t nb = std::min(wf.frames_in_flight, n_frames - done);
@@ -746,6 +820,17 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 			const bool last = depth >= pc.max_depth - 1;  // the last bounce only collects emission (path.rgen:57-62)
 			k_classify<<<grid_256, 256, 0, st>>>(rp, ctx->scene, depth, wf.counters, par, planes[par], wf.hit, wf.mat_queues, miss, wf.acc, wf.n_slots);
 			ctx->stats.kernel_launches += 1;
+			if (sky_march && depth < MISS_RANGES - 1) {  // the rays that escaped at this bounce: marched beside the bounces still to come
+				k_miss_mark<<<1, 1, 0, st>>>(wf.counters, wf.miss_marks, depth, depth == 0);
+				ctx->stats.kernel_launches += 1;
+				if (miss_side_blocks > 0 && !last) {
+					cudaEventRecord(ctx->ev_miss_ready, st);
+					cudaStreamWaitEvent(ctx->miss_stream, ctx->ev_miss_ready, 0);
+					k_miss<<<ctx->sm_count * miss_side_blocks, 128, 0, ctx->miss_stream>>>(rp, ctx->scene, wf.miss_marks, depth, depth, miss, wf.acc);
+					ctx->stats.kernel_launches += 1;
+					side_launched = true;
+				}
+			}
 			if (last) {
 				k_shade<0u, true><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(wf.mat_queues, 0));
 				ctx->stats.kernel_launches += 1;
@@ -778,9 +863,19 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 			}
 		}
 		if (prof) cudaEventRecord(ctx->ev[1], st);
-		if (pc.dir_light_idx != 0xFFFFFFFFu) {
-			k_miss<<<grid_wide, 128, 0, st>>>(rp, ctx->scene, wf.counters, miss, wf.acc);
+		if (sky_march) {
+			const int n_bounces = std::max(pc.max_depth, 1), n_ranges = std::min(n_bounces, MISS_RANGES);
+			if (n_bounces > MISS_RANGES - 1) {  // the bounces without a range of their own share the last one
+				k_miss_mark<<<1, 1, 0, st>>>(wf.counters, wf.miss_marks, MISS_RANGES - 1, false);
+				ctx->stats.kernel_launches += 1;
+			}
+			k_miss<<<grid_wide, 128, 0, st>>>(rp, ctx->scene, wf.miss_marks, 0, n_ranges - 1, miss, wf.acc);
 			ctx->stats.kernel_launches += 1;
+			if (side_launched) {
+				cudaEventRecord(ctx->ev_miss_done, ctx->miss_stream);
+				cudaStreamWaitEvent(st, ctx->ev_miss_done, 0);
+				side_launched = false;
+			}
 		}
 		k_film<<<grid_256, 256, 0, st>>>(rp, nb, film_mode, wf.acc, ctx->film, wf.stats);
 		ctx->stats.kernel_launches += 1;
