@@ -8,8 +8,8 @@ Workload (config.workload): the classroom configuration of BASELINE.json -- 1920
 diffuse / conductor materials. The reference's classroom meshes are not in its tree (scenes/classroom/how-to-obtain.txt),
 so the geometry is the labelled procedural stand-in of scenes/gen_classroom_standin.py, loaded through the same
 Mitsuba-XML path. One STEP = one pass of the hot path over one batch: every rank renders `frames_per_step` frames
-(samples per pixel) of the full image into its sum film; with N > 1 the films are summed by ONE NCCL all-reduce behind the C ABI
-(lmb_film_allreduce: snapshot -> ncclAllReduce -> "/ count" epilogue on the context's comm stream, overlapping the next step's
+(samples per pixel) of the full image into its sum film; with N > 1 the films are summed on rank 0 by ONE NCCL reduce behind the C ABI
+(lmb_film_reduce: snapshot -> ncclReduce -> "/ count" epilogue on the context's comm stream, overlapping the next step's
 rendering) and every rank gets the resolved image. Ranks take disjoint frame indices (frame = first + rank + k*N): per-GPU
 work is fixed -> weak scaling.
 
@@ -17,14 +17,14 @@ work is fixed -> weak scaling.
            torch.cuda.synchronize(), max over ranks.
 `e2e`    = same metric through the public C-ABI calls with HOST buffers inside the timed region: per step the push
            constants + camera UBO are handed over from host memory (lmb_render copies them) and the resolved RGBA32F film lands in
-           pinned host memory (lmb_download_async / lmb_film_allreduce's out pointer).
+           pinned host memory (lmb_download_async / lmb_film_reduce's out pointer on rank 0).
 `roofline`        the dominant kernel, k_trace, on this workload: ISSUE bound (the BVH is L2-resident): warp instructions issued
                   (the kernel's own counters x the per-counter costs of profiles/ktrace_calibration.json) / time, against
                   SMs x 4 schedulers x the SM clock sampled in this run. The algorithmic-bytes figure is kept as a secondary field.
 `roofline_config5` the same kernel on BASELINE config 5 (10 M-triangle torus grid, 2^24 incoherent rays: the HBM-sized case), measured in
                   this run (N = 1): algorithmic bytes / time against the measured HBM peak.
 `config4`         BASELINE config 4's shape beside the headline: 3840x2160, 2 pixel shards x N/2 sample shards, ONE frame per rank and
-                  step, reduced by the same all-reduce.
+                  step, reduced by the same call.
 `film_check`      (N > 1) the N-rank resolved film against the same frames rendered by rank 0 alone.
 `cpu_baseline`    the reference's own shader source compiled for the CPU (oracle/_ref/libglslref.so, kind "reference"; the oracle port
                   when that library is absent) on a bounded sample of the same workload at full resolution.
@@ -311,9 +311,10 @@ def main():
             dev.render(a_pc, a_ubo, first, frames_per_step, n_sshards, integrator.FILM_SUM)  # frames first, first + S, ... of this rank's rows
             state["frame"] += frames_per_step * n_sshards
             if world > 1:
-                # ONE fp32 all-reduce (rgb sums + valid-sample counts) over NVLink + the "/ count" epilogue, on the context's comm stream
-                # over a snapshot of the film; the film is cleared in stream order and the next step renders meanwhile
-                dev.film_allreduce(pinned.data_ptr() if download else resident.data_ptr(), clear_film=True)
+                # ONE fp32 sum-reduce to rank 0 (rgb sums + valid-sample counts) over NVLink + the "/ count" epilogue, on the context's comm
+                # stream over a snapshot of the film; the film is cleared in stream order and the next step renders meanwhile. The job's
+                # result is one image: rank 0 receives it (and, end to end, copies it home); the other ranks only contribute.
+                dev.film_reduce(0, (pinned.data_ptr() if download else resident.data_ptr()) if rank == 0 else None, clear_film=True)
             else:
                 dev.resolve()
                 if download:
@@ -361,7 +362,7 @@ def main():
         first = 500_000
         dev.clear_film()
         dev.render(pc, ubo, first + arm["s_shard"], fps, n_sshards, integrator.FILM_SUM)
-        dev.film_allreduce(arm["pinned"].data_ptr(), clear_film=True)
+        dev.film_reduce(0, arm["pinned"].data_ptr() if rank == 0 else None, clear_film=True)
         dev.sync()
         barrier()
         if rank == 0:
@@ -373,7 +374,7 @@ def main():
             rel = np.abs(reduced[..., :3] - alone[..., :3]) / np.maximum(np.abs(alone[..., :3]), 1e-3)
             film_check = {"max_rel_diff": float(rel.max()), "pixels_within_1e-4": float((rel.max(axis=2) <= 1e-4).mean()), "frames": fps * n_sshards,
                           "alpha_is_one": bool((reduced[..., 3] == 1.0).all()),
-                          "note": "resolved film of the N-rank all-reduce vs the same frames rendered by rank 0 alone (sum film + resolve); the fp32 sums differ only in association"}
+                          "note": "resolved film of the N-rank reduce (lmb_film_reduce, root 0) vs the same frames rendered by rank 0 alone (sum film + resolve); the fp32 sums differ only in association"}
         barrier()
 
     # ---- roofline of the dominant kernel (traversal), from a separately profiled pass of this run: per-stage CUDA events + the
@@ -398,7 +399,7 @@ def main():
                            "ms_per_step": e4["dt"] / 12 * 1e3},
                    "device_ms_render_per_step": r4["ms_render"] / 12, "steps": 12, "warmup": 3, "n_gpus": world,
                    "workload": f"classroom-standin 3840x2160 depth 8, {c4['n_pshards']} pixel shard(s) (interleaved rows) x {c4['n_sshards']} sample shard(s), 1 frame per rank and step"
-                               + (", films summed by one 133 MB lmb_film_allreduce per step (overlapped with the next step)" if world > 1 else ""),
+                               + (", films summed on rank 0 by one 133 MB lmb_film_reduce per step (overlapped with the next step)" if world > 1 else ""),
                    "note": "BASELINE config 4 (bedroom 4K, tile + sample sharding) on the stand-in geometry; scaling efficiency = value(N) / (N x value(1)) over the SCALE records"}
         dev.set_pixel_shard(0, 1)
         dev.init(WIDTH, HEIGHT, fps)
@@ -484,7 +485,7 @@ def main():
             "metric": "Mrays/s", "value": rays / dt / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak" if n_pshards == 1 else "mixed (pixel shards split the image, sample shards add frames)", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD.format(w=WIDTH, h=HEIGHT), "max_depth": MAX_DEPTH, "frames_per_step_per_gpu": fps, "triangles": int(scene.info.n_triangles),
-                       "sharding": (f"{n_pshards} pixel shard(s) (interleaved rows) x {n_sshards} sample shard(s) (frame index mod {n_sshards}), full scene + BVH replica per GPU, one lmb_film_allreduce (ncclAllReduce fp32 + resolve epilogue, overlapped with the next step) per step"
+                       "sharding": (f"{n_pshards} pixel shard(s) (interleaved rows) x {n_sshards} sample shard(s) (frame index mod {n_sshards}), full scene + BVH replica per GPU, one lmb_film_reduce to rank 0 (ncclReduce fp32 + resolve epilogue, overlapped with the next step) per step"
                                     if world > 1 else "single GPU"), "width": WIDTH, "height": HEIGHT,
                        "l2": f"256 MB flush before the timed region; per-step wavefront state (~{SLOT_BYTES * fps * WIDTH * HEIGHT / 1e9:.1f} GB) exceeds the 126 MB L2, the ~18 MB BVH stays L2-resident by design",
                        "libraries": {"liblumen_b200.so": "built in-tree (nvcc sm_100a)", "liblumen_host.so / liboracle.so / libglslref.so": "prebuilt in the build container (they compile against the reference checkout's third-party parsers / shader sources, which the GPU box does not have) and shipped with the snapshot",

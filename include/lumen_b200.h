@@ -167,6 +167,10 @@ int lmb_comm_info(lmb_ctx* ctx, int* rank, int* n_ranks, int* nccl_version); /* 
  * clear_film != 0, zeroed for the next batch; reduce, resolve and the copy to out_rgba run on the context's own high-priority
  * stream while lmb_render goes on with the next frames. */
 int lmb_film_allreduce(lmb_ctx* ctx, float* out_rgba, int clear_film);
+/* The same with ONE receiver (ncclReduce): rank `root` ends with the resolved image of all ranks (in its film, or in out_rgba with
+ * the snapshot form); the other ranks only contribute -- out_rgba is ignored there and may be NULL, clear_film alone selects the
+ * snapshot form. A progressive render shows one image: N - 1 ranks need neither the sum nor the copy home. */
+int lmb_film_reduce(lmb_ctx* ctx, int root, float* out_rgba, int clear_film);
 
 /* Device pointer of the film and the CUDA stream (cudaStream_t) the context works on, for zero-copy consumers
  * (e.g. an NCCL all-reduce issued by the caller). */

@@ -20,6 +20,7 @@ struct NcclApi {
 	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
 	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*GroupStart)() = nullptr;
 	ncclResult_t (*GroupEnd)() = nullptr;
 	const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -49,6 +50,7 @@ const NcclApi& nccl() {
 		a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
 		a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
 		a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
+		a.Reduce = (decltype(a.Reduce))sym("ncclReduce");
 		a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
 		a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
 		a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
@@ -174,22 +176,31 @@ int lmb_comm_info(lmb_ctx* ctx, int* rank, int* n_ranks, int* nccl_version) {
 	return LMB_OK;
 }
 
-// film (LMB_FILM_SUM, this rank's samples) -> sum over the ranks -> rgb / alpha.
-//   out_rgba == NULL: in place, in stream order on the render stream; the film holds the resolved image of ALL ranks afterwards.
+// film (LMB_FILM_SUM, this rank's samples) -> sum over the ranks -> rgb / alpha, on every rank (root < 0: ncclAllReduce) or on one
+// (root >= 0: ncclReduce; the other ranks only contribute -- a progressive renderer shows ONE image, so N - 1 ranks need neither the
+// sum nor the trip home of 133 MB at 4K).
+//   out_rgba == NULL: in place, in stream order on the render stream; the film holds the resolved image of ALL ranks afterwards
+//     (on the root only with a root; the other ranks' films are left as they were).
 //   out_rgba != NULL: the film is snapshotted in stream order (device-to-device copy) and, when clear_film is set, zeroed for the next
 //     batch; the snapshot is reduced, resolved and copied to out_rgba (host -- pinned for a truly asynchronous copy -- or device) on
-//     the context's high-priority comm stream while the render stream goes on with the next lmb_render.
+//     the context's high-priority comm stream while the render stream goes on with the next lmb_render. With a root, out_rgba is
+//     written on the root only and may be NULL elsewhere (the snapshot form is then chosen by clear_film).
 // Nothing waits on the host in either form; lmb_sync does.
-int lmb_film_allreduce(lmb_ctx* ctx, float* out_rgba, int clear_film) {
-	if (!ctx || !ctx->film) return set_error(ctx, LMB_ERR_INVALID, "lmb_film_allreduce: call lmb_init first");
-	if (!ctx->comm) return set_error(ctx, LMB_ERR_INVALID, "lmb_film_allreduce: call lmb_comm_init first");
+static int film_reduce(lmb_ctx* ctx, int root, float* out_rgba, int clear_film, const char* who) {
+	if (!ctx || !ctx->film) return set_error(ctx, LMB_ERR_INVALID, std::string(who) + ": call lmb_init first");
+	if (!ctx->comm) return set_error(ctx, LMB_ERR_INVALID, std::string(who) + ": call lmb_comm_init first");
+	if (root >= ctx->comm_size) return set_error(ctx, LMB_ERR_INVALID, std::string(who) + ": root is not a rank of the communicator");
 	cudaSetDevice(ctx->device);
 	const size_t n_pix = (size_t)ctx->width * ctx->height, bytes = n_pix * 16;
 	ncclComm_t comm = (ncclComm_t)ctx->comm;
-	if (!out_rgba) {
-		if (clear_film) return set_error(ctx, LMB_ERR_INVALID, "lmb_film_allreduce: clear_film needs out_rgba (the in-place form leaves the result in the film)");
-		LMB_NCCL(ctx, nccl().AllReduce(ctx->film, ctx->film, n_pix * 4, ncclFloat, ncclSum, comm, ctx->stream));
-		return launch_resolve_on(ctx, ctx->film, ctx->stream);
+	const bool mine = root < 0 || root == ctx->comm_rank;  // this rank receives the sum
+	auto reduce = [&](float4* buf, cudaStream_t st) {
+		return root < 0 ? nccl().AllReduce(buf, buf, n_pix * 4, ncclFloat, ncclSum, comm, st) : nccl().Reduce(buf, buf, n_pix * 4, ncclFloat, ncclSum, root, comm, st);
+	};
+	if (!out_rgba && !(root >= 0 && !mine && clear_film)) {
+		if (clear_film) return set_error(ctx, LMB_ERR_INVALID, std::string(who) + ": clear_film needs out_rgba (the in-place form leaves the result in the film)");
+		LMB_NCCL(ctx, reduce(ctx->film, ctx->stream));
+		return mine ? launch_resolve_on(ctx, ctx->film, ctx->stream) : LMB_OK;
 	}
 	if (!ctx->reduce_buf) LMB_CUDA(ctx, cudaMalloc((void**)&ctx->reduce_buf, bytes));
 	if (ctx->reduce_pending) LMB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm_done, 0));  // the previous reduce still owns the buffer
@@ -197,12 +208,23 @@ int lmb_film_allreduce(lmb_ctx* ctx, float* out_rgba, int clear_film) {
 	if (clear_film) LMB_CUDA(ctx, cudaMemsetAsync(ctx->film, 0, bytes, ctx->stream));
 	LMB_CUDA(ctx, cudaEventRecord(ctx->ev_comm_ready, ctx->stream));
 	LMB_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_comm_ready, 0));
-	LMB_NCCL(ctx, nccl().AllReduce(ctx->reduce_buf, ctx->reduce_buf, n_pix * 4, ncclFloat, ncclSum, comm, ctx->comm_stream));
-	if (const int rc = launch_resolve_on(ctx, ctx->reduce_buf, ctx->comm_stream)) return rc;
-	LMB_CUDA(ctx, cudaMemcpyAsync(out_rgba, ctx->reduce_buf, bytes, cudaMemcpyDefault, ctx->comm_stream));
+	LMB_NCCL(ctx, reduce(ctx->reduce_buf, ctx->comm_stream));
+	if (mine) {
+		if (const int rc = launch_resolve_on(ctx, ctx->reduce_buf, ctx->comm_stream)) return rc;
+		LMB_CUDA(ctx, cudaMemcpyAsync(out_rgba, ctx->reduce_buf, bytes, cudaMemcpyDefault, ctx->comm_stream));
+	}
 	LMB_CUDA(ctx, cudaEventRecord(ctx->ev_comm_done, ctx->comm_stream));
 	ctx->reduce_pending = true;
 	return LMB_OK;
+}
+
+int lmb_film_allreduce(lmb_ctx* ctx, float* out_rgba, int clear_film) { return film_reduce(ctx, -1, out_rgba, clear_film, "lmb_film_allreduce"); }
+
+int lmb_film_reduce(lmb_ctx* ctx, int root, float* out_rgba, int clear_film) {
+	if (root < 0) return set_error(ctx, LMB_ERR_INVALID, "lmb_film_reduce: root must be a rank (lmb_film_allreduce gives every rank the image)");
+	if (ctx && ctx->comm && root == ctx->comm_rank && clear_film && !out_rgba)
+		return set_error(ctx, LMB_ERR_INVALID, "lmb_film_reduce: clear_film needs out_rgba on the root (the in-place form leaves the result in the film)");
+	return film_reduce(ctx, root, out_rgba, clear_film, "lmb_film_reduce");
 }
 
 }  // extern "C"

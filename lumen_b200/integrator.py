@@ -64,6 +64,7 @@ def lib():
         L.lmb_comm_destroy.argtypes = [vp]
         L.lmb_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
         L.lmb_film_allreduce.argtypes = [vp, vp, i32]
+        L.lmb_film_reduce.argtypes = [vp, i32, vp, i32]
         L.lmb_download_async.argtypes = [vp, vp]
         L.lmb_sync.argtypes = [vp]
         L.lmb_download_half_bgr.argtypes = [vp, vp]
@@ -99,7 +100,7 @@ EXPORTS = ["lmb_create", "lmb_destroy", "lmb_last_error", "lmb_upload_scene", "l
            "lmb_resolve", "lmb_download", "lmb_upload_film", "lmb_film_add_from", "lmb_film_device_ptr", "lmb_stream", "lmb_set_profile_stages", "lmb_get_stats",
            "lmb_reset_stats", "lmb_trace_closest", "lmb_trace_any", "lmb_trace_closest_device", "lmb_accel_num_tris", "lmb_accel_download",
            "lmb_download_async", "lmb_sync", "lmb_download_half_bgr", "lmb_set_reference_image", "lmb_rmse",
-           "lmb_trace_closest_device_ex", "lmb_comm_get_unique_id", "lmb_comm_init", "lmb_comm_init_all", "lmb_comm_destroy", "lmb_comm_info", "lmb_film_allreduce"]
+           "lmb_trace_closest_device_ex", "lmb_comm_get_unique_id", "lmb_comm_init", "lmb_comm_init_all", "lmb_comm_destroy", "lmb_comm_info", "lmb_film_allreduce", "lmb_film_reduce"]
 TESTHOOK_EXPORTS = ["lmb_kat_pcg4d", "lmb_kat_rand", "lmb_kat_detmath", "lmb_kat_offset_ray", "lmb_kat_sample_bsdf", "lmb_kat_eval_bsdf",
                     "lmb_kat_atmosphere", "lmb_kat_sample_light", "lmb_kat_texture", "lmb_kat_wide_bvh_check", "lmb_kat_bdpt_frame_raw"]
 
@@ -264,6 +265,11 @@ class Device:
         """film -> NCCL sum over the ranks -> rgb / alpha. out_ptr None: in place on the render stream; else the snapshot is reduced
         on the comm stream and copied to out_ptr (host or device address) while rendering goes on; sync() waits."""
         self._ck(lib().lmb_film_allreduce(self._h, out_ptr, 1 if clear_film else 0), "lmb_film_allreduce")
+
+    def film_reduce(self, root, out_ptr=None, clear_film=False):
+        """film_allreduce with ONE receiver (ncclReduce): rank `root` gets the resolved image, the others only contribute (their
+        out_ptr is ignored; clear_film alone selects the snapshot form there)."""
+        self._ck(lib().lmb_film_reduce(self._h, int(root), out_ptr, 1 if clear_film else 0), "lmb_film_reduce")
 
     def film_device_ptr(self):
         p, n = C.c_void_p(), C.c_uint64()

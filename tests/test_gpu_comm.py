@@ -78,6 +78,17 @@ def test_single_rank_allreduce_resolves_in_place_and_overlapped():
         assert bits_equal(got, want2).all()
         with pytest.raises(RuntimeError, match="clear_film needs out_rgba"):
             dev.film_allreduce(None, clear_film=True)
+        # one receiver among one rank: lmb_film_reduce(root 0) is the same operation
+        dev.render(pc, ubo, 16, 4, 1, integrator.FILM_SUM)  # adds to the resolved film: alpha 1 + 4
+        a = dev.download()
+        dev.film_reduce(0)
+        dev.sync()
+        b = dev.download()
+        assert np.array_equal(b[..., :3], a[..., :3] / a[..., 3:4]) and (b[..., 3] == 1).all()
+        with pytest.raises(RuntimeError, match="clear_film needs out_rgba on the root"):
+            dev.film_reduce(0, None, clear_film=True)
+        with pytest.raises(RuntimeError, match="root must be a rank"):
+            dev.film_reduce(-1)
         # the mean of frames 0..7 is what the reference's running mean gives, to rounding
         cpu, _ = po.OracleScene(sc).render(pc, ubo, 0, 8)
         assert np.allclose(out[..., :3], cpu[..., :3], rtol=3e-6, atol=1e-7)
@@ -135,6 +146,16 @@ def test_two_gpus_allreduce_equals_the_single_gpu_film():
             d.render(pc, ubo, 0, 8, 1, integrator.FILM_SUM)
         each(devs, lambda r, d: (d.film_allreduce(outs[r].ctypes.data, clear_film=True), d.sync()))
         assert outs[0].tobytes() == outs[1].tobytes() == want_sum.tobytes()
+        # (c) one receiver (lmb_film_reduce, root 1): the root's image is the all-reduce's, the other rank keeps its own film and buffer
+        for r, d in enumerate(devs):
+            d.render(pc, ubo, 0, 8, 1, integrator.FILM_SUM)
+        before0 = devs[0].download()
+        root_out, other_out = np.zeros((96, 128, 4), dtype=np.float32), np.full((96, 128, 4), -7.0, dtype=np.float32)
+        each(devs, lambda r, d: (d.film_reduce(1, (root_out if r == 1 else other_out).ctypes.data, clear_film=(r == 1)), d.sync()))
+        assert root_out.tobytes() == want_sum.tobytes() and (other_out == -7.0).all()
+        assert devs[0].download().tobytes() == before0.tobytes() and (devs[1].download() == 0).all()
+        with pytest.raises(RuntimeError, match="root is not a rank"):
+            devs[0].film_reduce(2)
     finally:
         single.close()
         for d in devs:
