@@ -195,13 +195,14 @@ def config5_roofline(integrator, local_rank, hbm_peak, peak_src):
         torch.cuda.synchronize()
         reps = 4
         dev.trace_closest_device(rays.data_ptr(), n, hits.data_ptr(), 1)  # warm-up
-        ms_unsorted = dev.trace_closest_device(rays.data_ptr(), n, hits.data_ptr(), reps)
-        first = hits.clone()
-        # the product's way through an incoherent batch: order the rays by (origin cell, direction octant) inside the timed launch
-        dev.trace_closest_device(rays.data_ptr(), n, hits.data_ptr(), 1, sort_rays=True)  # warm-up (allocates the sort scratch)
         dev.reset_stats()
-        ms = dev.trace_closest_device(rays.data_ptr(), n, hits.data_ptr(), reps, sort_rays=True)
+        ms = dev.trace_closest_device(rays.data_ptr(), n, hits.data_ptr(), reps)
         s = dev.stats()
+        first = hits.clone()
+        # the same batch ordered by (origin cell, direction octant) INSIDE the timed launch (lmb_trace_closest_device_ex sort_rays = 1):
+        # paid for itself while the walker's shared memory left the L1 28 KB (1483 -> 1912 Mrays/s); with the L1 at 92 KB it no longer does
+        dev.trace_closest_device(rays.data_ptr(), n, hits.data_ptr(), 1, sort_rays=True)  # warm-up (allocates the sort scratch)
+        ms_sorted = dev.trace_closest_device(rays.data_ptr(), n, hits.data_ptr(), reps, sort_rays=True)
         same = bool(torch.equal(first.view(torch.int32), hits.view(torch.int32)))
         traced = max(s.rays_closest, 1)
         bytes_per_ray = (s.nodes_visited * NODE_BYTES + s.tris_tested * TRI_BYTES) / traced + RAY_BYTES + HIT_BYTES
@@ -212,8 +213,9 @@ def config5_roofline(integrator, local_rank, hbm_peak, peak_src):
                 "avg_launch_ms": ms / reps, "algorithmic_bytes_per_launch": bytes_per_ray * n, "bytes_per_ray": bytes_per_ray,
                 "nodes_per_ray": s.nodes_visited / traced, "tris_per_ray": s.tris_tested / traced, "traffic": profile_file("ktrace_config5_traffic.json").get("dram_bytes_per_launch"),
                 "traffic_stale": profile_file("ktrace_config5_traffic.json").get("stale"),
-                "ray_order": "counting sort by (origin cell, direction octant), 15-bit keys, INSIDE the timed launch (lmb_trace_closest_device_ex sort_rays = 1)",
-                "unsorted": {"mrays_per_s": n * reps / ms_unsorted / 1e3, "avg_launch_ms": ms_unsorted / reps, "frac": bytes_per_ray * (n * reps / ms_unsorted / 1e3) / 1e3 / hbm_peak},
+                "ray_order": "as given (uniformly random origins and directions)",
+                "sorted": {"mrays_per_s": n * reps / ms_sorted / 1e3, "avg_launch_ms": ms_sorted / reps, "frac": bytes_per_ray * (n * reps / ms_sorted / 1e3) / 1e3 / hbm_peak,
+                           "ray_order": "counting sort by (origin cell, direction octant), 15-bit keys, inside the timed launch (sort_rays = 1)"},
                 "hits_identical_sorted_vs_unsorted": same,
                 "lbvh_build_ms": {"total": b.ms_build_accel, "morton": b.ms_build_morton, "sort": b.ms_build_sort, "tree": b.ms_build_tree,
                                   "refit_pack": b.ms_build_refit, "wide": b.ms_build_wide}}

@@ -419,7 +419,7 @@ int build_lbvh(lmb_ctx* ctx) {
 		// there, because they price rays that never stop, while a closest-hit ray ends at the first surface.
 		double cost_ploc = 0.0, cost_karras = 0.0;
 		if ((rc = build_wide_bvh(ctx))) return rc;
-		// the traversal stack holds one entry per level (11 shared + 53 local = 64): a clustering deeper than 56 levels is not walked
+		// the traversal stack holds one entry per level (shared + local = 64, trace_wide.cuh): a clustering deeper than 56 levels is not walked
 		// at all, not even by the probe (it loses below and the canonical tree, whose depth the 62 key bits bound, is taken)
 		const bool ploc_walkable = ctx->wide.levels <= 56;
 		if (ploc_walkable && (rc = probe_wide_tree(ctx, 1u << 16, &cost_ploc))) return rc;

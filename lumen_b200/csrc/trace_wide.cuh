@@ -34,13 +34,25 @@ struct WideBvhView {
 #ifndef LMB_TRACE_THREADS
 #define LMB_TRACE_THREADS 128
 #endif
-#define LMB_WSTACK_SM 11
-#define LMB_WSTACK_LOCAL 53
+// Entries of the traversal stack kept in shared memory (the rest, up to 64, spill to local memory). Shared memory is taken from the
+// L1: with 11 entries, 8 blocks needed the 228 KB carve-out and left the L1 28 KB -- the 10 M-triangle grid ran at 1483 Mrays/s;
+// 6 entries fit the 196 KB step (L1 60 KB): 2239 Mrays/s, classroom stand-in trace 59.0 -> 58.5 ms (profiles/r02b_summary.md).
+// The unpinned instantiation (7 blocks per SM, wavefront.cu) keeps 4 and lands on the 164 KB step.
+#ifndef LMB_WSTACK_SM
+#define LMB_WSTACK_SM 6
+#endif
+#ifndef LMB_WSTACK_SM_UNPINNED
+#define LMB_WSTACK_SM_UNPINNED 4
+#endif
+#define LMB_WSTACK_TOTAL 64
 #ifndef LMB_WIDE_REFILL_LANES
 #define LMB_WIDE_REFILL_LANES 28
 #endif
 #ifndef LMB_WIDE_BLOCKS_PER_SM
 #define LMB_WIDE_BLOCKS_PER_SM 8
+#endif
+#ifndef LMB_WIDE_BLOCKS_PER_SM_UNPINNED
+#define LMB_WIDE_BLOCKS_PER_SM_UNPINNED 7
 #endif
 #ifndef LMB_TRI_ROUND_LANES
 #define LMB_TRI_ROUND_LANES 8
@@ -102,8 +114,9 @@ LMB_D bool tri_test(const TriRay& r, const float4& p0, const float4& p1, const f
 }
 
 // Shared memory of one traversal block.
+template <int WS>
 struct TraceSmem {
-	uint2 stack[LMB_WSTACK_SM][LMB_TRACE_THREADS];
+	uint2 stack[WS][LMB_TRACE_THREADS];
 	float4 ray_a[LMB_TRACE_THREADS];  // o.xyz, tmin            } TriRay of the ray each lane owns, written once per ray
 	float4 ray_b[LMB_TRACE_THREADS];  // Sx, Sy, Sz, k (bits)   }
 	float4 ray_c[LMB_TRACE_THREADS];  // guarded 1/d.xyz (tri_clamp_t)
@@ -120,8 +133,9 @@ struct TraceSmem {
 template <bool PIN, typename Source>
 __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, Source& src, uint32_t count, uint32_t* cursor, unsigned long long* stats,
 													  int stat_closest, int stat_any) {
-	__shared__ TraceSmem sm;
-	uint2 l_stack[LMB_WSTACK_LOCAL];
+	constexpr int WS = PIN ? LMB_WSTACK_SM : LMB_WSTACK_SM_UNPINNED;
+	__shared__ TraceSmem<WS> sm;
+	uint2 l_stack[LMB_WSTACK_TOTAL - WS];
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
 	const int wbase = tid & ~31;
@@ -245,11 +259,11 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 				const uint32_t slot = (uint32_t)(bit - 24) ^ (oct_inv4 & 7u);
 				const uint32_t node = ng.x + __popc(hits & 0xFFu & ((1u << slot) - 1u));
 				if (ng.y > 0x00FFFFFFu) {  // siblings still to visit
-					if (sp < LMB_WSTACK_SM) {
+					if (sp < WS) {
 						if (PIN) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(stack_base + (uint32_t)sp * (LMB_TRACE_THREADS * 8u)), "r"(ng.x), "r"(ng.y));
 						else sm.stack[sp][tid] = ng;
 					}
-					else l_stack[sp - LMB_WSTACK_SM] = ng;
+					else l_stack[sp - WS] = ng;
 					sp++;
 				}
 #ifndef LMB_TRACE_NO_STATS
@@ -402,7 +416,7 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 			if (has && tg.y == 0u && ng.y <= 0x00FFFFFFu) {
 				if (sp > 0) {
 					sp--;
-					if (sp >= LMB_WSTACK_SM) ng = l_stack[sp - LMB_WSTACK_SM];
+					if (sp >= WS) ng = l_stack[sp - WS];
 					else if (PIN) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ng.x), "=r"(ng.y) : "r"(stack_base + (uint32_t)sp * (LMB_TRACE_THREADS * 8u)));
 					else ng = sm.stack[sp][tid];
 				} else {

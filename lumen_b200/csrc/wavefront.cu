@@ -174,8 +174,13 @@ struct WavefrontSource {
 	}
 };
 
+// Blocks per SM of the wide walker. Issue bound (BVH in the L2, pinned instantiation): 8 x 128 threads at 64 registers = the whole register
+// file. Latency bound (BVH beyond the L2, unpinned instantiation): 7 -- one block's shared memory less puts the carve-out one step down
+// (164 KB) and leaves the L1 92 KB instead of 60 for nodes and triangles: 10 M-triangle grid 2239 -> 2338 Mrays/s; the classroom stand-in
+// loses 2.7 % with 7 (profiles/r02b_summary.md).
+constexpr int wide_blocks_per_sm(bool pin) { return pin ? LMB_WIDE_BLOCKS_PER_SM : LMB_WIDE_BLOCKS_PER_SM_UNPINNED; }
 template <bool PIN>
-__global__ void __launch_bounds__(LMB_TRACE_THREADS, LMB_WIDE_BLOCKS_PER_SM) k_trace(WideBvhView bvh, WavefrontSource src, uint32_t* counters, int parity, unsigned long long* stats) {
+__global__ void __launch_bounds__(LMB_TRACE_THREADS, wide_blocks_per_sm(PIN)) k_trace(WideBvhView bvh, WavefrontSource src, uint32_t* counters, int parity, unsigned long long* stats) {
 	reset_next_counters(counters, parity);
 	trace_wide_persistent<PIN>(bvh, src, counters[CNT_TRACE + parity * CNT_LINE], &counters[CNT_CURSOR + parity * CNT_LINE], stats, -1, -1);
 }
@@ -646,7 +651,7 @@ struct ArraySource {
 };
 
 template <bool PIN>
-__global__ void __launch_bounds__(LMB_TRACE_THREADS, LMB_WIDE_BLOCKS_PER_SM) k_trace_array(WideBvhView bvh, ArraySource src, uint32_t n, uint32_t* cursor, unsigned long long* stats,
+__global__ void __launch_bounds__(LMB_TRACE_THREADS, wide_blocks_per_sm(PIN)) k_trace_array(WideBvhView bvh, ArraySource src, uint32_t n, uint32_t* cursor, unsigned long long* stats,
 																							 int count_rays) {
 	trace_wide_persistent<PIN>(bvh, src, n, cursor, stats, count_rays ? ST_CLOSEST : -1, count_rays ? ST_SHADOW : -1);
 }
@@ -795,7 +800,7 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 			else if (pinned)
 				k_trace<true><<<grid_trace_wide, LMB_TRACE_THREADS, 0, st>>>(wide, src, wf.counters, par, wf.stats);
 			else
-				k_trace<false><<<grid_trace_wide, LMB_TRACE_THREADS, 0, st>>>(wide, src, wf.counters, par, wf.stats);
+				k_trace<false><<<ctx->sm_count * wide_blocks_per_sm(false), LMB_TRACE_THREADS, 0, st>>>(wide, src, wf.counters, par, wf.stats);
 			ctx->stats.kernel_launches += 1;
 			if (prof) cudaEventRecord(ctx->ev[2], st);
 			if (ctx->stats_per_launch) {
@@ -910,7 +915,7 @@ static int launch_trace_array(lmb_ctx* ctx, const float4* d_rays, uint32_t n, fl
 	else if (trace_pinned(ctx))
 		k_trace_array<true><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n, cursor, ctx->wf.stats, count_rays);
 	else
-		k_trace_array<false><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n, cursor, ctx->wf.stats, count_rays);
+		k_trace_array<false><<<ctx->sm_count * wide_blocks_per_sm(false), LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n, cursor, ctx->wf.stats, count_rays);
 	return check_cuda(ctx, cudaGetLastError(), "k_trace_array");
 }
 // Probe rays for the choice of the traversal tree (lbvh.cu): they leave a random point of a random triangle in a uniformly random
@@ -951,7 +956,7 @@ int probe_wide_tree(lmb_ctx* ctx, uint32_t n_rays, double* steps_per_ray) {
 	if (trace_pinned(ctx))
 		k_trace_array<true><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n_rays, cursor, st, 1);
 	else
-		k_trace_array<false><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n_rays, cursor, st, 1);
+		k_trace_array<false><<<ctx->sm_count * wide_blocks_per_sm(false), LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n_rays, cursor, st, 1);
 	unsigned long long h[ST_COUNT];
 	LMB_CUDA(ctx, cudaMemcpyAsync(h, st, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
 	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
