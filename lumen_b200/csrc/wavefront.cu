@@ -202,7 +202,7 @@ struct MissPlanes {
 // k_classify: walks list d. Paths that ended at bounce d-1 and only waited for k_connect hand their radiance to acc; escaped
 // rays get the constant sky or a miss record (path.rgen:49-55); the rest are sorted by the BSDF type of the surface they hit
 // (one byte per triangle, L2-resident) into one queue of POSITIONS per type, so that k_shade<TYPE> runs a single lobe's code.
-__global__ void __launch_bounds__(256) k_classify(RenderParams rp, DeviceScene sc, int depth, uint32_t* __restrict__ counters, int parity, PathPlanes pl,
+__global__ void __launch_bounds__(256) k_classify(const __grid_constant__ RenderParams rp, const __grid_constant__ DeviceScene sc, int depth, uint32_t* __restrict__ counters, int parity, PathPlanes pl,
 													   const float4* __restrict__ hit, uint32_t* __restrict__ mat_queues, MissPlanes ms, float4* __restrict__ acc,
 													   uint32_t n_slots) {
 	const uint32_t count = path_count(counters, parity);
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(256) k_classify(RenderParams rp, DeviceScene s
 // LAST = true is the bounce at depth max_depth - 1, which only collects emission (path.rgen:57-62) for any BSDF type and
 // walks list d directly.
 template <uint32_t TYPE, bool LAST>
-__global__ void __launch_bounds__(128, LAST ? 8 : (TYPE == LMB_BSDF_DIFFUSE ? LMB_SHADE_MIN_BLOCKS_DIFFUSE : LMB_SHADE_MIN_BLOCKS)) k_shade(RenderParams rp, DeviceScene sc, int depth, uint32_t* __restrict__ counters, int parity, int count_idx,
+__global__ void __launch_bounds__(128, LAST ? 8 : (TYPE == LMB_BSDF_DIFFUSE ? LMB_SHADE_MIN_BLOCKS_DIFFUSE : LMB_SHADE_MIN_BLOCKS)) k_shade(const __grid_constant__ RenderParams rp, const __grid_constant__ DeviceScene sc, int depth, uint32_t* __restrict__ counters, int parity, int count_idx,
 													const uint32_t* __restrict__ queue, PathPlanes pl, PathPlanes nx, const float4* __restrict__ hit,
 													uint32_t* __restrict__ trace_queue, float4* __restrict__ nee, uint32_t* __restrict__ nee_path,
 													float4* __restrict__ acc, uint32_t n_slots, unsigned long long* stats) {
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(128, LAST ? 8 : (TYPE == LMB_BSDF_DIFFUSE ? LM
 
 // pt_commons.glsl:23-27, 33-39 and the accumulation of path.rgen:78, once both rays of the light sample are traced: the
 // result goes to the radiance of the path at its position in the current list (before this bounce adds emission)
-__global__ void __launch_bounds__(128) k_connect(RenderParams rp, DeviceScene sc, const uint32_t* __restrict__ counters, int parity,
+__global__ void __launch_bounds__(128) k_connect(const __grid_constant__ RenderParams rp, const __grid_constant__ DeviceScene sc, const uint32_t* __restrict__ counters, int parity,
 												  const uint32_t* __restrict__ nee_path, const float4* __restrict__ nee, const float4* __restrict__ probe_hit,
 												  const uint32_t* __restrict__ shadow_occ, float4* __restrict__ colb, uint32_t n_slots) {
 	const uint32_t count = nee_count(counters, parity);
@@ -567,7 +567,7 @@ __global__ void k_miss_mark(const uint32_t* __restrict__ counters, uint32_t* __r
 	marks[range + 1] = counters[CNT_MISS];
 	marks[MISS_RANGES + 1 + range] = begin;
 }
-__global__ void __launch_bounds__(128, 8) k_miss(RenderParams rp, DeviceScene sc, uint32_t* __restrict__ marks, int range_first, int range_last, MissPlanes ms,
+__global__ void __launch_bounds__(128, 8) k_miss(const __grid_constant__ RenderParams rp, const __grid_constant__ DeviceScene sc, uint32_t* __restrict__ marks, int range_first, int range_last, MissPlanes ms,
 													 float4* __restrict__ acc) {
 	const int lane = threadIdx.x & 31;
 	for (int range = range_first; range <= range_last; range++) {
@@ -757,6 +757,9 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 	const WideBvhView wide = wide_view_of(ctx);
 	const bool pinned = trace_pinned(ctx);
 	const int grid_wide = ctx->sm_count * 16;
+	// k_shade walks its queue with a grid-stride loop: the grid is a whole number of waves of the blocks one SM holds (A/B: LMB_SHADE_GRID_PER_SM)
+	static const uint32_t shade_grid_per_sm = env_u32("LMB_SHADE_GRID_PER_SM", 16);
+	const int grid_shade = ctx->sm_count * (int)shade_grid_per_sm;
 	const int grid_256 = ctx->sm_count * 8;
 	const int grid_trace = ctx->sm_count * 7;  // persistent: 7 blocks x 32 KB stack fit one SM's shared memory
 	const int grid_trace_wide = ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM;
@@ -837,20 +840,20 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 				}
 			}
 			if (last) {
-				k_shade<0u, true><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(wf.mat_queues, 0));
+				k_shade<0u, true><<<grid_shade, 128, 0, st>>>(LMB_SHADE_ARGS(wf.mat_queues, 0));
 				ctx->stats.kernel_launches += 1;
 			} else {
 				for (int m = 0; m < N_MAT_QUEUES; m++) {
 					if (!(ctx->mat_queue_mask & (1u << m))) continue;  // BSDF type absent from the scene (ENABLE_* macros, LumenScene.cpp:217-228)
 					const uint32_t* mq = wf.mat_queues + (size_t)m * wf.n_slots;
 					switch (m) {
-						case 0: k_shade<LMB_BSDF_DIFFUSE, false><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
-						case 1: k_shade<LMB_BSDF_MIRROR, false><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
-						case 2: k_shade<LMB_BSDF_GLASS, false><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
-						case 3: k_shade<LMB_BSDF_DIELECTRIC, false><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
-						case 4: k_shade<LMB_BSDF_CONDUCTOR, false><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
-						case 5: k_shade<LMB_BSDF_PRINCIPLED, false><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
-						default: k_shade<0u, false><<<grid_wide, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
+						case 0: k_shade<LMB_BSDF_DIFFUSE, false><<<grid_shade, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
+						case 1: k_shade<LMB_BSDF_MIRROR, false><<<grid_shade, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
+						case 2: k_shade<LMB_BSDF_GLASS, false><<<grid_shade, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
+						case 3: k_shade<LMB_BSDF_DIELECTRIC, false><<<grid_shade, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
+						case 4: k_shade<LMB_BSDF_CONDUCTOR, false><<<grid_shade, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
+						case 5: k_shade<LMB_BSDF_PRINCIPLED, false><<<grid_shade, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
+						default: k_shade<0u, false><<<grid_shade, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
 					}
 					ctx->stats.kernel_launches += 1;
 				}
