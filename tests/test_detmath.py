@@ -36,3 +36,16 @@ def test_pow_matches_hardware_style_exp2_log2():
     assert rel.max() < 2e-5
     edge = po.detmath(np.float32([0.0, 1.0, 0.5, 0.0625]), np.float32([5.0, 5.0, 5.0, 0.0]))["pow"]
     assert edge.tolist() == [0.0, 1.0, 0.03125, 1.0]
+
+
+def test_expf_window_form_equals_expf(tmp_path):
+    """lmb_expf_fast (the form the sky march inlines, lmb_detmath.h) against lmb_expf on every 61st of the 2^32 bit patterns, NaNs and
+    both tails included; tools/check_expf_equiv.c without -DSTRIDE walks all of them (16 s on 8 cores: 0 mismatches)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "check_expf")
+    subprocess.run(["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-mfma", "-DSTRIDE=61", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tools", "check_expf_equiv.c"), "-lm", "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("mismatches = 0 of"), out.stdout
