@@ -90,6 +90,11 @@ def full(path, traffic):
              # duration-weighted means over the same launches: what the kernel is actually bound by when the BVH is L2-resident
              "issue_active_pct": sum(p[0] * p[1] for p in trace_pipe) / w, "alu_pipe_pct": sum(p[0] * p[2] for p in trace_pipe) / w,
              "fma_pipe_pct": sum(p[0] * p[3] for p in trace_pipe) / w, "active_lanes_per_instruction": sum(p[0] * p[4] for p in trace_pipe) / w}
+        # stamped with the CUDA sources of the tree this runs in: summarise a capture BEFORE changing the kernels again (bench.py prints
+        # "traffic_stale": true when the hash differs)
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from srchash import csrc_sha
+        d["csrc_sha"] = csrc_sha()
         json.dump(d, open(os.path.join(ROOT, "profiles", "ktrace_dram_traffic.json"), "w"), indent=1)
         print("\nwrote profiles/ktrace_dram_traffic.json:", d)
 
