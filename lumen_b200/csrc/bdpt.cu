@@ -1141,40 +1141,75 @@ __global__ void __launch_bounds__(128) k_bdpt_connect(const __grid_constant__ Bd
 #ifndef LMB_BDPT_PAIR_BLOCKS
 #define LMB_BDPT_PAIR_BLOCKS 6  // 4 / 6 / 8 blocks per SM: classroom stand-in 52.9 / 48.8 / 47.0 ms, cornell 3.98 / 4.02 / 4.32 ms per frame
 #endif
+// Which (slot, pixel) entries have work in pass MODE, as a dense list. A warp of the slot-major grid holds 32 neighbouring pixels of ONE
+// pair, but only the pixels whose sub-paths are long enough have that pair at all, and in the resolve pass only those whose shadow ray
+// was emitted and found nothing: on the classroom stand-in k_bdpt_pair<3> ran at 4.6 of 32 lanes with its ~3000 instructions of MIS
+// code out of the instruction cache (no_instruction 10.7 warps per issue, profiles/r02c). The list keeps the slot-major, pixel-ascending
+// order inside a block, so a warp of the pair kernel still works on one pair for pixels that are close: vertex reads stay mostly
+// coalesced and the (s, t) loops converge. Entries without work get their defaults here (dead ray / zero contribution).
 template <int MODE>
-__global__ void __launch_bounds__(128, LMB_BDPT_PAIR_BLOCKS) k_bdpt_pair(const __grid_constant__ BdptParams P, const __grid_constant__ DeviceScene sc, const uint8_t* __restrict__ pair_ts) {
+__global__ void __launch_bounds__(256) k_bdpt_worklist(const __grid_constant__ BdptParams P, const uint8_t* __restrict__ pair_ts, uint32_t* __restrict__ list, uint32_t* __restrict__ count) {
+	__shared__ uint32_t s_warp[8], s_base;
 	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t c = blockIdx.y;
 	const int t = pair_ts[2 * c], s = pair_ts[2 * c + 1];
-	uint32_t n_shadow = 0;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	bool work = false;
+	uint32_t i = 0;
 	if (pix < P.n_pix) {
-		const size_t i = (size_t)c * P.n_pix + pix;
+		i = c * P.n_pix + pix;
 		const int num_light_paths = (int)P.misc[MW_NLIGHT * (size_t)P.n_pix + pix];
 		const int num_cam_paths = __float_as_int(P.walk[WW_B * (size_t)P.n_pix + pix]) + 1;
+		work = t <= num_cam_paths && s <= num_light_paths;
 		// dead slot: NaN origin (hits nothing) and NaN tmin -- a connection ray always has tmin = 0, so .w tells the two apart exactly
-		if (MODE == 1) P.rays[2 * i] = make_float4(__int_as_float(0x7FC00000), 0.0f, 0.0f, __int_as_float(0x7FC00000));
-		float4 out = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
-		bool work = t <= num_cam_paths && s <= num_light_paths;
+		if (MODE == 1) P.rays[2 * (size_t)i] = make_float4(__int_as_float(0x7FC00000), 0.0f, 0.0f, __int_as_float(0x7FC00000));
 		if (MODE == 3 && work && s > 0) {
 			// every strategy with a light vertex is zero unless its shadow ray was emitted and found nothing: skip the re-evaluation
-			const float tmin = P.rays[2 * i].w;
+			const float tmin = P.rays[2 * (size_t)i].w;
 			work = tmin == tmin && P.occ[i] == 0;
 		}
-		if (work) {
-			const BvhView none{nullptr, nullptr, 0};
-			Kctx k = make_kctx(P, sc, none, pix, P.misc[MW_RNG * (size_t)P.n_pix + pix] + (s == 1 ? 4u * (uint32_t)(t - 2) : 0u));
-			k.light_pdf_pos = __uint_as_float(P.misc[MW_LPDFPOS * (size_t)P.n_pix + pix]);
-			k.slot = c;
-			if (t == 1) {
-				int cx, cy;
-				const V3 sp = connect_cam<MODE>(k, s, cx, cy);
-				if (MODE == 3 && luminance(sp) > 0) out = make_float4(sp.x, sp.y, sp.z, __uint_as_float((uint32_t)cy * P.width + (uint32_t)cx));
-			} else {
-				const V3 L = connect<MODE>(k, s, t);
-				out = make_float4(L.x, L.y, L.z, __uint_as_float(0xFFFFFFFFu));
-			}
-			n_shadow = k.n_shadow;
+		if (MODE == 3 && !work) P.contrib[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
+	}
+	const uint32_t b = __ballot_sync(0xFFFFFFFFu, work);
+	if (lane == 0) s_warp[warp] = (uint32_t)__popc(b);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t total = 0;
+		for (int w = 0; w < 8; w++) {
+			const uint32_t n = s_warp[w];
+			s_warp[w] = total;
+			total += n;
 		}
+		s_base = total ? atomicAdd(count, total) : 0u;
+	}
+	__syncthreads();
+	if (work) list[s_base + s_warp[warp] + (uint32_t)__popc(b & ((1u << lane) - 1u))] = i;
+}
+
+// One (pair, pixel) of the work list per thread: MODE 1 emits its shadow ray, MODE 3 weights what was visible.
+template <int MODE>
+__global__ void __launch_bounds__(128, LMB_BDPT_PAIR_BLOCKS) k_bdpt_pair(const __grid_constant__ BdptParams P, const __grid_constant__ DeviceScene sc, const uint8_t* __restrict__ pair_ts,
+																		   const uint32_t* __restrict__ list, const uint32_t* __restrict__ count) {
+	const uint32_t n = *count;
+	uint32_t n_shadow = 0;
+	for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+		const uint32_t i = list[j];
+		const uint32_t c = i / P.n_pix, pix = i - c * P.n_pix;
+		const int t = pair_ts[2 * c], s = pair_ts[2 * c + 1];
+		float4 out = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
+		const BvhView none{nullptr, nullptr, 0};
+		Kctx k = make_kctx(P, sc, none, pix, P.misc[MW_RNG * (size_t)P.n_pix + pix] + (s == 1 ? 4u * (uint32_t)(t - 2) : 0u));
+		k.light_pdf_pos = __uint_as_float(P.misc[MW_LPDFPOS * (size_t)P.n_pix + pix]);
+		k.slot = c;
+		if (t == 1) {
+			int cx, cy;
+			const V3 sp = connect_cam<MODE>(k, s, cx, cy);
+			if (MODE == 3 && luminance(sp) > 0) out = make_float4(sp.x, sp.y, sp.z, __uint_as_float((uint32_t)cy * P.width + (uint32_t)cx));
+		} else {
+			const V3 L = connect<MODE>(k, s, t);
+			out = make_float4(L.x, L.y, L.z, __uint_as_float(0xFFFFFFFFu));
+		}
+		n_shadow += k.n_shadow;
 		if (MODE == 3) P.contrib[i] = out;
 	}
 	flush_counts(P.stats, 0, n_shadow, 0, 0);
@@ -1237,7 +1272,7 @@ __global__ void __launch_bounds__(256) k_bdpt_film(uint32_t n_pix, uint32_t fram
 void bdpt_free(lmb_ctx* ctx) {
 	BdptState& b = ctx->bdpt;
 	cudaFree(b.light_verts), cudaFree(b.camera_verts), cudaFree(b.col), cudaFree(b.splat);
-	cudaFree(b.walk), cudaFree(b.misc), cudaFree(b.rays), cudaFree(b.hits), cudaFree(b.occ), cudaFree(b.contrib), cudaFree(b.pair_ts);
+	cudaFree(b.walk), cudaFree(b.misc), cudaFree(b.rays), cudaFree(b.hits), cudaFree(b.occ), cudaFree(b.contrib), cudaFree(b.pair_ts), cudaFree(b.work_list), cudaFree(b.work_count);
 	b = BdptState{};
 }
 
@@ -1297,6 +1332,8 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 			}
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.contrib, (size_t)n_pix * n_conn_slots * 16));
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.pair_ts, ts.size()));
+		LMB_CUDA(ctx, cudaMalloc((void**)&b.work_list, (size_t)n_pix * n_conn_slots * 4));
+		LMB_CUDA(ctx, cudaMalloc((void**)&b.work_count, 8));
 		LMB_CUDA(ctx, cudaMemcpy(b.pair_ts, ts.data(), ts.size(), cudaMemcpyHostToDevice));
 	}
 	LMB_CUDA(ctx, cudaMemsetAsync(b.splat, 0, (size_t)n_pix * 12, st));
@@ -1343,12 +1380,16 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 				k_bdpt_connect<2><<<grid, 128, 0, st>>>(P, ctx->scene);
 				ctx->stats.kernel_launches += 5 + 4 * (uint64_t)pc.max_depth;
 			} else {
-				const dim3 pgrid(grid, n_conn_slots);
-				k_bdpt_pair<1><<<pgrid, 128, 0, st>>>(P, ctx->scene, b.pair_ts);
+				const dim3 wgrid((n_pix + 255) / 256, n_conn_slots);
+				const int pair_grid = ctx->sm_count * LMB_BDPT_PAIR_BLOCKS * 2;
+				LMB_CUDA(ctx, cudaMemsetAsync(b.work_count, 0, 8, st));
+				k_bdpt_worklist<1><<<wgrid, 256, 0, st>>>(P, b.pair_ts, b.work_list, b.work_count);
+				k_bdpt_pair<1><<<pair_grid, 128, 0, st>>>(P, ctx->scene, b.pair_ts, b.work_list, b.work_count);
 				if ((rc = launch_trace_slots(ctx, b.rays, n_pix * n_conn_slots, nullptr, b.occ, true))) return rc;
-				k_bdpt_pair<3><<<pgrid, 128, 0, st>>>(P, ctx->scene, b.pair_ts);
+				k_bdpt_worklist<3><<<wgrid, 256, 0, st>>>(P, b.pair_ts, b.work_list, b.work_count + 1);
+				k_bdpt_pair<3><<<pair_grid, 128, 0, st>>>(P, ctx->scene, b.pair_ts, b.work_list, b.work_count + 1);
 				k_bdpt_gather<<<(n_pix + 255) / 256, 256, 0, st>>>(P, b.pair_ts);
-				ctx->stats.kernel_launches += 6 + 4 * (uint64_t)pc.max_depth;
+				ctx->stats.kernel_launches += 8 + 4 * (uint64_t)pc.max_depth;
 			}
 		}
 		if (raw_col) {  // test hook: the two images before the film update

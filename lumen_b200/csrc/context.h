@@ -111,6 +111,8 @@ struct BdptState {
 	uint8_t* occ = nullptr;   // n_conn_slots * n_pix
 	float4* contrib = nullptr;  // n_conn_slots * n_pix: weighted radiance of each pair (pair-parallel connections)
 	uint8_t* pair_ts = nullptr; // (t, s) of each connection slot
+	uint32_t* work_list = nullptr;   // n_conn_slots * n_pix: the (slot, pixel) entries that have work in the pass at hand (k_bdpt_worklist)
+	uint32_t* work_count = nullptr;  // [0] emit pass, [1] resolve pass
 	uint32_t n_pix = 0, n_verts = 0, n_conn_slots = 0;
 };
 
