@@ -1186,31 +1186,49 @@ __global__ void __launch_bounds__(256) k_bdpt_worklist(const __grid_constant__ B
 	if (work) list[s_base + s_warp[warp] + (uint32_t)__popc(b & ((1u << lane) - 1u))] = i;
 }
 
-// One (pair, pixel) of the work list per thread: MODE 1 emits its shadow ray, MODE 3 weights what was visible.
+// One (pair, pixel) of the work list per thread: MODE 1 emits its shadow ray (and notes the entry in emit_list: the any-hit launch walks
+// that list instead of all n_conn_slots * n_pix slots, most of which hold no ray), MODE 3 weights what was visible.
 template <int MODE>
 __global__ void __launch_bounds__(128, LMB_BDPT_PAIR_BLOCKS) k_bdpt_pair(const __grid_constant__ BdptParams P, const __grid_constant__ DeviceScene sc, const uint8_t* __restrict__ pair_ts,
-																		   const uint32_t* __restrict__ list, const uint32_t* __restrict__ count) {
+																		   const uint32_t* __restrict__ list, const uint32_t* __restrict__ count, uint32_t* __restrict__ emit_list,
+																		   uint32_t* __restrict__ emit_count) {
 	const uint32_t n = *count;
+	const int lane = threadIdx.x & 31;
 	uint32_t n_shadow = 0;
-	for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-		const uint32_t i = list[j];
-		const uint32_t c = i / P.n_pix, pix = i - c * P.n_pix;
-		const int t = pair_ts[2 * c], s = pair_ts[2 * c + 1];
-		float4 out = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
-		const BvhView none{nullptr, nullptr, 0};
-		Kctx k = make_kctx(P, sc, none, pix, P.misc[MW_RNG * (size_t)P.n_pix + pix] + (s == 1 ? 4u * (uint32_t)(t - 2) : 0u));
-		k.light_pdf_pos = __uint_as_float(P.misc[MW_LPDFPOS * (size_t)P.n_pix + pix]);
-		k.slot = c;
-		if (t == 1) {
-			int cx, cy;
-			const V3 sp = connect_cam<MODE>(k, s, cx, cy);
-			if (MODE == 3 && luminance(sp) > 0) out = make_float4(sp.x, sp.y, sp.z, __uint_as_float((uint32_t)cy * P.width + (uint32_t)cx));
-		} else {
-			const V3 L = connect<MODE>(k, s, t);
-			out = make_float4(L.x, L.y, L.z, __uint_as_float(0xFFFFFFFFu));
+	for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {  // warp-uniform trip count
+		const uint32_t j = base + lane;
+		uint32_t i = 0;
+		bool emitted = false;
+		if (j < n) {
+			i = list[j];
+			const uint32_t c = i / P.n_pix, pix = i - c * P.n_pix;
+			const int t = pair_ts[2 * c], s = pair_ts[2 * c + 1];
+			float4 out = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
+			const BvhView none{nullptr, nullptr, 0};
+			Kctx k = make_kctx(P, sc, none, pix, P.misc[MW_RNG * (size_t)P.n_pix + pix] + (s == 1 ? 4u * (uint32_t)(t - 2) : 0u));
+			k.light_pdf_pos = __uint_as_float(P.misc[MW_LPDFPOS * (size_t)P.n_pix + pix]);
+			k.slot = c;
+			if (t == 1) {
+				int cx, cy;
+				const V3 sp = connect_cam<MODE>(k, s, cx, cy);
+				if (MODE == 3 && luminance(sp) > 0) out = make_float4(sp.x, sp.y, sp.z, __uint_as_float((uint32_t)cy * P.width + (uint32_t)cx));
+			} else {
+				const V3 L = connect<MODE>(k, s, t);
+				out = make_float4(L.x, L.y, L.z, __uint_as_float(0xFFFFFFFFu));
+			}
+			n_shadow += k.n_shadow;
+			emitted = k.n_shadow != 0;  // shadow_visible<1> counts the ray it writes
+			if (MODE == 3) P.contrib[i] = out;
 		}
-		n_shadow += k.n_shadow;
-		if (MODE == 3) P.contrib[i] = out;
+		if (MODE == 1) {
+			const uint32_t m = __ballot_sync(0xFFFFFFFFu, emitted);
+			if (m) {
+				uint32_t at = 0;
+				if (lane == 0) at = atomicAdd(emit_count, (uint32_t)__popc(m));
+				at = __shfl_sync(0xFFFFFFFFu, at, 0);
+				if (emitted) emit_list[at + (uint32_t)__popc(m & ((1u << lane) - 1u))] = i;
+			}
+		}
 	}
 	flush_counts(P.stats, 0, n_shadow, 0, 0);
 }
@@ -1272,7 +1290,7 @@ __global__ void __launch_bounds__(256) k_bdpt_film(uint32_t n_pix, uint32_t fram
 void bdpt_free(lmb_ctx* ctx) {
 	BdptState& b = ctx->bdpt;
 	cudaFree(b.light_verts), cudaFree(b.camera_verts), cudaFree(b.col), cudaFree(b.splat);
-	cudaFree(b.walk), cudaFree(b.misc), cudaFree(b.rays), cudaFree(b.hits), cudaFree(b.occ), cudaFree(b.contrib), cudaFree(b.pair_ts), cudaFree(b.work_list), cudaFree(b.work_count);
+	cudaFree(b.walk), cudaFree(b.misc), cudaFree(b.rays), cudaFree(b.hits), cudaFree(b.occ), cudaFree(b.contrib), cudaFree(b.pair_ts), cudaFree(b.work_list), cudaFree(b.emit_list), cudaFree(b.work_count);
 	b = BdptState{};
 }
 
@@ -1333,7 +1351,8 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.contrib, (size_t)n_pix * n_conn_slots * 16));
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.pair_ts, ts.size()));
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.work_list, (size_t)n_pix * n_conn_slots * 4));
-		LMB_CUDA(ctx, cudaMalloc((void**)&b.work_count, 8));
+		LMB_CUDA(ctx, cudaMalloc((void**)&b.emit_list, (size_t)n_pix * n_conn_slots * 4));
+		LMB_CUDA(ctx, cudaMalloc((void**)&b.work_count, 12));
 		LMB_CUDA(ctx, cudaMemcpy(b.pair_ts, ts.data(), ts.size(), cudaMemcpyHostToDevice));
 	}
 	LMB_CUDA(ctx, cudaMemsetAsync(b.splat, 0, (size_t)n_pix * 12, st));
@@ -1382,12 +1401,12 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 			} else {
 				const dim3 wgrid((n_pix + 255) / 256, n_conn_slots);
 				const int pair_grid = ctx->sm_count * LMB_BDPT_PAIR_BLOCKS * 2;
-				LMB_CUDA(ctx, cudaMemsetAsync(b.work_count, 0, 8, st));
+				LMB_CUDA(ctx, cudaMemsetAsync(b.work_count, 0, 12, st));
 				k_bdpt_worklist<1><<<wgrid, 256, 0, st>>>(P, b.pair_ts, b.work_list, b.work_count);
-				k_bdpt_pair<1><<<pair_grid, 128, 0, st>>>(P, ctx->scene, b.pair_ts, b.work_list, b.work_count);
-				if ((rc = launch_trace_slots(ctx, b.rays, n_pix * n_conn_slots, nullptr, b.occ, true))) return rc;
+				k_bdpt_pair<1><<<pair_grid, 128, 0, st>>>(P, ctx->scene, b.pair_ts, b.work_list, b.work_count, b.emit_list, b.work_count + 2);
+				if ((rc = launch_trace_slot_list(ctx, b.rays, b.emit_list, b.work_count + 2, n_pix * n_conn_slots, nullptr, b.occ, true))) return rc;
 				k_bdpt_worklist<3><<<wgrid, 256, 0, st>>>(P, b.pair_ts, b.work_list, b.work_count + 1);
-				k_bdpt_pair<3><<<pair_grid, 128, 0, st>>>(P, ctx->scene, b.pair_ts, b.work_list, b.work_count + 1);
+				k_bdpt_pair<3><<<pair_grid, 128, 0, st>>>(P, ctx->scene, b.pair_ts, b.work_list, b.work_count + 1, nullptr, nullptr);
 				k_bdpt_gather<<<(n_pix + 255) / 256, 256, 0, st>>>(P, b.pair_ts);
 				ctx->stats.kernel_launches += 8 + 4 * (uint64_t)pc.max_depth;
 			}

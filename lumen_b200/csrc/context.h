@@ -112,7 +112,8 @@ struct BdptState {
 	float4* contrib = nullptr;  // n_conn_slots * n_pix: weighted radiance of each pair (pair-parallel connections)
 	uint8_t* pair_ts = nullptr; // (t, s) of each connection slot
 	uint32_t* work_list = nullptr;   // n_conn_slots * n_pix: the (slot, pixel) entries that have work in the pass at hand (k_bdpt_worklist)
-	uint32_t* work_count = nullptr;  // [0] emit pass, [1] resolve pass
+	uint32_t* work_count = nullptr;  // [0] emit pass, [1] resolve pass, [2] emitted connection rays
+	uint32_t* emit_list = nullptr;   // the (slot, pixel) entries whose shadow ray the emit pass wrote: what the any-hit launch traces
 	uint32_t n_pix = 0, n_verts = 0, n_conn_slots = 0;
 };
 
@@ -206,6 +207,7 @@ int sort_rays(lmb_ctx* ctx, const float4* d_rays, uint32_t n, const uint32_t** o
 int launch_trace_any(lmb_ctx* ctx, const float4* d_rays, uint32_t n, uint8_t* d_occ);
 // ray slots with dead entries (NaN origin = hits nothing): closest hits into d_hits or occlusion bytes into d_occ; rays are NOT counted
 int launch_trace_slots(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits, uint8_t* d_occ, bool any);
+int launch_trace_slot_list(lmb_ctx* ctx, const float4* d_rays, const uint32_t* list, const uint32_t* n_dev, uint32_t n_max, float4* d_hits, uint8_t* d_occ, bool any);
 int launch_resolve(lmb_ctx* ctx);
 int launch_resolve_on(lmb_ctx* ctx, float4* film, cudaStream_t stream);  // k_resolve on any RGBA32F sum image of the film's size
 void comm_free(lmb_ctx* ctx);

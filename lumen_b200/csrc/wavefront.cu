@@ -651,8 +651,9 @@ struct ArraySource {
 };
 
 template <bool PIN>
-__global__ void __launch_bounds__(LMB_TRACE_THREADS, wide_blocks_per_sm(PIN)) k_trace_array(WideBvhView bvh, ArraySource src, uint32_t n, uint32_t* cursor, unsigned long long* stats,
-																							 int count_rays) {
+__global__ void __launch_bounds__(LMB_TRACE_THREADS, wide_blocks_per_sm(PIN)) k_trace_array(WideBvhView bvh, ArraySource src, uint32_t n, const uint32_t* __restrict__ n_dev,
+																							 uint32_t* cursor, unsigned long long* stats, int count_rays) {
+	if (n_dev) n = min(n, *n_dev);  // a list whose length lives on the device (BDPT's emitted connection rays)
 	trace_wide_persistent<PIN>(bvh, src, n, cursor, stats, count_rays ? ST_CLOSEST : -1, count_rays ? ST_SHADOW : -1);
 }
 __global__ void __launch_bounds__(LMB_TRACE_THREADS) k_trace_array_bvh2(BvhView bvh, ArraySource src, uint32_t n, uint32_t* cursor, unsigned long long* stats, int count_rays) {
@@ -905,7 +906,8 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 }
 
 // count_rays = 0: the caller counts its own rays (BDPT's ray slots hold dead entries, which must not be counted)
-static int launch_trace_array(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits, uint8_t* d_occ, bool any, int count_rays = 1, const uint32_t* order = nullptr) {
+static int launch_trace_array(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits, uint8_t* d_occ, bool any, int count_rays = 1, const uint32_t* order = nullptr,
+							  const uint32_t* n_dev = nullptr) {
 	uint32_t* cursor = ctx->wf.trace_cursor;
 	if (!cursor) {
 		LMB_CUDA(ctx, cudaMalloc((void**)&ctx->wf.trace_cursor, 4));
@@ -916,9 +918,9 @@ static int launch_trace_array(lmb_ctx* ctx, const float4* d_rays, uint32_t n, fl
 	if (ctx->use_bvh2)
 		k_trace_array_bvh2<<<ctx->sm_count * 7, LMB_TRACE_THREADS, 0, ctx->stream>>>(view_of(ctx), src, n, cursor, ctx->wf.stats, count_rays);
 	else if (trace_pinned(ctx))
-		k_trace_array<true><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n, cursor, ctx->wf.stats, count_rays);
+		k_trace_array<true><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n, n_dev, cursor, ctx->wf.stats, count_rays);
 	else
-		k_trace_array<false><<<ctx->sm_count * wide_blocks_per_sm(false), LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n, cursor, ctx->wf.stats, count_rays);
+		k_trace_array<false><<<ctx->sm_count * wide_blocks_per_sm(false), LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n, n_dev, cursor, ctx->wf.stats, count_rays);
 	return check_cuda(ctx, cudaGetLastError(), "k_trace_array");
 }
 // Probe rays for the choice of the traversal tree (lbvh.cu): they leave a random point of a random triangle in a uniformly random
@@ -957,9 +959,9 @@ int probe_wide_tree(lmb_ctx* ctx, uint32_t n_rays, double* steps_per_ray) {
 	k_probe_rays<<<(n_rays + 255) / 256, 256, 0, ctx->stream>>>(ctx->bvh.n, ctx->bvh.tris, n_rays, rays);
 	const ArraySource src{rays, hits, nullptr, false};
 	if (trace_pinned(ctx))
-		k_trace_array<true><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n_rays, cursor, st, 1);
+		k_trace_array<true><<<ctx->sm_count * LMB_WIDE_BLOCKS_PER_SM, LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n_rays, nullptr, cursor, st, 1);
 	else
-		k_trace_array<false><<<ctx->sm_count * wide_blocks_per_sm(false), LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n_rays, cursor, st, 1);
+		k_trace_array<false><<<ctx->sm_count * wide_blocks_per_sm(false), LMB_TRACE_THREADS, 0, ctx->stream>>>(wide_view_of(ctx), src, n_rays, nullptr, cursor, st, 1);
 	unsigned long long h[ST_COUNT];
 	LMB_CUDA(ctx, cudaMemcpyAsync(h, st, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
 	LMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -974,6 +976,10 @@ int launch_trace_closest(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4*
 }
 int launch_trace_any(lmb_ctx* ctx, const float4* d_rays, uint32_t n, uint8_t* d_occ) { return launch_trace_array(ctx, d_rays, n, nullptr, d_occ, true); }
 int launch_trace_slots(lmb_ctx* ctx, const float4* d_rays, uint32_t n, float4* d_hits, uint8_t* d_occ, bool any) { return launch_trace_array(ctx, d_rays, n, d_hits, d_occ, any, 0); }
+// the slots list[0 .. *n_dev) only (at most n_max of them); results land at the slots' own positions
+int launch_trace_slot_list(lmb_ctx* ctx, const float4* d_rays, const uint32_t* list, const uint32_t* n_dev, uint32_t n_max, float4* d_hits, uint8_t* d_occ, bool any) {
+	return launch_trace_array(ctx, d_rays, n_max, d_hits, d_occ, any, 0, list, n_dev);
+}
 int launch_resolve_on(lmb_ctx* ctx, float4* film, cudaStream_t stream) {
 	k_resolve<<<ctx->sm_count * 8, 256, 0, stream>>>(ctx->width * ctx->height, film);
 	return check_cuda(ctx, cudaGetLastError(), "k_resolve");
