@@ -405,6 +405,12 @@ struct BdptParams {
 	uint8_t* occ;     // any-hit result of each connection slot
 	float4* contrib;  // pair-parallel resolve: weighted radiance of each (slot, pixel), .w = splat target pixel (bits) or ~0
 	uint32_t n_conn_slots;
+	// walkers in flight as dense pixel lists (set per launch): k_bdpt_walk reads alive_in[0 .. *n_alive_in) and appends the pixels whose
+	// walk goes on to alive_out; k_bdpt_begin / k_bdpt_mid start the lists
+	const uint32_t* alive_in;
+	const uint32_t* n_alive_in;
+	uint32_t* alive_out;
+	uint32_t* n_alive_out;
 };
 
 enum WalkWord { WW_POS = 0, WW_WI = 3, WW_THR = 6, WW_PDF = 9, WW_B = 10, WW_ALIVE = 11, WW_COUNT = 12 };
@@ -1043,6 +1049,18 @@ LMB_D void store_walk(const BdptParams& P, uint32_t pix, const WalkSt& st, uint3
 		P.rays[2 * (size_t)pix] = make_float4(__int_as_float(0x7FC00000), 0.0f, 0.0f, 0.0f);
 	}
 }
+// Every lane of the warp calls this: the pixels whose walk goes on are appended to the next list with one atomic per warp, in lane order.
+// On the classroom stand-in 3 of 32 light walkers and 13 of 32 eye walkers are alive after the first bounces (profiles/r02c): walking and
+// tracing per-pixel slots ran the ~2500-instruction step at that lane count.
+LMB_D void append_alive(const BdptParams& P, bool alive, uint32_t pix) {
+	const uint32_t m = __ballot_sync(0xFFFFFFFFu, alive);
+	if (m == 0u) return;
+	const int lane = threadIdx.x & 31;
+	uint32_t at = 0;
+	if (lane == 0) at = atomicAdd(P.n_alive_out, (uint32_t)__popc(m));
+	at = __shfl_sync(0xFFFFFFFFu, at, 0);
+	if (alive) P.alive_out[at + (uint32_t)__popc(m & ((1u << lane) - 1u))] = pix;
+}
 LMB_D WalkSt load_walk(const BdptParams& P, uint32_t pix) {
 	const float* w = P.walk + pix;
 	const size_t n = P.n_pix;
@@ -1059,6 +1077,7 @@ LMB_D WalkSt load_walk(const BdptParams& P, uint32_t pix) {
 __global__ void __launch_bounds__(128) k_bdpt_begin(const __grid_constant__ BdptParams P, const __grid_constant__ DeviceScene sc) {
 	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t n_closest = 0;
+	bool alive = false;
 	if (pix < P.n_pix) {
 		const BvhView none{nullptr, nullptr, 0};
 		Kctx k = make_kctx(P, sc, none, pix, 0u);
@@ -1070,30 +1089,34 @@ __global__ void __launch_bounds__(128) k_bdpt_begin(const __grid_constant__ Bdpt
 		P.misc[MW_RNG * (size_t)P.n_pix + pix] = k.seed.w;
 		P.misc[MW_LPDFPOS * (size_t)P.n_pix + pix] = __float_as_uint(k.light_pdf_pos);
 		P.misc[MW_NLIGHT * (size_t)P.n_pix + pix] = ok ? 1u : 0u;
+		alive = st.alive;
 	}
+	append_alive(P, alive, pix);
 	flush_counts(P.stats, n_closest, 0, 0, 0);
 }
 
 template <bool EYE>
 __global__ void __launch_bounds__(128) k_bdpt_walk(const __grid_constant__ BdptParams P, const __grid_constant__ DeviceScene sc) {
-	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
-	uint32_t n_closest = 0;
-	if (pix < P.n_pix) {
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if ((j & ~31u) >= *P.n_alive_in) return;  // warp-uniform: the whole warp is past the end of the list
+	uint32_t n_closest = 0, pix = 0;
+	bool alive = false;
+	if (j < *P.n_alive_in) {
+		pix = P.alive_in[j];
 		WalkSt st = load_walk(P, pix);
-		if (st.alive) {
-			const BvhView none{nullptr, nullptr, 0};
-			Kctx k = make_kctx(P, sc, none, pix, P.misc[MW_RNG * (size_t)P.n_pix + pix]);
-			const float4 h4 = P.hits[pix];
-			const Hit h{h4.x, h4.y, h4.z, __float_as_uint(h4.w)};
-			walk_step<EYE>(k, EYE ? k.cam : k.lig, P.max_depth, st, h);
-			store_walk(P, pix, st, n_closest);
-			P.misc[MW_RNG * (size_t)P.n_pix + pix] = k.seed.w;
-		}
+		const BvhView none{nullptr, nullptr, 0};
+		Kctx k = make_kctx(P, sc, none, pix, P.misc[MW_RNG * (size_t)P.n_pix + pix]);
+		const float4 h4 = P.hits[pix];
+		const Hit h{h4.x, h4.y, h4.z, __float_as_uint(h4.w)};
+		walk_step<EYE>(k, EYE ? k.cam : k.lig, P.max_depth, st, h);
+		store_walk(P, pix, st, n_closest);
+		P.misc[MW_RNG * (size_t)P.n_pix + pix] = k.seed.w;
+		alive = st.alive;
 	}
+	append_alive(P, alive, pix);
 	flush_counts(P.stats, n_closest, 0, 0, 0);
 }
 
-// end of the light sub-path, camera vertex 0, first ray of the eye walk
 __global__ void __launch_bounds__(128) k_bdpt_mid(const __grid_constant__ BdptParams P, const __grid_constant__ DeviceScene sc) {
 	const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t n_closest = 0;
@@ -1112,6 +1135,7 @@ __global__ void __launch_bounds__(128) k_bdpt_mid(const __grid_constant__ BdptPa
 		const WalkSt st{k.cam.v(0, W_POS), k.cam.v(0, W_DIR), v3(1.0f), pdf, 0, true};
 		store_walk(P, pix, st, n_closest);
 	}
+	append_alive(P, pix < P.n_pix, pix);
 	flush_counts(P.stats, n_closest, 0, 0, 0);
 }
 
@@ -1291,6 +1315,7 @@ void bdpt_free(lmb_ctx* ctx) {
 	BdptState& b = ctx->bdpt;
 	cudaFree(b.light_verts), cudaFree(b.camera_verts), cudaFree(b.col), cudaFree(b.splat);
 	cudaFree(b.walk), cudaFree(b.misc), cudaFree(b.rays), cudaFree(b.hits), cudaFree(b.occ), cudaFree(b.contrib), cudaFree(b.pair_ts), cudaFree(b.work_list), cudaFree(b.emit_list), cudaFree(b.work_count);
+	cudaFree(b.alive_list[0]), cudaFree(b.alive_list[1]), cudaFree(b.alive_count);
 	b = BdptState{};
 }
 
@@ -1337,6 +1362,8 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 		// a dead slot is marked in its first float4 only; the walker loads both halves of every slot, so the second must be defined
 		LMB_CUDA(ctx, cudaMemsetAsync(b.rays, 0, (size_t)n_pix * n_conn_slots * 32, st));
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.hits, (size_t)n_pix * 16));
+		for (int i = 0; i < 2; i++) LMB_CUDA(ctx, cudaMalloc((void**)&b.alive_list[i], (size_t)n_pix * 4));
+		LMB_CUDA(ctx, cudaMalloc((void**)&b.alive_count, (2 * 64 + 4) * 4));  // max_depth <= 64 (check_bdpt_args)
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.occ, (size_t)n_pix * n_conn_slots));
 		b.n_conn_slots = n_conn_slots;
 	}
@@ -1383,14 +1410,30 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 			k_bdpt<<<grid, 128, 0, st>>>(P, ctx->scene, bvh);
 			ctx->stats.kernel_launches += 1;
 		} else {
+			// walkers travel as dense pixel lists: list `cur` with its length at alive_count[step]; a step traces and walks that list and
+			// appends the survivors to the other buffer
+			const uint32_t n_steps = 2u * (uint32_t)pc.max_depth + 2u;
+			LMB_CUDA(ctx, cudaMemsetAsync(b.alive_count, 0, n_steps * 4, st));
+			uint32_t step = 0;
+			int cur = 0;
+			auto lists = [&](bool has_in) {
+				P.alive_in = has_in ? b.alive_list[cur] : nullptr, P.n_alive_in = has_in ? b.alive_count + step : nullptr;
+				if (has_in) cur ^= 1, step++;
+				P.alive_out = b.alive_list[cur], P.n_alive_out = b.alive_count + step;
+			};
+			lists(false);
 			k_bdpt_begin<<<grid, 128, 0, st>>>(P, ctx->scene);
 			for (int d = 0; d < pc.max_depth; d++) {
-				if ((rc = launch_trace_slots(ctx, b.rays, n_pix, b.hits, nullptr, false))) return rc;
+				if ((rc = launch_trace_slot_list(ctx, b.rays, b.alive_list[cur], b.alive_count + step, n_pix, b.hits, nullptr, false))) return rc;
+				lists(true);
 				k_bdpt_walk<false><<<grid, 128, 0, st>>>(P, ctx->scene);
 			}
+			step++;  // the eye walk starts a list of its own
+			lists(false);
 			k_bdpt_mid<<<grid, 128, 0, st>>>(P, ctx->scene);
 			for (int d = 0; d < pc.max_depth; d++) {
-				if ((rc = launch_trace_slots(ctx, b.rays, n_pix, b.hits, nullptr, false))) return rc;
+				if ((rc = launch_trace_slot_list(ctx, b.rays, b.alive_list[cur], b.alive_count + step, n_pix, b.hits, nullptr, false))) return rc;
+				lists(true);
 				k_bdpt_walk<true><<<grid, 128, 0, st>>>(P, ctx->scene);
 			}
 			if (per_pixel) {

@@ -113,6 +113,8 @@ struct BdptState {
 	uint8_t* pair_ts = nullptr; // (t, s) of each connection slot
 	uint32_t* work_list = nullptr;   // n_conn_slots * n_pix: the (slot, pixel) entries that have work in the pass at hand (k_bdpt_worklist)
 	uint32_t* work_count = nullptr;  // [0] emit pass, [1] resolve pass, [2] emitted connection rays
+	uint32_t* alive_list[2] = {nullptr, nullptr};  // n_pix each: the pixels whose walk is in flight (ping-pong)
+	uint32_t* alive_count = nullptr;               // 2 * max_depth + 2 list lengths of one frame
 	uint32_t* emit_list = nullptr;   // the (slot, pixel) entries whose shadow ray the emit pass wrote: what the any-hit launch traces
 	uint32_t n_pix = 0, n_verts = 0, n_conn_slots = 0;
 };
