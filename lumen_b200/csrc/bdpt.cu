@@ -1170,7 +1170,7 @@ __global__ void __launch_bounds__(128) k_bdpt_connect(const __grid_constant__ Bd
 // was emitted and found nothing: on the classroom stand-in k_bdpt_pair<3> ran at 4.6 of 32 lanes with its ~3000 instructions of MIS
 // code out of the instruction cache (no_instruction 10.7 warps per issue, profiles/r02c). The list keeps the slot-major, pixel-ascending
 // order inside a block, so a warp of the pair kernel still works on one pair for pixels that are close: vertex reads stay mostly
-// coalesced and the (s, t) loops converge. Entries without work get their defaults here (dead ray / zero contribution).
+// coalesced and the (s, t) loops converge. Entries without work get their zero contribution here.
 template <int MODE>
 __global__ void __launch_bounds__(256) k_bdpt_worklist(const __grid_constant__ BdptParams P, const uint8_t* __restrict__ pair_ts, uint32_t* __restrict__ list, uint32_t* __restrict__ count) {
 	__shared__ uint32_t s_warp[8], s_base;
@@ -1185,13 +1185,9 @@ __global__ void __launch_bounds__(256) k_bdpt_worklist(const __grid_constant__ B
 		const int num_light_paths = (int)P.misc[MW_NLIGHT * (size_t)P.n_pix + pix];
 		const int num_cam_paths = __float_as_int(P.walk[WW_B * (size_t)P.n_pix + pix]) + 1;
 		work = t <= num_cam_paths && s <= num_light_paths;
-		// dead slot: NaN origin (hits nothing) and NaN tmin -- a connection ray always has tmin = 0, so .w tells the two apart exactly
-		if (MODE == 1) P.rays[2 * (size_t)i] = make_float4(__int_as_float(0x7FC00000), 0.0f, 0.0f, __int_as_float(0x7FC00000));
-		if (MODE == 3 && work && s > 0) {
-			// every strategy with a light vertex is zero unless its shadow ray was emitted and found nothing: skip the re-evaluation
-			const float tmin = P.rays[2 * (size_t)i].w;
-			work = tmin == tmin && P.occ[i] == 0;
-		}
+		// every strategy with a light vertex is zero unless its shadow ray was emitted and found nothing: skip the re-evaluation. The host
+		// sets occ to 0xFF before the emit pass and the any-hit launch writes 0 / 1 for the rays that were emitted (only those are traced)
+		if (MODE == 3 && work && s > 0) work = P.occ[i] == 0;
 		if (MODE == 3 && !work) P.contrib[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
 	}
 	const uint32_t b = __ballot_sync(0xFFFFFFFFu, work);
@@ -1445,6 +1441,7 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 				const dim3 wgrid((n_pix + 255) / 256, n_conn_slots);
 				const int pair_grid = ctx->sm_count * LMB_BDPT_PAIR_BLOCKS * 2;
 				LMB_CUDA(ctx, cudaMemsetAsync(b.work_count, 0, 12, st));
+				LMB_CUDA(ctx, cudaMemsetAsync(b.occ, 0xFF, (size_t)n_pix * n_conn_slots, st));  // "no ray emitted" until the any-hit launch says otherwise
 				k_bdpt_worklist<1><<<wgrid, 256, 0, st>>>(P, b.pair_ts, b.work_list, b.work_count);
 				k_bdpt_pair<1><<<pair_grid, 128, 0, st>>>(P, ctx->scene, b.pair_ts, b.work_list, b.work_count, b.emit_list, b.work_count + 2);
 				if ((rc = launch_trace_slot_list(ctx, b.rays, b.emit_list, b.work_count + 2, n_pix * n_conn_slots, nullptr, b.occ, true))) return rc;
