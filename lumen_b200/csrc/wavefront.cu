@@ -37,6 +37,12 @@ namespace {
 #ifndef LMB_SHADE_PREFETCH
 #define LMB_SHADE_PREFETCH 1
 #endif
+#ifndef LMB_SHADE_PHASED_TYPES
+#define LMB_SHADE_PHASED_TYPES 56u  // mask of LMB_BSDF_* whose k_shade runs its stages block-synchronously: dielectric, conductor, principled
+#endif
+#ifndef LMB_SHADE_PHASED_THREADS
+#define LMB_SHADE_PHASED_THREADS 256  // block size of those kernels: 8 warps in step (128: shade 21.9 ms, 256: 21.3, 512: 21.4)
+#endif
 #ifndef LMB_SHADE_MIN_BLOCKS_DIFFUSE
 #define LMB_SHADE_MIN_BLOCKS_DIFFUSE LMB_SHADE_MIN_BLOCKS
 #endif
@@ -281,8 +287,13 @@ __global__ void __launch_bounds__(256) k_classify(const __grid_constant__ Render
 // other parity, the NEE record to the next free NEE position and <= 3 typed ray-queue entries.
 // LAST = true is the bounce at depth max_depth - 1, which only collects emission (path.rgen:57-62) for any BSDF type and
 // walks list d directly.
+constexpr bool shade_phased(uint32_t type, bool last) { return !last && ((LMB_SHADE_PHASED_TYPES) & type) != 0; }
+constexpr int shade_threads(uint32_t type, bool last) { return shade_phased(type, last) ? LMB_SHADE_PHASED_THREADS : 128; }
+constexpr int shade_min_blocks(uint32_t type, bool last) {
+	return last ? 8 : (type == LMB_BSDF_DIFFUSE ? LMB_SHADE_MIN_BLOCKS_DIFFUSE : LMB_SHADE_MIN_BLOCKS) * 128 / shade_threads(type, last);
+}
 template <uint32_t TYPE, bool LAST>
-__global__ void __launch_bounds__(128, LAST ? 8 : (TYPE == LMB_BSDF_DIFFUSE ? LMB_SHADE_MIN_BLOCKS_DIFFUSE : LMB_SHADE_MIN_BLOCKS)) k_shade(const __grid_constant__ RenderParams rp, const __grid_constant__ DeviceScene sc, int depth, uint32_t* __restrict__ counters, int parity, int count_idx,
+__global__ void __launch_bounds__(shade_threads(TYPE, LAST), shade_min_blocks(TYPE, LAST)) k_shade(const __grid_constant__ RenderParams rp, const __grid_constant__ DeviceScene sc, int depth, uint32_t* __restrict__ counters, int parity, int count_idx,
 													const uint32_t* __restrict__ queue, PathPlanes pl, PathPlanes nx, const float4* __restrict__ hit,
 													uint32_t* __restrict__ trace_queue, float4* __restrict__ nee, uint32_t* __restrict__ nee_path,
 													float4* __restrict__ acc, uint32_t n_slots, unsigned long long* stats) {
@@ -302,8 +313,14 @@ __global__ void __launch_bounds__(128, LAST ? 8 : (TYPE == LMB_BSDF_DIFFUSE ? LM
 		if (!LAST && i0 < count) at_ahead = queue[i0];
 	}
 #endif
-	for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride) {  // warp-uniform trip count
-		const uint32_t i = base + lane;
+	// PHASED (per BSDF type, LMB_SHADE_PHASED_TYPES): the warps of a block take the three stages of a trip in step, with a barrier between the
+	// stages. k_shade<principled> is 110 KB of code against a 32 KB instruction cache and its 16 warps per SM drift through it
+	// independently: ncu put 47 % of its stall time on no_instruction (5.5 warps per issue). In step, a block has ONE stage's code
+	// resident at a time: shade stage 23.15 -> 21.3 ms with dielectric / conductor / principled phased in 256-thread blocks; the diffuse
+	// kernel (45 KB, no_instruction 0.4) loses 0.9 ms to the barriers and stays as it was. The trip count is block-uniform here.
+	constexpr bool PHASED = shade_phased(TYPE, LAST);
+	for (uint32_t base = blockIdx.x * blockDim.x + (PHASED ? 0u : (threadIdx.x & ~31u)); base < count; base += stride) {  // warp- (block-) uniform trip count
+		const uint32_t i = base + (PHASED ? threadIdx.x : (uint32_t)lane);
 #if LMB_SHADE_PREFETCH
 		const uint32_t at_now = at_ahead;
 		at_ahead = (!LAST && i + stride < count) ? queue[i + stride] : 0xFFFFFFFFu;
@@ -387,6 +404,7 @@ __global__ void __launch_bounds__(128, LAST ? 8 : (TYPE == LMB_BSDF_DIFFUSE ? LM
 			asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.pix + at_ahead));
 		}
 #endif
+		if (PHASED) __syncthreads();
 		const uint32_t fb = slot / rp.n_pix, pix = slot - fb * rp.n_pix;
 		Rng seed{pix % rp.width, rp.row_first + (pix / rp.width) * rp.row_stride, rp.first_frame + fb * rp.frame_stride, rng_w};
 		// ---- stage 2: next-event estimation (path.rgen:75-80, pt_commons.glsl:3-20, 28-30). The NEE record goes straight to
@@ -444,6 +462,7 @@ __global__ void __launch_bounds__(128, LAST ? 8 : (TYPE == LMB_BSDF_DIFFUSE ? LM
 		if (prim_ahead != 0xFFFFFFFFu) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.tri_shade + 8 * (size_t)prim_ahead));
 #endif
 		// ---- stage 3: continuation sample, throughput, Russian roulette (path.rgen:81-100)
+		if (PHASED) __syncthreads();
 		bool alive = false;
 		V3 wi_next = v3(0.0f);
 		if (active) {
@@ -848,13 +867,13 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 					if (!(ctx->mat_queue_mask & (1u << m))) continue;  // BSDF type absent from the scene (ENABLE_* macros, LumenScene.cpp:217-228)
 					const uint32_t* mq = wf.mat_queues + (size_t)m * wf.n_slots;
 					switch (m) {
-						case 0: k_shade<LMB_BSDF_DIFFUSE, false><<<grid_shade, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
-						case 1: k_shade<LMB_BSDF_MIRROR, false><<<grid_shade, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
-						case 2: k_shade<LMB_BSDF_GLASS, false><<<grid_shade, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
-						case 3: k_shade<LMB_BSDF_DIELECTRIC, false><<<grid_shade, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
-						case 4: k_shade<LMB_BSDF_CONDUCTOR, false><<<grid_shade, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
-						case 5: k_shade<LMB_BSDF_PRINCIPLED, false><<<grid_shade, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
-						default: k_shade<0u, false><<<grid_shade, 128, 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
+						case 0: k_shade<LMB_BSDF_DIFFUSE, false><<<grid_shade * 128 / shade_threads(LMB_BSDF_DIFFUSE, false), shade_threads(LMB_BSDF_DIFFUSE, false), 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
+						case 1: k_shade<LMB_BSDF_MIRROR, false><<<grid_shade * 128 / shade_threads(LMB_BSDF_MIRROR, false), shade_threads(LMB_BSDF_MIRROR, false), 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
+						case 2: k_shade<LMB_BSDF_GLASS, false><<<grid_shade * 128 / shade_threads(LMB_BSDF_GLASS, false), shade_threads(LMB_BSDF_GLASS, false), 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
+						case 3: k_shade<LMB_BSDF_DIELECTRIC, false><<<grid_shade * 128 / shade_threads(LMB_BSDF_DIELECTRIC, false), shade_threads(LMB_BSDF_DIELECTRIC, false), 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
+						case 4: k_shade<LMB_BSDF_CONDUCTOR, false><<<grid_shade * 128 / shade_threads(LMB_BSDF_CONDUCTOR, false), shade_threads(LMB_BSDF_CONDUCTOR, false), 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
+						case 5: k_shade<LMB_BSDF_PRINCIPLED, false><<<grid_shade * 128 / shade_threads(LMB_BSDF_PRINCIPLED, false), shade_threads(LMB_BSDF_PRINCIPLED, false), 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
+						default: k_shade<0u, false><<<grid_shade * 128 / shade_threads(0u, false), shade_threads(0u, false), 0, st>>>(LMB_SHADE_ARGS(mq, CNT_MAT + m * CNT_LINE)); break;
 					}
 					ctx->stats.kernel_launches += 1;
 				}
