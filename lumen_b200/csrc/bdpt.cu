@@ -849,11 +849,13 @@ LMB_D bool splat_coord(float v, int& out) {
 }
 
 // bdpt_commons.glsl:472-530
+// connect_cam_eval / connect_eval return the UNWEIGHTED radiance and what calc_mis_weight needs of `sampled`; connect_cam / connect
+// apply the MIS weight. The pair kernels call the halves themselves, with a block barrier in between (k_bdpt_pair).
 template <int MODE>
-LMB_DN V3 connect_cam(Kctx& k, int s, int& cx, int& cy) {
+LMB_DN V3 connect_cam_eval(Kctx& k, int s, int& cx, int& cy, Sampled& sampled) {
 	const Verts& cam = k.cam;
 	const Verts& lig = k.lig;
-	Sampled sampled{v3(0.0f), v3(0.0f), 0.0f};
+	sampled = Sampled{v3(0.0f), v3(0.0f), 0.0f};
 	V3 L = v3(0.0f);
 	cx = cy = -1;
 	const V3 cam_pos = cam.v(0, W_POS), cam_n = cam.v(0, W_NS);
@@ -890,18 +892,28 @@ LMB_DN V3 connect_cam(Kctx& k, int s, int& cx, int& cy) {
 		return v3(0.0f);
 	}
 	if (cx < 0 || (uint32_t)cx >= k.P.width || cy < 0 || (uint32_t)cy >= k.P.height || dot(dir, cam_n) < 0) return v3(0.0f);
+	return L;
+}
+template <int MODE>
+LMB_D V3 mis_weighted_cam(Kctx& k, int s, const V3& L, const Sampled& sampled) {
 	float mis_weight = 1.0f;
 	if (luminance(L) != 0.0f) mis_weight = MODE == 3 ? calc_mis_weight_ro(k, s, 1, sampled) : calc_mis_weight(k, s, 1, sampled);
 	return mis_weight * L;
 }
+template <int MODE>
+LMB_D V3 connect_cam(Kctx& k, int s, int& cx, int& cy) {
+	Sampled sampled;
+	const V3 L = connect_cam_eval<MODE>(k, s, cx, cy, sampled);
+	return mis_weighted_cam<MODE>(k, s, L, sampled);
+}
 
 // bdpt_commons.glsl:532-641
 template <int MODE>
-LMB_DN V3 connect(Kctx& k, int s, int t) {
+LMB_DN V3 connect_eval(Kctx& k, int s, int t, Sampled& sampled) {
 	const Verts& cam = k.cam;
 	const Verts& lig = k.lig;
 	V3 L = v3(0.0f);
-	Sampled sampled{v3(0.0f), v3(0.0f), 0.0f};
+	sampled = Sampled{v3(0.0f), v3(0.0f), 0.0f};
 	if (s == 0) {
 		const lmb_material& mat = k.sc.materials[cam.u(t - 1, W_MAT)];  // `materials.m[mat_idx]`: un-textured, and material 0 for an escaped vertex (B3)
 		L = v3(mat.emissive_factor) * cam.v(t - 1, W_THR);
@@ -948,11 +960,21 @@ LMB_DN V3 connect(Kctx& k, int s, int t) {
 			}
 		}
 	}
+	return L;
+}
+template <int MODE>
+LMB_D V3 mis_weighted(Kctx& k, int s, int t, V3 L, const Sampled& sampled) {
 	if (luminance(L) != 0.0f) {
 		const float mis_weight = MODE == 3 ? calc_mis_weight_ro(k, s, t, sampled) : calc_mis_weight(k, s, t, sampled);
 		L *= mis_weight;
 	}
 	return L;
+}
+template <int MODE>
+LMB_D V3 connect(Kctx& k, int s, int t) {
+	Sampled sampled;
+	const V3 L = connect_eval<MODE>(k, s, t, sampled);
+	return mis_weighted<MODE>(k, s, t, L, sampled);
 }
 
 // bdpt.rgen:55-75: the (s, t) loop. Every pair the loop body reaches owns one connection slot (staged pipeline).
@@ -1162,6 +1184,12 @@ __global__ void __launch_bounds__(128) k_bdpt_connect(const __grid_constant__ Bd
 // a pixel whose sub-paths are shorter leaves the rest dead. The rand4 of the s == 1 strategy of camera vertex t is the (t - 2)-th
 // draw after the walks: every earlier t has that strategy too. MODE 1 emits the shadow rays, MODE 3 weights what was visible;
 // k_bdpt_gather adds a pixel's pairs in slot order = the order of the GLSL loop, so the float sum is the same.
+#ifndef LMB_BDPT_PAIR_SYNC
+#define LMB_BDPT_PAIR_SYNC 1  // barriers at the start of a trip and before the MIS half: see k_bdpt_pair
+#endif
+#ifndef LMB_BDPT_PAIR_THREADS
+#define LMB_BDPT_PAIR_THREADS 384  // 2 blocks per SM at 80 registers; 128 / 256 / 384 / 768: classroom stand-in 20.1 / 19.5 / 19.4 / 19.7 ms per frame
+#endif
 #ifndef LMB_BDPT_PAIR_BLOCKS
 #define LMB_BDPT_PAIR_BLOCKS 6  // 4 / 6 / 8 blocks per SM: classroom stand-in 52.9 / 48.8 / 47.0 ms, cornell 3.98 / 4.02 / 4.32 ms per frame
 #endif
@@ -1209,36 +1237,52 @@ __global__ void __launch_bounds__(256) k_bdpt_worklist(const __grid_constant__ B
 // One (pair, pixel) of the work list per thread: MODE 1 emits its shadow ray (and notes the entry in emit_list: the any-hit launch walks
 // that list instead of all n_conn_slots * n_pix slots, most of which hold no ray), MODE 3 weights what was visible.
 template <int MODE>
-__global__ void __launch_bounds__(128, LMB_BDPT_PAIR_BLOCKS) k_bdpt_pair(const __grid_constant__ BdptParams P, const __grid_constant__ DeviceScene sc, const uint8_t* __restrict__ pair_ts,
+__global__ void __launch_bounds__(LMB_BDPT_PAIR_THREADS, LMB_BDPT_PAIR_BLOCKS * 128 / LMB_BDPT_PAIR_THREADS) k_bdpt_pair(const __grid_constant__ BdptParams P, const __grid_constant__ DeviceScene sc, const uint8_t* __restrict__ pair_ts,
 																		   const uint32_t* __restrict__ list, const uint32_t* __restrict__ count, uint32_t* __restrict__ emit_list,
 																		   uint32_t* __restrict__ emit_count) {
 	const uint32_t n = *count;
 	const int lane = threadIdx.x & 31;
 	uint32_t n_shadow = 0;
-	for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {  // warp-uniform trip count
-		const uint32_t j = base + lane;
-		uint32_t i = 0;
+	for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {  // block-uniform trip count
+#if LMB_BDPT_PAIR_SYNC
+		__syncthreads();  // the warps of a block start every trip together: they walk the same ~170 KB of code, 32 KB of which the instruction cache holds
+#endif
+		const uint32_t j = base + threadIdx.x;
+		const bool valid = j < n;
+		uint32_t i = 0, c = 0, pix = 0;
+		int t = 1, s = 0, cx = -1, cy = -1;
 		bool emitted = false;
-		if (j < n) {
+		if (valid) {
 			i = list[j];
-			const uint32_t c = i / P.n_pix, pix = i - c * P.n_pix;
-			const int t = pair_ts[2 * c], s = pair_ts[2 * c + 1];
-			float4 out = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
-			const BvhView none{nullptr, nullptr, 0};
-			Kctx k = make_kctx(P, sc, none, pix, P.misc[MW_RNG * (size_t)P.n_pix + pix] + (s == 1 ? 4u * (uint32_t)(t - 2) : 0u));
+			c = i / P.n_pix, pix = i - c * P.n_pix;
+			t = pair_ts[2 * c], s = pair_ts[2 * c + 1];
+		}
+		const BvhView none{nullptr, nullptr, 0};
+		Kctx k = make_kctx(P, sc, none, pix, valid ? P.misc[MW_RNG * (size_t)P.n_pix + pix] + (s == 1 ? 4u * (uint32_t)(t - 2) : 0u) : 0u);
+		Sampled sampled{v3(0.0f), v3(0.0f), 0.0f};
+		V3 L = v3(0.0f);
+		if (valid) {  // the connection itself: geometry, BSDFs, light sample; MODE 1 writes the shadow ray, MODE 3 reads its result
 			k.light_pdf_pos = __uint_as_float(P.misc[MW_LPDFPOS * (size_t)P.n_pix + pix]);
 			k.slot = c;
-			if (t == 1) {
-				int cx, cy;
-				const V3 sp = connect_cam<MODE>(k, s, cx, cy);
-				if (MODE == 3 && luminance(sp) > 0) out = make_float4(sp.x, sp.y, sp.z, __uint_as_float((uint32_t)cy * P.width + (uint32_t)cx));
-			} else {
-				const V3 L = connect<MODE>(k, s, t);
-				out = make_float4(L.x, L.y, L.z, __uint_as_float(0xFFFFFFFFu));
-			}
+			L = t == 1 ? connect_cam_eval<MODE>(k, s, cx, cy, sampled) : connect_eval<MODE>(k, s, t, sampled);
 			n_shadow += k.n_shadow;
 			emitted = k.n_shadow != 0;  // shadow_visible<1> counts the ray it writes
-			if (MODE == 3) P.contrib[i] = out;
+		}
+		if (MODE == 3) {
+#if LMB_BDPT_PAIR_SYNC
+			__syncthreads();  // the MIS weights are the other half of the code: the block enters it together
+#endif
+			if (valid) {
+				float4 out = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
+				if (t == 1) {
+					const V3 sp = mis_weighted_cam<MODE>(k, s, L, sampled);
+					if (luminance(sp) > 0) out = make_float4(sp.x, sp.y, sp.z, __uint_as_float((uint32_t)cy * P.width + (uint32_t)cx));
+				} else {
+					L = mis_weighted<MODE>(k, s, t, L, sampled);
+					out = make_float4(L.x, L.y, L.z, __uint_as_float(0xFFFFFFFFu));
+				}
+				P.contrib[i] = out;
+			}
 		}
 		if (MODE == 1) {
 			const uint32_t m = __ballot_sync(0xFFFFFFFFu, emitted);
@@ -1443,10 +1487,10 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 				LMB_CUDA(ctx, cudaMemsetAsync(b.work_count, 0, 12, st));
 				LMB_CUDA(ctx, cudaMemsetAsync(b.occ, 0xFF, (size_t)n_pix * n_conn_slots, st));  // "no ray emitted" until the any-hit launch says otherwise
 				k_bdpt_worklist<1><<<wgrid, 256, 0, st>>>(P, b.pair_ts, b.work_list, b.work_count);
-				k_bdpt_pair<1><<<pair_grid, 128, 0, st>>>(P, ctx->scene, b.pair_ts, b.work_list, b.work_count, b.emit_list, b.work_count + 2);
+				k_bdpt_pair<1><<<pair_grid * 128 / LMB_BDPT_PAIR_THREADS, LMB_BDPT_PAIR_THREADS, 0, st>>>(P, ctx->scene, b.pair_ts, b.work_list, b.work_count, b.emit_list, b.work_count + 2);
 				if ((rc = launch_trace_slot_list(ctx, b.rays, b.emit_list, b.work_count + 2, n_pix * n_conn_slots, nullptr, b.occ, true))) return rc;
 				k_bdpt_worklist<3><<<wgrid, 256, 0, st>>>(P, b.pair_ts, b.work_list, b.work_count + 1);
-				k_bdpt_pair<3><<<pair_grid, 128, 0, st>>>(P, ctx->scene, b.pair_ts, b.work_list, b.work_count + 1, nullptr, nullptr);
+				k_bdpt_pair<3><<<pair_grid * 128 / LMB_BDPT_PAIR_THREADS, LMB_BDPT_PAIR_THREADS, 0, st>>>(P, ctx->scene, b.pair_ts, b.work_list, b.work_count + 1, nullptr, nullptr);
 				k_bdpt_gather<<<(n_pix + 255) / 256, 256, 0, st>>>(P, b.pair_ts);
 				ctx->stats.kernel_launches += 8 + 4 * (uint64_t)pc.max_depth;
 			}
