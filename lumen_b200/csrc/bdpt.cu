@@ -1117,8 +1117,11 @@ __global__ void __launch_bounds__(128) k_bdpt_begin(const __grid_constant__ Bdpt
 	flush_counts(P.stats, n_closest, 0, 0, 0);
 }
 
+#ifndef LMB_BDPT_WALK_THREADS
+#define LMB_BDPT_WALK_THREADS 256  // 128 / 256 / 384 / 768: classroom stand-in 19.29 / 19.04 / 18.99 / 19.04 ms per frame, cornell 2.75 / 2.78 / 2.80 / 2.82
+#endif
 template <bool EYE>
-__global__ void __launch_bounds__(128) k_bdpt_walk(const __grid_constant__ BdptParams P, const __grid_constant__ DeviceScene sc) {
+__global__ void __launch_bounds__(LMB_BDPT_WALK_THREADS, 768 / LMB_BDPT_WALK_THREADS) k_bdpt_walk(const __grid_constant__ BdptParams P, const __grid_constant__ DeviceScene sc) {
 	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	if ((j & ~31u) >= *P.n_alive_in) return;  // warp-uniform: the whole warp is past the end of the list
 	uint32_t n_closest = 0, pix = 0;
@@ -1466,7 +1469,7 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 			for (int d = 0; d < pc.max_depth; d++) {
 				if ((rc = launch_trace_slot_list(ctx, b.rays, b.alive_list[cur], b.alive_count + step, n_pix, b.hits, nullptr, false))) return rc;
 				lists(true);
-				k_bdpt_walk<false><<<grid, 128, 0, st>>>(P, ctx->scene);
+				k_bdpt_walk<false><<<(n_pix + LMB_BDPT_WALK_THREADS - 1) / LMB_BDPT_WALK_THREADS, LMB_BDPT_WALK_THREADS, 0, st>>>(P, ctx->scene);
 			}
 			step++;  // the eye walk starts a list of its own
 			lists(false);
@@ -1474,7 +1477,7 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 			for (int d = 0; d < pc.max_depth; d++) {
 				if ((rc = launch_trace_slot_list(ctx, b.rays, b.alive_list[cur], b.alive_count + step, n_pix, b.hits, nullptr, false))) return rc;
 				lists(true);
-				k_bdpt_walk<true><<<grid, 128, 0, st>>>(P, ctx->scene);
+				k_bdpt_walk<true><<<(n_pix + LMB_BDPT_WALK_THREADS - 1) / LMB_BDPT_WALK_THREADS, LMB_BDPT_WALK_THREADS, 0, st>>>(P, ctx->scene);
 			}
 			if (per_pixel) {
 				k_bdpt_connect<1><<<grid, 128, 0, st>>>(P, ctx->scene);
