@@ -145,6 +145,24 @@ def test_classroom_standin_parity(device, classroom):
     assert bits_equal(gpu, cpu).mean() >= 0.999
 
 
+@pytest.mark.parametrize("depth", [1, 2, 70])
+def test_sky_march_ranges_at_odd_depths(device, classroom, depth):
+    """k_miss hands out the escaped rays per bounce range (wavefront.cu: 63 bounces with a range of their own, deeper ones share the last):
+    depth 1 (the only bounce is the last), 2, and 70 (beyond the ranges; Russian roulette keeps it cheap) against the oracle."""
+    w, h = 96, 54
+    sc = host.Scene(classroom, w, h)
+    orc = po.OracleScene(sc)
+    device.upload_scene(sc.desc)
+    device.build_accel()
+    pc, ubo = sc.make_pc(depth, True), sc.make_ubo()
+    device.init(w, h, 2)
+    device.render(pc, ubo, 0, 3)  # two batches: the ranges start over
+    gpu, gs = device.download(), device.stats()
+    cpu, cs = orc.render(pc, ubo, 0, 3)
+    assert (gs.rays_closest, gs.rays_shadow, gs.rays_probe) == (cs.rays_closest, cs.rays_shadow, cs.rays_probe)
+    assert bits_equal(gpu, cpu).mean() >= 0.999
+
+
 def test_torus_grid_config5_small(device):
     """Config 5 at 4 x 4 x 4 tori (82 k triangles): bit-exact LBVH, valid wide tree, closest / any-hit parity on the
     incoherent-ray generator of the sweep, and primary-ray render parity."""
