@@ -390,7 +390,9 @@ struct Sampled {  // the fields of `PathVertex sampled` that calc_mis_weight rea
 
 struct BdptParams {
 	M4 inv_view, inv_proj, view, neg_proj;
-	uint32_t width, height, n_pix, frame, seed_z;
+	// n_pix = frames in flight x n_real: a "pixel" of the kernels below is a (frame of the batch, image pixel) pair, frame-major; frame fb of
+	// the batch is frame_first + fb * frame_stride and seeds with that number ^ time (bdpt.rgen:36-37)
+	uint32_t width, height, n_pix, n_real, frame_first, frame_stride, time;
 	int32_t num_lights, max_depth, light_triangle_count;
 	float* light_verts;
 	float* camera_verts;
@@ -993,7 +995,7 @@ LMB_D V3 connect_all(Kctx& k, int num_light_paths, int num_cam_paths) {
 				int cx, cy;
 				const V3 splat_col = connect_cam<MODE>(k, s, cx, cy);
 				if (MODE != 1 && luminance(splat_col) > 0) {
-					float* o = P.splat + 3 * ((size_t)cy * P.width + cx);
+					float* o = P.splat + 3 * ((size_t)(k.pix / P.n_real) * P.n_real + (size_t)cy * P.width + cx);  // the splat image of this pixel's frame
 					atomicAdd(o + 0, splat_col.x), atomicAdd(o + 1, splat_col.y), atomicAdd(o + 2, splat_col.z);
 				}
 			} else {
@@ -1023,8 +1025,9 @@ LMB_D void flush_counts(unsigned long long* stats, uint32_t n_closest, uint32_t 
 }
 
 LMB_D Kctx make_kctx(const BdptParams& P, const DeviceScene& sc, const BvhView& bvh, uint32_t pix, uint32_t rng_w) {
-	return Kctx{P, sc, bvh, Rng{pix % P.width, pix / P.width, P.seed_z, rng_w}, Verts{P.light_verts + pix, P.n_pix}, Verts{P.camera_verts + pix, P.n_pix}, 0.0f,
-				(float)(P.width * P.height), pix, 0u, 0u, 0u, 0u, 0u};
+	const uint32_t fb = pix / P.n_real, rpix = pix - fb * P.n_real;
+	return Kctx{P, sc, bvh, Rng{rpix % P.width, rpix / P.width, (P.frame_first + fb * P.frame_stride) ^ P.time, rng_w}, Verts{P.light_verts + pix, P.n_pix},
+				Verts{P.camera_verts + pix, P.n_pix}, 0.0f, (float)(P.width * P.height), pix, 0u, 0u, 0u, 0u, 0u};
 }
 
 // ---------------------------------------------------------------------------------------------- megakernel (LMB_BDPT=mega)
@@ -1041,7 +1044,7 @@ __global__ void __launch_bounds__(128) k_bdpt(const __grid_constant__ BdptParams
 			num_light_paths = random_walk<false>(k, k.lig, P.max_depth, thr, pdf_dir) + 1;
 			light_end(k);
 		}
-		const float pdf = camera_begin(k, pix % P.width, pix / P.width);
+		const float pdf = camera_begin(k, (pix % P.n_real) % P.width, (pix % P.n_real) / P.width);
 		const int num_cam_paths = random_walk<true>(k, k.cam, P.max_depth, v3(1.0f), pdf) + 1;
 		const V3 col = connect_all<0>(k, num_light_paths, num_cam_paths);
 		P.col[pix] = make_float4(col.x, col.y, col.z, 0.0f);
@@ -1156,7 +1159,7 @@ __global__ void __launch_bounds__(128) k_bdpt_mid(const __grid_constant__ BdptPa
 			light_end(k);
 		}
 		P.misc[MW_NLIGHT * (size_t)P.n_pix + pix] = num_light_paths;
-		const float pdf = camera_begin(k, pix % P.width, pix / P.width);
+		const float pdf = camera_begin(k, (pix % P.n_real) % P.width, (pix % P.n_real) / P.width);
 		const WalkSt st{k.cam.v(0, W_POS), k.cam.v(0, W_DIR), v3(1.0f), pdf, 0, true};
 		store_walk(P, pix, st, n_closest);
 	}
@@ -1313,7 +1316,7 @@ __global__ void __launch_bounds__(256) k_bdpt_gather(const __grid_constant__ Bdp
 		if (t == 1) {
 			const uint32_t target = __float_as_uint(v.w);
 			if (target != 0xFFFFFFFFu) {
-				float* o = P.splat + 3 * (size_t)target;
+				float* o = P.splat + 3 * ((size_t)(pix / P.n_real) * P.n_real + target);  // the splat image of this pixel's frame
 				atomicAdd(o + 0, v.x), atomicAdd(o + 1, v.y), atomicAdd(o + 2, v.z);
 			}
 		} else {
@@ -1325,29 +1328,33 @@ __global__ void __launch_bounds__(256) k_bdpt_gather(const __grid_constant__ Bdp
 
 // bdpt.rgen:76-89: own strategies + this frame's splats -> running-mean film (NaN samples leave the pixel untouched) or sum film;
 // clears the splat image for the next frame.
-__global__ void __launch_bounds__(256) k_bdpt_film(uint32_t n_pix, uint32_t frame, int film_mode, const float4* __restrict__ colb, float* __restrict__ splat,
-													float4* __restrict__ film, unsigned long long* stats) {
+__global__ void __launch_bounds__(256) k_bdpt_film(uint32_t n_real, uint32_t n_batch_frames, uint32_t frame_first, uint32_t frame_stride, int film_mode, const float4* __restrict__ colb,
+													float* __restrict__ splat, float4* __restrict__ film, unsigned long long* stats) {
 	uint32_t nan_count = 0;
-	for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n_pix; pix += gridDim.x * blockDim.x) {
-		V3 col = xyz(V4{colb[pix].x, colb[pix].y, colb[pix].z, 0.0f});
-		col += v3(splat[3 * (size_t)pix + 0], splat[3 * (size_t)pix + 1], splat[3 * (size_t)pix + 2]);
-		splat[3 * (size_t)pix + 0] = 0.0f, splat[3 * (size_t)pix + 1] = 0.0f, splat[3 * (size_t)pix + 2] = 0.0f;
-		const float lum = luminance(col);
-		if (lum != lum) {
-			nan_count++;
-			continue;
+	for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n_real; pix += gridDim.x * blockDim.x) {
+		float4 acc = film[pix];
+		for (uint32_t fb = 0; fb < n_batch_frames; fb++) {  // the frames of the batch in order: the running mean is the reference's
+			const size_t vp = (size_t)fb * n_real + pix;
+			const uint32_t frame = frame_first + fb * frame_stride;
+			V3 col = xyz(V4{colb[vp].x, colb[vp].y, colb[vp].z, 0.0f});
+			col += v3(splat[3 * vp + 0], splat[3 * vp + 1], splat[3 * vp + 2]);
+			splat[3 * vp + 0] = 0.0f, splat[3 * vp + 1] = 0.0f, splat[3 * vp + 2] = 0.0f;
+			const float lum = luminance(col);
+			if (lum != lum) {
+				nan_count++;
+				continue;
+			}
+			if (film_mode == LMB_FILM_SUM) {  // un-normalised sum, valid-sample count in alpha (multi-GPU sample-index shards; lmb_resolve divides)
+				acc = make_float4(acc.x + col.x, acc.y + col.y, acc.z + col.z, acc.w + 1.0f);
+			} else if (frame > 0) {
+				const float w = 1.0f / float(frame + 1);
+				const V3 m = mix(v3(acc.x, acc.y, acc.z), col, w);
+				acc = make_float4(m.x, m.y, m.z, 1.0f);
+			} else {
+				acc = make_float4(col.x, col.y, col.z, 1.0f);
+			}
 		}
-		if (film_mode == LMB_FILM_SUM) {  // un-normalised sum, valid-sample count in alpha (multi-GPU sample-index shards; lmb_resolve divides)
-			const float4 old = film[pix];
-			film[pix] = make_float4(old.x + col.x, old.y + col.y, old.z + col.z, old.w + 1.0f);
-		} else if (frame > 0) {
-			const float w = 1.0f / float(frame + 1);
-			const float4 old = film[pix];
-			const V3 m = mix(v3(old.x, old.y, old.z), col, w);
-			film[pix] = make_float4(m.x, m.y, m.z, 1.0f);
-		} else {
-			film[pix] = make_float4(col.x, col.y, col.z, 1.0f);
-		}
+		film[pix] = acc;
 	}
 	if (nan_count) atomicAdd(&stats[ST_NAN], (unsigned long long)nan_count);
 }
@@ -1385,15 +1392,23 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 	const bool per_pixel = mode_env && strcmp(mode_env, "pixel") == 0;  // staged, connections looped per pixel (k_bdpt_connect)
 	BdptState& b = ctx->bdpt;
 	cudaStream_t st = ctx->stream;
-	const uint32_t n_pix = ctx->width * ctx->height;
+	const uint32_t n_real = ctx->width * ctx->height;
 	const uint32_t n_verts = (uint32_t)pc.max_depth + 1;
 	const uint32_t n_conn_slots = count_conn_slots(pc.max_depth);
-	if ((uint64_t)n_pix * n_conn_slots > 0x7FFFFFFFull) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: width * height * connection slots out of range");
-	const size_t vert_bytes = (size_t)n_pix * n_verts * W_COUNT * 4;
+	if ((uint64_t)n_real * n_conn_slots > 0x7FFFFFFFull) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: width * height * connection slots out of range");
+	// Frames in flight: the kernels work on (frame of the batch, pixel) pairs, so that the ~17 closest / any-hit launches and the tails of
+	// every kernel are paid once per BATCH. Sized by memory (~4 KB per pixel and frame at depth 8: two sub-paths, ray slots, contributions,
+	// lists), at most 8, within the 31-bit slot index; LMB_BDPT_BATCH overrides; the single-frame test hook renders one at a time.
+	const uint64_t bytes_per_pixel = 2ull * n_verts * W_COUNT * 4 + (uint64_t)n_conn_slots * (32 + 16 + 4 + 4 + 1) + (WW_COUNT + MW_COUNT) * 4 + 16 + 8 + 16 + 12;
+	uint32_t batch = (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(1, (40ull << 30) / (bytes_per_pixel * n_real)));
+	batch = (uint32_t)std::min<uint64_t>(batch, 0x7FFFFFFFull / ((uint64_t)n_real * n_conn_slots));
+	if (const char* e = getenv("LMB_BDPT_BATCH")) batch = std::max(1, atoi(e));
+	if (raw_col || mega || per_pixel) batch = 1;
+	const uint32_t n_pix = n_real * batch;  // capacity of the buffers in (frame, pixel) pairs
 	if (b.n_pix != n_pix || b.n_verts != n_verts) {
 		bdpt_free(ctx);
-		LMB_CUDA(ctx, cudaMalloc((void**)&b.light_verts, vert_bytes));
-		LMB_CUDA(ctx, cudaMalloc((void**)&b.camera_verts, vert_bytes));
+		LMB_CUDA(ctx, cudaMalloc((void**)&b.light_verts, (size_t)n_pix * n_verts * W_COUNT * 4));
+		LMB_CUDA(ctx, cudaMalloc((void**)&b.camera_verts, (size_t)n_pix * n_verts * W_COUNT * 4));
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.col, (size_t)n_pix * 16));
 		LMB_CUDA(ctx, cudaMalloc((void**)&b.splat, (size_t)n_pix * 12));
 		b.n_pix = n_pix, b.n_verts = n_verts;
@@ -1435,17 +1450,19 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 	P.inv_view = load(ubo.inv_view), P.inv_proj = load(ubo.inv_projection), P.view = load(ubo.view);
 	P.neg_proj = load(ubo.projection);
 	for (int c = 0; c < 4; c++) P.neg_proj.c[c] = V4{-P.neg_proj.c[c].x, -P.neg_proj.c[c].y, -P.neg_proj.c[c].z, -P.neg_proj.c[c].w};
-	P.width = ctx->width, P.height = ctx->height, P.n_pix = n_pix;
+	P.width = ctx->width, P.height = ctx->height, P.n_real = n_real, P.frame_stride = frame_stride, P.time = pc.time;
 	P.num_lights = pc.num_lights, P.max_depth = pc.max_depth, P.light_triangle_count = pc.light_triangle_count;
 	P.light_verts = b.light_verts, P.camera_verts = b.camera_verts, P.col = b.col, P.splat = b.splat, P.stats = ctx->wf.stats;
 	P.walk = b.walk, P.misc = b.misc, P.rays = b.rays, P.hits = b.hits, P.occ = b.occ, P.contrib = b.contrib, P.n_conn_slots = n_conn_slots;
 	const BvhView bvh{ctx->bvh.nodes, ctx->bvh.tris, ctx->bvh.n};
-	const uint32_t grid = (n_pix + 127) / 128;
 	int rc;
 	cudaEventRecord(ctx->ev[0], st);
-	for (uint32_t i = 0; i < n_frames; i++) {
-		const uint32_t frame = first_frame + i * frame_stride;
-		P.frame = frame, P.seed_z = frame ^ pc.time;
+	for (uint32_t done = 0; done < n_frames;) {
+		const uint32_t nb = std::min(batch, n_frames - done);
+		const uint32_t n_pix = nb * n_real;  // (frame, pixel) pairs of THIS batch: also the stride of every struct-of-arrays below
+		const size_t vert_bytes = (size_t)n_pix * n_verts * W_COUNT * 4;
+		const uint32_t grid = (n_pix + 127) / 128;
+		P.n_pix = n_pix, P.frame_first = first_frame + done * frame_stride;
 		// BDPT.cpp:79-80: both vertex buffers are zeroed before every frame
 		LMB_CUDA(ctx, cudaMemsetAsync(b.light_verts, 0, vert_bytes, st));
 		LMB_CUDA(ctx, cudaMemsetAsync(b.camera_verts, 0, vert_bytes, st));
@@ -1502,8 +1519,9 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 			LMB_CUDA(ctx, cudaMemcpyAsync(raw_col, b.col, (size_t)n_pix * 16, cudaMemcpyDeviceToHost, st));
 			LMB_CUDA(ctx, cudaMemcpyAsync(raw_splat, b.splat, (size_t)n_pix * 12, cudaMemcpyDeviceToHost, st));
 		}
-		k_bdpt_film<<<ctx->sm_count * 8, 256, 0, st>>>(n_pix, frame, film_mode, b.col, b.splat, ctx->film, ctx->wf.stats);
+		k_bdpt_film<<<ctx->sm_count * 8, 256, 0, st>>>(n_real, nb, P.frame_first, frame_stride, film_mode, b.col, b.splat, ctx->film, ctx->wf.stats);
 		ctx->stats.kernel_launches += 1;
+		done += nb;
 	}
 	cudaEventRecord(ctx->ev[5], st);
 	LMB_CUDA(ctx, cudaStreamSynchronize(st));
