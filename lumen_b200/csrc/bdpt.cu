@@ -1398,9 +1398,13 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 	if ((uint64_t)n_real * n_conn_slots > 0x7FFFFFFFull) return set_error(ctx, LMB_ERR_INVALID, "lmb_render_bdpt: width * height * connection slots out of range");
 	// Frames in flight: the kernels work on (frame of the batch, pixel) pairs, so that the ~17 closest / any-hit launches and the tails of
 	// every kernel are paid once per BATCH. Sized by memory (~4 KB per pixel and frame at depth 8: two sub-paths, ray slots, contributions,
-	// lists), at most 8, within the 31-bit slot index; LMB_BDPT_BATCH overrides; the single-frame test hook renders one at a time.
+	// lists; 40 GB or half of what the device has free, whichever is less), at most 8, within the 31-bit slot index; LMB_BDPT_BATCH overrides; the single-frame test hook renders one at a time.
 	const uint64_t bytes_per_pixel = 2ull * n_verts * W_COUNT * 4 + (uint64_t)n_conn_slots * (32 + 16 + 4 + 4 + 1) + (WW_COUNT + MW_COUNT) * 4 + 16 + 8 + 16 + 12;
-	uint32_t batch = (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(1, (40ull << 30) / (bytes_per_pixel * n_real)));
+	size_t mem_free = 0, mem_total = 0;
+	cudaMemGetInfo(&mem_free, &mem_total);
+	const uint64_t have = (uint64_t)mem_free + (b.n_pix ? (uint64_t)b.n_pix * bytes_per_pixel : 0);  // what is free now + what this state already holds
+	const uint64_t budget = std::min<uint64_t>(40ull << 30, have / 2);
+	uint32_t batch = (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(1, budget / (bytes_per_pixel * n_real)));
 	batch = (uint32_t)std::min<uint64_t>(batch, 0x7FFFFFFFull / ((uint64_t)n_real * n_conn_slots));
 	if (const char* e = getenv("LMB_BDPT_BATCH")) batch = std::max(1, atoi(e));
 	if (raw_col || mega || per_pixel) batch = 1;

@@ -848,7 +848,7 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 			const bool last = depth >= pc.max_depth - 1;  // the last bounce only collects emission (path.rgen:57-62)
 			k_classify<<<grid_256, 256, 0, st>>>(rp, ctx->scene, depth, wf.counters, par, planes[par], wf.hit, wf.mat_queues, miss, wf.acc, wf.n_slots);
 			ctx->stats.kernel_launches += 1;
-			if (sky_march && depth < MISS_RANGES - 1) {  // the rays that escaped at this bounce: marched beside the bounces still to come
+			if (miss_side_blocks > 0 && depth < MISS_RANGES - 1) {  // the rays that escaped at this bounce: marched beside the bounces still to come
 				k_miss_mark<<<1, 1, 0, st>>>(wf.counters, wf.miss_marks, depth, depth == 0);
 				ctx->stats.kernel_launches += 1;
 				if (miss_side_blocks > 0 && !last) {
@@ -892,8 +892,13 @@ int wavefront_render(lmb_ctx* ctx, const lmb_pc_path& pc, const lmb_scene_ubo& u
 		}
 		if (prof) cudaEventRecord(ctx->ev[1], st);
 		if (sky_march) {
-			const int n_bounces = std::max(pc.max_depth, 1), n_ranges = std::min(n_bounces, MISS_RANGES);
-			if (n_bounces > MISS_RANGES - 1) {  // the bounces without a range of their own share the last one
+			const int n_bounces = std::max(pc.max_depth, 1);
+			int n_ranges = std::min(n_bounces, MISS_RANGES);
+			if (miss_side_blocks == 0) {  // nothing marched beside the loop: ONE range over every record of the batch
+				k_miss_mark<<<1, 1, 0, st>>>(wf.counters, wf.miss_marks, 0, true);
+				ctx->stats.kernel_launches += 1;
+				n_ranges = 1;
+			} else if (n_bounces > MISS_RANGES - 1) {  // the bounces without a range of their own share the last one
 				k_miss_mark<<<1, 1, 0, st>>>(wf.counters, wf.miss_marks, MISS_RANGES - 1, false);
 				ctx->stats.kernel_launches += 1;
 			}

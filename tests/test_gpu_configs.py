@@ -147,8 +147,9 @@ def test_classroom_standin_parity(device, classroom):
 
 @pytest.mark.parametrize("depth", [1, 2, 70])
 def test_sky_march_ranges_at_odd_depths(device, classroom, depth):
-    """k_miss hands out the escaped rays per bounce range (wavefront.cu: 63 bounces with a range of their own, deeper ones share the last):
-    depth 1 (the only bounce is the last), 2, and 70 (beyond the ranges; Russian roulette keeps it cheap) against the oracle."""
+    """k_miss hands out the escaped rays from cursors over ranges of the miss records -- one range per batch by default, one per bounce
+    (63 with a range of their own, deeper ones share the last) with LMB_MISS_SIDE_BLOCKS=n, which profiles/ runs exercise: depth 1 (the
+    only bounce is the last), 2, and 70 (beyond the ranges; Russian roulette keeps it cheap) against the oracle, over two batches."""
     w, h = 96, 54
     sc = host.Scene(classroom, w, h)
     orc = po.OracleScene(sc)
