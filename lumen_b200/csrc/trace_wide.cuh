@@ -55,7 +55,10 @@ struct WideBvhView {
 #define LMB_WIDE_BLOCKS_PER_SM_UNPINNED 7
 #endif
 #ifndef LMB_TRI_ROUND_LANES
-#define LMB_TRI_ROUND_LANES 8
+#define LMB_TRI_ROUND_LANES 10  // pinned walker (BVH in the L2): 8 / 9 / 10 / 11 / 12 = trace 58.56 / 58.22 / 58.28 / 58.65 / 59.35 ms
+#endif
+#ifndef LMB_TRI_ROUND_LANES_UNPINNED
+#define LMB_TRI_ROUND_LANES_UNPINNED 8  // 10 M-triangle grid: 2338 Mrays/s with 8, 2309 with 10
 #endif
 #ifndef LMB_DEFER_STORE
 #define LMB_DEFER_STORE 1

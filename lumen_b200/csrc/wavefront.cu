@@ -692,8 +692,9 @@ bool trace_pinned(const lmb_ctx* ctx) {
 }
 WideBvhView wide_view_of(const lmb_ctx* ctx) {
 	// scheduling thresholds of k_trace (results do not depend on them): tuning overrides for A/B runs
-	static const uint32_t refill = env_u32("LMB_REFILL_LANES", LMB_WIDE_REFILL_LANES), round = env_u32("LMB_TRI_ROUND_LANES", LMB_TRI_ROUND_LANES);
-	return WideBvhView{ctx->wide.nodes, ctx->wide.tris, ctx->wide.n_tris, 0x3F800000u, refill, round};
+	static const uint32_t refill = env_u32("LMB_REFILL_LANES", LMB_WIDE_REFILL_LANES), round = env_u32("LMB_TRI_ROUND_LANES", 0);
+	const uint32_t round_dflt = trace_pinned(ctx) ? LMB_TRI_ROUND_LANES : LMB_TRI_ROUND_LANES_UNPINNED;
+	return WideBvhView{ctx->wide.nodes, ctx->wide.tris, ctx->wide.n_tris, 0x3F800000u, refill, round ? round : round_dflt};
 }
 
 }  // namespace
