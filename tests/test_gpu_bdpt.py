@@ -84,6 +84,26 @@ def test_bdpt_film_matches_oracle(device):
     osc.close()
 
 
+@pytest.mark.parametrize("batch", ["1", "4"])
+def test_bdpt_frames_in_flight_do_not_change_the_film(device, monkeypatch, batch):
+    """Frames in flight (LMB_BDPT_BATCH; default up to 8): 6 frames as 4 + 2 (a short last batch changes the stride of every
+    struct-of-arrays buffer) and one at a time give the film of the default run; the own strategies are bit-equal per frame, the
+    light-tracer splats add in atomic order, hence the 1e-5 of the neighbouring test."""
+    sc, pc, ubo = _setup(device, "caustics", 64, 7)
+    device.clear_film()
+    device.reset_stats()
+    device.render_bdpt(pc, ubo, 3, 6, 2, integrator.FILM_SUM)  # frames 3, 5, .. 13 into a sum film (a strided running mean is refused)
+    want, st = device.download(), device.stats()
+    monkeypatch.setenv("LMB_BDPT_BATCH", batch)
+    device.clear_film()
+    device.reset_stats()
+    device.render_bdpt(pc, ubo, 3, 6, 2, integrator.FILM_SUM)
+    got, st2 = device.download(), device.stats()
+    assert (got[..., 3] == want[..., 3]).all()
+    assert pixel_agreement(got, want, rel=1e-5) >= 0.999
+    assert (st2.rays_closest, st2.rays_shadow) == (st.rays_closest, st.rays_shadow)
+
+
 def test_bdpt_time_enters_the_seed(device):
     """bdpt.rgen:36-37: seed.z = frame_num ^ pc.time. (frame 5, time 0) and (frame 4, time 1) are the same sample set."""
     sc, pc, ubo = _setup(device, "cornell", 64, 4)
