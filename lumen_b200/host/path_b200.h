@@ -102,8 +102,8 @@ class PathB200 final : public Integrator {
 // PathB200Multi: the same integrator over several GPUs of one box. Every device holds a full scene + BVH replica
 // and renders the frames f with f mod N == its rank over the whole image (sample-index sharding: perfect balance, no seams)
 // into an un-normalised sum film with the per-pixel valid-sample count in alpha (LMB_FILM_SUM); read_output() reduces the films
-// with ONE NCCL all-reduce over NVLink / NVSwitch followed by the "/ count" epilogue on every device (lmb_comm_init_all +
-// lmb_film_allreduce; the contexts must sit on distinct GPUs). Where the same GPU is listed twice (one-GPU test boxes) NCCL cannot
+// with ONE NCCL reduce to device 0 over NVLink / NVSwitch followed by the "/ count" epilogue there (lmb_comm_init_all +
+// lmb_film_reduce; the contexts must sit on distinct GPUs). Where the same GPU is listed twice (one-GPU test boxes) NCCL cannot
 // be used (one rank per device) and the films are added on device 0 by device-to-device copies instead (lmb_film_add_from).
 // One host thread per device, because lmb_render is synchronous on return. render() advances frame_num by N * frames_per_call.
 #include <thread>
@@ -200,9 +200,10 @@ class ShardedMulti : public Integrator {
 	void reduce() {
 		if (reduced) return;
 		if (use_nccl) {
-			// collective: every rank enqueues its all-reduce + resolve, then waits for its own stream
+			// collective: every rank enqueues its part of the reduce to device 0 (the one read_output / save_exr read; + resolve there),
+			// then waits for its own stream
 			each([&](size_t r) {
-				check(r, lmb_film_allreduce(ctx[r], nullptr, 0), "lmb_film_allreduce");
+				check(r, lmb_film_reduce(ctx[r], 0, nullptr, 0), "lmb_film_reduce");
 				check(r, lmb_sync(ctx[r]), "lmb_sync");
 			});
 		} else {
