@@ -66,6 +66,9 @@ struct WideBvhView {
 #ifndef LMB_TRACE_WCOUNT
 #define LMB_TRACE_WCOUNT 1  // warp-level scheduling counters kept by the walker: 0 none, 1 loop trips, 3 + triangle rounds and refills
 #endif
+#ifndef LMB_TRACE_FFMA2
+#define LMB_TRACE_FFMA2 1
+#endif
 #ifndef LMB_PREFETCH
 #define LMB_PREFETCH 0  // 1: leaf triangles, 2: + entered children, of the unpinned (BVH beyond the L2) instantiation
 #endif
@@ -294,12 +297,23 @@ __device__ __forceinline__ void trace_wide_persistent(const WideBvhView& bvh, So
 #pragma unroll
 					for (int j = 3; j >= 0; j--) {
 						const uint32_t sel = 0x7604u + (uint32_t)(j << 4);  // bytes (3F, 80, q_j, 00) = 1 + q_j * 2^-15
+#if LMB_TRACE_FFMA2
+						// near and far plane of one axis share A and B: one packed FFMA2 (fma.rn.f32x2, sm_100; each half an IEEE fma, same values)
+						// per axis and child instead of two FFMA. The FMA pipe does the same work (FFMA2 = 2 FFMA of pipe time, measured:
+						// tools/micro/ffma2_rate.cu); what is saved is the issue slot, which this kernel is short of: trace 58.24 -> 57.75 ms.
+						// (Packing the entry test of two children as well, with negated near planes, spilled at 64 registers: 64.6 ms.)
+						const float2 tx = __ffma2_rn(make_float2(__uint_as_float(__byte_perm(nx, one_bits, sel)), __uint_as_float(__byte_perm(fx, one_bits, sel))), make_float2(ax, ax), make_float2(bx, bx));
+						const float2 ty = __ffma2_rn(make_float2(__uint_as_float(__byte_perm(ny, one_bits, sel)), __uint_as_float(__byte_perm(fy, one_bits, sel))), make_float2(ay, ay), make_float2(by, by));
+						const float2 tz = __ffma2_rn(make_float2(__uint_as_float(__byte_perm(nz, one_bits, sel)), __uint_as_float(__byte_perm(fz, one_bits, sel))), make_float2(az, az), make_float2(bz, bz));
+						const float tx0 = tx.x, tx1 = tx.y, ty0 = ty.x, ty1 = ty.y, tz0 = tz.x, tz1 = tz.y;
+#else
 						const float tx0 = fmaf(__uint_as_float(__byte_perm(nx, one_bits, sel)), ax, bx);
 						const float ty0 = fmaf(__uint_as_float(__byte_perm(ny, one_bits, sel)), ay, by);
 						const float tz0 = fmaf(__uint_as_float(__byte_perm(nz, one_bits, sel)), az, bz);
 						const float tx1 = fmaf(__uint_as_float(__byte_perm(fx, one_bits, sel)), ax, bx);
 						const float ty1 = fmaf(__uint_as_float(__byte_perm(fy, one_bits, sel)), ay, by);
 						const float tz1 = fmaf(__uint_as_float(__byte_perm(fz, one_bits, sel)), az, bz);
+#endif
 						const float tn = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, tmin_box));
 						const float tf = fminf(fminf(tx1, ty1), fminf(tz1, h.t));
 						// entered <=> tn <= tf * pad. The sign of fma(tf, pad, -tn) says exactly that (tn > 0, so the result is never -0), one
