@@ -1408,41 +1408,53 @@ int bdpt_render(lmb_ctx* ctx, const lmb_pc_bdpt& pc, const lmb_scene_ubo& ubo, u
 	batch = (uint32_t)std::min<uint64_t>(batch, 0x7FFFFFFFull / ((uint64_t)n_real * n_conn_slots));
 	if (const char* e = getenv("LMB_BDPT_BATCH")) batch = std::max(1, atoi(e));
 	if (raw_col || mega || per_pixel) batch = 1;
-	const uint32_t n_pix = n_real * batch;  // capacity of the buffers in (frame, pixel) pairs
-	if (b.n_pix != n_pix || b.n_verts != n_verts) {
+	uint32_t n_pix = n_real * batch;  // capacity of the buffers in (frame, pixel) pairs
+	// all or nothing: a failed allocation (the batch takes tens of GB) must not leave a half-built state behind for the next call
+	auto allocate = [&]() -> int {
+		if (b.n_pix != n_pix || b.n_verts != n_verts) {
+			bdpt_free(ctx);
+			LMB_CUDA(ctx, cudaMalloc((void**)&b.light_verts, (size_t)n_pix * n_verts * W_COUNT * 4));
+			LMB_CUDA(ctx, cudaMalloc((void**)&b.camera_verts, (size_t)n_pix * n_verts * W_COUNT * 4));
+			LMB_CUDA(ctx, cudaMalloc((void**)&b.col, (size_t)n_pix * 16));
+			LMB_CUDA(ctx, cudaMalloc((void**)&b.splat, (size_t)n_pix * 12));
+			b.n_pix = n_pix, b.n_verts = n_verts;
+		}
+		if (!mega && !b.rays) {
+			LMB_CUDA(ctx, cudaMalloc((void**)&b.walk, (size_t)n_pix * WW_COUNT * 4));
+			LMB_CUDA(ctx, cudaMalloc((void**)&b.misc, (size_t)n_pix * MW_COUNT * 4));
+			LMB_CUDA(ctx, cudaMalloc((void**)&b.rays, (size_t)n_pix * n_conn_slots * 32));
+			// a dead slot is marked in its first float4 only; the walker loads both halves of every slot, so the second must be defined
+			LMB_CUDA(ctx, cudaMemsetAsync(b.rays, 0, (size_t)n_pix * n_conn_slots * 32, st));
+			LMB_CUDA(ctx, cudaMalloc((void**)&b.hits, (size_t)n_pix * 16));
+			for (int i = 0; i < 2; i++) LMB_CUDA(ctx, cudaMalloc((void**)&b.alive_list[i], (size_t)n_pix * 4));
+			LMB_CUDA(ctx, cudaMalloc((void**)&b.alive_count, (2 * 64 + 4) * 4));  // max_depth <= 64 (check_bdpt_args)
+			LMB_CUDA(ctx, cudaMalloc((void**)&b.occ, (size_t)n_pix * n_conn_slots));
+			b.n_conn_slots = n_conn_slots;
+		}
+		if (!mega && !per_pixel && !b.contrib) {
+			std::vector<uint8_t> ts;
+			for (int t = 1; t <= pc.max_depth + 1; t++)
+				for (int s = 0; s <= pc.max_depth + 1; s++) {
+					const int depth = s + t - 2;
+					if (depth > (pc.max_depth - 1) || depth < 0 || (s == 1 && t == 1)) continue;
+					ts.push_back((uint8_t)t), ts.push_back((uint8_t)s);
+				}
+			LMB_CUDA(ctx, cudaMalloc((void**)&b.contrib, (size_t)n_pix * n_conn_slots * 16));
+			LMB_CUDA(ctx, cudaMalloc((void**)&b.pair_ts, ts.size()));
+			LMB_CUDA(ctx, cudaMalloc((void**)&b.work_list, (size_t)n_pix * n_conn_slots * 4));
+			LMB_CUDA(ctx, cudaMalloc((void**)&b.emit_list, (size_t)n_pix * n_conn_slots * 4));
+			LMB_CUDA(ctx, cudaMalloc((void**)&b.work_count, 12));
+			LMB_CUDA(ctx, cudaMemcpy(b.pair_ts, ts.data(), ts.size(), cudaMemcpyHostToDevice));
+		}
+		return 0;
+	};
+	for (;;) {
+		const int rc_alloc = allocate();
+		if (rc_alloc == 0) break;
 		bdpt_free(ctx);
-		LMB_CUDA(ctx, cudaMalloc((void**)&b.light_verts, (size_t)n_pix * n_verts * W_COUNT * 4));
-		LMB_CUDA(ctx, cudaMalloc((void**)&b.camera_verts, (size_t)n_pix * n_verts * W_COUNT * 4));
-		LMB_CUDA(ctx, cudaMalloc((void**)&b.col, (size_t)n_pix * 16));
-		LMB_CUDA(ctx, cudaMalloc((void**)&b.splat, (size_t)n_pix * 12));
-		b.n_pix = n_pix, b.n_verts = n_verts;
-	}
-	if (!mega && !b.rays) {
-		LMB_CUDA(ctx, cudaMalloc((void**)&b.walk, (size_t)n_pix * WW_COUNT * 4));
-		LMB_CUDA(ctx, cudaMalloc((void**)&b.misc, (size_t)n_pix * MW_COUNT * 4));
-		LMB_CUDA(ctx, cudaMalloc((void**)&b.rays, (size_t)n_pix * n_conn_slots * 32));
-		// a dead slot is marked in its first float4 only; the walker loads both halves of every slot, so the second must be defined
-		LMB_CUDA(ctx, cudaMemsetAsync(b.rays, 0, (size_t)n_pix * n_conn_slots * 32, st));
-		LMB_CUDA(ctx, cudaMalloc((void**)&b.hits, (size_t)n_pix * 16));
-		for (int i = 0; i < 2; i++) LMB_CUDA(ctx, cudaMalloc((void**)&b.alive_list[i], (size_t)n_pix * 4));
-		LMB_CUDA(ctx, cudaMalloc((void**)&b.alive_count, (2 * 64 + 4) * 4));  // max_depth <= 64 (check_bdpt_args)
-		LMB_CUDA(ctx, cudaMalloc((void**)&b.occ, (size_t)n_pix * n_conn_slots));
-		b.n_conn_slots = n_conn_slots;
-	}
-	if (!mega && !per_pixel && !b.contrib) {
-		std::vector<uint8_t> ts;
-		for (int t = 1; t <= pc.max_depth + 1; t++)
-			for (int s = 0; s <= pc.max_depth + 1; s++) {
-				const int depth = s + t - 2;
-				if (depth > (pc.max_depth - 1) || depth < 0 || (s == 1 && t == 1)) continue;
-				ts.push_back((uint8_t)t), ts.push_back((uint8_t)s);
-			}
-		LMB_CUDA(ctx, cudaMalloc((void**)&b.contrib, (size_t)n_pix * n_conn_slots * 16));
-		LMB_CUDA(ctx, cudaMalloc((void**)&b.pair_ts, ts.size()));
-		LMB_CUDA(ctx, cudaMalloc((void**)&b.work_list, (size_t)n_pix * n_conn_slots * 4));
-		LMB_CUDA(ctx, cudaMalloc((void**)&b.emit_list, (size_t)n_pix * n_conn_slots * 4));
-		LMB_CUDA(ctx, cudaMalloc((void**)&b.work_count, 12));
-		LMB_CUDA(ctx, cudaMemcpy(b.pair_ts, ts.data(), ts.size(), cudaMemcpyHostToDevice));
+		cudaGetLastError();  // an out-of-memory error is not sticky: clear it
+		if (batch == 1) return rc_alloc;
+		batch = 1, n_pix = n_real;  // fall back to one frame in flight
 	}
 	LMB_CUDA(ctx, cudaMemsetAsync(b.splat, 0, (size_t)n_pix * 12, st));
 	auto load = [](const float* p) {
